@@ -1,0 +1,637 @@
+// dashing_b200.cu — the C ABI (include/dashing_b200.h) over the sm_100a kernels in sketch.cuh / dist.cuh.
+// Host orchestration only: device memory, streams, H2D/D2H, launch geometry.  No arithmetic of the
+// hot paths runs on the CPU here and there is no fallback: without a CUDA device every compute
+// entry point returns DB200_ENODEV.
+#include "common.cuh"
+#include "estimators.cuh"
+#include "sketch.cuh"
+#include "dist.cuh"
+
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+#include <vector>
+#include <memory>
+
+namespace db200 {
+
+static thread_local std::string t_err;
+std::atomic<uint64_t> g_kernel_launches{0};
+
+void set_error(const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    t_err = buf;
+}
+
+static int g_num_sms(int device) {
+    static int cache[64] = {0};
+    if (device < 64 && cache[device]) return cache[device];
+    int v = 148;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device);
+    if (device < 64) cache[device] = v;
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// packed genome store
+// ---------------------------------------------------------------------------------------------
+} // namespace db200
+
+struct db200_packed_genomes {
+    int device = 0, k = 0;
+    uint64_t nbases = 0, nblk = 0, ngenomes = 0, kmers = 0;
+    uint32_t nitems = 0;
+    db200::DevBuf bases2, nb, st, items;
+};
+
+namespace db200 {
+
+static uint64_t count_kmers(const uint64_t *rec_offsets, uint64_t nrecords, int k) {
+    // work items of the metric: sum over records of max(0, len - k + 1)   
+    uint64_t t = 0;
+    for (uint64_t r = 0; r < nrecords; ++r) {
+        const uint64_t len = rec_offsets[r + 1] - rec_offsets[r];
+        if (len >= (uint64_t)k) t += len - k + 1;
+    }
+    return t;
+}
+
+static int pack_genomes_impl(int device, const char *bases, const uint64_t *rec_offsets, uint64_t nrecords,
+                             const uint64_t *genome_rec_begin, uint64_t ngenomes, int k, db200_packed_genomes *pg,
+                             cudaStream_t stream) {
+    const uint64_t base0 = nrecords ? rec_offsets[0] : 0;
+    const uint64_t T = nrecords ? rec_offsets[nrecords] - base0 : 0;
+    pg->device = device; pg->k = k; pg->nbases = T; pg->ngenomes = ngenomes;
+    pg->nblk = (T + 63) / 64 + 1;  // +1: a zero guard block so the last block's successor reads are defined
+    pg->kmers = count_kmers(rec_offsets, nrecords, k);
+    DB200_TRY(pg->bases2.reserve(pg->nblk * 16));
+    DB200_TRY(pg->nb.reserve(pg->nblk * 8));
+    DB200_TRY(pg->st.reserve(pg->nblk * 8));
+    DB200_CUDA(cudaMemsetAsync(pg->st.ptr, 0, pg->nblk * 8, stream));
+    DB200_CUDA(cudaMemsetAsync(pg->nb.ptr, 0, pg->nblk * 8, stream));
+    DB200_CUDA(cudaMemsetAsync(pg->bases2.ptr, 0, pg->nblk * 16, stream));
+
+    // ASCII upload in 64-base-aligned chunks through two device staging buffers; the pack kernel of
+    // chunk c overlaps the H2D copy of chunk c+1.
+    const uint64_t CH = 64ull << 20;
+    DevBuf stage[2];
+    cudaStream_t cs = nullptr;
+    cudaEvent_t copied[2] = {nullptr, nullptr}, packed[2] = {nullptr, nullptr};
+    DB200_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+    int rc = DB200_OK;
+    auto cleanup = [&]() {
+        for (int i = 0; i < 2; ++i) { if (copied[i]) cudaEventDestroy(copied[i]); if (packed[i]) cudaEventDestroy(packed[i]); }
+        if (cs) cudaStreamDestroy(cs);
+    };
+    for (int i = 0; i < 2 && rc == DB200_OK; ++i) {
+        rc = stage[i].reserve(std::min<uint64_t>(CH, std::max<uint64_t>(T, 64)));
+        if (rc == DB200_OK && cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming) != cudaSuccess) rc = DB200_ECUDA;
+        if (rc == DB200_OK && cudaEventCreateWithFlags(&packed[i], cudaEventDisableTiming) != cudaSuccess) rc = DB200_ECUDA;
+    }
+    if (rc != DB200_OK) { cleanup(); return rc; }
+    uint64_t nchunks = (T + CH - 1) / CH;
+    for (uint64_t c = 0; c < nchunks; ++c) {
+        const int b = (int)(c & 1);
+        const uint64_t off = c * CH, len = std::min<uint64_t>(CH, T - off);
+        if (c >= 2) cudaStreamWaitEvent(cs, packed[b], 0);  // staging buffer free again
+        if (cudaMemcpyAsync(stage[b].ptr, bases + base0 + off, len, cudaMemcpyHostToDevice, cs) != cudaSuccess) { rc = DB200_ECUDA; break; }
+        cudaEventRecord(copied[b], cs);
+        cudaStreamWaitEvent(stream, copied[b], 0);
+        const uint64_t ngroups = (len + 15) / 16;
+        pack_kernel<<<(unsigned)((ngroups + 255) / 256), 256, 0, stream>>>(
+            stage[b].as<uint8_t>(), len, pg->bases2.as<uint32_t>() + off / 16, pg->nb.as<uint16_t>() + off / 16, ngroups);
+        DB200_LAUNCHED();
+        cudaEventRecord(packed[b], stream);
+    }
+    if (rc == DB200_OK && cudaGetLastError() != cudaSuccess) rc = DB200_ECUDA;
+    if (rc != DB200_OK) { set_error("packing genomes failed: %s", cudaGetErrorString(cudaGetLastError())); cudaStreamSynchronize(stream); cleanup(); return rc; }
+
+    // record starts
+    std::vector<uint64_t> starts;
+    starts.reserve(nrecords);
+    for (uint64_t r = 0; r < nrecords; ++r) {
+        const uint64_t pos = rec_offsets[r] - base0;
+        if (pos < T && rec_offsets[r + 1] > rec_offsets[r]) starts.push_back(pos);
+    }
+    DevBuf dstarts;
+    if (!starts.empty()) {
+        rc = dstarts.reserve(starts.size() * 8);
+        if (rc == DB200_OK && cudaMemcpyAsync(dstarts.ptr, starts.data(), starts.size() * 8, cudaMemcpyHostToDevice, stream) != cudaSuccess) rc = DB200_ECUDA;
+        if (rc == DB200_OK) {
+            mark_starts_kernel<<<(unsigned)((starts.size() + 255) / 256), 256, 0, stream>>>(dstarts.as<uint64_t>(), starts.size(), pg->st.as<uint32_t>());
+            DB200_LAUNCHED();
+        }
+    }
+    // work items: split every genome's base range into chunks so that all SMs have several items
+    std::vector<SketchItem> items;
+    {
+        const uint64_t target_items = (uint64_t)g_num_sms(device) * 16;
+        uint64_t chunk = T / std::max<uint64_t>(target_items, 1);
+        chunk = std::min<uint64_t>(std::max<uint64_t>(chunk, 1ull << 16), 1ull << 20);
+        chunk = (chunk + 63) & ~63ull;
+        for (uint64_t g = 0; g < ngenomes; ++g) {
+            const uint64_t gs = rec_offsets[genome_rec_begin[g]] - base0, ge = rec_offsets[genome_rec_begin[g + 1]] - base0;
+            for (uint64_t s = gs; s < ge;) {
+                uint64_t e = std::min(ge, ((s / chunk) + 1) * chunk);
+                items.push_back(SketchItem{s, e, (uint32_t)g, 0});
+                s = e;
+            }
+        }
+    }
+    pg->nitems = (uint32_t)items.size();
+    if (rc == DB200_OK && !items.empty()) {
+        rc = pg->items.reserve(items.size() * sizeof(SketchItem));
+        if (rc == DB200_OK && cudaMemcpyAsync(pg->items.ptr, items.data(), items.size() * sizeof(SketchItem), cudaMemcpyHostToDevice, stream) != cudaSuccess) rc = DB200_ECUDA;
+    }
+    cudaError_t e = cudaStreamSynchronize(stream);  // staging buffers / host vectors go out of scope
+    if (rc == DB200_OK && e != cudaSuccess) { set_error("pack_genomes: %s", cudaGetErrorString(e)); rc = DB200_ECUDA; }
+    cleanup();
+    return rc;
+}
+
+static int sketch_packed_impl(const db200_packed_genomes *pg, int p, int canon, uint8_t *d_regs, cudaStream_t stream) {
+    if (p < 7 || p > 24) { set_error("sketch: p=%d outside the GPU path's range [7,24]", p); return DB200_EUNSUPPORTED; }
+    if (pg->k < 1 || pg->k > 32) { set_error("sketch: k=%d outside [1,32]", pg->k); return DB200_EUNSUPPORTED; }
+    const uint64_t m = 1ull << p;
+    DB200_CUDA(cudaMemsetAsync(d_regs, 0, pg->ngenomes * m, stream));
+    if (pg->nitems == 0) return DB200_OK;
+    const bool smem_regs = m <= (128u << 10);
+    int occ = 1;
+    const size_t smem = smem_regs ? m : 0;
+    if (smem_regs) {
+        DB200_CUDA(cudaFuncSetAttribute(sketch_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 << 10));
+        DB200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sketch_kernel<true>, SK_THREADS, smem));
+    } else {
+        DB200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sketch_kernel<false>, SK_THREADS, 0));
+    }
+    occ = std::max(occ, 1);
+    const unsigned grid = (unsigned)std::min<uint64_t>(pg->nitems, (uint64_t)g_num_sms(pg->device) * occ);
+    if (smem_regs)
+        sketch_kernel<true><<<grid, SK_THREADS, smem, stream>>>(pg->bases2.as<uint4>(), pg->nb.as<uint64_t>(), pg->st.as<uint64_t>(),
+                                                                pg->items.as<SketchItem>(), pg->nitems, pg->k, p, canon, d_regs);
+    else
+        sketch_kernel<false><<<grid, SK_THREADS, 0, stream>>>(pg->bases2.as<uint4>(), pg->nb.as<uint64_t>(), pg->st.as<uint64_t>(),
+                                                              pg->items.as<SketchItem>(), pg->nitems, pg->k, p, canon, d_regs);
+    DB200_LAUNCHED();
+    DB200_CUDA(cudaGetLastError());
+    return DB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// TMA descriptor
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+    static PFN_encodeTiled fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(p);
+    });
+    return fn;
+}
+
+} // namespace db200
+
+// ---------------------------------------------------------------------------------------------
+// dist plan
+// ---------------------------------------------------------------------------------------------
+struct db200_dist_plan {
+    int device = 0;
+    uint64_t nrows = 0;            // rows of the plane tensor (symmetric: n; rect: qbase + nq)
+    uint64_t n1 = 0, qbase = 0, n2 = 0;  // valid row segments [0,n1) and [qbase, qbase+n2)
+    int p = 0, estim = -1, gmin = 0, gmax = 0, K = 0;
+    bool ready = false;
+    CUtensorMap tmap;
+    db200::DevBuf planes, counts, card, smin, smax, pmin, pmax, minmax, tiles;
+    // tile-list cache key
+    int tl_rect = -1; uint64_t tl_rb = 0, tl_re = 0, tl_nr = 0, tl_nq = 0, tl_n = 0; uint64_t ntiles = 0;
+    uint64_t last_pairs = 0, last_tiles = 0;
+    std::mutex mu;
+};
+
+namespace db200 {
+
+static int plan_prepare(db200_dist_plan *pl, const uint8_t *d_regs, uint64_t nrows, uint64_t n1, uint64_t qbase, uint64_t n2, int p,
+                        int estim, cudaStream_t stream) {
+    if (p < 10 || p > 16) { set_error("dist: p=%d outside the GPU path's range [10,16]", p); return DB200_EUNSUPPORTED; }
+    if (estim < 0 || estim > 2) { set_error("dist: unknown estimation method %d", estim); return DB200_EINVAL; }
+    if (nrows == 0 || nrows > (1ull << 31) - 64) { set_error("dist: %llu sketches unsupported", (unsigned long long)nrows); return DB200_EINVAL; }
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) { set_error("cuTensorMapEncodeTiled not available from the driver"); return DB200_ECUDA; }
+    pl->ready = false;
+    pl->nrows = nrows; pl->n1 = n1; pl->qbase = qbase; pl->n2 = n2; pl->p = p; pl->estim = estim;
+    pl->tl_rect = -1;
+    const uint64_t m = 1ull << p, W = m >> 5, npan = (nrows + DT - 1) / DT;
+    DB200_TRY(pl->minmax.reserve(8));
+    DB200_CUDA(cudaMemsetAsync(pl->minmax.ptr, 0xFF, 4, stream));
+    DB200_CUDA(cudaMemsetAsync(pl->minmax.as<uint8_t>() + 4, 0, 4, stream));
+    const int sms = g_num_sms(pl->device);
+    for (int seg = 0; seg < 2; ++seg) {
+        const uint64_t r0 = seg ? qbase : 0, cnt = seg ? n2 : n1;
+        if (!cnt) continue;
+        const uint64_t n16 = cnt * m / 16;
+        const unsigned grid = (unsigned)std::min<uint64_t>((n16 + 255) / 256, (uint64_t)sms * 8);
+        range_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const uint4 *>(d_regs + r0 * m), n16, pl->minmax.as<uint32_t>());
+        DB200_LAUNCHED();
+    }
+    uint32_t mm[2];
+    DB200_CUDA(cudaMemcpyAsync(mm, pl->minmax.ptr, 8, cudaMemcpyDeviceToHost, stream));
+    DB200_CUDA(cudaStreamSynchronize(stream));
+    if (mm[1] > (uint32_t)(64 - p + 1)) { set_error("dist: register value %u exceeds 64-p+1=%d (corrupt sketch?)", mm[1], 64 - p + 1); return DB200_EINVAL; }
+    pl->gmin = (int)mm[0]; pl->gmax = (int)mm[1]; pl->K = pl->gmax - pl->gmin;
+    const uint64_t Kalloc = std::max(pl->K, 1);
+    DB200_TRY(pl->planes.reserve(Kalloc * nrows * W * 4));
+    DB200_TRY(pl->counts.reserve(nrows * 64 * 4));
+    DB200_TRY(pl->card.reserve(nrows * 8));
+    DB200_TRY(pl->smin.reserve(nrows));
+    DB200_TRY(pl->smax.reserve(nrows));
+    DB200_TRY(pl->pmin.reserve(npan * 4));
+    DB200_TRY(pl->pmax.reserve(npan * 4));
+    DB200_CUDA(cudaMemsetAsync(pl->pmin.ptr, 0xFF, npan * 4, stream));
+    DB200_CUDA(cudaMemsetAsync(pl->pmax.ptr, 0, npan * 4, stream));
+    if (n1 + n2 != nrows || pl->K == 0) {  // padding rows (or the K==0 dummy plane) must read as "below every threshold"
+        DB200_CUDA(cudaMemsetAsync(pl->planes.ptr, 0, Kalloc * nrows * W * 4, stream));
+        DB200_CUDA(cudaMemsetAsync(pl->smin.ptr, 0, nrows, stream));
+        DB200_CUDA(cudaMemsetAsync(pl->smax.ptr, 0, nrows, stream));
+        DB200_CUDA(cudaMemsetAsync(pl->card.ptr, 0, nrows * 8, stream));
+    }
+    DB200_CUDA(cudaMemsetAsync(pl->counts.ptr, 0, nrows * 64 * 4, stream));
+    for (int seg = 0; seg < 2; ++seg) {
+        const uint64_t r0 = seg ? qbase : 0, cnt = seg ? n2 : n1;
+        if (!cnt) continue;
+        if (pl->K > 0) {
+            planes_kernel<<<(unsigned)cnt, 128, 0, stream>>>(reinterpret_cast<const uint32_t *>(d_regs), nrows, r0, p, pl->gmin, pl->K,
+                                                            pl->planes.as<uint32_t>(), pl->counts.as<uint32_t>());
+            DB200_LAUNCHED();
+        }
+        card_kernel<<<(unsigned)((cnt + 127) / 128), 128, 0, stream>>>(pl->counts.as<uint32_t>(), r0, cnt, p, pl->gmin, pl->gmax, estim,
+                                                                      pl->card.as<double>(), pl->smin.as<uint8_t>(), pl->smax.as<uint8_t>(),
+                                                                      pl->pmin.as<uint32_t>(), pl->pmax.as<uint32_t>());
+        DB200_LAUNCHED();
+    }
+    DB200_CUDA(cudaGetLastError());
+    // 3-D tensor {W words, nrows sketches, K thresholds}, box {32, 32, 1}, 128-byte swizzle
+    cuuint64_t dims[3] = {W, nrows, Kalloc};
+    cuuint64_t strides[2] = {W * 4, nrows * W * 4};
+    cuuint32_t box[3] = {32, (cuuint32_t)DT, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&pl->tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, pl->planes.ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return DB200_ECUDA; }
+    pl->ready = true;
+    return DB200_OK;
+}
+
+static int plan_tiles(db200_dist_plan *pl, int rect, uint64_t rb, uint64_t re, uint64_t nr, uint64_t nq, cudaStream_t stream) {
+    if (pl->tl_rect == rect && pl->tl_rb == rb && pl->tl_re == re && pl->tl_nr == nr && pl->tl_nq == nq && pl->tl_n == pl->nrows) return DB200_OK;
+    std::vector<DistTile> tiles;
+    const uint32_t SR = 8;  // panel rows per super-row: concurrent CTAs share A panels and sweep B panels together (L2 reuse)
+    if (!rect) {
+        const uint64_t n = pl->nrows;
+        const uint32_t nb = (uint32_t)((n + DT - 1) / DT);
+        const uint32_t a0 = (uint32_t)(rb / DT), a1 = re > rb ? (uint32_t)((re - 1) / DT) + 1 : a0;
+        for (uint32_t sr = a0; sr < a1; sr += SR)
+            for (uint32_t b = sr; b < nb; ++b)
+                for (uint32_t a = sr; a < std::min(sr + SR, a1) && a <= b; ++a) tiles.push_back(DistTile{a, b});
+    } else {
+        const uint32_t na = (uint32_t)((nq + DT - 1) / DT), nb = (uint32_t)((nr + DT - 1) / DT);
+        for (uint32_t sr = 0; sr < na; sr += SR)
+            for (uint32_t b = 0; b < nb; ++b)
+                for (uint32_t a = sr; a < std::min(sr + SR, na); ++a) tiles.push_back(DistTile{a, b});
+    }
+    pl->ntiles = tiles.size();
+    if (!tiles.empty()) {
+        DB200_TRY(pl->tiles.reserve(tiles.size() * sizeof(DistTile)));
+        DB200_CUDA(cudaMemcpyAsync(pl->tiles.ptr, tiles.data(), tiles.size() * sizeof(DistTile), cudaMemcpyHostToDevice, stream));
+        DB200_CUDA(cudaStreamSynchronize(stream));  // `tiles` is pageable host memory about to go out of scope
+    }
+    pl->tl_rect = rect; pl->tl_rb = rb; pl->tl_re = re; pl->tl_nr = nr; pl->tl_nq = nq; pl->tl_n = pl->nrows;
+    return DB200_OK;
+}
+
+static int plan_run(db200_dist_plan *pl, const db200_dist_params *prm, int rect, uint64_t rb, uint64_t re, uint64_t nr, uint64_t nq,
+                    float *d_out, cudaStream_t stream) {
+    if (!pl->ready) { set_error("dist plan not prepared"); return DB200_EINVAL; }
+    if (prm->p != pl->p || prm->estim != pl->estim) { set_error("dist params (p=%d, estim=%d) differ from the prepared plan (p=%d, estim=%d)", prm->p, prm->estim, pl->p, pl->estim); return DB200_EINVAL; }
+    if (prm->jestim == DB200_ERTL_JOINT_MLE) { set_error("dist: joint MLE (-J) is not on the GPU path yet"); return DB200_EUNSUPPORTED; }
+    if (prm->result_type < 0 || prm->result_type > 8) { set_error("dist: unknown result type %d", prm->result_type); return DB200_EINVAL; }
+    if (prm->k < 1) { set_error("dist: k must be positive"); return DB200_EINVAL; }
+    DB200_TRY(plan_tiles(pl, rect, rb, re, nr, nq, stream));
+    pl->last_tiles = pl->ntiles;
+    if (pl->ntiles == 0) { pl->last_pairs = 0; return DB200_OK; }
+    DistArgs a;
+    a.tiles = pl->tiles.as<DistTile>();
+    a.smin = pl->smin.as<uint8_t>(); a.smax = pl->smax.as<uint8_t>();
+    a.pmin = pl->pmin.as<uint32_t>(); a.pmax = pl->pmax.as<uint32_t>();
+    a.card = pl->card.as<double>();
+    a.out = d_out;
+    a.n = pl->nrows; a.row_begin = rb; a.row_end = re;
+    a.out_base = rect ? 0 : (rb * (2 * pl->nrows - rb - 1)) / 2;
+    a.nr = nr; a.nq = nq; a.qbase = pl->qbase;
+    a.ksinv = (double)(float)(1. / prm->k);  // const float ksinv = 1./k, src/sketch_and_cmp.h:797
+    a.p = pl->p; a.gmin = pl->gmin; a.gmax = pl->gmax; a.K = pl->K;
+    a.estim = prm->estim; a.rtype = prm->result_type; a.rect = rect;
+    // shared memory: S stages of 8 KiB + K x 2 KiB threshold counts + barriers; aim for two CTAs per SM
+    const size_t gbytes = (size_t)std::max(pl->K, 1) * DT * DT * 2;
+    int S = 6;
+    const size_t budget2 = 113 << 10, budget1 = 226 << 10;
+    if (gbytes + (size_t)S * STAGE_BYTES + 1024 > budget2) S = (int)std::min<size_t>(12, (budget1 - gbytes - 1024) / STAGE_BYTES);
+    if (S < 2) { set_error("dist: %d live thresholds do not fit in shared memory", pl->K); return DB200_EUNSUPPORTED; }
+    a.stages = S;
+    const size_t smem = (size_t)S * STAGE_BYTES + gbytes + 2 * S * 8;
+    DB200_CUDA(cudaFuncSetAttribute(dist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 << 10));
+    dist_kernel<<<(unsigned)pl->ntiles, DIST_THREADS, smem, stream>>>(pl->tmap, a);
+    DB200_LAUNCHED();
+    DB200_CUDA(cudaGetLastError());
+    if (rect) pl->last_pairs = nr * nq;
+    else {
+        const uint64_t n = pl->nrows;
+        auto tri = [n](uint64_t r) { return (r * (2 * n - r - 1)) / 2; };
+        pl->last_pairs = tri(std::min(re, n)) - tri(rb);
+    }
+    return DB200_OK;
+}
+
+// Default per-device resources for the host-pointer entry points.
+struct HostCtx {
+    std::mutex mu;
+    cudaStream_t stream = nullptr;
+    DevBuf regs, out, cards;
+    std::unique_ptr<db200_dist_plan> plan;
+    int init(int device) {
+        if (!stream) DB200_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        if (!plan) { plan.reset(new db200_dist_plan); plan->device = device; }
+        return DB200_OK;
+    }
+};
+static HostCtx &host_ctx(int device) {
+    static HostCtx ctx[64];
+    return ctx[device & 63];
+}
+
+} // namespace db200
+
+using namespace db200;
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+const char *db200_last_error(void) { return t_err.c_str(); }
+int db200_version(void) { return DB200_VERSION; }
+uint64_t db200_kernel_launches(void) { return g_kernel_launches.load(); }
+
+int db200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int db200_host_alloc(void **out, size_t bytes) {
+    if (!out) { set_error("db200_host_alloc: null out"); return DB200_EINVAL; }
+    DB200_TRY(check_device(0));
+    DB200_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+    return DB200_OK;
+}
+int db200_host_free(void *ptr) {
+    if (ptr) DB200_CUDA(cudaFreeHost(ptr));
+    return DB200_OK;
+}
+
+// ---- sketching ------------------------------------------------------------------------------
+int db200_pack_genomes(int device, const char *bases, const uint64_t *rec_offsets, uint64_t nrecords, const uint64_t *genome_rec_begin,
+                       uint64_t ngenomes, int k, db200_packed_genomes **out) {
+    if (!out || !rec_offsets || !genome_rec_begin || (!bases && nrecords)) { set_error("db200_pack_genomes: null argument"); return DB200_EINVAL; }
+    if (k < 1 || k > 32) { set_error("sketch: k=%d outside [1,32]", k); return DB200_EUNSUPPORTED; }
+    if (ngenomes >= (1ull << 32)) { set_error("too many genomes"); return DB200_EINVAL; }
+    DB200_TRY(check_device(device));
+    HostCtx &hc = host_ctx(device);
+    std::lock_guard<std::mutex> lk(hc.mu);
+    DB200_TRY(hc.init(device));
+    std::unique_ptr<db200_packed_genomes> pg(new db200_packed_genomes);
+    DB200_TRY(pack_genomes_impl(device, bases, rec_offsets, nrecords, genome_rec_begin, ngenomes, k, pg.get(), hc.stream));
+    *out = pg.release();
+    return DB200_OK;
+}
+
+int db200_packed_genomes_free(db200_packed_genomes *g) {
+    if (g) { cudaSetDevice(g->device); delete g; }
+    return DB200_OK;
+}
+
+int db200_packed_genomes_stats(const db200_packed_genomes *g, uint64_t *packed_bytes, uint64_t *kmers, uint64_t *bases) {
+    if (!g) { set_error("null store"); return DB200_EINVAL; }
+    // algorithmic bytes of SURVEY.md §8(d): ceil(L/4) 2-bit bases + ceil(L/8) validity plane (+ the record-start plane this design adds)
+    if (packed_bytes) *packed_bytes = (g->nbases + 3) / 4 + 2 * ((g->nbases + 7) / 8);
+    if (kmers) *kmers = g->kmers;
+    if (bases) *bases = g->nbases;
+    return DB200_OK;
+}
+
+int db200_sketch_packed_dev(const db200_packed_genomes *g, int p, int canon, uint8_t *d_registers, void *stream) {
+    if (!g || !d_registers) { set_error("db200_sketch_packed_dev: null argument"); return DB200_EINVAL; }
+    DB200_TRY(check_device(g->device));
+    return sketch_packed_impl(g, p, canon, d_registers, (cudaStream_t)stream);
+}
+
+int db200_sketch_batch(int device, int p, int k, int canon, const char *bases, const uint64_t *rec_offsets, uint64_t nrecords,
+                       const uint64_t *genome_rec_begin, uint64_t ngenomes, uint8_t *registers_out) {
+    if (!registers_out && ngenomes) { set_error("db200_sketch_batch: null output"); return DB200_EINVAL; }
+    if (p < 7 || p > 24) { set_error("sketch: p=%d outside the GPU path's range [7,24]", p); return DB200_EUNSUPPORTED; }
+    db200_packed_genomes *pg = nullptr;
+    DB200_TRY(db200_pack_genomes(device, bases, rec_offsets, nrecords, genome_rec_begin, ngenomes, k, &pg));
+    std::unique_ptr<db200_packed_genomes> guard(pg);
+    HostCtx &hc = host_ctx(device);
+    std::lock_guard<std::mutex> lk(hc.mu);
+    const uint64_t bytes = ngenomes << p;
+    DB200_TRY(hc.regs.reserve(std::max<uint64_t>(bytes, 16)));
+    DB200_TRY(sketch_packed_impl(pg, p, canon, hc.regs.as<uint8_t>(), hc.stream));
+    DB200_CUDA(cudaMemcpyAsync(registers_out, hc.regs.ptr, bytes, cudaMemcpyDeviceToHost, hc.stream));
+    DB200_CUDA(cudaStreamSynchronize(hc.stream));
+    return DB200_OK;
+}
+
+} // extern "C"
+
+// streaming sketcher: per-slot host staging of the records handed over by the reference's kseq loop
+struct db200_sketcher {
+    int p, k, canon, device;
+    struct Slot { std::vector<char> bases; std::vector<uint64_t> offs{0}; };
+    std::vector<Slot> slots;
+};
+
+extern "C" {
+
+int db200_sketcher_create(int p, int k, int canon, int device, uint32_t nslots, db200_sketcher **out) {
+    if (!out || nslots == 0) { set_error("db200_sketcher_create: bad arguments"); return DB200_EINVAL; }
+    if (k < 1 || k > 32) { set_error("sketch: k=%d outside [1,32]", k); return DB200_EUNSUPPORTED; }
+    if (p < 7 || p > 24) { set_error("sketch: p=%d outside the GPU path's range [7,24]", p); return DB200_EUNSUPPORTED; }
+    DB200_TRY(check_device(device));
+    db200_sketcher *h = new db200_sketcher{p, k, canon, device, {}};
+    h->slots.resize(nslots);
+    *out = h;
+    return DB200_OK;
+}
+
+int db200_sketcher_add_record(db200_sketcher *h, uint32_t slot, const char *bases, uint64_t len) {
+    if (!h || slot >= h->slots.size() || (!bases && len)) { set_error("db200_sketcher_add_record: bad arguments"); return DB200_EINVAL; }
+    auto &s = h->slots[slot];
+    try {
+        s.bases.insert(s.bases.end(), bases, bases + len);
+        s.offs.push_back(s.bases.size());
+    } catch (const std::bad_alloc &) { set_error("out of host memory staging a record"); return DB200_ENOMEM; }
+    return DB200_OK;
+}
+
+int db200_sketcher_finish(db200_sketcher *h, uint32_t slot, uint8_t *registers_out) {
+    if (!h || slot >= h->slots.size() || !registers_out) { set_error("db200_sketcher_finish: bad arguments"); return DB200_EINVAL; }
+    auto &s = h->slots[slot];
+    const uint64_t grb[2] = {0, s.offs.size() - 1};
+    const int rc = db200_sketch_batch(h->device, h->p, h->k, h->canon, s.bases.data(), s.offs.data(), s.offs.size() - 1, grb, 1, registers_out);
+    s.bases.clear();
+    s.offs.assign(1, 0);
+    return rc;
+}
+
+int db200_sketcher_destroy(db200_sketcher *h) { delete h; return DB200_OK; }
+
+// ---- cardinalities --------------------------------------------------------------------------
+int db200_cardinalities(int device, const uint8_t *regs, uint64_t n, int p, int estim, double *out) {
+    if ((!regs || !out) && n) { set_error("db200_cardinalities: null argument"); return DB200_EINVAL; }
+    if (p < 7 || p > 24) { set_error("cardinalities: p=%d outside the GPU path's range [7,24]", p); return DB200_EUNSUPPORTED; }
+    if (estim < 0 || estim > 2) { set_error("unknown estimation method %d", estim); return DB200_EINVAL; }
+    DB200_TRY(check_device(device));
+    if (n == 0) return DB200_OK;
+    HostCtx &hc = host_ctx(device);
+    std::lock_guard<std::mutex> lk(hc.mu);
+    DB200_TRY(hc.init(device));
+    DB200_TRY(hc.regs.reserve(n << p));
+    DB200_TRY(hc.cards.reserve(n * 8));
+    DB200_CUDA(cudaMemcpyAsync(hc.regs.ptr, regs, n << p, cudaMemcpyHostToDevice, hc.stream));
+    cardinality_kernel<<<(unsigned)n, 128, 0, hc.stream>>>(hc.regs.as<uint32_t>(), p, estim, hc.cards.as<double>());
+    DB200_LAUNCHED();
+    DB200_CUDA(cudaGetLastError());
+    DB200_CUDA(cudaMemcpyAsync(out, hc.cards.ptr, n * 8, cudaMemcpyDeviceToHost, hc.stream));
+    DB200_CUDA(cudaStreamSynchronize(hc.stream));
+    return DB200_OK;
+}
+
+// ---- dist plan ------------------------------------------------------------------------------
+int db200_dist_plan_create(int device, db200_dist_plan **out) {
+    if (!out) { set_error("db200_dist_plan_create: null out"); return DB200_EINVAL; }
+    DB200_TRY(check_device(device));
+    db200_dist_plan *pl = new db200_dist_plan;
+    pl->device = device;
+    *out = pl;
+    return DB200_OK;
+}
+int db200_dist_plan_destroy(db200_dist_plan *pl) {
+    if (pl) { cudaSetDevice(pl->device); delete pl; }
+    return DB200_OK;
+}
+int db200_dist_plan_prepare_dev(db200_dist_plan *pl, const uint8_t *d_regs, uint64_t n, int p, int estim, void *stream) {
+    if (!pl || !d_regs) { set_error("db200_dist_plan_prepare_dev: null argument"); return DB200_EINVAL; }
+    DB200_TRY(check_device(pl->device));
+    std::lock_guard<std::mutex> lk(pl->mu);
+    return plan_prepare(pl, d_regs, n, n, 0, 0, p, estim, (cudaStream_t)stream);
+}
+int db200_dist_plan_run_symmetric_dev(db200_dist_plan *pl, const db200_dist_params *prm, uint64_t row_begin, uint64_t row_end, float *d_out,
+                                      void *stream) {
+    if (!pl || !prm || !d_out) { set_error("db200_dist_plan_run_symmetric_dev: null argument"); return DB200_EINVAL; }
+    DB200_TRY(check_device(pl->device));
+    std::lock_guard<std::mutex> lk(pl->mu);
+    if (row_end > pl->nrows) row_end = pl->nrows;
+    if (row_begin > row_end) { set_error("row_begin > row_end"); return DB200_EINVAL; }
+    return plan_run(pl, prm, 0, row_begin, row_end, 0, 0, d_out, (cudaStream_t)stream);
+}
+int db200_dist_plan_run_rect_dev(db200_dist_plan *pl, const db200_dist_params *prm, uint64_t nr, uint64_t nq, float *d_out, void *stream) {
+    if (!pl || !prm || !d_out) { set_error("db200_dist_plan_run_rect_dev: null argument"); return DB200_EINVAL; }
+    DB200_TRY(check_device(pl->device));
+    std::lock_guard<std::mutex> lk(pl->mu);
+    if (pl->qbase == 0) {
+        // plan prepared through prepare_dev on a plain [refs; queries] matrix: queries must start on a panel boundary
+        if (nr % DT != 0 || nr + nq != pl->nrows) { set_error("rect run on a symmetric plan needs nr %% %d == 0 and nr + nq == n", DT); return DB200_EINVAL; }
+        pl->qbase = nr;
+        const int rc = plan_run(pl, prm, 1, 0, 0, nr, nq, d_out, (cudaStream_t)stream);
+        pl->qbase = 0;
+        return rc;
+    }
+    return plan_run(pl, prm, 1, 0, 0, nr, nq, d_out, (cudaStream_t)stream);
+}
+int db200_dist_plan_cardinalities_dev(db200_dist_plan *pl, const double **d_card) {
+    if (!pl || !d_card || !pl->ready) { set_error("plan not prepared"); return DB200_EINVAL; }
+    *d_card = pl->card.as<double>();
+    return DB200_OK;
+}
+int db200_dist_plan_last_run_info(const db200_dist_plan *pl, uint64_t *pairs, uint64_t *tiles, int *thresholds) {
+    if (!pl) { set_error("null plan"); return DB200_EINVAL; }
+    if (pairs) *pairs = pl->last_pairs;
+    if (tiles) *tiles = pl->last_tiles;
+    if (thresholds) *thresholds = pl->K;
+    return DB200_OK;
+}
+
+// ---- host-pointer all-pairs -----------------------------------------------------------------
+int db200_dist_symmetric_rows(int device, const uint8_t *regs, uint64_t n, const db200_dist_params *prm, uint64_t row_begin, uint64_t row_end,
+                              float *out) {
+    if (!prm || (!regs && n)) { set_error("db200_dist_symmetric_rows: null argument"); return DB200_EINVAL; }
+    DB200_TRY(check_device(device));
+    if (row_end > n) row_end = n;
+    if (row_begin > row_end) { set_error("row_begin > row_end"); return DB200_EINVAL; }
+    if (n < 2 || row_begin == row_end) return DB200_OK;
+    HostCtx &hc = host_ctx(device);
+    std::lock_guard<std::mutex> lk(hc.mu);
+    DB200_TRY(hc.init(device));
+    const uint64_t m = 1ull << prm->p;
+    auto tri = [n](uint64_t r) { return (r * (2 * n - r - 1)) / 2; };
+    const uint64_t npairs = tri(row_end) - tri(row_begin);
+    if (npairs && !out) { set_error("null output"); return DB200_EINVAL; }
+    if (prm->p < 10 || prm->p > 16) { set_error("dist: p=%d outside the GPU path's range [10,16]", prm->p); return DB200_EUNSUPPORTED; }
+    DB200_TRY(hc.regs.reserve(n * m));
+    DB200_TRY(hc.out.reserve(std::max<uint64_t>(npairs, 1) * 4));
+    DB200_CUDA(cudaMemcpyAsync(hc.regs.ptr, regs, n * m, cudaMemcpyHostToDevice, hc.stream));
+    DB200_TRY(plan_prepare(hc.plan.get(), hc.regs.as<uint8_t>(), n, n, 0, 0, prm->p, prm->estim, hc.stream));
+    DB200_TRY(plan_run(hc.plan.get(), prm, 0, row_begin, row_end, 0, 0, hc.out.as<float>(), hc.stream));
+    DB200_CUDA(cudaMemcpyAsync(out, hc.out.ptr, npairs * 4, cudaMemcpyDeviceToHost, hc.stream));
+    DB200_CUDA(cudaStreamSynchronize(hc.stream));
+    return DB200_OK;
+}
+
+int db200_dist_symmetric(int device, const uint8_t *regs, uint64_t n, const db200_dist_params *prm, float *out) {
+    return db200_dist_symmetric_rows(device, regs, n, prm, 0, n, out);
+}
+
+int db200_dist_rect(int device, const uint8_t *ref_regs, uint64_t nr, const uint8_t *qry_regs, uint64_t nq, const db200_dist_params *prm,
+                    float *out) {
+    if (!prm || ((!ref_regs || !qry_regs || !out) && nr && nq)) { set_error("db200_dist_rect: null argument"); return DB200_EINVAL; }
+    DB200_TRY(check_device(device));
+    if (nr == 0 || nq == 0) return DB200_OK;
+    if (prm->p < 10 || prm->p > 16) { set_error("dist: p=%d outside the GPU path's range [10,16]", prm->p); return DB200_EUNSUPPORTED; }
+    HostCtx &hc = host_ctx(device);
+    std::lock_guard<std::mutex> lk(hc.mu);
+    DB200_TRY(hc.init(device));
+    const uint64_t m = 1ull << prm->p;
+    const uint64_t qbase = (nr + DT - 1) / DT * DT, nrows = qbase + nq;
+    DB200_TRY(hc.regs.reserve(nrows * m));
+    DB200_TRY(hc.out.reserve(nr * nq * 4));
+    DB200_CUDA(cudaMemcpyAsync(hc.regs.ptr, ref_regs, nr * m, cudaMemcpyHostToDevice, hc.stream));
+    DB200_CUDA(cudaMemcpyAsync(hc.regs.as<uint8_t>() + qbase * m, qry_regs, nq * m, cudaMemcpyHostToDevice, hc.stream));
+    DB200_TRY(plan_prepare(hc.plan.get(), hc.regs.as<uint8_t>(), nrows, nr, qbase, nq, prm->p, prm->estim, hc.stream));
+    DB200_TRY(plan_run(hc.plan.get(), prm, 1, 0, 0, nr, nq, hc.out.as<float>(), hc.stream));
+    DB200_CUDA(cudaMemcpyAsync(out, hc.out.ptr, nr * nq * 4, cudaMemcpyDeviceToHost, hc.stream));
+    DB200_CUDA(cudaStreamSynchronize(hc.stream));
+    return DB200_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,323 @@
+// dist.cuh — hot path (ii): all-pairs union cardinality / Jaccard / Mash over HLL register arrays.
+//
+// Replaces the per-pair work of
+//   hllbase_t::union_size        bonsai/hll/include/sketch/hll.h:1125-1141  (byte max + 2^p histogram increments)
+//   detail::ertl_ml_estimate     hll.h:567-627
+//   hllbase_t::jaccard_index     hll.h:1174-1183, full_set_comparison :1165-1173
+//   bns::result_cmp              src/dashing.h:568-592
+// and the loop nests of perform_core_op (src/sketch_and_cmp.h:699-710), dist_loop (:785-880),
+// partdist_loop (src/dashing.h:660-712).
+//
+// Exact reformulation of the pair histogram.  For threshold k let A_k be the 2^p-bit mask
+// [reg_a >= k] ("threshold bit-plane").  Then #{ i : max(a_i,b_i) >= k } = popc(A_k | B_k), and the
+// histogram the reference builds with 2^p scalar increments is c[k] = G[k] - G[k+1] with
+// G[k] = popc(A_k | B_k).  It is integer-exact, needs no shared-memory atomics, and turns the pair
+// loop into OR + POPC over 2^p/32 words per live threshold.  Thresholds outside the value range of
+// the sketches involved are known without reading anything (G = 2^p below the minimum, 0 above the
+// maximum).  Any fixed permutation of register positions may be used when building the planes —
+// the histogram does not depend on it — so planes are built with whatever bit order coalesces best.
+//
+// HBM layout: planes[t][s][w] (uint32), t = k - gmin - 1 over the global live range (gmin, gmax],
+// s = sketch, w < W = 2^p/32; viewed by TMA as a 3-D tensor {W, n, K} with 128-byte swizzled boxes
+// of 32 words x 32 sketches.
+#pragma once
+#include "common.cuh"
+#include "estimators.cuh"
+#include <cuda.h>
+
+namespace db200 {
+
+constexpr int DT = 32;                 // sketches per panel (tile is DT x DT pairs)
+constexpr int DIST_CONSUMERS = 256;    // 8 consumer warps
+constexpr int DIST_THREADS = DIST_CONSUMERS + 32;  // + 1 TMA producer warp
+constexpr int BOX_BYTES = DT * 128;    // 32 sketches x 32 words
+constexpr int STAGE_BYTES = 2 * BOX_BYTES;
+
+// ---------------------------------------------------------------------------------------------
+// global register range (min / max over the whole matrix)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) range_kernel(const uint4 *__restrict__ regs16, uint64_t n16, uint32_t *minmax) {
+    uint32_t mn = 0xFFFFFFFFu, mx = 0u;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint4 v = __ldg(regs16 + i);
+        mn = __vminu4(__vminu4(mn, v.x), __vminu4(v.y, __vminu4(v.z, v.w)));
+        mx = __vmaxu4(__vmaxu4(mx, v.x), __vmaxu4(v.y, __vmaxu4(v.z, v.w)));
+    }
+    uint32_t lo = min(min(mn & 0xFF, (mn >> 8) & 0xFF), min((mn >> 16) & 0xFF, mn >> 24));
+    uint32_t hi = max(max(mx & 0xFF, (mx >> 8) & 0xFF), max((mx >> 16) & 0xFF, mx >> 24));
+    lo = __reduce_min_sync(0xFFFFFFFFu, lo);
+    hi = __reduce_max_sync(0xFFFFFFFFu, hi);
+    if ((threadIdx.x & 31) == 0) { atomicMin(minmax, lo); atomicMax(minmax + 1, hi); }
+}
+
+// ---------------------------------------------------------------------------------------------
+// threshold bit-planes + per-sketch threshold counts.  One CTA (4 warps) per sketch; a warp turns
+// 1024 registers (8 coalesced 128-byte loads) into 32 plane words per threshold with ballots.
+// Register r = g*1024 + gg*128 + lane*4 + j lands in word g*32 + gg*4 + j, bit `lane`.
+// counts[s][t] = #{ registers of sketch s >= gmin + 1 + t }.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) planes_kernel(const uint32_t *__restrict__ regs32, uint64_t n, uint64_t row0, int p, int gmin, int K,
+                                                     uint32_t *__restrict__ planes, uint32_t *__restrict__ counts /*[n][64]*/) {
+    __shared__ uint32_t cnt[64];
+    const uint64_t s = row0 + blockIdx.x;
+    const uint32_t m = 1u << p, W = m >> 5, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x < 64) cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t *src = regs32 + s * (m >> 2);
+    for (uint32_t g = warp; g < (m >> 10); g += 4) {
+        uint32_t x[8];
+#pragma unroll
+        for (int gg = 0; gg < 8; ++gg) x[gg] = __ldg(src + g * 256 + gg * 32 + lane);
+        for (int t = 0; t < K; ++t) {
+            const uint32_t k4 = (uint32_t)(gmin + 1 + t) * 0x01010101u;
+            uint32_t kept = 0;
+#pragma unroll
+            for (int gg = 0; gg < 8; ++gg) {
+                const uint32_t ge = __vcmpgeu4(x[gg], k4);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t word = __ballot_sync(0xFFFFFFFFu, (ge >> (8 * j)) & 1u);
+                    if (lane == (uint32_t)(gg * 4 + j)) kept = word;
+                }
+            }
+            planes[((uint64_t)t * n + s) * W + g * 32 + lane] = kept;
+            const uint32_t tot = __reduce_add_sync(0xFFFFFFFFu, (uint32_t)__popc(kept));
+            if (lane == 0) atomicAdd(&cnt[t], tot);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 64) counts[s * 64 + threadIdx.x] = threadIdx.x < (uint32_t)K ? cnt[threadIdx.x] : 0u;
+}
+
+// Histogram accessor over per-sketch threshold counts: G(k) = #{reg >= k}.
+struct SketchCounts {
+    const uint32_t *g;  // counts row of the sketch
+    uint32_t m;
+    int gmin, gmax;
+    __device__ __forceinline__ uint32_t G(int k) const { return k <= gmin ? m : (k > gmax ? 0u : g[k - gmin - 1]); }
+    __device__ __forceinline__ uint32_t operator()(int k) const { return G(k) - G(k + 1); }
+};
+
+// per-sketch cardinality + value range, per-panel value range
+__global__ void __launch_bounds__(128) card_kernel(const uint32_t *__restrict__ counts, uint64_t row0, uint64_t nrows, int p, int gmin, int gmax, int estim,
+                                                   double *__restrict__ card, uint8_t *__restrict__ smin, uint8_t *__restrict__ smax,
+                                                   uint32_t *__restrict__ pmin, uint32_t *__restrict__ pmax) {
+    const uint64_t s = row0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= row0 + nrows) return;
+    SketchCounts c{counts + s * 64, 1u << p, gmin, gmax};
+    int lo = gmin, hi = gmax;
+    while (lo < gmax && c.G(lo + 1) == c.m) ++lo;   // largest k with every register >= k
+    while (hi > gmin && c.G(hi) == 0) --hi;          // largest register value
+    card[s] = calculate_estimate(c, estim, p, lo, hi);
+    smin[s] = (uint8_t)lo;
+    smax[s] = (uint8_t)hi;
+    atomicMin(pmin + s / DT, (uint32_t)lo);
+    atomicMax(pmax + s / DT, (uint32_t)hi);
+}
+
+// ---------------------------------------------------------------------------------------------
+// S2 standalone: per-sketch 64-bin histogram (hll.h:515-532) + estimator, one CTA per sketch.
+// ---------------------------------------------------------------------------------------------
+struct ArrayCounts {
+    const uint32_t *c;
+    __device__ __forceinline__ uint32_t operator()(int k) const { return c[k]; }
+};
+
+__global__ void __launch_bounds__(128) cardinality_kernel(const uint32_t *__restrict__ regs32, int p, int estim, double *__restrict__ out) {
+    __shared__ uint32_t wh[4][64];
+    __shared__ uint32_t hist[64];
+    const uint32_t m4 = 1u << (p - 2), lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t i = threadIdx.x; i < 256; i += 128) (&wh[0][0])[i] = 0;
+    __syncthreads();
+    const uint32_t *src = regs32 + (uint64_t)blockIdx.x * m4;
+    for (uint32_t i = threadIdx.x; i < m4; i += 128) {
+        const uint32_t x = __ldg(src + i);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) atomicAdd(&wh[warp][(x >> (8 * j)) & 63u], 1u);
+    }
+    (void)lane;
+    __syncthreads();
+    if (threadIdx.x < 64) hist[threadIdx.x] = wh[0][threadIdx.x] + wh[1][threadIdx.x] + wh[2][threadIdx.x] + wh[3][threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x == 0) out[blockIdx.x] = calculate_estimate(ArrayCounts{hist}, estim, p);
+}
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers: mbarrier + TMA
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra.uni WAIT_DONE;\n\t"
+        "bra.uni WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *tmap, int c0, int c1, int c2, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+        "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+        : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// the all-pairs kernel
+// ---------------------------------------------------------------------------------------------
+struct DistTile { uint32_t a, b; };  // panel indices: A panel = sketches [rowA(a), +32), B panel = [32*b, +32)
+
+struct DistArgs {
+    const DistTile *tiles;
+    const uint8_t *smin, *smax;       // per sketch
+    const uint32_t *pmin, *pmax;      // per 32-sketch panel
+    const double *card;               // per sketch (estimator `estim`)
+    float *out;
+    uint64_t n;                       // sketches in the plane tensor
+    uint64_t row_begin, row_end;      // symmetric: rows computed; rect: unused
+    uint64_t out_base;                // symmetric: distmat offset of row_begin
+    uint64_t nr, nq, qbase;           // rect: references rows [0,nr), queries rows [qbase, qbase+nq); qbase % DT == 0
+    double ksinv;
+    int p, gmin, gmax, K;
+    int estim, rtype;
+    int rect;                         // 0 symmetric, 1 rectangular (A = queries, B = references)
+    int stages;
+};
+
+// Pair histogram accessor over the tile's threshold counts in shared memory (uint16, see wrap rule).
+struct PairCounts {
+    const uint16_t *g;   // &G[0][pair]
+    uint32_t m;
+    int lo, hi;          // tile value range: thresholds lo+1..hi are stored
+    int kmax_pair;       // max register value of the pair (for the 2^16 wrap rule)
+    __device__ __forceinline__ uint32_t G(int k) const {
+        if (k <= lo) return m;
+        if (k > hi) return 0u;
+        const uint32_t v = g[(k - lo - 1) * (DT * DT)];
+        // counts are stored mod 2^16; 0 inside the pair's live range can only mean 2^16 (p == 16)
+        return (v == 0u && k <= kmax_pair) ? m : v;
+    }
+    __device__ __forceinline__ uint32_t operator()(int k) const { return G(k) - G(k + 1); }
+};
+
+__global__ void __launch_bounds__(DIST_THREADS, 2) dist_kernel(const __grid_constant__ CUtensorMap tmap, const DistArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int S = a.stages;
+    uint8_t *stage_mem = smem;                                             // S x {A box, B box}
+    uint16_t *G = reinterpret_cast<uint16_t *>(smem + (size_t)S * STAGE_BYTES);  // [K][1024]
+    const int Kcap = a.K > 0 ? a.K : 1;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)S * STAGE_BYTES + (size_t)Kcap * DT * DT * 2);
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + S);
+
+    const DistTile tile = a.tiles[blockIdx.x];
+    const uint64_t rowA0 = a.rect ? a.qbase + (uint64_t)tile.a * DT : (uint64_t)tile.a * DT;
+    const uint64_t rowB0 = (uint64_t)tile.b * DT;
+    const uint32_t panA = (uint32_t)(rowA0 / DT), panB = tile.b;
+    const int lo = (int)min(a.pmin[panA], a.pmin[panB]);
+    const int hi = (int)max(a.pmax[panA], a.pmax[panB]);
+    const int Kt = hi - lo;
+    const int W = 1 << (a.p - 5), nbox = W >> 5;
+    const int iters = Kt * nbox;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, DIST_CONSUMERS / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == DIST_CONSUMERS / 32) {
+        // ---------------- TMA producer ----------------
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+            for (int it = 0; it < iters; ++it) {
+                const int s = it % S;
+                const uint32_t ph = (uint32_t)(it / S) & 1u;
+                mbar_wait(empty0 + 8 * s, ph ^ 1u);
+                const int t = lo - a.gmin + it / nbox, wb = it % nbox;
+                const uint32_t dst = smem_u32(stage_mem + (size_t)s * STAGE_BYTES);
+                mbar_expect_tx(full0 + 8 * s, STAGE_BYTES);
+                tma_load_3d(dst, &tmap, wb * 32, (int)rowA0, t, full0 + 8 * s);
+                tma_load_3d(dst + BOX_BYTES, &tmap, wb * 32, (int)rowB0, t, full0 + 8 * s);
+            }
+        }
+    } else {
+        // ---------------- consumers: OR + POPC ----------------
+        const uint32_t ti = threadIdx.x >> 4, tj = threadIdx.x & 15;  // A rows {ti, ti+16}, B rows {tj, tj+16}
+        const uint32_t swA = (ti & 7) << 4, swB = (tj & 7) << 4;
+        uint32_t acc00 = 0, acc01 = 0, acc10 = 0, acc11 = 0;
+        for (int it = 0; it < iters; ++it) {
+            const int s = it % S;
+            const uint32_t ph = (uint32_t)(it / S) & 1u;
+            mbar_wait(full0 + 8 * s, ph);
+            const uint8_t *A = stage_mem + (size_t)s * STAGE_BYTES, *B = A + BOX_BYTES;
+            const uint8_t *a0p = A + ti * 128, *a1p = A + (ti + 16) * 128;
+            const uint8_t *b0p = B + tj * 128, *b1p = B + (tj + 16) * 128;
+#pragma unroll
+            for (uint32_t c = 0; c < 8; ++c) {
+                const uint32_t oa = (c << 4) ^ swA, ob = (c << 4) ^ swB;
+                const uint4 a0 = *reinterpret_cast<const uint4 *>(a0p + oa);
+                const uint4 a1 = *reinterpret_cast<const uint4 *>(a1p + oa);
+                const uint4 b0 = *reinterpret_cast<const uint4 *>(b0p + ob);
+                const uint4 b1 = *reinterpret_cast<const uint4 *>(b1p + ob);
+                acc00 += __popc(a0.x | b0.x) + __popc(a0.y | b0.y) + __popc(a0.z | b0.z) + __popc(a0.w | b0.w);
+                acc01 += __popc(a0.x | b1.x) + __popc(a0.y | b1.y) + __popc(a0.z | b1.z) + __popc(a0.w | b1.w);
+                acc10 += __popc(a1.x | b0.x) + __popc(a1.y | b0.y) + __popc(a1.z | b0.z) + __popc(a1.w | b0.w);
+                acc11 += __popc(a1.x | b1.x) + __popc(a1.y | b1.y) + __popc(a1.z | b1.z) + __popc(a1.w | b1.w);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty0 + 8 * s);
+            if ((it + 1) % nbox == 0) {
+                uint16_t *g = G + (size_t)(it / nbox) * (DT * DT);
+                g[ti * DT + tj] = (uint16_t)acc00;
+                g[ti * DT + tj + 16] = (uint16_t)acc01;
+                g[(ti + 16) * DT + tj] = (uint16_t)acc10;
+                g[(ti + 16) * DT + tj + 16] = (uint16_t)acc11;
+                acc00 = acc01 = acc10 = acc11 = 0;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---------------- estimator + emission, one pair per thread at a time ----------------
+    const uint32_t m = 1u << a.p;
+    for (uint32_t pair = threadIdx.x; pair < DT * DT; pair += DIST_THREADS) {
+        const uint32_t il = pair >> 5, jl = pair & 31;
+        const uint64_t i = rowA0 + il, j = rowB0 + jl;
+        uint64_t oidx;
+        if (a.rect) {
+            if (i >= a.qbase + a.nq || j >= a.nr) continue;
+            oidx = (i - a.qbase) * a.nr + j;
+        } else {
+            if (i >= j || j >= a.n || i < a.row_begin || i >= a.row_end) continue;
+            oidx = (i * (2 * a.n - i - 1)) / 2 - a.out_base + (j - i - 1);
+        }
+        const int kmin_pair = max((int)a.smin[i], (int)a.smin[j]);
+        const int kmax_pair = max((int)a.smax[i], (int)a.smax[j]);
+        PairCounts c{G + pair, m, lo, hi, kmax_pair};
+        const double us = calculate_estimate(c, a.estim, a.p, kmin_pair, kmax_pair);
+        // non-joint path is symmetric in its operands (IEEE addition commutes): lhs = A, rhs = B
+        const double cl = a.card[i], cr = a.card[j];
+        // jaccard_index, hll.h:1179-1182
+        const double r = (cl + cr - us) / us;
+        const double ji = 0. < r ? r : 0.;
+        // full_set_comparison, hll.h:1169-1172
+        double is = cl + cr - us;
+        is = is < 0. ? 0. : is;
+        double t0 = cl - is, t1 = cr - is;
+        t0 = t0 < 0. ? 0. : t0;
+        t1 = t1 < 0. ? 0. : t1;
+        a.out[oidx] = emit_value(a.rtype, ji, t0, t1, is, a.ksinv);
+    }
+}
+
+} // namespace db200

@@ -1,0 +1,167 @@
+/* dashing_b200.h — C ABI of the B200-native HyperLogLog engine (libdashing_b200.so).
+ *
+ * The reference (dnbaker/dashing) has no plugin / FFI interface: its two hot paths are C++
+ * templates called in-process.  This header therefore declares exactly the seams a maintainer
+ * would cut at the reference's own call sites (paths relative to the reference tree):
+ *
+ *   S1  sketch      body of the OpenMP genome loop in sketch_core      src/sketch_and_cmp.h:496-520
+ *                   and in dist_sketch_and_cmp phase A                 src/sketch_and_cmp.h:338-352
+ *                   (today: Encoder::for_each(lambda addh, path, kseq)  bonsai/include/bonsai/encoder.h:509-529,
+ *                    hll_t::addh                                         bonsai/hll/include/sketch/hll.h:843-846)
+ *   S2  sizes       the serial cardinality loop                        src/sketch_and_cmp.h:377-383
+ *                   (hll_t::report -> sum_counts + calculate_estimate   hll.h:773-803, :515-532, :199-246)
+ *   S3  all pairs   dist_loop / perform_core_op / partdist_loop        src/sketch_and_cmp.h:785-880, :699-710,
+ *                   / dm::parallel_fill oracle                          src/dashing.h:660-712, distmat/distmat.h:459-512
+ *                   (result_cmp src/dashing.h:568-592 -> hll_t::jaccard_index / full_set_comparison
+ *                    hll.h:1174-1183, :1165-1173, ertl_joint :636-684, ertl_ml_estimate :567-627)
+ *
+ * Conventions
+ *   - Plain C: pointers + sizes, no C++/torch types.  Every function returns 0 on success and a
+ *     non-zero DB200_E* code on failure; db200_last_error() returns the calling thread's message.
+ *     (The reference's convention is print-and-exit(1), bonsai/include/bonsai/util.h:547-554; the
+ *     host wrapper turns a non-zero return into UNRECOVERABLE_ERROR(db200_last_error()).)
+ *   - There is NO CPU fallback inside the library: without a usable CUDA device every compute
+ *     entry point fails with DB200_ENODEV.  Flag combinations the GPU path does not cover are
+ *     rejected with DB200_EUNSUPPORTED so the host keeps using the reference's own code for them.
+ *   - Register matrices are row-major uint8_t[n][2^p] (what hll_t::data() yields, hll.h:1029).
+ *   - Host-pointer entry points own all device memory and streams internally and are blocking.
+ *     `_dev` entry points take DEVICE pointers plus a cudaStream_t (passed as void*), enqueue
+ *     work on that stream and return without synchronising, so callers can bracket them with
+ *     CUDA events (bench.py) or chain them after a collective (multi-GPU driver).
+ */
+#ifndef DASHING_B200_H
+#define DASHING_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DB200_VERSION 100
+#if defined(__GNUC__)
+#define DB200_API __attribute__((visibility("default")))
+#else
+#define DB200_API
+#endif
+
+enum db200_status {
+    DB200_OK = 0,
+    DB200_EINVAL = 1,       /* bad argument */
+    DB200_EUNSUPPORTED = 2, /* valid for the reference, not covered by the GPU path */
+    DB200_ENODEV = 3,       /* no CUDA device / driver */
+    DB200_ECUDA = 4,        /* CUDA runtime error (message has the details) */
+    DB200_ENOMEM = 5
+};
+
+/* sketch::hll::EstimationMethod — hll.h:61-65 */
+enum db200_estim { DB200_ORIGINAL = 0, DB200_ERTL_IMPROVED = 1, DB200_ERTL_MLE = 2 };
+/* sketch::hll::JointEstimationMethod — hll.h:76-81; values 0..2 mean "union + estim", 3 = Ertl joint MLE */
+enum db200_jestim { DB200_ERTL_JOINT_MLE = 3 };
+/* bns::EmissionType — src/enums.h:13-23 */
+enum db200_emission {
+    DB200_MASH_DIST = 0, DB200_JI = 1, DB200_SIZES = 2, DB200_FULL_MASH_DIST = 3,
+    DB200_FULL_CONTAINMENT_DIST = 4, DB200_CONTAINMENT_INDEX = 5, DB200_CONTAINMENT_DIST = 6,
+    DB200_SYMMETRIC_CONTAINMENT_INDEX = 7, DB200_SYMMETRIC_CONTAINMENT_DIST = 8
+};
+/* Operand order of result_cmp in the symmetric loop: the reference's TSV/PHYLIP path evaluates
+ * cmp(sketches[j], sketches[i]) for j > i (perform_core_op, src/sketch_and_cmp.h:702) while its
+ * binary paths evaluate cmp(sketches[i], sketches[j]) (:829, :849).  Only the joint MLE is
+ * sensitive to it (last ulp). */
+enum db200_order { DB200_ORDER_ROW_FIRST = 0 /* cmp(s[i], s[j]) */, DB200_ORDER_COL_FIRST = 1 /* cmp(s[j], s[i]) */ };
+
+typedef struct db200_dist_params {
+    int32_t p;           /* log2 registers per sketch; GPU path: 10 <= p <= 16 */
+    int32_t k;           /* k-mer length (only enters Mash/containment distances through ksinv = (float)(1./k)) */
+    int32_t estim;       /* enum db200_estim: estimator behind creport() and the union estimate */
+    int32_t jestim;      /* DB200_ERTL_JOINT_MLE or anything else for the union path */
+    int32_t result_type; /* enum db200_emission */
+    int32_t order;       /* enum db200_order (symmetric mode only) */
+} db200_dist_params;
+
+/* ------------------------------------------------------------------------------------------ */
+DB200_API const char *db200_last_error(void);
+DB200_API int db200_version(void);
+/* Number of usable CUDA devices (0 when there is no driver/GPU; never fails). */
+DB200_API int db200_device_count(void);
+/* Page-locked host memory, so host-pointer entry points can DMA straight from caller buffers. */
+DB200_API int db200_host_alloc(void **out, size_t bytes);
+DB200_API int db200_host_free(void *ptr);
+
+/* ---- S1: sketching ------------------------------------------------------------------------
+ * Streaming form, a drop-in for `enc.for_each([&](u64 kmer){h.addh(kmer);}, path, kseq)`:
+ * the host keeps gz/FASTA parsing (kseq) and hands every record over exactly as kseq_read yields
+ * it (ks->seq.s, ks->seq.l); records are never joined (encoder.h:444).  `slot` selects one of
+ * `nslots` independent sketches (one per OpenMP worker in the reference's loop); calls on
+ * distinct slots may come from different threads concurrently.
+ * finish() writes the slot's 2^p registers to host memory — the caller copies them into
+ * hll_t::mutable_core() (hll.h:1028) and calls not_ready() (:1012) — and clears the slot.
+ * GPU path: 1 <= k <= 32, 7 <= p <= 24, unspaced, unwindowed, DNA4 alphabet, WangHash. */
+typedef struct db200_sketcher db200_sketcher;
+DB200_API int db200_sketcher_create(int p, int k, int canon, int device, uint32_t nslots, db200_sketcher **out);
+DB200_API int db200_sketcher_add_record(db200_sketcher *h, uint32_t slot, const char *bases, uint64_t len);
+DB200_API int db200_sketcher_finish(db200_sketcher *h, uint32_t slot, uint8_t *registers_out);
+DB200_API int db200_sketcher_destroy(db200_sketcher *h);
+
+/* Batch form (what the OpenMP genome loop of sketch_core becomes): genome g owns records
+ * [genome_rec_begin[g], genome_rec_begin[g+1]); record r is bases[rec_offsets[r] .. rec_offsets[r+1]).
+ * registers_out is uint8_t[ngenomes][2^p] in host memory. */
+DB200_API int db200_sketch_batch(int device, int p, int k, int canon,
+                       const char *bases, const uint64_t *rec_offsets, uint64_t nrecords,
+                       const uint64_t *genome_rec_begin, uint64_t ngenomes, uint8_t *registers_out);
+
+/* Device-resident form used by bench.py (`value`) and the multi-GPU driver.  The packed genome
+ * store is the HBM-resident input format of the sketch kernel: 2-bit bases (64 per 16-byte word),
+ * a validity bit-plane and a record-start bit-plane (DESIGN.md "Data layout"). */
+typedef struct db200_packed_genomes db200_packed_genomes;
+/* Packs host ASCII (same arguments as db200_sketch_batch) into a device-resident store. */
+DB200_API int db200_pack_genomes(int device, const char *bases, const uint64_t *rec_offsets, uint64_t nrecords,
+                       const uint64_t *genome_rec_begin, uint64_t ngenomes, int k, db200_packed_genomes **out);
+DB200_API int db200_packed_genomes_free(db200_packed_genomes *g);
+/* Bytes the sketch kernel streams for this store (2-bit + validity + start planes) and its k-mer count. */
+DB200_API int db200_packed_genomes_stats(const db200_packed_genomes *g, uint64_t *packed_bytes, uint64_t *kmers, uint64_t *bases);
+/* Sketches every genome of the store into d_registers (device, uint8_t[ngenomes][2^p], overwritten). */
+DB200_API int db200_sketch_packed_dev(const db200_packed_genomes *g, int p, int canon, uint8_t *d_registers, void *stream);
+
+/* ---- S2: per-sketch cardinalities ---------------------------------------------------------- */
+DB200_API int db200_cardinalities(int device, const uint8_t *regs, uint64_t n, int p, int estim, double *out);
+
+/* ---- S3: all-pairs ------------------------------------------------------------------------
+ * Symmetric mode: out is the packed upper triangle in distmat order,
+ *   idx(i,j) = i(2n-i-1)/2 + j-i-1 for i < j   (distmat/distmat.h:260-276),
+ * n(n-1)/2 floats; db200_dist_symmetric_rows computes rows [row_begin,row_end) only and writes
+ * them contiguously starting at out[0] (rows are contiguous in distmat order), which is how the
+ * multi-GPU driver shards the triangle by block-row.
+ * Rectangular mode (-Q/-F, partdist_loop): out[q*nr + j] = result_cmp(refs[j], queries[q]). */
+DB200_API int db200_dist_symmetric(int device, const uint8_t *regs, uint64_t n, const db200_dist_params *prm, float *out);
+DB200_API int db200_dist_symmetric_rows(int device, const uint8_t *regs, uint64_t n, const db200_dist_params *prm,
+                              uint64_t row_begin, uint64_t row_end, float *out);
+DB200_API int db200_dist_rect(int device, const uint8_t *ref_regs, uint64_t nr, const uint8_t *qry_regs, uint64_t nq,
+                    const db200_dist_params *prm, float *out);
+
+/* Device-resident form.  A plan owns the derived HBM structures (threshold bit-planes,
+ * per-sketch cardinalities and value ranges); prepare() builds them from a device register
+ * matrix, run_*() enqueue the all-pairs kernel.  `stream` is a cudaStream_t. */
+typedef struct db200_dist_plan db200_dist_plan;
+DB200_API int db200_dist_plan_create(int device, db200_dist_plan **out);
+DB200_API int db200_dist_plan_destroy(db200_dist_plan *pl);
+/* d_regs: device uint8_t[n][2^p].  Synchronises once (reads back the global register range). */
+DB200_API int db200_dist_plan_prepare_dev(db200_dist_plan *pl, const uint8_t *d_regs, uint64_t n, int p, int estim, void *stream);
+/* Rows [row_begin,row_end) of the symmetric matrix into d_out (device floats, rows contiguous from d_out[0]). */
+DB200_API int db200_dist_plan_run_symmetric_dev(db200_dist_plan *pl, const db200_dist_params *prm,
+                                      uint64_t row_begin, uint64_t row_end, float *d_out, void *stream);
+/* Rectangular: sketches [0,nr) of the prepared matrix are references, [nr, nr+nq) queries. */
+DB200_API int db200_dist_plan_run_rect_dev(db200_dist_plan *pl, const db200_dist_params *prm, uint64_t nr, uint64_t nq,
+                                 float *d_out, void *stream);
+/* Device pointer to the plan's per-sketch cardinalities (double[n]) — valid until the next prepare/destroy. */
+DB200_API int db200_dist_plan_cardinalities_dev(db200_dist_plan *pl, const double **d_card);
+/* Launch accounting for bench.py: kernels launched by this library since process start. */
+DB200_API uint64_t db200_kernel_launches(void);
+/* Name and algorithmic-byte model of the last all-pairs run (for the roofline object). */
+DB200_API int db200_dist_plan_last_run_info(const db200_dist_plan *pl, uint64_t *pairs, uint64_t *tiles, int *thresholds);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DASHING_B200_H */

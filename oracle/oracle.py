@@ -1,0 +1,364 @@
+"""oracle/oracle.py — TEST INFRASTRUCTURE: ctypes loaders for the two checkers.
+
+* ``port()``  -> oracle/_build/liboracle_port.so   (plain-C restatement, oracle_port.c)
+* ``ref()``   -> oracle/_ref/libdashing_ref_*.so   (ref_driver.cpp compiled against the unmodified
+                                                     reference headers; built where /root/reference exists)
+
+Only tests/, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference`` legs
+may import this module.  The product package ``dashing_b200`` never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from functools import lru_cache
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+PORT_SO = os.path.join(HERE, "_build", "liboracle_port.so")
+REF_DIR = os.path.join(HERE, "_ref")
+
+u8p = C.POINTER(C.c_uint8)
+u32p = C.POINTER(C.c_uint32)
+u64p = C.POINTER(C.c_uint64)
+f32p = C.POINTER(C.c_float)
+f64p = C.POINTER(C.c_double)
+
+
+def _ptr(a: np.ndarray, t):
+    return a.ctypes.data_as(t)
+
+
+def build(port: bool = True, ref: bool = True) -> None:
+    """(Re)build the checkers.  The reference driver is only rebuilt where /root/reference exists."""
+    if port:
+        subprocess.check_call(["make", "-s", "-C", HERE, "port"])
+    if ref and os.path.isdir("/root/reference"):
+        subprocess.check_call(["make", "-s", "-C", HERE, "ref"])
+
+
+def _cpu_flags() -> set:
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("flags"):
+                    return set(line.split(":", 1)[1].split())
+    except OSError:
+        pass
+    return set()
+
+
+def ref_available() -> bool:
+    return any(os.path.exists(os.path.join(REF_DIR, n)) for n in ("libdashing_ref_avx2.so", "libdashing_ref_avx512.so"))
+
+
+@lru_cache(maxsize=None)
+def _load_ref():
+    flags = _cpu_flags()
+    cands = []
+    if {"avx512f", "avx512bw", "avx512dq", "avx512vl", "avx512cd"} <= flags:
+        cands.append("libdashing_ref_avx512.so")
+    cands.append("libdashing_ref_avx2.so")
+    for n in cands:
+        path = os.path.join(REF_DIR, n)
+        if os.path.exists(path):
+            return C.CDLL(path), n
+    raise FileNotFoundError("oracle/_ref is not built (run `make -C oracle ref` where /root/reference exists)")
+
+
+@lru_cache(maxsize=None)
+def _load_port():
+    if not os.path.exists(PORT_SO):
+        build(port=True, ref=False)
+    return C.CDLL(PORT_SO)
+
+
+def pack_records(records):
+    """records: list of bytes -> (bases uint8[], offsets uint64[nrec+1])"""
+    offs = np.zeros(len(records) + 1, dtype=np.uint64)
+    if records:
+        offs[1:] = np.cumsum([len(r) for r in records], dtype=np.uint64)
+    bases = np.frombuffer(b"".join(records), dtype=np.uint8).copy() if records else np.zeros(0, np.uint8)
+    if bases.size == 0:
+        bases = np.zeros(1, np.uint8)
+    return bases, offs
+
+
+class _Common:
+    """Shared python-side conveniences; subclasses bind the C symbols."""
+
+    def sketch(self, records, k, p, canon=True):
+        bases, offs = pack_records(records)
+        regs = np.zeros(1 << p, dtype=np.uint8)
+        self._sketch(bases, offs, len(records), k, p, int(canon), regs)
+        return regs
+
+
+class Port(_Common):
+    kind = "port"
+
+    def __init__(self):
+        l = self.l = _load_port()
+        l.orc_wang.restype = C.c_uint64
+        l.orc_wang.argtypes = [C.c_uint64]
+        l.orc_canonical.restype = C.c_uint64
+        l.orc_canonical.argtypes = [C.c_uint64, C.c_int]
+        l.orc_kmers.restype = C.c_uint64
+        l.orc_kmers.argtypes = [C.c_char_p, C.c_uint64, C.c_int, C.c_int, u64p, C.c_uint64]
+        l.orc_sketch.argtypes = [u8p, u64p, C.c_uint64, C.c_int, C.c_int, C.c_int, u8p]
+        l.orc_histogram.argtypes = [u8p, C.c_int, u32p]
+        l.orc_mle.restype = C.c_double
+        l.orc_mle.argtypes = [u32p, C.c_int, C.c_int]
+        l.orc_estimate.restype = C.c_double
+        l.orc_estimate.argtypes = [u32p, C.c_int, C.c_int]
+        l.orc_cardinality.restype = C.c_double
+        l.orc_cardinality.argtypes = [u8p, C.c_int, C.c_int]
+        l.orc_jaccard.restype = C.c_double
+        l.orc_jaccard.argtypes = [u8p, u8p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double]
+        l.orc_union_size.restype = C.c_double
+        l.orc_union_size.argtypes = [u8p, u8p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double]
+        l.orc_triple.argtypes = [u8p, u8p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, f64p]
+        l.orc_result_cmp.restype = C.c_float
+        l.orc_result_cmp.argtypes = [u8p, u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double]
+        l.orc_dist_rows.argtypes = [u8p, C.c_uint64] + [C.c_int] * 6 + [C.c_uint64, C.c_uint64, f32p]
+        l.orc_dist_rect.argtypes = [u8p, C.c_uint64, u8p, C.c_uint64] + [C.c_int] * 5 + [f32p]
+        l.orc_hll_payload.restype = C.c_uint64
+        l.orc_hll_payload.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_double, u8p, C.c_uint64]
+
+    def wang(self, x):
+        return int(self.l.orc_wang(C.c_uint64(x & 0xFFFFFFFFFFFFFFFF)))
+
+    def kmers(self, s: bytes, k, canon=True):
+        cap = max(len(s), 1)
+        out = np.zeros(cap, dtype=np.uint64)
+        n = self.l.orc_kmers(s, len(s), k, int(canon), _ptr(out, u64p), cap)
+        return out[:n].copy()
+
+    def _sketch(self, bases, offs, nrec, k, p, canon, regs):
+        self.l.orc_sketch(_ptr(bases, u8p), _ptr(offs, u64p), nrec, k, p, canon, _ptr(regs, u8p))
+
+    def histogram(self, regs, p):
+        c = np.zeros(64, dtype=np.uint32)
+        self.l.orc_histogram(_ptr(np.ascontiguousarray(regs), u8p), p, _ptr(c, u32p))
+        return c
+
+    def mle(self, c64, p, q=None):
+        c = np.ascontiguousarray(c64, dtype=np.uint32)
+        return float(self.l.orc_mle(_ptr(c, u32p), p, 64 - p if q is None else q))
+
+    def estimate(self, c64, p, estim):
+        c = np.ascontiguousarray(c64, dtype=np.uint32)
+        return float(self.l.orc_estimate(_ptr(c, u32p), p, estim))
+
+    def cardinality(self, regs, p, estim=2):
+        return float(self.l.orc_cardinality(_ptr(np.ascontiguousarray(regs), u8p), p, estim))
+
+    def cardinalities(self, regs2d, p, estim=2):
+        return np.array([self.cardinality(r, p, estim) for r in regs2d], dtype=np.float64)
+
+    def pair(self, lhs, rhs, p, estim=2, jestim=2, rtype=1, k=31):
+        cl, cr = self.cardinality(lhs, p, estim), self.cardinality(rhs, p, estim)
+        return float(self.l.orc_result_cmp(_ptr(np.ascontiguousarray(lhs), u8p), _ptr(np.ascontiguousarray(rhs), u8p),
+                                           p, estim, jestim, rtype, k, cl, cr))
+
+    def jaccard(self, lhs, rhs, p, estim=2, jestim=2):
+        cl, cr = self.cardinality(lhs, p, estim), self.cardinality(rhs, p, estim)
+        return float(self.l.orc_jaccard(_ptr(np.ascontiguousarray(lhs), u8p), _ptr(np.ascontiguousarray(rhs), u8p),
+                                        p, estim, jestim, cl, cr))
+
+    def triple(self, lhs, rhs, p, estim=2, jestim=2):
+        cl, cr = self.cardinality(lhs, p, estim), self.cardinality(rhs, p, estim)
+        out = np.zeros(3)
+        self.l.orc_triple(_ptr(np.ascontiguousarray(lhs), u8p), _ptr(np.ascontiguousarray(rhs), u8p), p, estim, jestim,
+                          cl, cr, _ptr(out, f64p))
+        return out
+
+    def dist_rows(self, regs2d, p, k=31, estim=2, jestim=2, rtype=1, order=0, row_begin=0, row_end=None, nthreads=0):
+        regs2d = np.ascontiguousarray(regs2d, dtype=np.uint8)
+        n = regs2d.shape[0]
+        out = np.zeros(n * (n - 1) // 2, dtype=np.float32)
+        self.l.orc_dist_rows(_ptr(regs2d, u8p), n, p, k, estim, jestim, rtype, order, row_begin,
+                             n if row_end is None else row_end, _ptr(out, f32p))
+        return out
+
+    def dist_symmetric(self, regs2d, p, **kw):
+        return self.dist_rows(regs2d, p, **kw)
+
+    def dist_rect(self, refs, qrys, p, k=31, estim=2, jestim=2, rtype=1, nthreads=0):
+        refs = np.ascontiguousarray(refs, dtype=np.uint8)
+        qrys = np.ascontiguousarray(qrys, dtype=np.uint8)
+        out = np.zeros((qrys.shape[0], refs.shape[0]), dtype=np.float32)
+        self.l.orc_dist_rect(_ptr(refs, u8p), refs.shape[0], _ptr(qrys, u8p), qrys.shape[0], p, k, estim, jestim, rtype,
+                             _ptr(out, f32p))
+        return out
+
+    def hll_payload(self, regs, p, estim=2, jestim=2, value=-1.0):
+        out = np.zeros(28 + (1 << p), dtype=np.uint8)
+        n = self.l.orc_hll_payload(_ptr(np.ascontiguousarray(regs), u8p), p, estim, jestim, value, _ptr(out, u8p), out.size)
+        assert n == out.size
+        return out.tobytes()
+
+
+class Ref(_Common):
+    kind = "reference"
+
+    def __init__(self):
+        l, self.libname = _load_ref()
+        self.l = l
+        l.dref_simd_tier.restype = C.c_int
+        l.dref_max_threads.restype = C.c_int
+        l.dref_wang.restype = C.c_uint64
+        l.dref_wang.argtypes = [C.c_uint64]
+        l.dref_kmers.restype = C.c_uint64
+        l.dref_kmers.argtypes = [C.c_char_p, C.c_uint64, C.c_int, C.c_int, u64p, C.c_uint64]
+        l.dref_sketch.argtypes = [u8p, u64p, C.c_uint64, C.c_int, C.c_int, C.c_int, u8p]
+        l.dref_sketch_many.argtypes = [u8p, u64p, u64p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, u8p]
+        l.dref_histogram.argtypes = [u8p, C.c_int, u32p]
+        l.dref_mle.restype = C.c_double
+        l.dref_mle.argtypes = [u32p, C.c_int, C.c_int]
+        l.dref_estimate_from_counts.restype = C.c_double
+        l.dref_estimate_from_counts.argtypes = [u32p, C.c_int, C.c_int]
+        l.dref_cardinality.restype = C.c_double
+        l.dref_cardinality.argtypes = [u8p, C.c_int, C.c_int]
+        l.dref_cardinalities.argtypes = [u8p, C.c_uint64, C.c_int, C.c_int, f64p]
+        l.dref_pair.restype = C.c_float
+        l.dref_pair.argtypes = [u8p, u8p] + [C.c_int] * 5
+        l.dref_jaccard.restype = C.c_double
+        l.dref_jaccard.argtypes = [u8p, u8p, C.c_int, C.c_int, C.c_int]
+        l.dref_union_size.restype = C.c_double
+        l.dref_union_size.argtypes = [u8p, u8p, C.c_int, C.c_int, C.c_int]
+        l.dref_triple.argtypes = [u8p, u8p, C.c_int, C.c_int, C.c_int, f64p]
+        l.dref_dist_rows.argtypes = [u8p, C.c_uint64] + [C.c_int] * 6 + [C.c_uint64, C.c_uint64, C.c_int, f32p]
+        l.dref_dist_rect.argtypes = [u8p, C.c_uint64, u8p, C.c_uint64] + [C.c_int] * 6 + [f32p]
+        l.dref_hll_write.argtypes = [C.c_char_p, u8p, C.c_int, C.c_int, C.c_int, C.c_int]
+        l.dref_hll_read.argtypes = [C.c_char_p, u8p, C.c_uint64, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                    C.POINTER(C.c_int), f64p]
+        l.dref_make_fname.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_char_p, C.c_char_p,
+                                      C.c_char_p, C.c_uint64]
+
+    def simd_tier(self):
+        return int(self.l.dref_simd_tier())
+
+    def max_threads(self):
+        return int(self.l.dref_max_threads())
+
+    def wang(self, x):
+        return int(self.l.dref_wang(C.c_uint64(x & 0xFFFFFFFFFFFFFFFF)))
+
+    def kmers(self, s: bytes, k, canon=True):
+        cap = max(len(s), 1)
+        out = np.zeros(cap, dtype=np.uint64)
+        n = self.l.dref_kmers(s, len(s), k, int(canon), _ptr(out, u64p), cap)
+        return out[:n].copy()
+
+    def _sketch(self, bases, offs, nrec, k, p, canon, regs):
+        self.l.dref_sketch(_ptr(bases, u8p), _ptr(offs, u64p), nrec, k, p, canon, _ptr(regs, u8p))
+
+    def sketch_many(self, bases, offs, genome_rec_begin, k, p, canon=True, nthreads=0):
+        ng = len(genome_rec_begin) - 1
+        regs = np.zeros((ng, 1 << p), dtype=np.uint8)
+        grb = np.ascontiguousarray(genome_rec_begin, dtype=np.uint64)
+        self.l.dref_sketch_many(_ptr(bases, u8p), _ptr(offs, u64p), _ptr(grb, u64p), ng, k, p, int(canon), nthreads,
+                                _ptr(regs, u8p))
+        return regs
+
+    def histogram(self, regs, p):
+        c = np.zeros(64, dtype=np.uint32)
+        self.l.dref_histogram(_ptr(np.ascontiguousarray(regs), u8p), p, _ptr(c, u32p))
+        return c
+
+    def mle(self, c64, p, q=None):
+        c = np.ascontiguousarray(c64, dtype=np.uint32)
+        return float(self.l.dref_mle(_ptr(c, u32p), p, 64 - p if q is None else q))
+
+    def estimate(self, c64, p, estim):
+        c = np.ascontiguousarray(c64, dtype=np.uint32)
+        return float(self.l.dref_estimate_from_counts(_ptr(c, u32p), p, estim))
+
+    def cardinality(self, regs, p, estim=2):
+        return float(self.l.dref_cardinality(_ptr(np.ascontiguousarray(regs), u8p), p, estim))
+
+    def cardinalities(self, regs2d, p, estim=2):
+        regs2d = np.ascontiguousarray(regs2d, dtype=np.uint8)
+        out = np.zeros(regs2d.shape[0])
+        self.l.dref_cardinalities(_ptr(regs2d, u8p), regs2d.shape[0], p, estim, _ptr(out, f64p))
+        return out
+
+    def pair(self, lhs, rhs, p, estim=2, jestim=2, rtype=1, k=31):
+        return float(self.l.dref_pair(_ptr(np.ascontiguousarray(lhs), u8p), _ptr(np.ascontiguousarray(rhs), u8p),
+                                      p, estim, jestim, rtype, k))
+
+    def jaccard(self, lhs, rhs, p, estim=2, jestim=2):
+        return float(self.l.dref_jaccard(_ptr(np.ascontiguousarray(lhs), u8p), _ptr(np.ascontiguousarray(rhs), u8p),
+                                         p, estim, jestim))
+
+    def union_size(self, lhs, rhs, p, estim=2, jestim=2):
+        return float(self.l.dref_union_size(_ptr(np.ascontiguousarray(lhs), u8p), _ptr(np.ascontiguousarray(rhs), u8p),
+                                            p, estim, jestim))
+
+    def triple(self, lhs, rhs, p, estim=2, jestim=2):
+        out = np.zeros(3)
+        self.l.dref_triple(_ptr(np.ascontiguousarray(lhs), u8p), _ptr(np.ascontiguousarray(rhs), u8p), p, estim, jestim,
+                           _ptr(out, f64p))
+        return out
+
+    def dist_rows(self, regs2d, p, k=31, estim=2, jestim=2, rtype=1, order=0, row_begin=0, row_end=None, nthreads=0,
+                  out=None):
+        regs2d = np.ascontiguousarray(regs2d, dtype=np.uint8)
+        n = regs2d.shape[0]
+        if out is None:
+            out = np.zeros(n * (n - 1) // 2, dtype=np.float32)
+        self.l.dref_dist_rows(_ptr(regs2d, u8p), n, p, k, estim, jestim, rtype, order, row_begin,
+                              n if row_end is None else row_end, nthreads, _ptr(out, f32p))
+        return out
+
+    def dist_symmetric(self, regs2d, p, **kw):
+        return self.dist_rows(regs2d, p, **kw)
+
+    def dist_rect(self, refs, qrys, p, k=31, estim=2, jestim=2, rtype=1, nthreads=0):
+        refs = np.ascontiguousarray(refs, dtype=np.uint8)
+        qrys = np.ascontiguousarray(qrys, dtype=np.uint8)
+        out = np.zeros((qrys.shape[0], refs.shape[0]), dtype=np.float32)
+        self.l.dref_dist_rect(_ptr(refs, u8p), refs.shape[0], _ptr(qrys, u8p), qrys.shape[0], p, k, estim, jestim, rtype,
+                              nthreads, _ptr(out, f32p))
+        return out
+
+    def hll_write(self, path, regs, p, estim=2, jestim=2, calculated=False):
+        rc = self.l.dref_hll_write(os.fsencode(path), _ptr(np.ascontiguousarray(regs), u8p), p, estim, jestim,
+                                   int(calculated))
+        if rc:
+            raise RuntimeError("dref_hll_write failed")
+
+    def hll_read(self, path, max_p=24):
+        regs = np.zeros(1 << max_p, dtype=np.uint8)
+        p, e, j, v = C.c_int(), C.c_int(), C.c_int(), C.c_double()
+        rc = self.l.dref_hll_read(os.fsencode(path), _ptr(regs, u8p), regs.size, C.byref(p), C.byref(e), C.byref(j),
+                                  C.byref(v))
+        if rc:
+            raise RuntimeError("dref_hll_read failed")
+        return regs[: 1 << p.value].copy(), p.value, e.value, j.value, v.value
+
+    def make_fname(self, path, p, wsz, k, csz, spacing="", suffix="", prefix=""):
+        buf = C.create_string_buffer(4096)
+        rc = self.l.dref_make_fname(os.fsencode(path), p, wsz, k, csz, spacing.encode(), suffix.encode(), prefix.encode(),
+                                    buf, 4096)
+        if rc:
+            raise RuntimeError("dref_make_fname failed")
+        return buf.value.decode()
+
+
+@lru_cache(maxsize=None)
+def port() -> Port:
+    return Port()
+
+
+@lru_cache(maxsize=None)
+def ref() -> Ref:
+    return Ref()
+
+
+def best():
+    """The strongest checker available: the real reference if built, else the pinned C port."""
+    return ref() if ref_available() else port()

@@ -1,0 +1,237 @@
+// oracle/ref_driver.cpp — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+//
+// A thin extern "C" driver around the UNMODIFIED reference headers under
+// /root/reference (dnbaker/dashing @ 0635bea).  It contains no arithmetic of
+// its own: every number it returns is produced by the reference's own
+// templates, instantiated here exactly as the reference's drivers do:
+//
+//   k-mer stream      bns::Encoder<score::Lex>::for_each(func, str, len)
+//                       bonsai/include/bonsai/encoder.h:415-441 -> :218-232 -> :240-271
+//   register update   sketch::hll_t::addh           bonsai/hll/include/sketch/hll.h:843-846, :828-836
+//   cardinality       sketch::hll_t::report         hll.h:773-803 (sum_counts :515-532, calculate_estimate :199-246)
+//   MLE               hll::detail::ertl_ml_estimate hll.h:567-627
+//   pair value        bns::result_cmp               src/dashing.h:568-592 (jaccard_index hll.h:1174-1183,
+//                                                   full_set_comparison :1165-1173, ertl_joint :636-684)
+//   all-pairs loops   mirrors perform_core_op (src/sketch_and_cmp.h:699-710), dist_loop BINARY branch
+//                     (:838-850 operand order cmp(s[i], s[j])) and partdist_loop (src/dashing.h:675-681)
+//   .hll files        sketch::hll_t::write/read(path) hll.h:1039-1087
+//
+// Built by oracle/Makefile with g++ directly on this one file (the reference's
+// own build system is never run); the output goes to oracle/_ref/ only.
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline/--impl reference
+// legs may load the resulting library.
+#include "dashing.h"
+#include <omp.h>
+#include <cstring>
+#include <vector>
+#include <memory>
+
+using namespace bns;
+using namespace sketch;
+
+namespace {
+using hll_t = hll::hll_t;
+
+static hll_t make_sketch(const uint8_t *regs, int p, int estim, int jestim) {
+    hll_t h(p, (hll::EstimationMethod)estim, (hll::JointEstimationMethod)jestim);
+    std::memcpy(h.mutable_core().data(), regs, h.size());
+    h.not_ready();
+    return h;
+}
+
+static std::vector<hll_t> make_sketches(const uint8_t *regs, uint64_t n, int p, int estim, int jestim) {
+    // Mirrors dist_sketch_and_cmp: construct, set_estim_and_jestim (src/sketch_and_cmp.h:285-288),
+    // then the serial sizes loop calls cardinality_estimate -> report() on every sketch (:377-383),
+    // so every sketch enters the pair loop with its cached value_ "ready".
+    std::vector<hll_t> v;
+    v.reserve(n);
+    const size_t m = size_t(1) << p;
+    for(uint64_t i = 0; i < n; ++i) {
+        v.emplace_back(make_sketch(regs + i * m, p, estim, jestim));
+        v.back().report();
+    }
+    return v;
+}
+} // namespace
+
+extern "C" {
+
+int dref_simd_tier() {
+#if HAS_AVX_512 && __AVX512BW__
+    return 512;
+#elif __AVX2__
+    return 256;
+#else
+    return 128;
+#endif
+}
+
+int dref_max_threads() { return omp_get_max_threads(); }
+
+uint64_t dref_wang(uint64_t x) { return hash::WangHash()(x); }
+
+// Emits the k-mers of ONE record exactly as Encoder::for_each(func, str, l) does.
+uint64_t dref_kmers(const char *s, uint64_t len, int k, int canon, uint64_t *out, uint64_t cap) {
+    Encoder<score::Lex> enc(Spacer(k, k), canon != 0);
+    uint64_t n = 0;
+    enc.for_each([&](u64 km) { if(n < cap) out[n] = km; ++n; }, s, len);
+    return n;
+}
+
+// One genome = records [0, nrec) delimited by offsets[0..nrec]; every record is fed separately
+// (k-mers never span records: encoder.h:444, :201-205).
+int dref_sketch(const char *bases, const uint64_t *offsets, uint64_t nrec, int k, int p, int canon, uint8_t *regs_out) {
+    hll_t h(p);
+    Encoder<score::Lex> enc(Spacer(k, k), canon != 0);
+    for(uint64_t r = 0; r < nrec; ++r)
+        enc.for_each([&](u64 km) { h.addh(km); }, bases + offsets[r], offsets[r + 1] - offsets[r]);
+    std::memcpy(regs_out, h.data(), h.size());
+    return 0;
+}
+
+// Many genomes, one OpenMP task per genome like sketch_core (src/sketch_and_cmp.h:484-523):
+// genome g owns records [genome_rec_begin[g], genome_rec_begin[g+1]).
+int dref_sketch_many(const char *bases, const uint64_t *offsets, const uint64_t *genome_rec_begin, uint64_t ngenomes,
+                     int k, int p, int canon, int nthreads, uint8_t *regs_out) {
+    if(nthreads <= 0) nthreads = omp_get_max_threads();
+    const size_t m = size_t(1) << p;
+    #pragma omp parallel for schedule(dynamic) num_threads(nthreads)
+    for(uint64_t g = 0; g < ngenomes; ++g) {
+        hll_t h(p);
+        Encoder<score::Lex> enc(Spacer(k, k), canon != 0);
+        for(uint64_t r = genome_rec_begin[g]; r < genome_rec_begin[g + 1]; ++r)
+            enc.for_each([&](u64 km) { h.addh(km); }, bases + offsets[r], offsets[r + 1] - offsets[r]);
+        std::memcpy(regs_out + g * m, h.data(), m);
+    }
+    return 0;
+}
+
+void dref_histogram(const uint8_t *regs, int p, uint32_t *out64) {
+    hll_t h = make_sketch(regs, p, hll::ERTL_MLE, hll::ERTL_MLE);
+    auto c = hll::detail::sum_counts(h.core());
+    std::memcpy(out64, c.data(), sizeof(uint32_t) * 64);
+}
+
+double dref_mle(const uint32_t *c64, int p, int q) {
+    std::array<uint32_t, 64> c;
+    std::memcpy(c.data(), c64, sizeof(uint32_t) * 64);
+    return hll::detail::ertl_ml_estimate(c, (unsigned)p, (unsigned)q);
+}
+
+double dref_estimate_from_counts(const uint32_t *c64, int p, int estim) {
+    std::array<uint32_t, 64> c;
+    std::memcpy(c.data(), c64, sizeof(uint32_t) * 64);
+    const uint64_t m = uint64_t(1) << p;
+    return hll::detail::calculate_estimate(c, (hll::EstimationMethod)estim, m, p, hll::make_alpha(m));
+}
+
+double dref_cardinality(const uint8_t *regs, int p, int estim) {
+    hll_t h = make_sketch(regs, p, estim, hll::ERTL_MLE);
+    return h.report();
+}
+
+void dref_cardinalities(const uint8_t *regs, uint64_t n, int p, int estim, double *out) {
+    const size_t m = size_t(1) << p;
+    for(uint64_t i = 0; i < n; ++i) out[i] = dref_cardinality(regs + i * m, p, estim);
+}
+
+// One pair through result_cmp, both sketches "ready" as in the dist flow.
+float dref_pair(const uint8_t *lhs, const uint8_t *rhs, int p, int estim, int jestim, int rtype, int k) {
+    hll_t A = make_sketch(lhs, p, estim, jestim), B = make_sketch(rhs, p, estim, jestim);
+    A.report(); B.report();
+    const float ksinv = 1. / k; // src/sketch_and_cmp.h:797
+    return result_cmp(A, B, (EmissionType)rtype, ksinv);
+}
+
+double dref_jaccard(const uint8_t *lhs, const uint8_t *rhs, int p, int estim, int jestim) {
+    hll_t A = make_sketch(lhs, p, estim, jestim), B = make_sketch(rhs, p, estim, jestim);
+    A.report(); B.report();
+    return static_cast<const hll_t &>(A).jaccard_index(static_cast<const hll_t &>(B));
+}
+
+double dref_union_size(const uint8_t *lhs, const uint8_t *rhs, int p, int estim, int jestim) {
+    hll_t A = make_sketch(lhs, p, estim, jestim), B = make_sketch(rhs, p, estim, jestim);
+    A.report(); B.report();
+    return A.union_size(B);
+}
+
+void dref_triple(const uint8_t *lhs, const uint8_t *rhs, int p, int estim, int jestim, double *out3) {
+    hll_t A = make_sketch(lhs, p, estim, jestim), B = make_sketch(rhs, p, estim, jestim);
+    A.report(); B.report();
+    auto t = A.full_set_comparison(B);
+    out3[0] = t[0]; out3[1] = t[1]; out3[2] = t[2];
+}
+
+// Rows [row_begin, row_end) of the symmetric all-pairs matrix, written at their distmat offsets
+// (distmat/distmat.h:260-276) into `out` (length n(n-1)/2).
+//   order 0: value = cmp(sketches[i], sketches[j])   (BINARY paths, src/sketch_and_cmp.h:829, :849)
+//   order 1: value = cmp(sketches[j], sketches[i])   (TSV / PHYLIP path via perform_core_op, :699-710)
+int dref_dist_rows(const uint8_t *regs, uint64_t n, int p, int k, int estim, int jestim, int rtype, int order,
+                   uint64_t row_begin, uint64_t row_end, int nthreads, float *out) {
+    if(nthreads <= 0) nthreads = omp_get_max_threads();
+    std::vector<hll_t> sk = make_sketches(regs, n, p, estim, jestim);
+    const float ksinv = 1. / k;
+    const EmissionType rt = (EmissionType)rtype;
+    for(uint64_t i = row_begin; i < row_end && i + 1 < n; ++i) {
+        float *dists = out + (i * (2 * n - i - 1)) / 2; // row_ptr(i)
+        const hll_t &h1 = sk[i];
+        #pragma omp parallel for schedule(dynamic) num_threads(nthreads)
+        for(uint64_t j = i + 1; j < n; ++j)
+            dists[j - i - 1] = order ? result_cmp(sk[j], h1, rt, ksinv) : result_cmp(h1, sk[j], rt, ksinv);
+    }
+    return 0;
+}
+
+int dref_dist_symmetric(const uint8_t *regs, uint64_t n, int p, int k, int estim, int jestim, int rtype, int order,
+                        int nthreads, float *out) {
+    return dref_dist_rows(regs, n, p, k, estim, jestim, rtype, order, 0, n, nthreads, out);
+}
+
+// partdist_loop (src/dashing.h:675-681): out[q * nr + j] = result_cmp(refs[j], queries[q]).
+int dref_dist_rect(const uint8_t *ref_regs, uint64_t nr, const uint8_t *qry_regs, uint64_t nq, int p, int k,
+                   int estim, int jestim, int rtype, int nthreads, float *out) {
+    if(nthreads <= 0) nthreads = omp_get_max_threads();
+    std::vector<hll_t> refs = make_sketches(ref_regs, nr, p, estim, jestim);
+    std::vector<hll_t> qrys = make_sketches(qry_regs, nq, p, estim, jestim);
+    const float ksinv = 1. / k;
+    const EmissionType rt = (EmissionType)rtype;
+    for(uint64_t qi = 0; qi < nq; ++qi) {
+        const hll_t &hq = qrys[qi];
+        float *arr = out + qi * nr;
+        #pragma omp parallel for schedule(dynamic) num_threads(nthreads)
+        for(uint64_t j = 0; j < nr; ++j) arr[j] = result_cmp(refs[j], hq, rt, ksinv);
+    }
+    return 0;
+}
+
+// .hll container via the reference's own writer/reader (gz).  A freshly sketched hll_t is written
+// with value_ = -1 ("not calculated"), as sketch_core does (src/sketch_and_cmp.h:522).
+int dref_hll_write(const char *path, const uint8_t *regs, int p, int estim, int jestim, int calculated) {
+    try {
+        hll_t h = make_sketch(regs, p, estim, jestim);
+        if(calculated) h.report();
+        h.write(path);
+    } catch(const std::exception &e) { std::fprintf(stderr, "dref_hll_write: %s\n", e.what()); return 1; }
+    return 0;
+}
+
+int dref_hll_read(const char *path, uint8_t *regs_out, uint64_t cap, int *p_out, int *estim_out, int *jestim_out, double *value_out) {
+    try {
+        hll_t h(path);
+        if(h.size() > cap) return 2;
+        std::memcpy(regs_out, h.data(), h.size());
+        *p_out = h.p(); *estim_out = h.get_estim(); *jestim_out = h.get_jestim(); *value_out = h.creport();
+    } catch(const std::exception &e) { std::fprintf(stderr, "dref_hll_read: %s\n", e.what()); return 1; }
+    return 0;
+}
+
+// make_fname (src/dashing.h:497-526) for the HLL sketch type.
+int dref_make_fname(const char *path, int p, int wsz, int k, int csz, const char *spacing, const char *suffix,
+                    const char *prefix, char *out, uint64_t cap) {
+    std::string s = make_fname<hll_t>(path, p, wsz, k, csz, spacing, suffix, prefix);
+    if(s.size() + 1 > cap) return 1;
+    std::memcpy(out, s.data(), s.size() + 1);
+    return 0;
+}
+
+} // extern "C"
