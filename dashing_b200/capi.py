@@ -165,12 +165,17 @@ class PackedGenomes:
     """Device-resident 2-bit genome store (the sketch kernel's HBM input format)."""
 
     def __init__(self, bases, rec_offsets, genome_rec_begin, k, device=0):
-        bases = _np(bases, np.uint8)
+        """bases: uint8 numpy array (host) or an int device pointer to ASCII bases."""
+        if isinstance(bases, int):
+            bases_ptr = vp(bases)
+        else:
+            bases = _np(bases, np.uint8)
+            bases_ptr = bases.ctypes.data_as(vp)
         offs = _np(rec_offsets, np.uint64)
         grb = _np(genome_rec_begin, np.uint64)
         self.h = vp()
         self.ngenomes = grb.size - 1
-        _check(lib.db200_pack_genomes(device, bases.ctypes.data_as(vp), offs.ctypes.data_as(u64p), offs.size - 1,
+        _check(lib.db200_pack_genomes(device, bases_ptr, offs.ctypes.data_as(u64p), offs.size - 1,
                                       grb.ctypes.data_as(u64p), self.ngenomes, k, C.byref(self.h)))
         pb, km, nb = C.c_uint64(), C.c_uint64(), C.c_uint64()
         _check(lib.db200_packed_genomes_stats(self.h, C.byref(pb), C.byref(km), C.byref(nb)))

@@ -94,14 +94,25 @@ static int pack_genomes_impl(int device, const char *bases, const uint64_t *rec_
     }
     if (rc != DB200_OK) { cleanup(); return rc; }
     uint64_t nchunks = (T + CH - 1) / CH;
+    // `bases` may already live in device memory (unified addressing): pack straight from it when aligned
+    cudaPointerAttributes pat;
+    const bool on_dev = T && cudaPointerGetAttributes(&pat, bases) == cudaSuccess && pat.type == cudaMemoryTypeDevice &&
+                        ((reinterpret_cast<uintptr_t>(bases) + base0) & 15) == 0;
+    cudaGetLastError();
     for (uint64_t c = 0; c < nchunks; ++c) {
         const int b = (int)(c & 1);
         const uint64_t off = c * CH, len = std::min<uint64_t>(CH, T - off);
+        const uint64_t ngroups = (len + 15) / 16;
+        if (on_dev) {
+            pack_kernel<<<(unsigned)((ngroups + 255) / 256), 256, 0, stream>>>(
+                reinterpret_cast<const uint8_t *>(bases) + base0 + off, len, pg->bases2.as<uint32_t>() + off / 16, pg->nb.as<uint16_t>() + off / 16, ngroups);
+            DB200_LAUNCHED();
+            continue;
+        }
         if (c >= 2) cudaStreamWaitEvent(cs, packed[b], 0);  // staging buffer free again
-        if (cudaMemcpyAsync(stage[b].ptr, bases + base0 + off, len, cudaMemcpyHostToDevice, cs) != cudaSuccess) { rc = DB200_ECUDA; break; }
+        if (cudaMemcpyAsync(stage[b].ptr, bases + base0 + off, len, cudaMemcpyDefault, cs) != cudaSuccess) { rc = DB200_ECUDA; break; }
         cudaEventRecord(copied[b], cs);
         cudaStreamWaitEvent(stream, copied[b], 0);
-        const uint64_t ngroups = (len + 15) / 16;
         pack_kernel<<<(unsigned)((ngroups + 255) / 256), 256, 0, stream>>>(
             stage[b].as<uint8_t>(), len, pg->bases2.as<uint32_t>() + off / 16, pg->nb.as<uint16_t>() + off / 16, ngroups);
         DB200_LAUNCHED();
@@ -211,10 +222,10 @@ struct db200_dist_plan {
     uint64_t n1 = 0, qbase = 0, n2 = 0;  // valid row segments [0,n1) and [qbase, qbase+n2)
     int p = 0, estim = -1, gmin = 0, gmax = 0, K = 0;
     bool ready = false;
-    CUtensorMap tmap;
+    CUtensorMap tmap, tmap16;   // boxes of 32 / 16 sketches
     db200::DevBuf planes, counts, card, smin, smax, pmin, pmax, minmax, tiles;
     // tile-list cache key
-    int tl_rect = -1; uint64_t tl_rb = 0, tl_re = 0, tl_nr = 0, tl_nq = 0, tl_n = 0; uint64_t ntiles = 0;
+    int tl_rect = -1, tl_ta = 0; uint64_t tl_rb = 0, tl_re = 0, tl_nr = 0, tl_nq = 0, tl_n = 0; uint64_t ntiles = 0;
     uint64_t last_pairs = 0, last_tiles = 0;
     std::mutex mu;
 };
@@ -288,23 +299,30 @@ static int plan_prepare(db200_dist_plan *pl, const uint8_t *d_regs, uint64_t nro
     CUresult r = enc(&pl->tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, pl->planes.ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return DB200_ECUDA; }
+    box[1] = (cuuint32_t)JT;
+    r = enc(&pl->tmap16, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, pl->planes.ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (16-row box) failed with CUresult %d", (int)r); return DB200_ECUDA; }
     pl->ready = true;
     return DB200_OK;
 }
 
-static int plan_tiles(db200_dist_plan *pl, int rect, uint64_t rb, uint64_t re, uint64_t nr, uint64_t nq, cudaStream_t stream) {
-    if (pl->tl_rect == rect && pl->tl_rb == rb && pl->tl_re == re && pl->tl_nr == nr && pl->tl_nq == nq && pl->tl_n == pl->nrows) return DB200_OK;
+static int plan_tiles(db200_dist_plan *pl, int rect, int ta, uint64_t rb, uint64_t re, uint64_t nr, uint64_t nq, cudaStream_t stream) {
+    if (pl->tl_rect == rect && pl->tl_ta == ta && pl->tl_rb == rb && pl->tl_re == re && pl->tl_nr == nr && pl->tl_nq == nq && pl->tl_n == pl->nrows) return DB200_OK;
+    // A panels have `ta` rows (32, or 16 for the joint-MLE kernel), B panels DT = 32.  Tiles are ordered in
+    // super-rows of A panels: concurrent CTAs share their A panels and sweep the B panels together (L2 reuse).
     std::vector<DistTile> tiles;
-    const uint32_t SR = 8;  // panel rows per super-row: concurrent CTAs share A panels and sweep B panels together (L2 reuse)
+    const uint32_t f = (uint32_t)(DT / ta);          // A panels per B panel
+    const uint32_t SR = 8 * f;
     if (!rect) {
         const uint64_t n = pl->nrows;
         const uint32_t nb = (uint32_t)((n + DT - 1) / DT);
-        const uint32_t a0 = (uint32_t)(rb / DT), a1 = re > rb ? (uint32_t)((re - 1) / DT) + 1 : a0;
+        const uint32_t a0 = (uint32_t)(rb / ta), a1 = re > rb ? (uint32_t)((re - 1) / ta) + 1 : a0;
         for (uint32_t sr = a0; sr < a1; sr += SR)
-            for (uint32_t b = sr; b < nb; ++b)
-                for (uint32_t a = sr; a < std::min(sr + SR, a1) && a <= b; ++a) tiles.push_back(DistTile{a, b});
+            for (uint32_t b = sr / f; b < nb; ++b)
+                for (uint32_t a = sr; a < std::min(sr + SR, a1) && a / f <= b; ++a) tiles.push_back(DistTile{a, b});
     } else {
-        const uint32_t na = (uint32_t)((nq + DT - 1) / DT), nb = (uint32_t)((nr + DT - 1) / DT);
+        const uint32_t na = (uint32_t)((nq + ta - 1) / ta), nb = (uint32_t)((nr + DT - 1) / DT);
         for (uint32_t sr = 0; sr < na; sr += SR)
             for (uint32_t b = 0; b < nb; ++b)
                 for (uint32_t a = sr; a < std::min(sr + SR, na); ++a) tiles.push_back(DistTile{a, b});
@@ -315,7 +333,7 @@ static int plan_tiles(db200_dist_plan *pl, int rect, uint64_t rb, uint64_t re, u
         DB200_CUDA(cudaMemcpyAsync(pl->tiles.ptr, tiles.data(), tiles.size() * sizeof(DistTile), cudaMemcpyHostToDevice, stream));
         DB200_CUDA(cudaStreamSynchronize(stream));  // `tiles` is pageable host memory about to go out of scope
     }
-    pl->tl_rect = rect; pl->tl_rb = rb; pl->tl_re = re; pl->tl_nr = nr; pl->tl_nq = nq; pl->tl_n = pl->nrows;
+    pl->tl_rect = rect; pl->tl_ta = ta; pl->tl_rb = rb; pl->tl_re = re; pl->tl_nr = nr; pl->tl_nq = nq; pl->tl_n = pl->nrows;
     return DB200_OK;
 }
 
@@ -323,10 +341,10 @@ static int plan_run(db200_dist_plan *pl, const db200_dist_params *prm, int rect,
                     float *d_out, cudaStream_t stream) {
     if (!pl->ready) { set_error("dist plan not prepared"); return DB200_EINVAL; }
     if (prm->p != pl->p || prm->estim != pl->estim) { set_error("dist params (p=%d, estim=%d) differ from the prepared plan (p=%d, estim=%d)", prm->p, prm->estim, pl->p, pl->estim); return DB200_EINVAL; }
-    if (prm->jestim == DB200_ERTL_JOINT_MLE) { set_error("dist: joint MLE (-J) is not on the GPU path yet"); return DB200_EUNSUPPORTED; }
     if (prm->result_type < 0 || prm->result_type > 8) { set_error("dist: unknown result type %d", prm->result_type); return DB200_EINVAL; }
     if (prm->k < 1) { set_error("dist: k must be positive"); return DB200_EINVAL; }
-    DB200_TRY(plan_tiles(pl, rect, rb, re, nr, nq, stream));
+    const bool joint = prm->jestim == DB200_ERTL_JOINT_MLE;
+    DB200_TRY(plan_tiles(pl, rect, joint ? JT : DT, rb, re, nr, nq, stream));
     pl->last_tiles = pl->ntiles;
     if (pl->ntiles == 0) { pl->last_pairs = 0; return DB200_OK; }
     DistArgs a;
@@ -341,16 +359,28 @@ static int plan_run(db200_dist_plan *pl, const db200_dist_params *prm, int rect,
     a.ksinv = (double)(float)(1. / prm->k);  // const float ksinv = 1./k, src/sketch_and_cmp.h:797
     a.p = pl->p; a.gmin = pl->gmin; a.gmax = pl->gmax; a.K = pl->K;
     a.estim = prm->estim; a.rtype = prm->result_type; a.rect = rect;
-    // shared memory: S stages of 8 KiB + K x 2 KiB threshold counts + barriers; aim for two CTAs per SM
-    const size_t gbytes = (size_t)std::max(pl->K, 1) * DT * DT * 2;
-    int S = 6;
-    const size_t budget2 = 113 << 10, budget1 = 226 << 10;
-    if (gbytes + (size_t)S * STAGE_BYTES + 1024 > budget2) S = (int)std::min<size_t>(12, (budget1 - gbytes - 1024) / STAGE_BYTES);
-    if (S < 2) { set_error("dist: %d live thresholds do not fit in shared memory", pl->K); return DB200_EUNSUPPORTED; }
-    a.stages = S;
-    const size_t smem = (size_t)S * STAGE_BYTES + gbytes + 2 * S * 8;
-    DB200_CUDA(cudaFuncSetAttribute(dist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 << 10));
-    dist_kernel<<<(unsigned)pl->ntiles, DIST_THREADS, smem, stream>>>(pl->tmap, a);
+    if (!joint) {
+        // shared memory: S stages of 8 KiB + K x 2 KiB threshold counts + barriers; aim for two CTAs per SM
+        const size_t gbytes = (size_t)std::max(pl->K, 1) * DT * DT * 2;
+        int S = 6;
+        const size_t budget2 = 113 << 10, budget1 = 226 << 10;
+        if (gbytes + (size_t)S * STAGE_BYTES + 1024 > budget2) S = (int)std::min<size_t>(12, (budget1 - gbytes - 1024) / STAGE_BYTES);
+        if (S < 2) { set_error("dist: %d live thresholds do not fit in shared memory", pl->K); return DB200_EUNSUPPORTED; }
+        a.stages = S;
+        const size_t smem = (size_t)S * STAGE_BYTES + gbytes + 2 * S * 8;
+        DB200_CUDA(cudaFuncSetAttribute(dist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 << 10));
+        dist_kernel<<<(unsigned)pl->ntiles, DIST_THREADS, smem, stream>>>(pl->tmap, a);
+    } else {
+        const size_t gbytes = (size_t)3 * std::max(pl->K, 1) * JPAIRS * 2;
+        const size_t budget1 = 226 << 10;
+        const int S = (int)std::min<size_t>(6, (budget1 - gbytes - 1024) / JSTAGE_BYTES);
+        if (S < 2) { set_error("dist (joint MLE): %d live thresholds do not fit in shared memory", pl->K); return DB200_EUNSUPPORTED; }
+        a.stages = S;
+        const size_t smem = (size_t)S * JSTAGE_BYTES + gbytes + 2 * S * 8;
+        const int lhs_is_b = rect ? 1 : (prm->order == DB200_ORDER_COL_FIRST ? 1 : 0);
+        DB200_CUDA(cudaFuncSetAttribute(dist_jmle_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 << 10));
+        dist_jmle_kernel<<<(unsigned)pl->ntiles, DIST_THREADS, smem, stream>>>(pl->tmap16, pl->tmap, a, lhs_is_b);
+    }
     DB200_LAUNCHED();
     DB200_CUDA(cudaGetLastError());
     if (rect) pl->last_pairs = nr * nq;

@@ -198,11 +198,14 @@ struct PairCounts {
     const uint16_t *g;   // &G[0][pair]
     uint32_t m;
     int lo, hi;          // tile value range: thresholds lo+1..hi are stored
-    int kmax_pair;       // max register value of the pair (for the 2^16 wrap rule)
+    int kmax_pair;       // upper bound on the histogram's largest value (for the 2^16 wrap rule)
+    int stride;          // elements between consecutive thresholds
+    int cap;             // G(k) = 0 for k > cap
     __device__ __forceinline__ uint32_t G(int k) const {
+        if (k > cap) return 0u;
         if (k <= lo) return m;
         if (k > hi) return 0u;
-        const uint32_t v = g[(k - lo - 1) * (DT * DT)];
+        const uint32_t v = g[(k - lo - 1) * stride];
         // counts are stored mod 2^16; 0 inside the pair's live range can only mean 2^16 (p == 16)
         return (v == 0u && k <= kmax_pair) ? m : v;
     }
@@ -303,7 +306,7 @@ __global__ void __launch_bounds__(DIST_THREADS, 2) dist_kernel(const __grid_cons
         }
         const int kmin_pair = max((int)a.smin[i], (int)a.smin[j]);
         const int kmax_pair = max((int)a.smax[i], (int)a.smax[j]);
-        PairCounts c{G + pair, m, lo, hi, kmax_pair};
+        PairCounts c{G + pair, m, lo, hi, kmax_pair, DT * DT, 64};
         const double us = calculate_estimate(c, a.estim, a.p, kmin_pair, kmax_pair);
         // non-joint path is symmetric in its operands (IEEE addition commutes): lhs = A, rhs = B
         const double cl = a.card[i], cr = a.card[j];
@@ -317,6 +320,136 @@ __global__ void __launch_bounds__(DIST_THREADS, 2) dist_kernel(const __grid_cons
         t0 = t0 < 0. ? 0. : t0;
         t1 = t1 < 0. ? 0. : t1;
         a.out[oidx] = emit_value(a.rtype, ji, t0, t1, is, a.ksinv);
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Joint-MLE (-J) variant: ertl_joint, hll.h:636-684.  Besides the union histogram the reference
+// builds countsAXBhalf[v] = cg1[v] + ceq[v] + cg2[v+1] (hll.h:660-674) — which is exactly the histogram
+// of max(a_i, b_i - 1) — and its mirror image.  In threshold form
+//     #{max(a, b-1) >= k} = popc(A_k | B_{k+1}),      #{max(a-1, b) >= k} = popc(A_{k+1} | B_k),
+// so one pass over the planes k and k+1 yields all three count families.  Tile = 16 x 32 pairs
+// (three uint16 count families must fit in shared memory for up to 52 thresholds).
+// ---------------------------------------------------------------------------------------------
+constexpr int JT = 16;                                 // A-panel rows of the joint tile
+constexpr int JBOX_A = JT * 128, JBOX_B = DT * 128;
+constexpr int JSTAGE_BYTES = 2 * (JBOX_A + JBOX_B);    // A_k, A_{k+1}, B_k, B_{k+1}
+constexpr int JPAIRS = JT * DT;
+
+__global__ void __launch_bounds__(DIST_THREADS, 1) dist_jmle_kernel(const __grid_constant__ CUtensorMap tmapA,
+                                                                    const __grid_constant__ CUtensorMap tmapB, const DistArgs a,
+                                                                    const int lhs_is_b) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int S = a.stages;
+    uint8_t *stage_mem = smem;
+    uint16_t *G = reinterpret_cast<uint16_t *>(smem + (size_t)S * JSTAGE_BYTES);  // [3][K][512]
+    const int Kcap = a.K > 0 ? a.K : 1;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)S * JSTAGE_BYTES + (size_t)3 * Kcap * JPAIRS * 2);
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + S);
+
+    const DistTile tile = a.tiles[blockIdx.x];          // tile.a counts 16-row half panels
+    const uint64_t rowA0 = (a.rect ? a.qbase : 0) + (uint64_t)tile.a * JT;
+    const uint64_t rowB0 = (uint64_t)tile.b * DT;
+    const uint32_t panA = (uint32_t)(rowA0 / DT), panB = tile.b;
+    const int lo = (int)min(a.pmin[panA], a.pmin[panB]);
+    const int hi = (int)max(a.pmax[panA], a.pmax[panB]);
+    const int Kt = hi - lo;
+    const int W = 1 << (a.p - 5), nbox = W >> 5;
+    const int iters = Kt * nbox;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, DIST_CONSUMERS / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == DIST_CONSUMERS / 32) {
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmapA) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmapB) : "memory");
+            for (int it = 0; it < iters; ++it) {
+                const int s = it % S;
+                const uint32_t ph = (uint32_t)(it / S) & 1u;
+                mbar_wait(empty0 + 8 * s, ph ^ 1u);
+                const int t = lo - a.gmin + it / nbox, wb = it % nbox;   // plane of threshold k = lo + 1 + it/nbox
+                const uint32_t dst = smem_u32(stage_mem + (size_t)s * JSTAGE_BYTES);
+                mbar_expect_tx(full0 + 8 * s, JSTAGE_BYTES);
+                // plane t+1 beyond the last stored threshold is out of bounds -> zero fill == "no register that large"
+                tma_load_3d(dst, &tmapA, wb * 32, (int)rowA0, t, full0 + 8 * s);
+                tma_load_3d(dst + JBOX_A, &tmapA, wb * 32, (int)rowA0, t + 1, full0 + 8 * s);
+                tma_load_3d(dst + 2 * JBOX_A, &tmapB, wb * 32, (int)rowB0, t, full0 + 8 * s);
+                tma_load_3d(dst + 2 * JBOX_A + JBOX_B, &tmapB, wb * 32, (int)rowB0, t + 1, full0 + 8 * s);
+            }
+        }
+    } else {
+        const uint32_t ti = threadIdx.x >> 4, tj = threadIdx.x & 15;   // A row ti, B rows {tj, tj+16}
+        const uint32_t swA = (ti & 7) << 4, swB = (tj & 7) << 4;
+        uint32_t u0 = 0, u1 = 0, x0 = 0, x1 = 0, y0 = 0, y1 = 0;
+        for (int it = 0; it < iters; ++it) {
+            const int s = it % S;
+            const uint32_t ph = (uint32_t)(it / S) & 1u;
+            mbar_wait(full0 + 8 * s, ph);
+            const uint8_t *A0 = stage_mem + (size_t)s * JSTAGE_BYTES, *A1 = A0 + JBOX_A, *B0 = A0 + 2 * JBOX_A, *B1 = B0 + JBOX_B;
+#pragma unroll
+            for (uint32_t c = 0; c < 8; ++c) {
+                const uint32_t oa = ti * 128 + ((c << 4) ^ swA), ob0 = tj * 128 + ((c << 4) ^ swB), ob1 = ob0 + 16 * 128;
+                const uint4 ak = *reinterpret_cast<const uint4 *>(A0 + oa), an = *reinterpret_cast<const uint4 *>(A1 + oa);
+                const uint4 bk0 = *reinterpret_cast<const uint4 *>(B0 + ob0), bn0 = *reinterpret_cast<const uint4 *>(B1 + ob0);
+                const uint4 bk1 = *reinterpret_cast<const uint4 *>(B0 + ob1), bn1 = *reinterpret_cast<const uint4 *>(B1 + ob1);
+#define DB200_POP4(p, q) (__popc(p.x | q.x) + __popc(p.y | q.y) + __popc(p.z | q.z) + __popc(p.w | q.w))
+                u0 += DB200_POP4(ak, bk0); x0 += DB200_POP4(ak, bn0); y0 += DB200_POP4(an, bk0);
+                u1 += DB200_POP4(ak, bk1); x1 += DB200_POP4(ak, bn1); y1 += DB200_POP4(an, bk1);
+#undef DB200_POP4
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty0 + 8 * s);
+            if ((it + 1) % nbox == 0) {
+                const size_t tl = (size_t)(it / nbox);
+                uint16_t *gu = G + tl * JPAIRS, *gx = G + ((size_t)Kcap + tl) * JPAIRS, *gy = G + ((size_t)2 * Kcap + tl) * JPAIRS;
+                const uint32_t p0 = ti * DT + tj, p1 = p0 + 16;
+                gu[p0] = (uint16_t)u0; gu[p1] = (uint16_t)u1;
+                gx[p0] = (uint16_t)x0; gx[p1] = (uint16_t)x1;
+                gy[p0] = (uint16_t)y0; gy[p1] = (uint16_t)y1;
+                u0 = u1 = x0 = x1 = y0 = y1 = 0;
+            }
+        }
+    }
+    __syncthreads();
+
+    const uint32_t m = 1u << a.p;
+    const int q = 64 - a.p;
+    for (uint32_t pair = threadIdx.x; pair < (uint32_t)JPAIRS; pair += DIST_THREADS) {
+        const uint32_t il = pair >> 5, jl = pair & 31;
+        const uint64_t i = rowA0 + il, j = rowB0 + jl;
+        uint64_t oidx;
+        if (a.rect) {
+            if (i >= a.qbase + a.nq || j >= a.nr) continue;
+            oidx = (i - a.qbase) * a.nr + j;
+        } else {
+            if (i >= j || j >= a.n || i < a.row_begin || i >= a.row_end) continue;
+            oidx = (i * (2 * a.n - i - 1)) / 2 - a.out_base + (j - i - 1);
+        }
+        const int amin = a.smin[i], amax = a.smax[i], bmin = a.smin[j], bmax = a.smax[j];
+        // union histogram -> cABX (always the MLE, hll.h:658)
+        PairCounts cu{G + pair, m, lo, hi, max(amax, bmax), JPAIRS, 64};
+        const double cABX = ertl_mle(cu, a.p, q, max(amin, bmin), max(amax, bmax));
+        // tile families: X = max(A, B-1), Y = max(A-1, B); bins above q-1 fold into bin q (hll.h:660-674)
+        PairCounts cx{G + (size_t)Kcap * JPAIRS + pair, m, lo, hi, max(amax, bmax - 1), JPAIRS, q};
+        PairCounts cy{G + (size_t)2 * Kcap * JPAIRS + pair, m, lo, hi, max(amax - 1, bmax), JPAIRS, q};
+        const double eX = ertl_mle(cx, a.p, q - 1, max(amin, bmin - 1) < 0 ? 0 : max(amin, bmin - 1), max(amax, bmax - 1));
+        const double eY = ertl_mle(cy, a.p, q - 1, max(amin - 1, bmin) < 0 ? 0 : max(amin - 1, bmin), max(amax - 1, bmax));
+        // lhs / rhs of result_cmp: lhs = A (row sketch) unless lhs_is_b
+        const double cAX = lhs_is_b ? a.card[j] : a.card[i], cBX = lhs_is_b ? a.card[i] : a.card[j];
+        const double cAXBhalf = lhs_is_b ? eY : eX, cBXAhalf = lhs_is_b ? eX : eY;
+        const double t0 = cABX - cBX, t1 = cABX - cAX;
+        const double cX1 = 1.5 * cBX + 1.5 * cAX - cBXAhalf - cAXBhalf;
+        const double cX2 = 2. * (cBXAhalf + cAXBhalf) - 3. * cABX;
+        const double h = 0.5 * (cX1 + cX2);
+        const double t2 = 0. < h ? h : 0.;
+        const double ji = t2 / (t0 + t1 + t2);   // hll.h:1175-1178
+        a.out[oidx] = emit_value(a.rtype, ji, t0, t1, t2, a.ksinv);
     }
 }
 

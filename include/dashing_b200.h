@@ -115,7 +115,8 @@ DB200_API int db200_sketch_batch(int device, int p, int k, int canon,
  * store is the HBM-resident input format of the sketch kernel: 2-bit bases (64 per 16-byte word),
  * a validity bit-plane and a record-start bit-plane (DESIGN.md "Data layout"). */
 typedef struct db200_packed_genomes db200_packed_genomes;
-/* Packs host ASCII (same arguments as db200_sketch_batch) into a device-resident store. */
+/* Packs ASCII (same arguments as db200_sketch_batch) into a device-resident store.  `bases` is a host
+ * pointer (pinned memory is DMA'd directly) or, under unified addressing, a device pointer. */
 DB200_API int db200_pack_genomes(int device, const char *bases, const uint64_t *rec_offsets, uint64_t nrecords,
                        const uint64_t *genome_rec_begin, uint64_t ngenomes, int k, db200_packed_genomes **out);
 DB200_API int db200_packed_genomes_free(db200_packed_genomes *g);

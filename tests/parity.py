@@ -1,0 +1,49 @@
+"""Parity policy shared by the tests (DESIGN.md "Parity bar").
+
+Integer / byte results (registers, histograms, k-mers, file payloads): bit-exact.
+
+Floating point (estimator values, Jaccard / Mash / containment floats): BASELINE.json's tolerance,
+1e-6 relative.  Two refinements, both forced by the reference's own arithmetic:
+
+* Cancellation residues.  Quantities such as |A \\ B| = cA - I are differences of ~1e5-sized doubles;
+  when the true value is 0 the reference returns whatever its compiler's FMA contraction leaves
+  (0, 1.4e-11, 2.9e-11 ...).  The error is therefore measured relative to max(|got|, |want|, scale),
+  scale = 1 for index/distance outputs and the largest finite cardinality for SIZES.
+* Discontinuity at 0.  dist_index / containment_dist map ji == 0 to exactly 1 and ji = 1e-17 to ~1.17
+  (src/dashing.h:154-165), and 0/0 vs 1e-11/1e-11 decides between NaN and 1.  Where the checker's own
+  intersection size for a pair is such a residue (< 1e-9 of the largest cardinality), infinite or
+  NaN, the values derived from it are not compared (`unstable_size`).
+"""
+import numpy as np
+
+RTOL = 1e-6
+
+
+def rel_err(got, want, scale=1.0):
+    got = np.asarray(got, dtype=np.float64)
+    want = np.asarray(want, dtype=np.float64)
+    same = (got == want) | (np.isnan(got) & np.isnan(want))
+    with np.errstate(invalid="ignore", divide="ignore"):
+        err = np.abs(got - want) / np.maximum(np.maximum(np.abs(got), np.abs(want)), scale)
+    err = np.where(same, 0.0, err)
+    return np.where(np.isnan(err), np.inf, err)
+
+
+def assert_close(got, want, scale=1.0, rtol=RTOL, what="", ignore=None):
+    err = rel_err(got, want, scale)
+    if ignore is not None:
+        err = np.where(ignore, 0.0, err)
+    bad = err > rtol
+    if bad.any():
+        idx = np.nonzero(bad.ravel())[0][:5]
+        g = np.asarray(got, dtype=np.float64).ravel()[idx]
+        w = np.asarray(want, dtype=np.float64).ravel()[idx]
+        raise AssertionError(f"{what}: {int(bad.sum())}/{bad.size} values differ by > {rtol:g} rel; first idx {idx}, got {g}, want {w}")
+
+
+def unstable_size(intersection_want, scale, eps=1e-9):
+    """Pairs whose intersection size in the checker is a cancellation residue (|I| < eps * scale),
+    infinite or NaN: every value derived from it (similarities, and distances through the
+    discontinuity at 0) is decided by rounding noise in the reference itself and is not compared."""
+    s = np.asarray(intersection_want, dtype=np.float64)
+    return ~(np.isfinite(s) & (np.abs(s) >= eps * scale))

@@ -1,0 +1,121 @@
+"""GPU parity, hot path (ii): cardinalities and all-pairs values through the C ABI vs the oracle.
+Floats: 1e-6 relative (BASELINE.json), policy in tests/parity.py."""
+import os
+
+import numpy as np
+import pytest
+
+from parity import assert_close, unstable_size
+from dashing_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def test_cardinalities_all_estimators(gpu, checker, golden_dir):
+    d = np.load(os.path.join(golden_dir, "dist.npz"))
+    for estim in (0, 1, 2):
+        assert_close(gpu.cardinalities(d["regs"], 10, estim), d[f"card_e{estim}"], rtol=1e-9, what=f"golden card estim {estim}")
+    for p in (7, 10, 14, 16, 18):
+        regs = np.concatenate([synth.registers(p, 9, p, card=1e3 * (1 << (p // 2))), synth.adversarial_registers(2, p)])
+        for estim in (0, 1, 2):
+            assert_close(gpu.cardinalities(regs, p, estim), checker.cardinalities(regs, p, estim), rtol=1e-9, what=f"p={p} estim={estim}")
+
+
+def test_pair_matrices_golden(gpu, golden_dir):
+    d = np.load(os.path.join(golden_dir, "dist.npz"))
+    p, k, regs = int(d["p"]), int(d["k"]), d["regs"]
+    for estim in (0, 1, 2):
+        card = d[f"card_e{estim}"]
+        scale = float(np.max(card[np.isfinite(card)]))
+        for jestim in (2, 3):
+            for order in (0, 1):
+                ign = unstable_size(d[f"pairs_e{estim}_j{jestim}_r2_o{order}"], scale)
+                for rtype in range(9):
+                    got = gpu.dist_symmetric(regs, p, k=k, estim=estim, jestim=jestim, result_type=rtype, order=order)
+                    assert_close(got, d[f"pairs_e{estim}_j{jestim}_r{rtype}_o{order}"], scale=scale if rtype == 2 else 1.0, ignore=ign,
+                                 what=f"estim={estim} jestim={jestim} rtype={rtype} order={order}")
+    assert_close(gpu.dist_rect(regs[:20], regs[20:], p, k=k, result_type=1), d["rect_e2_j2_r1"], what="rect JI")
+    assert_close(gpu.dist_rect(regs[:20], regs[20:], p, k=k, jestim=3, result_type=0), d["rect_e2_j3_r0"], what="rect JMLE mash",
+                 ignore=unstable_size(gpu.dist_rect(regs[:20], regs[20:], p, k=k, jestim=3, result_type=2), 4e5))
+    assert_close(gpu.dist_symmetric(d["regs14"], 14, k=k, result_type=1), d["pairs14_ji"], what="p14 JI")
+    assert_close(gpu.dist_symmetric(d["regs14"], 14, k=k, result_type=0), d["pairs14_mash"], what="p14 Mash")
+    assert_close(gpu.dist_symmetric(d["regs14"], 14, k=k, jestim=3, result_type=1), d["pairs14_jmle"], what="p14 JMLE")
+
+
+def test_reference_bundled_genomes(gpu, golden_dir):
+    kat = np.load(os.path.join(golden_dir, "kat.npz"))
+    ji = gpu.dist_symmetric(kat["gcf_regs_p10"], 10, k=31, result_type=1)
+    mash = gpu.dist_symmetric(kat["gcf_regs_p14"], 14, k=31, result_type=0)
+    assert_close(ji, kat["gcf_ji_p10"]); assert_close(mash, kat["gcf_mash_p14"])
+    assert "%.6g" % ji[5] == "0.550403"
+    assert ["%.6g" % v for v in mash] == ["0.238361", "1", "1", "1", "0.152908", "0.0106825"]
+
+
+@pytest.mark.parametrize("p", [10, 11, 12, 13, 14, 15, 16])
+def test_all_pairs_vs_oracle(gpu, checker, p):
+    n = 75 if p < 15 else 45   # ragged: not a multiple of the 32-sketch panel
+    regs = np.concatenate([synth.registers(100 + p, n, p, card=40.0 * (1 << p)), synth.adversarial_registers(4, p)])
+    for estim, jestim, rtypes in ((2, 2, range(9)), (0, 2, (1, 2)), (1, 2, (0, 7)), (2, 3, (0, 1, 2, 5, 7)), (0, 3, (1,))):
+        card = checker.cardinalities(regs, p, estim)
+        scale = float(np.max(card[np.isfinite(card)]))
+        ign = unstable_size(checker.dist_rows(regs, p, estim=estim, jestim=jestim, rtype=2), scale)
+        for rtype in rtypes:
+            for order in ((0, 1) if jestim == 3 else (0,)):
+                got = gpu.dist_symmetric(regs, p, k=21, estim=estim, jestim=jestim, result_type=rtype, order=order)
+                want = checker.dist_rows(regs, p, k=21, estim=estim, jestim=jestim, rtype=rtype, order=order)
+                assert_close(got, want, scale=scale if rtype == 2 else 1.0, ignore=ign, what=f"p={p} estim={estim} jestim={jestim} rtype={rtype} order={order}")
+
+
+def test_rect_and_row_sharding(gpu, checker):
+    p = 12
+    regs = synth.registers(31, 150, p, card=2e5)
+    full = gpu.dist_symmetric(regs, p, result_type=0)
+    # block-row shards (the multi-GPU decomposition) concatenate to the full packed triangle
+    parts = [gpu.dist_symmetric(regs, p, result_type=0, row_begin=a, row_end=b) for a, b in ((0, 1), (1, 40), (40, 97), (97, 150))]
+    np.testing.assert_array_equal(np.concatenate(parts), full)
+    # rectangular mode == the corresponding entries of the symmetric matrix (union path is operand-symmetric)
+    nr = 83
+    rect = gpu.dist_rect(regs[:nr], regs[nr:], p, result_type=0)
+    n = len(regs)
+    idx = lambda i, j: i * (2 * n - i - 1) // 2 + j - i - 1
+    want = np.array([[full[idx(j, nr + q)] for j in range(nr)] for q in range(n - nr)], dtype=np.float32)
+    np.testing.assert_array_equal(rect, want)
+    assert_close(rect, checker.dist_rect(regs[:nr], regs[nr:], p, rtype=0), what="rect vs oracle")
+
+
+def test_properties_at_bench_scale(gpu, checker):
+    """BASELINE dist config is 10,000 p=14 sketches; the oracle needs minutes for that, so at N=3000 check
+    size-independent properties plus a random sample of pairs against the oracle."""
+    p, n = 14, 3000
+    regs = synth.registers(2026, n, p)
+    regs[17] = regs[5]                                   # identical sketches -> JI == 1, Mash == 0
+    regs[100] = np.maximum(regs[7], regs[9])             # union sketch
+    ji = gpu.dist_symmetric(regs, p, result_type=1)
+    mash = gpu.dist_symmetric(regs, p, result_type=0)
+    idx = lambda i, j: i * (2 * n - i - 1) // 2 + j - i - 1
+    assert ji.shape == (n * (n - 1) // 2,) and np.isfinite(ji).all() and (ji >= 0).all() and (ji <= 1.0 + 1e-6).all()
+    assert ji[idx(5, 17)] == 1.0 and mash[idx(5, 17)] == 0.0
+    # Mash is the documented function of JI (dist_index)
+    ksinv = np.float64(np.float32(1.0 / 31))
+    with np.errstate(divide="ignore"):
+        want = np.where(ji > 0, -np.log(2.0 * ji.astype(np.float64) / (1.0 + ji)) * ksinv, 1.0)
+    assert_close(mash, want, rtol=2e-6, what="mash = f(ji)")
+    # containment of a sketch in the union that contains it: |A ∩ (A ∪ B)| = |A|  -> SIZES equals cardinality
+    sizes = gpu.dist_symmetric(regs, p, result_type=2)
+    card = gpu.cardinalities(regs, p)
+    assert_close(sizes[idx(7, 100)], card[7], rtol=1e-6)
+    # random sample against the oracle
+    rng = np.random.default_rng(3)
+    for _ in range(300):
+        i, j = sorted(rng.choice(n, 2, replace=False))
+        assert_close(ji[idx(i, j)], checker.pair(regs[i], regs[j], p, rtype=1), what=f"pair {i},{j}")
+    # symmetric result == rect result on a slab
+    rect = gpu.dist_rect(regs[:64], regs[2000:2040], p, result_type=1)
+    np.testing.assert_array_equal(rect, np.array([[ji[idx(j, 2000 + q)] for j in range(64)] for q in range(40)], dtype=np.float32))
+
+
+def test_unsupported_is_loud(gpu):
+    regs = np.zeros((4, 1 << 9), np.uint8)
+    with pytest.raises(gpu.Db200Error) as ei:
+        gpu.dist_symmetric(regs, 9)
+    assert ei.value.code == gpu.EUNSUPPORTED
