@@ -45,8 +45,27 @@ struct db200_packed_genomes {
     int device = 0, k = 0;
     uint64_t nbases = 0, nblk = 0, ngenomes = 0, kmers = 0;
     uint32_t nitems = 0;
-    db200::DevBuf bases2, nb, st, items;
+    db200::DevBuf bases2, nb, st, items, counter, starts;
 };
+
+namespace db200 {
+// ASCII upload pipeline state (two device staging buffers, a copy stream and events), kept across calls:
+// cudaMalloc/cudaFree of multi-GB buffers costs more than the transfers they serve.
+struct Uploader {
+    DevBuf stage[2];
+    cudaStream_t cs = nullptr;
+    cudaEvent_t copied[2] = {nullptr, nullptr}, packed[2] = {nullptr, nullptr};
+    int init() {
+        if (cs) return DB200_OK;
+        DB200_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            DB200_CUDA(cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming));
+            DB200_CUDA(cudaEventCreateWithFlags(&packed[i], cudaEventDisableTiming));
+        }
+        return DB200_OK;
+    }
+};
+} // namespace db200
 
 namespace db200 {
 
@@ -62,64 +81,58 @@ static uint64_t count_kmers(const uint64_t *rec_offsets, uint64_t nrecords, int 
 
 static int pack_genomes_impl(int device, const char *bases, const uint64_t *rec_offsets, uint64_t nrecords,
                              const uint64_t *genome_rec_begin, uint64_t ngenomes, int k, db200_packed_genomes *pg,
-                             cudaStream_t stream) {
+                             Uploader &up, cudaStream_t stream) {
     const uint64_t base0 = nrecords ? rec_offsets[0] : 0;
     const uint64_t T = nrecords ? rec_offsets[nrecords] - base0 : 0;
     pg->device = device; pg->k = k; pg->nbases = T; pg->ngenomes = ngenomes;
-    pg->nblk = (T + 63) / 64 + 1;  // +1: a zero guard block so the last block's successor reads are defined
+    pg->nblk = (T + 63) / 64 + 1;  // +1: an all-invalid guard block (idle lanes and the predecessor of block 0 read it)
     pg->kmers = count_kmers(rec_offsets, nrecords, k);
     DB200_TRY(pg->bases2.reserve(pg->nblk * 16));
     DB200_TRY(pg->nb.reserve(pg->nblk * 8));
     DB200_TRY(pg->st.reserve(pg->nblk * 8));
+    DB200_TRY(pg->counter.reserve(16));
     DB200_CUDA(cudaMemsetAsync(pg->st.ptr, 0, pg->nblk * 8, stream));
-    DB200_CUDA(cudaMemsetAsync(pg->nb.ptr, 0, pg->nblk * 8, stream));
-    DB200_CUDA(cudaMemsetAsync(pg->bases2.ptr, 0, pg->nblk * 16, stream));
+    // the pack kernel writes whole 16-base groups; only the tail of the last block and the guard block need zeroing
+    const uint64_t full_blk = T / 64;
+    DB200_CUDA(cudaMemsetAsync(pg->nb.as<uint64_t>() + full_blk, 0, (pg->nblk - full_blk) * 8, stream));
+    DB200_CUDA(cudaMemsetAsync(pg->bases2.as<uint4>() + full_blk, 0, (pg->nblk - full_blk) * 16, stream));
 
     // ASCII upload in 64-base-aligned chunks through two device staging buffers; the pack kernel of
     // chunk c overlaps the H2D copy of chunk c+1.
     const uint64_t CH = 64ull << 20;
-    DevBuf stage[2];
-    cudaStream_t cs = nullptr;
-    cudaEvent_t copied[2] = {nullptr, nullptr}, packed[2] = {nullptr, nullptr};
-    DB200_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
-    int rc = DB200_OK;
-    auto cleanup = [&]() {
-        for (int i = 0; i < 2; ++i) { if (copied[i]) cudaEventDestroy(copied[i]); if (packed[i]) cudaEventDestroy(packed[i]); }
-        if (cs) cudaStreamDestroy(cs);
-    };
-    for (int i = 0; i < 2 && rc == DB200_OK; ++i) {
-        rc = stage[i].reserve(std::min<uint64_t>(CH, std::max<uint64_t>(T, 64)));
-        if (rc == DB200_OK && cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming) != cudaSuccess) rc = DB200_ECUDA;
-        if (rc == DB200_OK && cudaEventCreateWithFlags(&packed[i], cudaEventDisableTiming) != cudaSuccess) rc = DB200_ECUDA;
-    }
-    if (rc != DB200_OK) { cleanup(); return rc; }
-    uint64_t nchunks = (T + CH - 1) / CH;
+    const uint64_t nchunks = (T + CH - 1) / CH;
     // `bases` may already live in device memory (unified addressing): pack straight from it when aligned
     cudaPointerAttributes pat;
     const bool on_dev = T && cudaPointerGetAttributes(&pat, bases) == cudaSuccess && pat.type == cudaMemoryTypeDevice &&
                         ((reinterpret_cast<uintptr_t>(bases) + base0) & 15) == 0;
     cudaGetLastError();
+    if (!on_dev && T) {
+        DB200_TRY(up.init());
+        for (int i = 0; i < 2; ++i) DB200_TRY(up.stage[i].reserve(std::min<uint64_t>(CH, T)));
+        // the copy stream must not run ahead of work already queued on `stream` that still reads the staging buffers
+        DB200_CUDA(cudaEventRecord(up.packed[0], stream));
+        DB200_CUDA(cudaStreamWaitEvent(up.cs, up.packed[0], 0));
+    }
     for (uint64_t c = 0; c < nchunks; ++c) {
         const int b = (int)(c & 1);
         const uint64_t off = c * CH, len = std::min<uint64_t>(CH, T - off);
         const uint64_t ngroups = (len + 15) / 16;
+        const uint8_t *src;
         if (on_dev) {
-            pack_kernel<<<(unsigned)((ngroups + 255) / 256), 256, 0, stream>>>(
-                reinterpret_cast<const uint8_t *>(bases) + base0 + off, len, pg->bases2.as<uint32_t>() + off / 16, pg->nb.as<uint16_t>() + off / 16, ngroups);
-            DB200_LAUNCHED();
-            continue;
+            src = reinterpret_cast<const uint8_t *>(bases) + base0 + off;
+        } else {
+            if (c >= 2) DB200_CUDA(cudaStreamWaitEvent(up.cs, up.packed[b], 0));  // staging buffer free again
+            DB200_CUDA(cudaMemcpyAsync(up.stage[b].ptr, bases + base0 + off, len, cudaMemcpyDefault, up.cs));
+            DB200_CUDA(cudaEventRecord(up.copied[b], up.cs));
+            DB200_CUDA(cudaStreamWaitEvent(stream, up.copied[b], 0));
+            src = up.stage[b].as<uint8_t>();
         }
-        if (c >= 2) cudaStreamWaitEvent(cs, packed[b], 0);  // staging buffer free again
-        if (cudaMemcpyAsync(stage[b].ptr, bases + base0 + off, len, cudaMemcpyDefault, cs) != cudaSuccess) { rc = DB200_ECUDA; break; }
-        cudaEventRecord(copied[b], cs);
-        cudaStreamWaitEvent(stream, copied[b], 0);
-        pack_kernel<<<(unsigned)((ngroups + 255) / 256), 256, 0, stream>>>(
-            stage[b].as<uint8_t>(), len, pg->bases2.as<uint32_t>() + off / 16, pg->nb.as<uint16_t>() + off / 16, ngroups);
+        pack_kernel<<<(unsigned)((ngroups + 255) / 256), 256, 0, stream>>>(src, len, pg->bases2.as<uint32_t>() + off / 16,
+                                                                          pg->nb.as<uint16_t>() + off / 16, ngroups);
         DB200_LAUNCHED();
-        cudaEventRecord(packed[b], stream);
+        if (!on_dev) DB200_CUDA(cudaEventRecord(up.packed[b], stream));
     }
-    if (rc == DB200_OK && cudaGetLastError() != cudaSuccess) rc = DB200_ECUDA;
-    if (rc != DB200_OK) { set_error("packing genomes failed: %s", cudaGetErrorString(cudaGetLastError())); cudaStreamSynchronize(stream); cleanup(); return rc; }
+    DB200_CUDA(cudaGetLastError());
 
     // record starts
     std::vector<uint64_t> starts;
@@ -128,40 +141,41 @@ static int pack_genomes_impl(int device, const char *bases, const uint64_t *rec_
         const uint64_t pos = rec_offsets[r] - base0;
         if (pos < T && rec_offsets[r + 1] > rec_offsets[r]) starts.push_back(pos);
     }
-    DevBuf dstarts;
     if (!starts.empty()) {
-        rc = dstarts.reserve(starts.size() * 8);
-        if (rc == DB200_OK && cudaMemcpyAsync(dstarts.ptr, starts.data(), starts.size() * 8, cudaMemcpyHostToDevice, stream) != cudaSuccess) rc = DB200_ECUDA;
-        if (rc == DB200_OK) {
-            mark_starts_kernel<<<(unsigned)((starts.size() + 255) / 256), 256, 0, stream>>>(dstarts.as<uint64_t>(), starts.size(), pg->st.as<uint32_t>());
-            DB200_LAUNCHED();
-        }
+        DB200_TRY(pg->starts.reserve(starts.size() * 8));
+        DB200_CUDA(cudaMemcpyAsync(pg->starts.ptr, starts.data(), starts.size() * 8, cudaMemcpyHostToDevice, stream));
+        mark_starts_kernel<<<(unsigned)((starts.size() + 255) / 256), 256, 0, stream>>>(pg->starts.as<uint64_t>(), starts.size(), pg->st.as<uint32_t>());
+        DB200_LAUNCHED();
     }
-    // work items: split every genome's base range into chunks so that all SMs have several items
+    // work items: every genome is cut into equal chunks of ~1 Mbase (at least ~16 items per SM overall); items are
+    // ordered chunk-major so that by the time chunk c+1 of a genome starts, chunk c has been merged into HBM and
+    // seeds the staged registers (fewer updates).
     std::vector<SketchItem> items;
     {
         const uint64_t target_items = (uint64_t)g_num_sms(device) * 16;
         uint64_t chunk = T / std::max<uint64_t>(target_items, 1);
         chunk = std::min<uint64_t>(std::max<uint64_t>(chunk, 1ull << 16), 1ull << 20);
-        chunk = (chunk + 63) & ~63ull;
+        std::vector<std::pair<uint32_t, SketchItem>> tmp;
         for (uint64_t g = 0; g < ngenomes; ++g) {
             const uint64_t gs = rec_offsets[genome_rec_begin[g]] - base0, ge = rec_offsets[genome_rec_begin[g + 1]] - base0;
-            for (uint64_t s = gs; s < ge;) {
-                uint64_t e = std::min(ge, ((s / chunk) + 1) * chunk);
-                items.push_back(SketchItem{s, e, (uint32_t)g, 0});
-                s = e;
-            }
+            if (ge <= gs) continue;
+            const uint64_t nch = (ge - gs + chunk - 1) / chunk;
+            const uint64_t step = (((ge - gs + nch - 1) / nch) + 63) & ~63ull;
+            uint32_t ci = 0;
+            for (uint64_t s = gs; s < ge; s += step, ++ci) tmp.push_back({ci, SketchItem{s, std::min(ge, s + step), (uint32_t)g, 0}});
         }
+        std::stable_sort(tmp.begin(), tmp.end(), [](const auto &a, const auto &b) { return a.first < b.first; });
+        items.reserve(tmp.size());
+        for (auto &t : tmp) items.push_back(t.second);
     }
     pg->nitems = (uint32_t)items.size();
-    if (rc == DB200_OK && !items.empty()) {
-        rc = pg->items.reserve(items.size() * sizeof(SketchItem));
-        if (rc == DB200_OK && cudaMemcpyAsync(pg->items.ptr, items.data(), items.size() * sizeof(SketchItem), cudaMemcpyHostToDevice, stream) != cudaSuccess) rc = DB200_ECUDA;
+    if (!items.empty()) {
+        DB200_TRY(pg->items.reserve(items.size() * sizeof(SketchItem)));
+        DB200_CUDA(cudaMemcpyAsync(pg->items.ptr, items.data(), items.size() * sizeof(SketchItem), cudaMemcpyHostToDevice, stream));
     }
-    cudaError_t e = cudaStreamSynchronize(stream);  // staging buffers / host vectors go out of scope
-    if (rc == DB200_OK && e != cudaSuccess) { set_error("pack_genomes: %s", cudaGetErrorString(e)); rc = DB200_ECUDA; }
-    cleanup();
-    return rc;
+    const cudaError_t e = cudaStreamSynchronize(stream);  // the host vectors above go out of scope
+    if (e != cudaSuccess) { set_error("pack_genomes: %s", cudaGetErrorString(e)); return DB200_ECUDA; }
+    return DB200_OK;
 }
 
 static int sketch_packed_impl(const db200_packed_genomes *pg, int p, int canon, uint8_t *d_regs, cudaStream_t stream) {
@@ -170,23 +184,44 @@ static int sketch_packed_impl(const db200_packed_genomes *pg, int p, int canon, 
     const uint64_t m = 1ull << p;
     DB200_CUDA(cudaMemsetAsync(d_regs, 0, pg->ngenomes * m, stream));
     if (pg->nitems == 0) return DB200_OK;
-    const bool smem_regs = m <= (128u << 10);
+    DB200_CUDA(cudaMemsetAsync(pg->counter.ptr, 0, 4, stream));
+    const int mode = (m * 4 <= (128u << 10)) ? 0 : (m <= (128u << 10)) ? 1 : 2;
+    const size_t smem = mode == 0 ? m * 4 : mode == 1 ? m : 0;
+    const int k = pg->k, kclass = k <= 16 ? 0 : (k < 32 ? 1 : 2), rcshift = 2 * (k - 1);
+    SketchConsts kc;
+    kc.four = 4u; kc.neg1 = 0xFFFFFFFFu;
+    kc.rc_mul_lo = rcshift < 32 ? (1u << rcshift) : 0u;
+    kc.rc_mul_hi = rcshift >= 32 ? (1u << (rcshift - 32)) : 0u;
+    kc.rho_mul = 1u << p; kc.rho_add = 1u << (p - 1);
     int occ = 1;
-    const size_t smem = smem_regs ? m : 0;
-    if (smem_regs) {
-        DB200_CUDA(cudaFuncSetAttribute(sketch_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 << 10));
-        DB200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sketch_kernel<true>, SK_THREADS, smem));
-    } else {
-        DB200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sketch_kernel<false>, SK_THREADS, 0));
-    }
-    occ = std::max(occ, 1);
-    const unsigned grid = (unsigned)std::min<uint64_t>(pg->nitems, (uint64_t)g_num_sms(pg->device) * occ);
-    if (smem_regs)
-        sketch_kernel<true><<<grid, SK_THREADS, smem, stream>>>(pg->bases2.as<uint4>(), pg->nb.as<uint64_t>(), pg->st.as<uint64_t>(),
-                                                                pg->items.as<SketchItem>(), pg->nitems, pg->k, p, canon, d_regs);
-    else
-        sketch_kernel<false><<<grid, SK_THREADS, 0, stream>>>(pg->bases2.as<uint4>(), pg->nb.as<uint64_t>(), pg->st.as<uint64_t>(),
-                                                              pg->items.as<SketchItem>(), pg->nitems, pg->k, p, canon, d_regs);
+    const unsigned sms = (unsigned)g_num_sms(pg->device);
+#define DB200_SKETCH_LAUNCH(MODE, KC, CANON)                                                                                  \
+    do {                                                                                                                      \
+        auto kern = sketch_kernel<MODE, KC, CANON>;                                                                           \
+        if (smem) DB200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 << 10));             \
+        DB200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, SK_THREADS, smem));                              \
+        const unsigned grid = (unsigned)std::min<uint64_t>(pg->nitems, (uint64_t)sms * std::max(occ, 1));                     \
+        kern<<<grid, SK_THREADS, smem, stream>>>(pg->bases2.as<uint4>(), pg->nb.as<uint64_t>(), pg->st.as<uint64_t>(),        \
+                                                 pg->items.as<SketchItem>(), pg->nitems, pg->nblk - 1, k, p, d_regs,          \
+                                                 pg->counter.as<uint32_t>(), kc);                                             \
+    } while (0)
+#define DB200_SKETCH_KC(MODE, CANON)                                        \
+    do {                                                                    \
+        if (kclass == 0) DB200_SKETCH_LAUNCH(MODE, 0, CANON);               \
+        else if (kclass == 1) DB200_SKETCH_LAUNCH(MODE, 1, CANON);          \
+        else DB200_SKETCH_LAUNCH(MODE, 2, CANON);                           \
+    } while (0)
+#define DB200_SKETCH_MODE(MODE)                                             \
+    do {                                                                    \
+        if (canon) DB200_SKETCH_KC(MODE, true);                             \
+        else DB200_SKETCH_KC(MODE, false);                                  \
+    } while (0)
+    if (mode == 0) DB200_SKETCH_MODE(0);
+    else if (mode == 1) DB200_SKETCH_MODE(1);
+    else DB200_SKETCH_MODE(2);
+#undef DB200_SKETCH_MODE
+#undef DB200_SKETCH_KC
+#undef DB200_SKETCH_LAUNCH
     DB200_LAUNCHED();
     DB200_CUDA(cudaGetLastError());
     return DB200_OK;
@@ -397,10 +432,13 @@ struct HostCtx {
     std::mutex mu;
     cudaStream_t stream = nullptr;
     DevBuf regs, out, cards;
+    Uploader up;
     std::unique_ptr<db200_dist_plan> plan;
+    std::unique_ptr<db200_packed_genomes> store;   // reused by db200_sketch_batch
     int init(int device) {
         if (!stream) DB200_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         if (!plan) { plan.reset(new db200_dist_plan); plan->device = device; }
+        if (!store) store.reset(new db200_packed_genomes);
         return DB200_OK;
     }
 };
@@ -450,7 +488,7 @@ int db200_pack_genomes(int device, const char *bases, const uint64_t *rec_offset
     std::lock_guard<std::mutex> lk(hc.mu);
     DB200_TRY(hc.init(device));
     std::unique_ptr<db200_packed_genomes> pg(new db200_packed_genomes);
-    DB200_TRY(pack_genomes_impl(device, bases, rec_offsets, nrecords, genome_rec_begin, ngenomes, k, pg.get(), hc.stream));
+    DB200_TRY(pack_genomes_impl(device, bases, rec_offsets, nrecords, genome_rec_begin, ngenomes, k, pg.get(), hc.up, hc.stream));
     *out = pg.release();
     return DB200_OK;
 }
@@ -478,12 +516,16 @@ int db200_sketch_packed_dev(const db200_packed_genomes *g, int p, int canon, uin
 int db200_sketch_batch(int device, int p, int k, int canon, const char *bases, const uint64_t *rec_offsets, uint64_t nrecords,
                        const uint64_t *genome_rec_begin, uint64_t ngenomes, uint8_t *registers_out) {
     if (!registers_out && ngenomes) { set_error("db200_sketch_batch: null output"); return DB200_EINVAL; }
+    if (!rec_offsets || !genome_rec_begin || (!bases && nrecords)) { set_error("db200_sketch_batch: null argument"); return DB200_EINVAL; }
+    if (k < 1 || k > 32) { set_error("sketch: k=%d outside [1,32]", k); return DB200_EUNSUPPORTED; }
     if (p < 7 || p > 24) { set_error("sketch: p=%d outside the GPU path's range [7,24]", p); return DB200_EUNSUPPORTED; }
-    db200_packed_genomes *pg = nullptr;
-    DB200_TRY(db200_pack_genomes(device, bases, rec_offsets, nrecords, genome_rec_begin, ngenomes, k, &pg));
-    std::unique_ptr<db200_packed_genomes> guard(pg);
+    if (ngenomes >= (1ull << 32)) { set_error("too many genomes"); return DB200_EINVAL; }
+    DB200_TRY(check_device(device));
     HostCtx &hc = host_ctx(device);
     std::lock_guard<std::mutex> lk(hc.mu);
+    DB200_TRY(hc.init(device));
+    db200_packed_genomes *pg = hc.store.get();   // device buffers persist across calls
+    DB200_TRY(pack_genomes_impl(device, bases, rec_offsets, nrecords, genome_rec_begin, ngenomes, k, pg, hc.up, hc.stream));
     const uint64_t bytes = ngenomes << p;
     DB200_TRY(hc.regs.reserve(std::max<uint64_t>(bytes, 16)));
     DB200_TRY(sketch_packed_impl(pg, p, canon, hc.regs.as<uint8_t>(), hc.stream));

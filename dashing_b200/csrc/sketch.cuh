@@ -78,14 +78,43 @@ __global__ void mark_starts_kernel(const uint64_t *__restrict__ starts, uint64_t
 // ---------------------------------------------------------------------------------------------
 // helpers
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint64_t wang64(uint64_t key) {
-    key = ~key + (key << 21);
+// Runtime "constants" handed to the kernel as arguments.  They exist only so that ptxas cannot strength-reduce
+// the multiplications below into shift/LEA sequences: the ALU pipe (shifts, logic, compares) is the binding
+// unit of this kernel while the FMA pipe (IMAD) is otherwise idle, so every op moved across is a win.
+struct SketchConsts {
+    uint32_t four;      // 4
+    uint32_t neg1;      // 0xFFFFFFFF
+    uint32_t rc_mul_lo; // 2^rcshift        if rcshift <  32 else 0
+    uint32_t rc_mul_hi; // 2^(rcshift-32)   if rcshift >= 32 else 0
+    uint32_t rho_mul;   // 2^p
+    uint32_t rho_add;   // 2^(p-1)
+};
+
+// r = a * c + add (64-bit a, 32-bit c): IMAD.WIDE.U32 + IMAD
+__device__ __forceinline__ uint64_t mad64c(uint64_t a, uint32_t c, uint64_t add) {
+    uint64_t r;
+    asm("{\n\t.reg .u32 lo, ahi, rlo, rhi;\n\t"
+        "mov.b64 {lo, ahi}, %1;\n\t"
+        "mad.wide.u32 %0, lo, %2, %3;\n\t"
+        "mov.b64 {rlo, rhi}, %0;\n\t"
+        "mad.lo.u32 rhi, ahi, %2, rhi;\n\t"
+        "mov.b64 %0, {rlo, rhi};\n\t}"
+        : "=l"(r)
+        : "l"(a), "r"(c), "l"(add));
+    return r;
+}
+
+// Thomas Wang's 64-bit mix (bonsai/hll/include/sketch/hash.h:40-49) with the shift-add steps written as
+// multiplications: ~k + (k<<21) = k*(2^21-1) - 1, k + (k<<3) + (k<<8) = 265k, k + (k<<2) + (k<<4) = 21k,
+// k + (k<<31) = (2^31+1)k  (all mod 2^64).  `ones` must be 2^64-1 (see SketchConsts).
+__device__ __forceinline__ uint64_t wang64(uint64_t key, uint64_t ones) {
+    key = mad64c(key, 0x1FFFFFu, ones);
     key ^= key >> 24;
-    key = (key + (key << 3)) + (key << 8);
+    key = mad64c(key, 265u, 0ull);
     key ^= key >> 14;
-    key = (key + (key << 2)) + (key << 4);
+    key = mad64c(key, 21u, 0ull);
     key ^= key >> 28;
-    key += key << 31;
+    key = mad64c(key, 0x80000001u, 0ull);
     return key;
 }
 
@@ -93,18 +122,16 @@ __device__ __forceinline__ uint64_t wang64(uint64_t key) {
 // none but the first is a record start.  prev_* are the planes of the preceding block.
 __device__ __forceinline__ uint64_t emit_mask(uint64_t prev_nb, uint64_t prev_st, uint64_t nb, uint64_t st, int k) {
     // 128-bit window: low = previous block, high = this block
-    uint64_t clo = prev_nb & ~prev_st, chi = nb & ~st;  // "continuation" bits
-    uint64_t alo = ~0ull, ahi = ~0ull;                  // run-AND of cont over the last (k-1) positions
+    const uint64_t clo = prev_nb & ~prev_st, chi = nb & ~st;  // "continuation" bits
+    uint64_t alo = ~0ull, ahi = ~0ull;                        // run-AND of cont over the last (k-1) positions
     int L = k - 1;
     if (L > 0) {
         // binary lifting: r = AND of cont over a window of length `len`
         uint64_t rlo = clo, rhi = chi;
         int len = 1;
-        alo = ahi = ~0ull;
         int done = 0;  // positions already covered in (alo,ahi), counted back from the current one
         while (L) {
             if (L & 1) {
-                // a &= r << done
                 uint64_t slo, shi;
                 if (done == 0) { slo = rlo; shi = rhi; }
                 else { shi = (rhi << done) | (rlo >> (64 - done)); slo = rlo << done; }
@@ -113,7 +140,6 @@ __device__ __forceinline__ uint64_t emit_mask(uint64_t prev_nb, uint64_t prev_st
             }
             L >>= 1;
             if (L) {
-                // r &= r << len
                 const uint64_t shi = (rhi << len) | (rlo >> (64 - len));
                 const uint64_t slo = rlo << len;
                 rlo &= slo; rhi &= shi;
@@ -138,62 +164,118 @@ __device__ __forceinline__ void byte_max(uint32_t *word, uint32_t shift, uint32_
     }
 }
 
+// element-wise byte max of a packed word into HBM/L2
+__device__ __forceinline__ void merge_word(uint32_t *g, uint32_t v) {
+    uint32_t old = *g;
+    for (;;) {
+        const uint32_t nw = __vmaxu4(old, v);
+        if (nw == old) break;
+        const uint32_t prev = atomicCAS(g, old, nw);
+        if (prev == old) break;
+        old = prev;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
-// The sketch kernel.  256 threads; each thread owns runs of BPT consecutive 64-base blocks.
-// SMEM_REGS: registers of the item's genome are staged in shared memory (2^p bytes) and merged into
-// HBM once per item; otherwise (2^p too large) updates go straight to HBM/L2.
+// The sketch kernel.  Persistent CTAs of 512 threads pull work items from an atomic counter.  Inside an
+// item every warp sweeps warp-tiles of 32 x BPT consecutive 64-base blocks with WARP-UNIFORM loop bounds
+// (lanes past the end run on an all-invalid guard block), so the only divergent code is the rare
+// register update.
+//   MODE 0: registers staged in shared memory as one 32-bit word each -> a single ATOMS.MAX, no retry loop
+//           (2^p * 4 bytes: p <= 15)
+//   MODE 1: registers staged in shared memory as bytes, CAS loop + explicit warp reconvergence (p <= 17)
+//   MODE 2: no staging, CAS on HBM/L2 directly (larger p)
+// The staged copy is seeded from the registers already merged into HBM by earlier items of the same
+// genome, which keeps the update rate (and the ATOMS traffic) low.
 // ---------------------------------------------------------------------------------------------
-constexpr int SK_THREADS = 256;
+constexpr int SK_THREADS = 512;  // 16 warps share one staged sketch: 3 CTAs/SM at p=14 -> 48 resident warps
 constexpr int SK_BPT = 4;
 
-template <bool SMEM_REGS>
+// KCLASS: 0 -> k <= 16 (k-mer lives in the low word), 1 -> 16 < k < 32, 2 -> k == 32 (no mask at all)
+template <int MODE, int KCLASS, bool CANON>
 __global__ void __launch_bounds__(SK_THREADS) sketch_kernel(const uint4 *__restrict__ bases2, const uint64_t *__restrict__ nbp,
                                                             const uint64_t *__restrict__ stp,
-                                                            const SketchItem *__restrict__ items, uint32_t nitems, int k,
-                                                            int p, int canon, uint8_t *__restrict__ regs) {
+                                                            const SketchItem *__restrict__ items, uint32_t nitems, uint64_t guard_blk,
+                                                            int k, int p, uint8_t *__restrict__ regs,
+                                                            uint32_t *__restrict__ item_counter, const SketchConsts kc) {
     extern __shared__ __align__(16) uint8_t sregs[];
+    __shared__ uint32_t s_item;
     const uint32_t m = 1u << p;
     const uint64_t kmask = k == 32 ? ~0ull : ((1ull << (2 * k)) - 1);
-    const int rcshift = 2 * (k - 1);
-    const int idx_shift = 64 - p;
+    const uint32_t mask_lo = (uint32_t)kmask, mask_hi = (uint32_t)(kmask >> 32);
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t ones = ((uint64_t)kc.neg1 << 32) | kc.neg1;
+    const int idx_shift = 32 - p;   // p <= 24
+    constexpr uint32_t NWARPS = SK_THREADS / 32;
 
-    for (uint32_t it = blockIdx.x; it < nitems; it += gridDim.x) {
+    // one base: roll the forward and reverse-complement k-mers
+#define DB200_ROLL(c)                                                                                       \
+    do {                                                                                                    \
+        /* fwd = (fwd << 2) | c: three IMADs, no carry can leave the low word because c < 4 */              \
+        const uint32_t flo = (uint32_t)fwd, fhi = (uint32_t)(fwd >> 32);                                    \
+        const uint32_t nlo = flo * kc.four + (c);                                                           \
+        uint32_t nhi = fhi * kc.four + __umulhi(flo, kc.four);                                              \
+        if (KCLASS == 0) fwd = nlo & mask_lo;                                                               \
+        else { if (KCLASS == 1) nhi &= mask_hi; fwd = ((uint64_t)nhi << 32) | nlo; }                        \
+        /* rc = (rc >> 2) | ((3 - c) << 2(k-1)) */                                                          \
+        const uint32_t cc = (c) * kc.neg1 + 3u;                                                             \
+        const uint32_t rlo = __funnelshift_r((uint32_t)rc, (uint32_t)(rc >> 32), 2);                        \
+        const uint32_t rhi = (uint32_t)(rc >> 32) >> 2;                                                     \
+        rc = ((uint64_t)(cc * kc.rc_mul_hi + rhi) << 32) | (uint32_t)(cc * kc.rc_mul_lo + rlo);             \
+    } while (0)
+
+    for (;;) {
+        if (threadIdx.x == 0) s_item = atomicAdd(item_counter, 1u);
+        __syncthreads();
+        const uint32_t it = s_item;
+        if (it >= nitems) break;
         const SketchItem item = items[it];
         uint8_t *greg = regs + (uint64_t)item.genome * m;
-        if (SMEM_REGS) {
-            for (uint32_t w = threadIdx.x; w < m / 16; w += SK_THREADS) reinterpret_cast<uint4 *>(sregs)[w] = make_uint4(0, 0, 0, 0);
-            __syncthreads();
+        uint32_t *g32 = reinterpret_cast<uint32_t *>(greg);
+        // seed the staged registers from HBM
+        if (MODE == 0) {
+            uint4 *s4 = reinterpret_cast<uint4 *>(sregs);
+            for (uint32_t w = threadIdx.x; w < m / 4; w += SK_THREADS) {
+                const uint32_t v = g32[w];
+                s4[w] = make_uint4(v & 0xFFu, (v >> 8) & 0xFFu, (v >> 16) & 0xFFu, v >> 24);
+            }
+        } else if (MODE == 1) {
+            for (uint32_t w = threadIdx.x; w < m / 4; w += SK_THREADS) reinterpret_cast<uint32_t *>(sregs)[w] = g32[w];
         }
-        uint8_t *r8 = SMEM_REGS ? sregs : greg;
+        __syncthreads();
+        uint32_t *r32 = reinterpret_cast<uint32_t *>(sregs);
+        uint8_t *r8 = MODE == 1 ? sregs : greg;
 
         const uint64_t blk_lo = item.pos_begin >> 6, blk_hi = (item.pos_end + 63) >> 6;
-        for (uint64_t b0 = blk_lo + (uint64_t)threadIdx.x * SK_BPT; b0 < blk_hi; b0 += (uint64_t)SK_THREADS * SK_BPT) {
-            uint64_t fwd = 0, rc = 0, prev_nb = 0, prev_st = 0;
-            if (b0 > 0) {
-                // warm the rolling k-mers with the last 32 bases of the preceding block
-                const uint4 pw = __ldg(bases2 + b0 - 1);
-                prev_nb = __ldg(nbp + b0 - 1);
-                prev_st = __ldg(stp + b0 - 1);
-                const uint32_t pws[2] = {pw.z, pw.w};
+        for (uint64_t wb = blk_lo + (uint64_t)warp * (32 * SK_BPT); wb < blk_hi; wb += (uint64_t)NWARPS * 32 * SK_BPT) {
+            const uint64_t b0 = wb + (uint64_t)lane * SK_BPT;
+            uint64_t fwd = 0, rc = 0;
+            // warm the rolling k-mers with the last 32 bases of the preceding block
+            const uint64_t pb = (b0 > 0 && b0 < blk_hi) ? b0 - 1 : guard_blk;
+            const uint4 pw = __ldg(bases2 + pb);
+            uint64_t prev_nb = __ldg(nbp + pb), prev_st = __ldg(stp + pb);
+#pragma unroll 1
+            for (int wi = 0; wi < 2; ++wi) {
+                const uint32_t word = wi == 0 ? pw.z : pw.w;
 #pragma unroll
-                for (int wi = 0; wi < 2; ++wi) {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const uint32_t c = (pws[wi] >> (2 * i)) & 3u;
-                        fwd = ((fwd << 2) | c) & kmask;
-                        rc = (rc >> 2) | ((uint64_t)(c ^ 3u) << rcshift);
-                    }
+                for (int i = 0; i < 16; ++i) {
+                    const uint32_t c = (word >> (2 * i)) & 3u;
+                    DB200_ROLL(c);
                 }
             }
-            const uint64_t b1 = (b0 + SK_BPT < blk_hi) ? b0 + SK_BPT : blk_hi;
-            for (uint64_t b = b0; b < b1; ++b) {
-                const uint4 w4 = __ldg(bases2 + b);
-                const uint64_t nb = __ldg(nbp + b), st = __ldg(stp + b);
+#pragma unroll 1
+            for (int j = 0; j < SK_BPT; ++j) {
+                const uint64_t b = b0 + j;
+                const bool valid = b < blk_hi;
+                const uint64_t bl = valid ? b : guard_blk;
+                const uint4 w4 = __ldg(bases2 + bl);
+                const uint64_t nb = __ldg(nbp + bl), st = __ldg(stp + bl);
                 uint64_t E = emit_mask(prev_nb, prev_st, nb, st, k);
                 // clip to the item's position range
                 const uint64_t base = b << 6;
                 if (item.pos_begin > base) E &= (item.pos_begin - base >= 64) ? 0ull : (~0ull << (item.pos_begin - base));
                 if (item.pos_end < base + 64) E &= (item.pos_end <= base) ? 0ull : (~0ull >> (64 - (item.pos_end - base)));
+                if (!valid) E = 0;
                 prev_nb = nb; prev_st = st;
 #pragma unroll 1
                 for (int wi = 0; wi < 4; ++wi) {
@@ -202,39 +284,43 @@ __global__ void __launch_bounds__(SK_THREADS) sketch_kernel(const uint4 *__restr
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
                         const uint32_t c = (word >> (2 * i)) & 3u;
-                        fwd = ((fwd << 2) | c) & kmask;
-                        rc = (rc >> 2) | ((uint64_t)(c ^ 3u) << rcshift);
-                        if ((e16 >> i) & 1u) {
-                            const uint64_t x = (canon && rc < fwd) ? rc : fwd;
-                            const uint64_t h = wang64(x);
-                            const uint32_t idx = (uint32_t)(h >> idx_shift);
-                            const uint32_t rho = (uint32_t)__clzll((long long)(((h << 1) | 1ull) << (p - 1))) + 1u;
-                            if (r8[idx] < rho) byte_max(reinterpret_cast<uint32_t *>(r8) + (idx >> 2), (idx & 3u) * 8u, rho);
+                        DB200_ROLL(c);
+                        const uint64_t x = (CANON && rc < fwd) ? rc : fwd;
+                        const uint64_t h = wang64(x, ones);
+                        const uint32_t hlo = (uint32_t)h, hhi = (uint32_t)(h >> 32);
+                        const uint32_t idx = hhi >> idx_shift;
+                        // rho = clz(((h << 1) | 1) << (p - 1)) + 1   (hll.h:830): leading zeros of the low 64-p bits
+                        const uint32_t thi = __funnelshift_l(hlo, hhi, p);
+                        uint32_t rho = (uint32_t)__clz((int)thi) + 1u;
+                        if (__builtin_expect(thi == 0u, 0)) rho = 33u + (uint32_t)__clz((int)(hlo * kc.rho_mul + kc.rho_add));
+                        const bool emit = (e16 >> i) & 1u;
+                        if (MODE == 0) {
+                            if (emit && r32[idx] < rho) atomicMax(r32 + idx, rho);
+                        } else {
+                            const bool upd = emit && r8[idx] < rho;
+                            if (__any_sync(0xFFFFFFFFu, upd)) {
+                                if (upd) byte_max(reinterpret_cast<uint32_t *>(r8) + (idx >> 2), (idx & 3u) * 8u, rho);
+                                __syncwarp();  // the CAS loop is not a forced reconvergence point: re-join here
+                            }
                         }
                     }
                 }
             }
         }
-        if (SMEM_REGS) {
-            __syncthreads();
-            uint32_t *g32 = reinterpret_cast<uint32_t *>(greg);
-            const uint32_t *s32 = reinterpret_cast<const uint32_t *>(sregs);
+        __syncthreads();
+        if (MODE == 0) {
+            const uint4 *s4 = reinterpret_cast<const uint4 *>(sregs);
             for (uint32_t w = threadIdx.x; w < m / 4; w += SK_THREADS) {
-                const uint32_t v = s32[w];
-                if (v) {
-                    uint32_t old = g32[w];
-                    for (;;) {
-                        const uint32_t nw = __vmaxu4(old, v);
-                        if (nw == old) break;
-                        const uint32_t prev = atomicCAS(g32 + w, old, nw);
-                        if (prev == old) break;
-                        old = prev;
-                    }
-                }
+                const uint4 v = s4[w];
+                merge_word(g32 + w, v.x | (v.y << 8) | (v.z << 16) | (v.w << 24));
             }
-            __syncthreads();
+        } else if (MODE == 1) {
+            const uint32_t *s32 = reinterpret_cast<const uint32_t *>(sregs);
+            for (uint32_t w = threadIdx.x; w < m / 4; w += SK_THREADS) merge_word(g32 + w, s32[w]);
         }
+        __syncthreads();
     }
+#undef DB200_ROLL
 }
 
 } // namespace db200

@@ -232,6 +232,10 @@ class Ref(_Common):
         l.dref_triple.argtypes = [u8p, u8p, C.c_int, C.c_int, C.c_int, f64p]
         l.dref_dist_rows.argtypes = [u8p, C.c_uint64] + [C.c_int] * 6 + [C.c_uint64, C.c_uint64, C.c_int, f32p]
         l.dref_dist_rect.argtypes = [u8p, C.c_uint64, u8p, C.c_uint64] + [C.c_int] * 6 + [f32p]
+        l.dref_set_create.restype = C.c_void_p
+        l.dref_set_create.argtypes = [u8p, C.c_uint64, C.c_int, C.c_int, C.c_int]
+        l.dref_set_free.argtypes = [C.c_void_p]
+        l.dref_set_dist_rows.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_int, f32p]
         l.dref_hll_write.argtypes = [C.c_char_p, u8p, C.c_int, C.c_int, C.c_int, C.c_int]
         l.dref_hll_read.argtypes = [C.c_char_p, u8p, C.c_uint64, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                     C.POINTER(C.c_int), f64p]
@@ -316,6 +320,21 @@ class Ref(_Common):
 
     def dist_symmetric(self, regs2d, p, **kw):
         return self.dist_rows(regs2d, p, **kw)
+
+    # prepared set: build the n hll_t objects once, then time row ranges of the pair loop only
+    def set_create(self, regs2d, p, estim=2, jestim=2):
+        regs2d = np.ascontiguousarray(regs2d, dtype=np.uint8)
+        return (self.l.dref_set_create(_ptr(regs2d, u8p), regs2d.shape[0], p, estim, jestim), regs2d.shape[0])
+
+    def set_dist_rows(self, hset, k, rtype, order, row_begin, row_end, nthreads=0):
+        h, n = hset
+        tri = lambda r: r * (2 * n - r - 1) // 2
+        out = np.zeros(max(tri(min(row_end, n)) - tri(row_begin), 1), dtype=np.float32)
+        self.l.dref_set_dist_rows(C.c_void_p(h), k, rtype, order, row_begin, row_end, nthreads, _ptr(out, f32p))
+        return out
+
+    def set_free(self, hset):
+        self.l.dref_set_free(C.c_void_p(hset[0]))
 
     def dist_rect(self, refs, qrys, p, k=31, estim=2, jestim=2, rtype=1, nthreads=0):
         refs = np.ascontiguousarray(refs, dtype=np.uint8)

@@ -182,6 +182,37 @@ int dref_dist_rows(const uint8_t *regs, uint64_t n, int p, int k, int estim, int
     return 0;
 }
 
+// Prepared form of the same loop: the sketches are built (and report()ed) once, so a bounded sample of rows can
+// be timed without the per-call construction of n hll_t objects.
+struct dref_set { std::vector<hll_t> sk; uint64_t n; };
+
+void *dref_set_create(const uint8_t *regs, uint64_t n, int p, int estim, int jestim) {
+    dref_set *s = new dref_set;
+    s->sk = make_sketches(regs, n, p, estim, jestim);
+    s->n = n;
+    return s;
+}
+
+void dref_set_free(void *h) { delete static_cast<dref_set *>(h); }
+
+int dref_set_dist_rows(void *h, int k, int rtype, int order, uint64_t row_begin, uint64_t row_end, int nthreads, float *out) {
+    dref_set *s = static_cast<dref_set *>(h);
+    if(nthreads <= 0) nthreads = omp_get_max_threads();
+    const uint64_t n = s->n;
+    const float ksinv = 1. / k;
+    const EmissionType rt = (EmissionType)rtype;
+    const float *base = out;
+    for(uint64_t i = row_begin; i < row_end && i + 1 < n; ++i) {
+        // rows are written contiguously from out[0] (the caller sizes `out` for the sampled rows only)
+        float *dists = const_cast<float *>(base) + ((i * (2 * n - i - 1)) / 2 - (row_begin * (2 * n - row_begin - 1)) / 2);
+        const hll_t &h1 = s->sk[i];
+        #pragma omp parallel for schedule(dynamic) num_threads(nthreads)
+        for(uint64_t j = i + 1; j < n; ++j)
+            dists[j - i - 1] = order ? result_cmp(s->sk[j], h1, rt, ksinv) : result_cmp(h1, s->sk[j], rt, ksinv);
+    }
+    return 0;
+}
+
 int dref_dist_symmetric(const uint8_t *regs, uint64_t n, int p, int k, int estim, int jestim, int rtype, int order,
                         int nthreads, float *out) {
     return dref_dist_rows(regs, n, p, k, estim, jestim, rtype, order, 0, n, nthreads, out);
