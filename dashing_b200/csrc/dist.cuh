@@ -257,7 +257,34 @@ __global__ void __launch_bounds__(DIST_THREADS, 2) dist_kernel(const __grid_cons
         // ---------------- consumers: OR + POPC ----------------
         const uint32_t ti = threadIdx.x >> 4, tj = threadIdx.x & 15;  // A rows {ti, ti+16}, B rows {tj, tj+16}
         const uint32_t swA = (ti & 7) << 4, swB = (tj & 7) << 4;
+        // POPC runs on the 16-lane/clk XU pipe, which binds this kernel (ncu: XU 91 %, ALU 45 %).  Half of every box is
+        // therefore counted with a carry-save adder tree on the ALU pipe instead (Harley-Seal): 8 OR-words are reduced by
+        // 7 CSAs (2 LOP3 each) into bit-planes of weight 1, 2, 4 that persist in registers, plus ONE weight-8 plane that is
+        // popcounted.  The planes are flushed with three POPCs when the threshold ends.  Still integer-exact.
         uint32_t acc00 = 0, acc01 = 0, acc10 = 0, acc11 = 0;
+        uint32_t o00 = 0, o01 = 0, o10 = 0, o11 = 0;   // weight-1 planes
+        uint32_t t00 = 0, t01 = 0, t10 = 0, t11 = 0;   // weight-2 planes
+        uint32_t f00 = 0, f01 = 0, f10 = 0, f11 = 0;   // weight-4 planes
+#define DB200_CSA(h, l, a, b, c)                                        \
+    do {                                                                \
+        const uint32_t u__ = (a), v__ = (b), w__ = (c);                 \
+        asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(h) : "r"(u__), "r"(v__), "r"(w__)); /* majority */ \
+        asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(l) : "r"(u__), "r"(v__), "r"(w__)); /* parity   */ \
+    } while (0)
+        // 8 OR-words (two 16-byte chunks of A row `x` and B row `y`) -> planes (o,t,f) + 8 * popc(eights)
+#define DB200_HS8(acc, o, t, f, x0, x1, y0, y1)                                                   \
+    do {                                                                                          \
+        uint32_t c1, c2, c3, c4, d1, d2, e;                                                       \
+        DB200_CSA(c1, o, o, x0.x | y0.x, x0.y | y0.y);                                            \
+        DB200_CSA(c2, o, o, x0.z | y0.z, x0.w | y0.w);                                            \
+        DB200_CSA(d1, t, t, c1, c2);                                                              \
+        DB200_CSA(c3, o, o, x1.x | y1.x, x1.y | y1.y);                                            \
+        DB200_CSA(c4, o, o, x1.z | y1.z, x1.w | y1.w);                                            \
+        DB200_CSA(d2, t, t, c3, c4);                                                              \
+        DB200_CSA(e, f, f, d1, d2);                                                               \
+        acc += 8u * (uint32_t)__popc(e);                                                          \
+    } while (0)
+#define DB200_POP4(p, q) (__popc(p.x | q.x) + __popc(p.y | q.y) + __popc(p.z | q.z) + __popc(p.w | q.w))
         for (int it = 0; it < iters; ++it) {
             const int s = it % S;
             const uint32_t ph = (uint32_t)(it / S) & 1u;
@@ -265,29 +292,47 @@ __global__ void __launch_bounds__(DIST_THREADS, 2) dist_kernel(const __grid_cons
             const uint8_t *A = stage_mem + (size_t)s * STAGE_BYTES, *B = A + BOX_BYTES;
             const uint8_t *a0p = A + ti * 128, *a1p = A + (ti + 16) * 128;
             const uint8_t *b0p = B + tj * 128, *b1p = B + (tj + 16) * 128;
+            // chunks 0-3: direct POPC
 #pragma unroll
-            for (uint32_t c = 0; c < 8; ++c) {
+            for (uint32_t c = 0; c < 4; ++c) {
                 const uint32_t oa = (c << 4) ^ swA, ob = (c << 4) ^ swB;
                 const uint4 a0 = *reinterpret_cast<const uint4 *>(a0p + oa);
                 const uint4 a1 = *reinterpret_cast<const uint4 *>(a1p + oa);
                 const uint4 b0 = *reinterpret_cast<const uint4 *>(b0p + ob);
                 const uint4 b1 = *reinterpret_cast<const uint4 *>(b1p + ob);
-                acc00 += __popc(a0.x | b0.x) + __popc(a0.y | b0.y) + __popc(a0.z | b0.z) + __popc(a0.w | b0.w);
-                acc01 += __popc(a0.x | b1.x) + __popc(a0.y | b1.y) + __popc(a0.z | b1.z) + __popc(a0.w | b1.w);
-                acc10 += __popc(a1.x | b0.x) + __popc(a1.y | b0.y) + __popc(a1.z | b0.z) + __popc(a1.w | b0.w);
-                acc11 += __popc(a1.x | b1.x) + __popc(a1.y | b1.y) + __popc(a1.z | b1.z) + __popc(a1.w | b1.w);
+                acc00 += DB200_POP4(a0, b0);
+                acc01 += DB200_POP4(a0, b1);
+                acc10 += DB200_POP4(a1, b0);
+                acc11 += DB200_POP4(a1, b1);
+            }
+            // chunks 4-7: carry-save adders
+#pragma unroll
+            for (uint32_t c = 4; c < 8; c += 2) {
+                const uint32_t oa = (c << 4) ^ swA, ob = (c << 4) ^ swB, oa2 = ((c + 1) << 4) ^ swA, ob2 = ((c + 1) << 4) ^ swB;
+                const uint4 a0 = *reinterpret_cast<const uint4 *>(a0p + oa), a0n = *reinterpret_cast<const uint4 *>(a0p + oa2);
+                const uint4 a1 = *reinterpret_cast<const uint4 *>(a1p + oa), a1n = *reinterpret_cast<const uint4 *>(a1p + oa2);
+                const uint4 b0 = *reinterpret_cast<const uint4 *>(b0p + ob), b0n = *reinterpret_cast<const uint4 *>(b0p + ob2);
+                const uint4 b1 = *reinterpret_cast<const uint4 *>(b1p + ob), b1n = *reinterpret_cast<const uint4 *>(b1p + ob2);
+                DB200_HS8(acc00, o00, t00, f00, a0, a0n, b0, b0n);
+                DB200_HS8(acc01, o01, t01, f01, a0, a0n, b1, b1n);
+                DB200_HS8(acc10, o10, t10, f10, a1, a1n, b0, b0n);
+                DB200_HS8(acc11, o11, t11, f11, a1, a1n, b1, b1n);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(empty0 + 8 * s);
             if ((it + 1) % nbox == 0) {
                 uint16_t *g = G + (size_t)(it / nbox) * (DT * DT);
-                g[ti * DT + tj] = (uint16_t)acc00;
-                g[ti * DT + tj + 16] = (uint16_t)acc01;
-                g[(ti + 16) * DT + tj] = (uint16_t)acc10;
-                g[(ti + 16) * DT + tj + 16] = (uint16_t)acc11;
+                g[ti * DT + tj] = (uint16_t)(acc00 + __popc(o00) + 2 * __popc(t00) + 4 * __popc(f00));
+                g[ti * DT + tj + 16] = (uint16_t)(acc01 + __popc(o01) + 2 * __popc(t01) + 4 * __popc(f01));
+                g[(ti + 16) * DT + tj] = (uint16_t)(acc10 + __popc(o10) + 2 * __popc(t10) + 4 * __popc(f10));
+                g[(ti + 16) * DT + tj + 16] = (uint16_t)(acc11 + __popc(o11) + 2 * __popc(t11) + 4 * __popc(f11));
                 acc00 = acc01 = acc10 = acc11 = 0;
+                o00 = o01 = o10 = o11 = t00 = t01 = t10 = t11 = f00 = f01 = f10 = f11 = 0;
             }
         }
+#undef DB200_POP4
+#undef DB200_HS8
+#undef DB200_CSA
     }
     __syncthreads();
 
