@@ -1,0 +1,610 @@
+// dashing_host.cpp — see dashing_host.hpp.  Host-side mirror of the reference's sketch / dist drivers and formats.
+#include "dashing_host.hpp"
+#include "../../include/dashing_b200.h"
+
+#include <algorithm>
+#include <cctype>
+#include <cinttypes>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <getopt.h>
+#include <sys/stat.h>
+#include <zlib.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+namespace db200h {
+
+static void check(int rc) {
+    if (rc != DB200_OK) throw Error(db200_last_error());
+}
+
+static bool isfile(const std::string &p) {
+    struct stat st;
+    return ::stat(p.c_str(), &st) == 0 && S_ISREG(st.st_mode);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// .hll container
+// ---------------------------------------------------------------------------------------------------------------
+std::vector<uint8_t> hll_payload(const uint8_t *regs, uint32_t p, int estim, int jestim, double value) {
+    const size_t m = size_t(1) << p;
+    std::vector<uint8_t> out(28 + m);
+    const uint32_t hdr[5] = {value >= 0. ? 1u : 0u, (uint32_t)estim, (uint32_t)jestim, 1u, p};   // hll.h:1041-1044
+    std::memcpy(out.data(), hdr, 20);
+    std::memcpy(out.data() + 20, &value, 8);
+    std::memcpy(out.data() + 28, regs, m);
+    return out;
+}
+
+void write_hll(const std::string &path, const uint8_t *regs, uint32_t p, int estim, int jestim, double value) {
+    gzFile fp = gzopen(path.c_str(), "wb");
+    if (!fp) throw Error("Could not open file at '" + path + "' for writing");
+    const auto buf = hll_payload(regs, p, estim, jestim, value);
+    const bool ok = gzwrite(fp, buf.data(), (unsigned)buf.size()) == (int)buf.size();
+    gzclose(fp);
+    if (!ok) throw Error("Error writing to file.");
+}
+
+HllFile read_hll(const std::string &path) {
+    gzFile fp = gzopen(path.c_str(), "rb");
+    if (!fp) throw Error("Could not open file at '" + path + "' for reading");
+    HllFile h;
+    uint32_t bf[5];
+    auto rd = [&](void *dst, size_t len) {
+        if ((size_t)gzread(fp, dst, (unsigned)len) != len) { gzclose(fp); throw Error("Error reading from file " + path); }
+    };
+    rd(bf, 20);
+    h.is_calculated = bf[0]; h.estim = bf[1]; h.jestim = bf[2]; h.marker = bf[3]; h.p = bf[4];
+    rd(&h.value, 8);
+    if (h.p > 40) { gzclose(fp); throw Error("implausible sketch size in " + path); }
+    h.core.resize(size_t(1) << h.p);
+    rd(h.core.data(), h.core.size());
+    gzclose(fp);
+    return h;
+}
+
+std::string make_fname(const char *path, size_t sketch_p, int /*wsz*/, int k, int /*csz*/, const std::string &spacing,
+                       const std::string &suffix, const std::string &prefix) {
+    std::string ret(prefix);
+    if (!ret.empty()) ret += '/';
+    const char *p = std::strchr(path, ' ');
+    p = p ? p + 1 : path;                       // multi-file paths are named after what follows the first separator
+    const char *p2;
+    if (!ret.empty() && (p2 = std::strrchr(p, '/'))) ret += std::string(p2 + 1);
+    else ret += p;
+    ret += ".w";                                // the window size never makes it into the name (src/dashing.h:510 is a no-op)
+    ret += ".";
+    ret += std::to_string(k);
+    ret += ".spacing";
+    ret += spacing;
+    ret += '.';
+    if (!suffix.empty()) { ret += "suf"; ret += suffix; ret += '.'; }
+    ret += std::to_string(sketch_p);
+    ret += ".hll";
+    return ret;
+}
+
+std::vector<std::string> split_paths(const std::string &s, char sep) {
+    std::vector<std::string> out;
+    size_t a = 0;
+    for (;;) {
+        const size_t b = s.find(sep, a);
+        std::string tok = s.substr(a, b == std::string::npos ? std::string::npos : b - a);
+        const bool blank = std::all_of(tok.begin(), tok.end(), [](unsigned char c) { return std::isspace(c); });
+        if (!out.empty() && blank) break;      // the reference stops at the first blank token (src/substrs.h:23)
+        out.push_back(std::move(tok));
+        if (b == std::string::npos) break;
+        a = b + 1;
+    }
+    return out;
+}
+
+std::vector<std::string> get_paths(const std::string &file) {
+    std::ifstream is(file);
+    if (!is.good()) throw Error("Could not open file at " + file);
+    std::vector<std::string> out;
+    for (std::string line; std::getline(is, line);) {
+        if (!line.empty() && line.back() == '\r') line.pop_back();
+        if (!line.empty()) out.push_back(line);
+    }
+    return out;
+}
+
+void sort_paths_by_fsize(std::vector<std::string> &paths) {
+    if (paths.size() < 2) return;
+    std::vector<std::pair<uint32_t, std::string>> ps;
+    for (auto &p : paths) {
+        size_t tot = 0;
+        for (auto &f : split_paths(p)) { struct stat st; if (::stat(f.c_str(), &st) == 0) tot += st.st_size; }
+        ps.emplace_back((uint32_t)tot, p);
+    }
+    // the reference uses an unstable std::sort on size only; equal sizes are order-unspecified there — use --avoid-sorting for parity
+    std::stable_sort(ps.begin(), ps.end(), [](const auto &x, const auto &y) { return x.first > y.first; });
+    for (size_t i = 0; i < paths.size(); ++i) paths[i] = std::move(ps[i].second);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// FASTA / FASTQ
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+struct LineReader {
+    gzFile fp;
+    std::vector<char> buf;
+    size_t pos = 0, end = 0;
+    bool eof = false;
+    explicit LineReader(gzFile f) : fp(f), buf(1 << 18) {}
+    int peek() {
+        if (pos == end) fill();
+        return pos < end ? (unsigned char)buf[pos] : -1;
+    }
+    void fill() {
+        if (eof) return;
+        const int n = gzread(fp, buf.data(), (unsigned)buf.size());
+        pos = 0; end = n > 0 ? (size_t)n : 0;
+        if (n <= 0) eof = true;
+    }
+    // appends the rest of the current line (without the newline / trailing CR) to `out` (or discards it)
+    void line(std::string *out) {
+        for (;;) {
+            if (pos == end) { fill(); if (pos == end) return; }
+            const char *s = buf.data() + pos;
+            const char *nl = (const char *)std::memchr(s, '\n', end - pos);
+            const size_t len = nl ? (size_t)(nl - s) : end - pos;
+            if (out) out->append(s, len);
+            pos += len + (nl ? 1 : 0);
+            if (nl) { if (out && !out->empty() && out->back() == '\r') out->pop_back(); return; }
+        }
+    }
+};
+} // namespace
+
+void for_each_record(const std::string &file, const std::function<void(const char *, size_t)> &fn) {
+    gzFile fp = gzopen(file.c_str(), "rb");
+    if (!fp) throw Error("Could not open file at " + file + ". Abort!");
+    gzbuffer(fp, 1 << 18);
+    LineReader lr(fp);
+    std::string seq, tmp;
+    int c;
+    while ((c = lr.peek()) != -1) {
+        if (c != '>' && c != '@') { lr.line(nullptr); continue; }   // skip to the next header
+        lr.line(nullptr);                                          // name + comment
+        seq.clear();
+        while ((c = lr.peek()) != -1 && c != '>' && c != '+' && c != '@') lr.line(&seq);
+        if (c == '+') {                                            // FASTQ: skip the '+' line and the qualities
+            lr.line(nullptr);
+            size_t got = 0;
+            while (got < seq.size() && lr.peek() != -1) { tmp.clear(); lr.line(&tmp); got += tmp.size(); }
+        }
+        fn(seq.data(), seq.size());
+    }
+    gzclose(fp);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// emitters
+// ---------------------------------------------------------------------------------------------------------------
+static void appendf(std::string &s, const char *fmt, double v) {
+    char b[64];
+    const int n = std::snprintf(b, sizeof b, fmt, v);
+    s.append(b, n);
+}
+
+std::string format_sizes(const std::vector<std::string> &paths, const double *card) {
+    std::string s("#Path\tSize (est.)\n");                       // src/sketch_and_cmp.h:372
+    char b[32];
+    for (size_t i = 0; i < paths.size(); ++i) {
+        s += paths[i];
+        const int n = std::snprintf(b, sizeof b, "\t%zu\n", size_t(card[i]));   // :382
+        s.append(b, n);
+    }
+    return s;
+}
+
+std::string format_ut_tsv_header(const std::vector<std::string> &paths) {
+    std::string s("##Names\t");                                   // :388-393
+    for (auto &p : paths) { s += p; s += '\t'; }
+    s.back() = '\n';
+    return s;
+}
+
+void append_ut_row(std::string &buf, const std::string &name, const float *row, size_t n, size_t index, EmissionFormat fmt) {
+    buf += name;                                                  // submit_emit_dists, :16-35
+    if (fmt == UT_TSV) {
+        for (size_t k = 0; k < index + 1; ++k) buf += "\t-";
+    } else if (name.size() < 9) {
+        buf.append(9 - name.size(), ' ');
+    }
+    for (size_t k = 0; k < n - index - 1; ++k) appendf(buf, "\t%.6g", row[k]);
+    buf += '\n';
+}
+
+std::string format_symmetric(const std::vector<std::string> &paths, const float *packed, EmissionFormat fmt, const float *packed_lower) {
+    const size_t n = paths.size();
+    std::string s;
+    auto rowp = [n](const float *base, size_t i) { return base + (i * (2 * n - i - 1)) / 2; };
+    if (fmt == UT_TSV || fmt == UPPER_TRIANGULAR) {
+        if (fmt == UT_TSV) s = format_ut_tsv_header(paths);
+        else s = std::to_string(n) + "\n";                       // :394-397
+        for (size_t i = 0; i < n; ++i) append_ut_row(s, paths[i], rowp(packed, i), n, i, fmt);
+        return s;
+    }
+    if (fmt != FULL_TSV) throw Error("Invalid emit_fmt");
+    if (!packed_lower) packed_lower = packed;
+    s = "#Names";                                                 // :853-857 — no separator after "#Names" in the reference
+    for (size_t i = 0; i < n; ++i) { s += paths[i]; s += (i == n - 1 ? '\n' : '\t'); }
+    for (size_t i = 0; i < n; ++i) {
+        s += paths[i]; s += '\t';
+        for (size_t j = 0; j < n; ++j) {
+            const double v = j == i ? 0. : (i < j ? rowp(packed, i)[j - i - 1] : rowp(packed_lower, j)[i - j - 1]);
+            appendf(s, "%0.6g", v);
+            s += (j == n - 1 ? '\n' : '\t');
+        }
+    }
+    return s;
+}
+
+std::string format_rect_row(const std::string &qname, const float *row, size_t nr) {
+    std::string s(qname);                                         // src/dashing.h:695-699
+    for (size_t i = 0; i < nr; ++i) appendf(s, "\t%g", row[i]);
+    s += '\n';
+    return s;
+}
+
+void write_binary_matrix(std::FILE *fp, const float *packed, uint64_t n) {
+    std::fputc('\0', fp);                                         // distmat magic for float, distmat.h:188-208
+    if (std::fwrite(&n, sizeof n, 1, fp) != 1) throw Error("Failure");
+    const uint64_t cnt = n * (n - 1) / 2;
+    if (cnt && std::fwrite(packed, sizeof(float), cnt, fp) != cnt) throw Error("Error writing to binary file");
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// drivers
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+
+struct Genome {                 // the records of all files behind one input path
+    std::string bases;
+    std::vector<uint64_t> offs{0};
+};
+
+Genome load_genome(const std::string &path) {
+    Genome g;
+    for (auto &f : split_paths(path))
+        for_each_record(f, [&](const char *s, size_t l) { g.bases.append(s, l); g.offs.push_back(g.bases.size()); });
+    return g;
+}
+
+// Sketch a list of paths in batches through db200_sketch_batch; out[i] receives 2^p registers.
+void sketch_paths(const SketchOptions &o, const std::vector<std::string> &paths, const std::vector<size_t> &which,
+                  const std::function<void(size_t, const uint8_t *)> &sink) {
+    const size_t m = size_t(1) << o.p;
+    size_t at = 0;
+    while (at < which.size()) {
+        // parse a batch of genomes in parallel (kseq + gz inflate are the host's job, as in the reference)
+        std::vector<Genome> gs;
+        size_t bytes = 0, b0 = at;
+        while (at < which.size() && (gs.empty() || bytes < o.batch_bytes)) {
+            const size_t chunk = std::min<size_t>(which.size() - at, std::max(1, o.nthreads));
+            std::vector<Genome> part(chunk);
+            std::string err;
+#pragma omp parallel for schedule(dynamic) num_threads(std::max(1, o.nthreads))
+            for (size_t i = 0; i < chunk; ++i) {
+                try { part[i] = load_genome(paths[which[at + i]]); }
+                catch (const std::exception &e) {
+#pragma omp critical
+                    err = e.what();
+                }
+            }
+            if (!err.empty()) throw Error(err);
+            for (auto &g : part) { bytes += g.bases.size(); gs.push_back(std::move(g)); }
+            at += chunk;
+        }
+        // one contiguous buffer + offsets
+        std::string all;
+        all.reserve(bytes);
+        std::vector<uint64_t> rec_offs{0}, grb{0};
+        for (auto &g : gs) {
+            const uint64_t base = all.size();
+            all += g.bases;
+            for (size_t r = 1; r < g.offs.size(); ++r) rec_offs.push_back(base + g.offs[r]);
+            grb.push_back(rec_offs.size() - 1);
+        }
+        std::vector<uint8_t> regs(gs.size() * m);
+        check(db200_sketch_batch(o.device, o.p, o.k, o.canon, all.data(), rec_offs.data(), rec_offs.size() - 1, grb.data(), gs.size(), regs.data()));
+        for (size_t i = 0; i < gs.size(); ++i) sink(which[b0 + i], regs.data() + i * m);
+    }
+}
+
+} // namespace
+
+void sketch_core(const SketchOptions &o, std::vector<std::string> paths) {
+    if (!o.avoid_sorting) sort_paths_by_fsize(paths);
+    std::vector<std::string> fnames(paths.size());
+    std::vector<size_t> todo;
+    for (size_t i = 0; i < paths.size(); ++i) {
+        fnames[i] = make_fname(paths[i].c_str(), o.p, o.k, o.k, o.k, "", o.suffix, o.prefix);
+        if (o.skip_cached && isfile(fnames[i])) continue;           // src/sketch_and_cmp.h:492-495
+        todo.push_back(i);
+    }
+    sketch_paths(o, paths, todo, [&](size_t i, const uint8_t *regs) { write_hll(fnames[i], regs, o.p, 2, 2, -1.); });
+}
+
+void dist_sketch_and_cmp(const DistOptions &o, std::vector<std::string> inpaths, size_t nq) {
+    const size_t n = inpaths.size(), m = size_t(1) << o.p;
+    if (nq > n) throw Error("more queries than paths");
+    std::vector<uint8_t> regs(n * m);
+    // ---- phase A: load or sketch (src/sketch_and_cmp.h:314-360)
+    std::vector<size_t> todo;
+    std::vector<std::string> fnames(n);
+    for (size_t i = 0; i < n; ++i) {
+        if (o.presketched) {
+            HllFile h = read_hll(inpaths[i]);
+            if (h.p != (uint32_t)o.p) throw Error("sketch " + inpaths[i] + " has p=" + std::to_string(h.p) + ", expected " + std::to_string(o.p));
+            std::memcpy(&regs[i * m], h.core.data(), m);
+            continue;
+        }
+        fnames[i] = make_fname(inpaths[i].c_str(), o.p, o.k, o.k, o.k, "", o.suffix, o.prefix);
+        if (o.cache_sketches && isfile(fnames[i])) {
+            HllFile h = read_hll(fnames[i]);
+            if (h.p != (uint32_t)o.p) throw Error("cached sketch " + fnames[i] + " has the wrong size");
+            std::memcpy(&regs[i * m], h.core.data(), m);
+        } else todo.push_back(i);
+    }
+    sketch_paths(o, inpaths, todo, [&](size_t i, const uint8_t *r) {
+        std::memcpy(&regs[i * m], r, m);
+        if (o.cache_sketches) write_hll(fnames[i], r, o.p, 2, 2, -1.);
+    });
+    // ---- phase B: sizes (:372-385)
+    std::vector<double> card(n);
+    check(db200_cardinalities(o.device, regs.data(), n, o.p, o.estim, card.data()));
+    {
+        const std::string s = format_sizes(inpaths, card.data());
+        std::FILE *fp = o.sizes_path.empty() ? stdout : std::fopen(o.sizes_path.c_str(), "w");
+        if (!fp) throw Error("Could not open file at " + o.sizes_path + " for writing.");
+        std::fwrite(s.data(), 1, s.size(), fp);
+        if (fp != stdout) std::fclose(fp); else std::fflush(fp);
+    }
+    // ---- phase C: all pairs (:785-880, src/dashing.h:660-712)
+    std::FILE *pfp = o.dist_path.empty() ? stdout : std::fopen(o.dist_path.c_str(), "wb");
+    if (!pfp) throw Error("Could not open file at " + o.dist_path + " for writing.");
+    db200_dist_params prm{o.p, o.k, o.estim, o.jestim, o.result_type, DB200_ORDER_ROW_FIRST};
+    const bool joint = o.jestim == DB200_ERTL_JOINT_MLE;
+    if (nq) {
+        if (nq >= n) throw Error("Wrong number of query/references.");
+        const size_t nr = n - nq;
+        std::vector<float> out(nr * nq);
+        check(db200_dist_rect(o.device, regs.data(), nr, regs.data() + nr * m, nq, &prm, out.data()));
+        if (o.emit_fmt == UPPER_TRIANGULAR) std::fprintf(pfp, "%zu\n", n);     // :394-397 runs before dist_loop even in this mode
+        for (size_t q = 0; q < nq; ++q) {
+            if (o.emit_fmt == BINARY) { if (std::fwrite(&out[q * nr], sizeof(float), nr, pfp) != nr) throw Error("Error writing to binary file"); }
+            else { const std::string s = format_rect_row(inpaths[nr + q], &out[q * nr], nr); std::fwrite(s.data(), 1, s.size(), pfp); }
+        }
+    } else {
+        const int rt = o.result_type;
+        if (rt == DB200_CONTAINMENT_INDEX || rt == DB200_CONTAINMENT_DIST || rt == DB200_FULL_CONTAINMENT_DIST)
+            throw Error("Can't perform symmetric distance comparisons with a symmetric method. Provide the same list of filenames to both -Q and -F.");
+        const size_t np = n * (n - 1) / 2;
+        std::vector<float> out(std::max<size_t>(np, 1)), lower;
+        // operand order: TSV / PHYLIP rows come from perform_core_op (cmp(s[j], s[i])), binary and the upper half of FULL_TSV
+        // from cmp(s[i], s[j]); only the joint MLE can tell the difference
+        prm.order = (o.emit_fmt == UT_TSV || o.emit_fmt == UPPER_TRIANGULAR) ? DB200_ORDER_COL_FIRST : DB200_ORDER_ROW_FIRST;
+        if (n >= 2) check(db200_dist_symmetric(o.device, regs.data(), n, &prm, out.data()));
+        if (o.emit_fmt == BINARY) {
+            write_binary_matrix(pfp, out.data(), n);
+            if (!o.dist_path.empty()) {                                      // src/distmain.cpp:191-200
+                std::FILE *lf = std::fopen((o.dist_path + ".labels").c_str(), "wb");
+                if (!lf) throw Error("Could not open file at '" + o.dist_path + ".labels' for writing");
+                for (auto &p : inpaths) { std::fwrite(p.data(), p.size(), 1, lf); std::fputc('\n', lf); }
+                std::fclose(lf);
+            }
+        } else {
+            if (o.emit_fmt == FULL_TSV && joint && n >= 2) {
+                lower.resize(np);
+                prm.order = DB200_ORDER_COL_FIRST;
+                check(db200_dist_symmetric(o.device, regs.data(), n, &prm, lower.data()));
+            }
+            const std::string s = format_symmetric(inpaths, out.data(), o.emit_fmt, lower.empty() ? nullptr : lower.data());
+            std::fwrite(s.data(), 1, s.size(), pfp);
+        }
+    }
+    if (pfp != stdout) std::fclose(pfp); else std::fflush(pfp);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// CLI (hot subset of src/distmain.cpp:47-100 and src/dashing.cpp:307-337)
+// ---------------------------------------------------------------------------------------------------------------
+[[noreturn]] static void unsupported(const char *flag) {
+    throw Error(std::string("flag ") + flag + " selects a code path outside the B200 engine (spaced/windowed k-mers, count-min, non-HLL sketches, "
+                "nearest neighbours): run the reference binary for it");
+}
+
+int dist_main(int argc, char **argv) {
+    DistOptions o;
+    std::string paths_file;
+    std::vector<std::string> querypaths;
+    int lo_result = -1, lo_fmt = -1, flag_sort = 0, flag_presk = 0, flag_cache = 0, flag_nocanon = 0;
+    static option longopts[] = {
+        {"avoid-sorting", no_argument, nullptr, 'n'}, {"cache-sketches", no_argument, nullptr, 'W'}, {"emit-binary", no_argument, nullptr, 'b'},
+        {"full-mash-dist", no_argument, nullptr, 'l'}, {"full-tsv", no_argument, nullptr, 'T'}, {"no-canon", no_argument, nullptr, 'C'},
+        {"phylip", no_argument, nullptr, 'U'}, {"presketched", no_argument, nullptr, 'H'}, {"sizes", no_argument, nullptr, 'Z'},
+        {"ertl-joint-mle", no_argument, nullptr, 'J'}, {"ertl-mle", no_argument, nullptr, 'm'}, {"improved", no_argument, nullptr, 'I'},
+        {"original", no_argument, nullptr, 'E'}, {"kmer-length", required_argument, nullptr, 'k'}, {"nthreads", required_argument, nullptr, 'p'},
+        {"out-dists", required_argument, nullptr, 'O'}, {"out-sizes", required_argument, nullptr, 'o'}, {"paths", required_argument, nullptr, 'F'},
+        {"prefix", required_argument, nullptr, 'P'}, {"query-paths", required_argument, nullptr, 'Q'}, {"sketch-size", required_argument, nullptr, 'S'},
+        {"suffix", required_argument, nullptr, 'x'}, {"mash-dist", no_argument, nullptr, 'M'},
+        {"containment-index", no_argument, nullptr, 131}, {"containment-dist", no_argument, nullptr, 132}, {"full-containment-dist", no_argument, nullptr, 133},
+        {"symmetric-containment-index", no_argument, nullptr, 137}, {"symmetric-containment-dist", no_argument, nullptr, 138},
+        {"spacing", required_argument, nullptr, 's'}, {"window-size", required_argument, nullptr, 'w'}, {"countmin", no_argument, nullptr, 'y'},
+        {"use-bb-minhash", no_argument, nullptr, '8'}, {"nearest-neighbors", required_argument, nullptr, 143}, {"device", required_argument, nullptr, 1001},
+        {nullptr, 0, nullptr, 0}};
+    (void)lo_result; (void)lo_fmt; (void)flag_sort; (void)flag_presk; (void)flag_cache; (void)flag_nocanon;
+    optind = 1;
+    int co;
+    while ((co = getopt_long(argc, argv, "nQ:P:x:F:p:o:s:w:O:S:k:8TlICbMEHJZUmWy", longopts, nullptr)) >= 0) {
+        switch (co) {
+            case 'n': o.avoid_sorting = true; break;
+            case 'W': o.cache_sketches = true; break;
+            case 'b': o.emit_fmt = BINARY; break;
+            case 'l': o.result_type = DB200_FULL_MASH_DIST; break;
+            case 'T': o.emit_fmt = FULL_TSV; break;
+            case 'C': o.canon = false; break;
+            case 'U': o.emit_fmt = UPPER_TRIANGULAR; break;
+            case 'H': o.presketched = true; break;
+            case 'Z': o.result_type = DB200_SIZES; break;
+            case 'M': o.result_type = DB200_MASH_DIST; break;
+            case 'J': o.jestim = DB200_ERTL_JOINT_MLE; break;
+            case 'm': o.jestim = o.estim = DB200_ERTL_MLE; break;
+            case 'I': o.jestim = o.estim = DB200_ERTL_IMPROVED; break;
+            case 'E': o.jestim = o.estim = DB200_ORIGINAL; break;
+            case 'k': o.k = std::atoi(optarg); break;
+            case 'p': o.nthreads = std::atoi(optarg); break;
+            case 'S': o.p = std::atoi(optarg); break;       // bytesl2_to_arg(S, HLL) == S, src/sketch_and_cmp.h:42
+            case 'O': o.dist_path = optarg; break;
+            case 'o': o.sizes_path = optarg; break;
+            case 'F': paths_file = optarg; break;
+            case 'Q': querypaths = get_paths(optarg); break;
+            case 'P': o.prefix = optarg; break;
+            case 'x': o.suffix = optarg; break;
+            case 131: o.result_type = DB200_CONTAINMENT_INDEX; break;
+            case 132: o.result_type = DB200_CONTAINMENT_DIST; break;
+            case 133: o.result_type = DB200_FULL_CONTAINMENT_DIST; break;
+            case 137: o.result_type = DB200_SYMMETRIC_CONTAINMENT_INDEX; break;
+            case 138: o.result_type = DB200_SYMMETRIC_CONTAINMENT_DIST; break;
+            case 1001: o.device = std::atoi(optarg); break;
+            case 's': unsupported("-s/--spacing");
+            case 'w': unsupported("-w/--window-size");
+            case 'y': unsupported("-y/--countmin");
+            case '8': unsupported("-8/--use-bb-minhash");
+            case 143: unsupported("--nearest-neighbors");
+            default: throw Error("unknown option; see the reference's `dashing dist` usage for the supported subset");
+        }
+    }
+    if (o.k > 32) throw Error("k must be <= 32 for non-rolling hashes.");     // src/distmain.cpp:101-102
+    if (o.nthreads < 1) o.nthreads = 1;
+    std::vector<std::string> inpaths = paths_file.empty() ? std::vector<std::string>(argv + optind, argv + argc) : get_paths(paths_file);
+    if (inpaths.empty()) throw Error("No paths. See usage.");
+    size_t nq = querypaths.size();
+    const int rt = o.result_type;
+    if (nq == 0 && (rt == DB200_CONTAINMENT_INDEX || rt == DB200_CONTAINMENT_DIST || rt == DB200_FULL_CONTAINMENT_DIST)) {
+        querypaths = inpaths; nq = querypaths.size();                          // :119-124
+    }
+    if (!o.presketched && !o.avoid_sorting) { sort_paths_by_fsize(inpaths); sort_paths_by_fsize(querypaths); }
+    for (auto &q : querypaths) inpaths.push_back(q);
+    dist_sketch_and_cmp(o, inpaths, nq);
+    return 0;
+}
+
+int sketch_main(int argc, char **argv) {
+    SketchOptions o;
+    std::string paths_file;
+    static option longopts[] = {
+        {"avoid-sorting", no_argument, nullptr, 'n'}, {"skip-cached", no_argument, nullptr, 'c'}, {"no-canon", no_argument, nullptr, 'C'},
+        {"kmer-length", required_argument, nullptr, 'k'}, {"nthreads", required_argument, nullptr, 'p'}, {"paths", required_argument, nullptr, 'F'},
+        {"prefix", required_argument, nullptr, 'P'}, {"sketch-size", required_argument, nullptr, 'S'}, {"suffix", required_argument, nullptr, 'x'},
+        {"spacing", required_argument, nullptr, 's'}, {"window-size", required_argument, nullptr, 'w'}, {"device", required_argument, nullptr, 1001},
+        {nullptr, 0, nullptr, 0}};
+    optind = 1;
+    int co;
+    while ((co = getopt_long(argc, argv, "nP:F:p:x:s:S:k:w:cC", longopts, nullptr)) >= 0) {
+        switch (co) {
+            case 'n': o.avoid_sorting = true; break;
+            case 'c': o.skip_cached = true; break;
+            case 'C': o.canon = false; break;
+            case 'k': o.k = std::atoi(optarg); break;
+            case 'p': o.nthreads = std::atoi(optarg); break;
+            case 'S': o.p = std::atoi(optarg); break;
+            case 'F': paths_file = optarg; break;
+            case 'P': o.prefix = optarg; break;
+            case 'x': o.suffix = optarg; break;
+            case 1001: o.device = std::atoi(optarg); break;
+            case 's': unsupported("-s/--spacing");
+            case 'w': unsupported("-w/--window-size");
+            default: throw Error("unknown option; see the reference's `dashing sketch` usage for the supported subset");
+        }
+    }
+    if (o.k > 32) throw Error("k must be <= 32 for non-rolling hashes.");
+    o.nthreads = std::max(o.nthreads, 1);
+    std::vector<std::string> inpaths = (!paths_file.empty() && isfile(paths_file)) ? get_paths(paths_file) : std::vector<std::string>(argv + optind, argv + argc);
+    if (inpaths.empty()) throw Error("No paths. See usage.");
+    sketch_core(o, inpaths);
+    return 0;
+}
+
+int cli_main(int argc, char **argv) {
+    try {
+        if (argc < 2) throw Error("usage: dashing_b200 <sketch|dist|cmp> [options] (the hot subset of dashing's flags)");
+        const std::string sub = argv[1];
+        if (sub == "sketch") return sketch_main(argc - 1, argv + 1);
+        if (sub == "dist" || sub == "cmp") return dist_main(argc - 1, argv + 1);
+        throw Error("subcommand '" + sub + "' is outside the B200 engine's scope (sketch, dist, cmp)");
+    } catch (const std::exception &e) {
+        std::fprintf(stderr, "%s\n", e.what());                   // UNRECOVERABLE_ERROR: message + exit(1)
+        return 1;
+    }
+}
+
+} // namespace db200h
+
+// ---- C hooks for ctypes-based tests (no compute: formats and naming only, plus the CLI) ---------------------------
+extern "C" {
+#define DB200H_API __attribute__((visibility("default")))
+DB200H_API int db200h_cli(int argc, char **argv) { return db200h::cli_main(argc, argv); }
+DB200H_API int db200h_make_fname(const char *path, int p, int wsz, int k, int csz, const char *spacing, const char *suffix, const char *prefix, char *out, uint64_t cap) {
+    const std::string s = db200h::make_fname(path, p, wsz, k, csz, spacing, suffix, prefix);
+    if (s.size() + 1 > cap) return 1;
+    std::memcpy(out, s.c_str(), s.size() + 1);
+    return 0;
+}
+DB200H_API int db200h_write_hll(const char *path, const uint8_t *regs, int p, int estim, int jestim, double value) {
+    try { db200h::write_hll(path, regs, p, estim, jestim, value); } catch (const std::exception &e) { std::fprintf(stderr, "%s\n", e.what()); return 1; }
+    return 0;
+}
+DB200H_API int db200h_read_hll(const char *path, uint8_t *regs, uint64_t cap, uint32_t *hdr5, double *value) {
+    try {
+        const auto h = db200h::read_hll(path);
+        if (h.core.size() > cap) return 2;
+        std::memcpy(regs, h.core.data(), h.core.size());
+        hdr5[0] = h.is_calculated; hdr5[1] = h.estim; hdr5[2] = h.jestim; hdr5[3] = h.marker; hdr5[4] = h.p;
+        *value = h.value;
+    } catch (const std::exception &e) { std::fprintf(stderr, "%s\n", e.what()); return 1; }
+    return 0;
+}
+// formats a symmetric result (packed upper triangle) into `out`; names are '\n'-separated.  Returns bytes needed.
+DB200H_API uint64_t db200h_format_symmetric(const char *names_nl, uint64_t n, const float *packed, const float *packed_lower, int fmt, char *out, uint64_t cap) {
+    std::vector<std::string> names;
+    const char *p = names_nl;
+    for (uint64_t i = 0; i < n; ++i) { const char *e = std::strchr(p, '\n'); names.emplace_back(p, e ? e - p : std::strlen(p)); p = e ? e + 1 : p + std::strlen(p); }
+    const std::string s = db200h::format_symmetric(names, packed, (db200h::EmissionFormat)fmt, packed_lower);
+    if (s.size() <= cap) std::memcpy(out, s.data(), s.size());
+    return s.size();
+}
+DB200H_API uint64_t db200h_format_sizes(const char *names_nl, uint64_t n, const double *card, char *out, uint64_t cap) {
+    std::vector<std::string> names;
+    const char *p = names_nl;
+    for (uint64_t i = 0; i < n; ++i) { const char *e = std::strchr(p, '\n'); names.emplace_back(p, e ? e - p : std::strlen(p)); p = e ? e + 1 : p + std::strlen(p); }
+    const std::string s = db200h::format_sizes(names, card);
+    if (s.size() <= cap) std::memcpy(out, s.data(), s.size());
+    return s.size();
+}
+DB200H_API uint64_t db200h_format_rect_row(const char *qname, const float *row, uint64_t nr, char *out, uint64_t cap) {
+    const std::string s = db200h::format_rect_row(qname, row, nr);
+    if (s.size() <= cap) std::memcpy(out, s.data(), s.size());
+    return s.size();
+}
+// parses a FASTA/FASTQ(.gz) file; writes concatenated records and their offsets.  Returns the number of records.
+DB200H_API int64_t db200h_read_records(const char *path, char *bases, uint64_t cap, uint64_t *offs, uint64_t maxrec) {
+    try {
+        uint64_t at = 0, nrec = 0;
+        bool overflow = false;
+        offs[0] = 0;
+        db200h::for_each_record(path, [&](const char *s, size_t l) {
+            if (at + l > cap || nrec + 1 > maxrec) { overflow = true; return; }
+            std::memcpy(bases + at, s, l); at += l; offs[++nrec] = at;
+        });
+        return overflow ? -2 : (int64_t)nrec;
+    } catch (const std::exception &e) { std::fprintf(stderr, "%s\n", e.what()); return -1; }
+}
+}

@@ -1,0 +1,78 @@
+// dashing_host.hpp — host side above the C ABI, mirroring the reference's interface for the two hot paths:
+// file formats (.hll, sizes file, distance-matrix outputs), file naming, FASTA feeding and the `sketch` / `dist`
+// drivers.  All arithmetic of the hot paths happens in libdashing_b200.so (CUDA); this layer only parses, moves
+// bytes and formats.  Citations are relative to the reference tree.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <functional>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace db200h {
+
+// bns::EmissionFormat — src/enums.h:25-34
+enum EmissionFormat : unsigned { UT_TSV = 0, BINARY = 1, UPPER_TRIANGULAR = 2, FULL_TSV = 3 };
+
+// UNRECOVERABLE_ERROR (bonsai/include/bonsai/util.h:547-554) prints and exit(1)s; here it is an exception the
+// CLI turns into exactly that.
+struct Error : std::runtime_error { using std::runtime_error::runtime_error; };
+
+// ---- .hll container — hll_t::write / read, bonsai/hll/include/sketch/hll.h:1039-1080 --------------------------
+struct HllFile {
+    uint32_t is_calculated = 0, estim = 2, jestim = 2, marker = 1, p = 0;
+    double value = -1.;
+    std::vector<uint8_t> core;
+};
+std::vector<uint8_t> hll_payload(const uint8_t *regs, uint32_t p, int estim, int jestim, double value);
+void write_hll(const std::string &path, const uint8_t *regs, uint32_t p, int estim = 2, int jestim = 2, double value = -1.);
+HllFile read_hll(const std::string &path);
+// make_fname<hll_t>, src/dashing.h:497-526
+std::string make_fname(const char *path, size_t sketch_p, int wsz, int k, int csz, const std::string &spacing,
+                       const std::string &suffix = "", const std::string &prefix = "");
+// for_each_substr over FNAME_SEP (src/substrs.h:7-26): one "path" may name several files folded into one sketch
+std::vector<std::string> split_paths(const std::string &s, char sep = ' ');
+// get_paths (bonsai/include/bonsai/util.h:1185): one path per line
+std::vector<std::string> get_paths(const std::string &file);
+// sort_paths_by_fsize (src/finalizers.cpp:6-21): descending total file size (uint32_t sizes as in the reference)
+void sort_paths_by_fsize(std::vector<std::string> &paths);
+
+// ---- FASTA / FASTQ records with kseq semantics (bonsai/klib/kseq.h:177-218), gz transparent --------------------
+void for_each_record(const std::string &file, const std::function<void(const char *, size_t)> &fn);
+
+// ---- emitters — src/sketch_and_cmp.h:16-35, :372-397, :838-878; src/dashing.h:675-705 -------------------------
+std::string format_sizes(const std::vector<std::string> &paths, const double *card);
+std::string format_ut_tsv_header(const std::vector<std::string> &paths);
+// one row of the upper-triangular TSV / PHYLIP output: `row` holds the n-1-index values (i, j>i)
+void append_ut_row(std::string &buf, const std::string &name, const float *row, size_t n, size_t index, EmissionFormat fmt);
+// rows of the packed upper triangle -> full text output
+std::string format_symmetric(const std::vector<std::string> &paths, const float *packed, EmissionFormat fmt,
+                             const float *packed_lower = nullptr /* FULL_TSV only: values for i > j */);
+std::string format_rect_row(const std::string &qname, const float *row, size_t nr);
+void write_binary_matrix(std::FILE *fp, const float *packed, uint64_t n);   // '\0' + u64 n + floats (distmat.h:188-208)
+
+// ---- drivers ----------------------------------------------------------------------------------------------------
+struct SketchOptions {
+    int k = 31, p = 10, nthreads = 1, device = 0;
+    bool canon = true, skip_cached = false, avoid_sorting = false;
+    std::string prefix, suffix;
+    size_t batch_bytes = size_t(1) << 30;   // ASCII handed to one db200_sketch_batch call
+};
+struct DistOptions : SketchOptions {
+    int estim = 2, jestim = 2, result_type = 1 /* JI */;
+    EmissionFormat emit_fmt = UT_TSV;
+    bool presketched = false, cache_sketches = false;
+    std::string sizes_path, dist_path;       // empty -> stdout
+};
+// sketch_core<hll_t>, src/sketch_and_cmp.h:445-538: one .hll per input path
+void sketch_core(const SketchOptions &o, std::vector<std::string> paths);
+// dist_sketch_and_cmp<hll_t> + dist_loop / partdist_loop, src/sketch_and_cmp.h:268-417, :785-880; src/dashing.h:660-712.
+// The last nq entries of inpaths are queries (rectangular mode).
+void dist_sketch_and_cmp(const DistOptions &o, std::vector<std::string> inpaths, size_t nq);
+// sketch_main / dist_main (src/dashing.cpp:294-409, src/distmain.cpp:28-204): the hot subset of the flags
+int sketch_main(int argc, char **argv);
+int dist_main(int argc, char **argv);
+int cli_main(int argc, char **argv);
+
+} // namespace db200h

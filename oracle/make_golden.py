@@ -19,6 +19,7 @@ from __future__ import annotations
 
 import glob
 import gzip
+import json
 import os
 import sys
 import tempfile
@@ -147,8 +148,85 @@ def main():
     h["fname"] = np.array(R.make_fname("/data/genomes/g1.fna.gz", 14, 31, 31, 31, "", "", "/out"))
     h["fname_nopfx"] = np.array(R.make_fname("g1.fna.gz", 10, 0, 21, 21, "", "x", ""))
     np.savez_compressed(os.path.join(OUT, "hll_payload.npz"), **h)
+    make_cli_golden(R)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+def write_fasta(path, records, width=70, gz=False, crlf=False, fastq=False):
+    op = gzip.open if gz else open
+    nl = b"\r\n" if crlf else b"\n"
+    with op(path, "wb") as f:
+        for i, r in enumerate(records):
+            if fastq:
+                f.write(b"@r%d some comment" % i + nl + r + nl + b"+" + nl + b"I" * len(r) + nl)
+            else:
+                f.write(b">rec%d description" % i + nl)
+                for j in range(0, len(r), width):
+                    f.write(r[j:j + width] + nl)
+
+
+def cli_inputs():
+    """Small FASTA/FASTQ inputs exercising the reader: multi-record, gz, CRLF, lower case, N runs, FASTQ, short records."""
+    rng = np.random.default_rng(777)
+    gs = synth.genomes(777, 6, 24000, group=3)
+    g1 = synth.sprinkle(rng, gs[1], n_runs=5)
+    files = {
+        "a.fa": dict(records=[gs[0].tobytes()]),
+        "b.fa": dict(records=[g1.tobytes()], width=60),
+        "c.fa.gz": dict(records=[gs[2][:9000].tobytes(), gs[2][9000:9020].tobytes(), gs[2][9020:].tobytes()], gz=True),
+        "d.fa": dict(records=[gs[3].tobytes()], crlf=True),
+        "e.fq": dict(records=[gs[4][i:i + 150].tobytes() for i in range(0, 24000, 150)], fastq=True),
+        "f.fa": dict(records=[gs[5][:18000].tobytes(), b"ACGTACGT", gs[5][18000:].tobytes()], width=80),
+    }
+    return files
+
+
+def make_cli_golden(R):
+    """Outputs of the reference's own drivers (sketch_core<hll_t>, dist_sketch_and_cmp<hll_t>) on the small inputs."""
+    files = cli_inputs()
+    names = list(files)
+    out = {"names": np.array(names)}
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as td:
+        os.chdir(td)
+        try:
+            for n, kw in files.items():
+                write_fasta(n, **kw)
+                out["file_" + n] = np.frombuffer(open(n, "rb").read(), dtype=np.uint8)
+            os.makedirs("sk", exist_ok=True)
+            R.cli_sketch(names, k=31, p=10, prefix="sk")
+            for n in names:
+                hp = R.make_fname(n, 10, 31, 31, 31, "", "", "sk")
+                out["hllname_" + n] = np.array(hp)
+                out["hll_" + n] = np.frombuffer(gzip.open(hp, "rb").read(), dtype=np.uint8)
+            runs = {
+                "tsv_ji": dict(rtype=1, emit_fmt=0),
+                "phylip_mash": dict(rtype=0, emit_fmt=2),
+                "bin_mash": dict(rtype=0, emit_fmt=1),
+                "full_jmle": dict(rtype=1, emit_fmt=3, jestim=3),
+                "tsv_sizes_orig": dict(rtype=2, emit_fmt=0, estim=0, jestim=0),
+                "tsv_symcont_k21_p12": dict(rtype=7, emit_fmt=0, k=21, p=12),
+                "rect_tsv_cont": dict(rtype=5, emit_fmt=0, nq=2),
+                "rect_bin_ji": dict(rtype=1, emit_fmt=1, nq=2),
+                "rect_phylip_mash_jmle": dict(rtype=0, emit_fmt=2, nq=3, jestim=3),
+            }
+            out["runs"] = np.array(list(runs))
+            for rn, kw in runs.items():
+                R.cli_dist(names, "sizes.txt", "dist.out", **kw)
+                out[f"{rn}_sizes"] = np.frombuffer(open("sizes.txt", "rb").read(), dtype=np.uint8)
+                out[f"{rn}_dist"] = np.frombuffer(open("dist.out", "rb").read(), dtype=np.uint8)
+                out[f"{rn}_kw"] = np.array(json.dumps(kw))
+                if kw.get("emit_fmt") == 1 and not kw.get("nq"):
+                    out[f"{rn}_labels"] = np.frombuffer(open("dist.out.labels", "rb").read(), dtype=np.uint8)
+            # presketched: same distances from the .hll files written above
+            hpaths = [str(out["hllname_" + n]) for n in names]
+            R.cli_dist(hpaths, "sizes.txt", "dist.out", rtype=0, emit_fmt=0, presketched=True)
+            out["presketched_tsv_mash_sizes"] = np.frombuffer(open("sizes.txt", "rb").read(), dtype=np.uint8)
+            out["presketched_tsv_mash_dist"] = np.frombuffer(open("dist.out", "rb").read(), dtype=np.uint8)
+        finally:
+            os.chdir(cwd)
+    np.savez_compressed(os.path.join(OUT, "cli.npz"), **out)
 
 
 if __name__ == "__main__":

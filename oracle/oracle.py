@@ -236,6 +236,8 @@ class Ref(_Common):
         l.dref_set_create.argtypes = [u8p, C.c_uint64, C.c_int, C.c_int, C.c_int]
         l.dref_set_free.argtypes = [C.c_void_p]
         l.dref_set_dist_rows.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_int, f32p]
+        l.dref_cli_dist.argtypes = [C.c_int, C.POINTER(C.c_char_p)] + [C.c_int] * 10 + [C.c_char_p, C.c_char_p, C.c_int, C.c_char_p, C.c_char_p]
+        l.dref_cli_sketch.argtypes = [C.c_int, C.POINTER(C.c_char_p)] + [C.c_int] * 4 + [C.c_char_p, C.c_char_p, C.c_int]
         l.dref_hll_write.argtypes = [C.c_char_p, u8p, C.c_int, C.c_int, C.c_int, C.c_int]
         l.dref_hll_read.argtypes = [C.c_char_p, u8p, C.c_uint64, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                     C.POINTER(C.c_int), f64p]
@@ -358,6 +360,22 @@ class Ref(_Common):
         if rc:
             raise RuntimeError("dref_hll_read failed")
         return regs[: 1 << p.value].copy(), p.value, e.value, j.value, v.value
+
+    def cli_dist(self, paths, sizes_path, dist_path, nq=0, k=31, p=10, canon=True, estim=2, jestim=2, rtype=1, emit_fmt=0,
+                 presketched=False, nthreads=1, cache=False, prefix="", suffix=""):
+        """The reference's dist_sketch_and_cmp<hll_t> (sizes file + distance output), paths in final order."""
+        arr = (C.c_char_p * len(paths))(*[os.fsencode(p_) for p_ in paths])
+        rc = self.l.dref_cli_dist(len(paths), arr, nq, k, p, int(canon), estim, jestim, rtype, emit_fmt, int(presketched), nthreads,
+                                  os.fsencode(sizes_path), os.fsencode(dist_path), int(cache), prefix.encode(), suffix.encode())
+        if rc:
+            raise RuntimeError(f"dref_cli_dist failed ({rc})")
+
+    def cli_sketch(self, paths, k=31, p=10, canon=True, nthreads=1, prefix="", suffix="", skip_cached=False):
+        """The reference's sketch_core<hll_t>: one .hll per path."""
+        arr = (C.c_char_p * len(paths))(*[os.fsencode(p_) for p_ in paths])
+        rc = self.l.dref_cli_sketch(len(paths), arr, k, p, int(canon), nthreads, prefix.encode(), suffix.encode(), int(skip_cached))
+        if rc:
+            raise RuntimeError(f"dref_cli_sketch failed ({rc})")
 
     def make_fname(self, path, p, wsz, k, csz, spacing="", suffix="", prefix=""):
         buf = C.create_string_buffer(4096)

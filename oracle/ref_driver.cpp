@@ -15,16 +15,23 @@
 //   all-pairs loops   mirrors perform_core_op (src/sketch_and_cmp.h:699-710), dist_loop BINARY branch
 //                     (:838-850 operand order cmp(s[i], s[j])) and partdist_loop (src/dashing.h:675-681)
 //   .hll files        sketch::hll_t::write/read(path) hll.h:1039-1087
+//   whole drivers     bns::sketch_core<hll_t>          src/sketch_and_cmp.h:445-538   (FASTA in, .hll files out)
+//                     bns::dist_sketch_and_cmp<hll_t>  src/sketch_and_cmp.h:268-417   (sizes file + every output format,
+//                                                       through the reference's own dist_loop / partdist_loop / emitters)
 //
 // Built by oracle/Makefile with g++ directly on this one file (the reference's
 // own build system is never run); the output goes to oracle/_ref/ only.
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline/--impl reference
 // legs may load the resulting library.
-#include "dashing.h"
+#include "sketch_and_cmp.h"   // pulls in dashing.h; gives access to the reference's own drivers
 #include <omp.h>
 #include <cstring>
 #include <vector>
 #include <memory>
+
+// process-global option block of the reference (declared extern in src/dashing.h:264, defined in src/dashing.cpp:8,
+// which is not linked here)
+namespace bns { GlobalArgs gargs; }
 
 using namespace bns;
 using namespace sketch;
@@ -262,6 +269,51 @@ int dref_make_fname(const char *path, int p, int wsz, int k, int csz, const char
     std::string s = make_fname<hll_t>(path, p, wsz, k, csz, spacing, suffix, prefix);
     if(s.size() + 1 > cap) return 1;
     std::memcpy(out, s.data(), s.size() + 1);
+    return 0;
+}
+
+
+// ---- the reference's own drivers, end to end -------------------------------------------------------------------
+// `dashing dist` for the HLL sketch type: what dist_main does after option parsing (src/distmain.cpp:150-178), minus
+// the file-size sort (callers pass paths in final order, i.e. --avoid-sorting).  The last nq paths are queries.
+int dref_cli_dist(int npaths, const char **paths, int nq, int k, int p, int canon, int estim, int jestim, int rtype, int emit_fmt,
+                  int presketched, int nthreads, const char *sizes_path, const char *dist_path, int cache, const char *prefix,
+                  const char *suffix) {
+    try {
+        std::vector<std::string> inpaths(paths, paths + npaths);
+        std::vector<CountingSketch> cms;
+        KSeqBufferHolder kseqs(nthreads);
+        std::FILE *ofp = std::fopen(sizes_path, "w"), *pairofp = std::fopen(dist_path, "wb");
+        if(!ofp || !pairofp) return 2;
+        omp_set_num_threads(nthreads);
+        Spacer sp(k, 0);
+        dist_sketch_and_cmp<hll::hll_t>(inpaths, cms, kseqs, ofp, pairofp, dist_path, sp, p, 5, (hll::EstimationMethod)estim,
+                                        (hll::JointEstimationMethod)jestim, cache != 0, (EmissionType)rtype, (EmissionFormat)emit_fmt,
+                                        presketched != 0, nthreads, false, suffix, prefix, canon != 0, false, "", nq, BONSAI);
+        if(pairofp) std::fclose(pairofp);
+        if(emit_fmt == BINARY) { // labels file, src/distmain.cpp:191-200
+            std::FILE *fp = std::fopen((std::string(dist_path) + ".labels").data(), "wb");
+            for(const auto &path: inpaths) std::fwrite(path.data(), path.size(), 1, fp), std::fputc('\n', fp);
+            std::fclose(fp);
+        }
+    } catch(const std::exception &e) { std::fprintf(stderr, "dref_cli_dist: %s\n", e.what()); return 1; }
+    return 0;
+}
+
+// `dashing sketch` for the HLL sketch type (src/dashing.cpp:374-394 -> sketch_core<hll_t>), paths in final order.
+int dref_cli_sketch(int npaths, const char **paths, int k, int p, int canon, int nthreads, const char *prefix, const char *suffix,
+                    int skip_cached) {
+    try {
+        std::vector<std::string> inpaths(paths, paths + npaths);
+        std::vector<CountingSketch> cms;
+        std::vector<bool> use_filter;
+        KSeqBufferHolder kseqs(nthreads);
+        omp_set_num_threads(nthreads);
+        Spacer sp(k, 0);
+        const int flags = skip_cached | (int(canon != 0) << 1);       // src/dashing.cpp:375
+        sketch_core<hll::hll_t>(p, nthreads, sp.c_, k, sp, inpaths, suffix, prefix, cms, hll::ERTL_MLE,
+                                (hll::JointEstimationMethod)hll::ERTL_MLE, kseqs, use_filter, "", flags, 1, BONSAI, "");
+    } catch(const std::exception &e) { std::fprintf(stderr, "dref_cli_sketch: %s\n", e.what()); return 1; }
     return 0;
 }
 

@@ -1,0 +1,119 @@
+"""GPU end-to-end through the host layer's CLI (`dashing_b200 sketch|dist`): FASTA files in, .hll / sizes / distance
+files out, compared with what the reference's own drivers wrote for the same inputs (tests/golden/cli.npz; and, where
+oracle/_ref travelled, with the reference run live).  Registers bit-exact; text outputs same structure, numbers within
+2e-5 (the reference prints 6 significant digits); binary outputs within 1e-6."""
+import gzip
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import hostlib
+from parity import assert_close
+
+pytestmark = pytest.mark.gpu
+
+FMT_FLAG = {0: [], 1: ["-b"], 2: ["-U"], 3: ["-T"]}
+RTYPE_FLAG = {0: ["-M"], 1: [], 2: ["--sizes"], 3: ["-l"], 4: ["--full-containment-dist"], 5: ["--containment-index"],
+              6: ["--containment-dist"], 7: ["--symmetric-containment-index"], 8: ["--symmetric-containment-dist"]}
+
+
+def run_cli(cwd, *args):
+    r = subprocess.run([hostlib.CLI, *args], cwd=cwd, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, f"dashing_b200 {' '.join(args)} failed:\n{r.stderr}"
+    return r
+
+
+@pytest.fixture(scope="module")
+def cli(golden_dir):
+    return np.load(os.path.join(golden_dir, "cli.npz"))
+
+
+def test_cli_sketch_writes_reference_hll_files(gpu, cli, tmp_path):
+    names = hostlib.materialise_inputs(cli, str(tmp_path))
+    os.makedirs(tmp_path / "sk")
+    run_cli(str(tmp_path), "sketch", "-k31", "-S10", "-p2", "-P", "sk", "--avoid-sorting", *names)
+    for n in names:
+        hp = tmp_path / str(cli["hllname_" + n])
+        assert hp.exists(), hp
+        assert gzip.open(hp, "rb").read() == cli["hll_" + n].tobytes(), f"decompressed .hll payload of {n} differs"
+    # --skip-cached leaves existing files alone
+    before = {n: os.path.getmtime(tmp_path / str(cli["hllname_" + n])) for n in names}
+    run_cli(str(tmp_path), "sketch", "-k31", "-S10", "-P", "sk", "--avoid-sorting", "--skip-cached", *names)
+    assert before == {n: os.path.getmtime(tmp_path / str(cli["hllname_" + n])) for n in names}
+
+
+def test_cli_dist_all_formats(gpu, cli, tmp_path):
+    names = hostlib.materialise_inputs(cli, str(tmp_path))
+    for run in [str(r) for r in cli["runs"]]:
+        kw = json.loads(str(cli[run + "_kw"]))
+        nq = kw.get("nq", 0)
+        args = ["dist", f"-k{kw.get('k', 31)}", f"-S{kw.get('p', 10)}", "-p2", "--avoid-sorting", "-o", "sizes.txt", "-O", "dist.out"]
+        args += FMT_FLAG[kw.get("emit_fmt", 0)] + RTYPE_FLAG[kw.get("rtype", 1)]
+        if kw.get("jestim") == 3:
+            args.append("-J")
+        if kw.get("estim") == 0:
+            args.append("-E")
+        if nq:
+            (tmp_path / "refs.txt").write_text("\n".join(names[:-nq]) + "\n")
+            (tmp_path / "qry.txt").write_text("\n".join(names[-nq:]) + "\n")
+            args += ["-F", "refs.txt", "-Q", "qry.txt"]
+        else:
+            args += names
+        run_cli(str(tmp_path), *args)
+        assert (tmp_path / "sizes.txt").read_bytes() == cli[run + "_sizes"].tobytes(), f"{run}: sizes file"
+        got, want = (tmp_path / "dist.out").read_bytes(), cli[run + "_dist"].tobytes()
+        if kw.get("emit_fmt") == 1:
+            hdr = 0 if nq else 9
+            assert got[:hdr] == want[:hdr] and len(got) == len(want), run
+            assert_close(np.frombuffer(got[hdr:], np.float32), np.frombuffer(want[hdr:], np.float32), what=run)
+            if not nq:
+                assert (tmp_path / "dist.out.labels").read_bytes() == cli[run + "_labels"].tobytes()
+        else:
+            hostlib.assert_text_matches(got, want, what=run)
+
+
+def test_cli_presketched_and_cache(gpu, cli, tmp_path):
+    names = hostlib.materialise_inputs(cli, str(tmp_path))
+    os.makedirs(tmp_path / "sk")
+    # -W (cache sketches) writes the same .hll files `sketch` would ...
+    run_cli(str(tmp_path), "dist", "-k31", "-S10", "-M", "-W", "-P", "sk", "--avoid-sorting", "-o", "s1.txt", "-O", "d1.txt", *names)
+    hpaths = [str(cli["hllname_" + n]) for n in names]
+    for n, hp in zip(names, hpaths):
+        assert gzip.open(tmp_path / hp, "rb").read() == cli["hll_" + n].tobytes()
+    # ... and --presketched on them reproduces the reference's presketched output
+    run_cli(str(tmp_path), "dist", "-k31", "-S10", "-M", "--presketched", "-o", "s2.txt", "-O", "d2.txt", *hpaths)
+    assert (tmp_path / "s2.txt").read_bytes() == cli["presketched_tsv_mash_sizes"].tobytes()
+    hostlib.assert_text_matches((tmp_path / "d2.txt").read_bytes(), cli["presketched_tsv_mash_dist"].tobytes(), what="presketched")
+
+
+def test_cli_live_against_reference_drivers(gpu, ref, cli, tmp_path):
+    """Where oracle/_ref travelled: the reference's dist_sketch_and_cmp<hll_t> run live on fresh inputs, p=14."""
+    from dashing_b200 import synth
+    from oracle.make_golden import write_fasta
+    gs = synth.genomes(31337, 5, 120_000, group=5)
+    names = []
+    for i, g in enumerate(gs):
+        n = f"x{i}.fa"
+        write_fasta(str(tmp_path / n), [g[:50_000].tobytes(), g[50_000:].tobytes()], width=80, gz=False)
+        names.append(n)
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        ref.cli_dist(names, "ref_sizes.txt", "ref_dist.txt", k=21, p=14, rtype=0, emit_fmt=0, nthreads=2)
+    finally:
+        os.chdir(cwd)
+    run_cli(str(tmp_path), "dist", "-k21", "-S14", "-M", "--avoid-sorting", "-o", "sizes.txt", "-O", "dist.txt", *names)
+    assert (tmp_path / "sizes.txt").read_bytes() == (tmp_path / "ref_sizes.txt").read_bytes()
+    hostlib.assert_text_matches((tmp_path / "dist.txt").read_bytes(), (tmp_path / "ref_dist.txt").read_bytes(), what="live dist")
+
+
+def test_cli_declines_out_of_scope_flags(gpu, cli, tmp_path):
+    names = hostlib.materialise_inputs(cli, str(tmp_path))
+    for flags in (["-s", "1,1,1"], ["-w", "50"], ["--countmin"], ["-8"]):
+        r = subprocess.run([hostlib.CLI, "dist", "-k31", *flags, *names], cwd=tmp_path, capture_output=True, text=True)
+        assert r.returncode == 1 and "outside the B200 engine" in r.stderr
+    r = subprocess.run([hostlib.CLI, "dist", "-k33", *names], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 1 and "k must be <= 32" in r.stderr

@@ -1,0 +1,111 @@
+"""CPU tests of the host layer (no GPU compute): file naming, the .hll container, the FASTA/FASTQ reader and every
+output format, against fixtures written by the reference's own drivers (tests/golden/cli.npz, hll_payload.npz)."""
+import gzip
+import os
+import re
+
+import numpy as np
+import pytest
+
+import hostlib
+
+pytestmark = pytest.mark.skipif(not os.path.exists(hostlib.HOST_SO), reason="host layer not built (run __graft_entry__.build())")
+
+
+@pytest.fixture(scope="module")
+def host():
+    return hostlib.load()
+
+
+@pytest.fixture(scope="module")
+def cli(golden_dir):
+    return np.load(os.path.join(golden_dir, "cli.npz"))
+
+
+def test_make_fname(host, golden_dir, cli):
+    h = np.load(os.path.join(golden_dir, "hll_payload.npz"))
+    assert hostlib.make_fname(host, "/data/genomes/g1.fna.gz", 14, 31, prefix="/out") == str(h["fname"]) == "/out/g1.fna.gz.w.31.spacing.14.hll"
+    assert hostlib.make_fname(host, "g1.fna.gz", 10, 21, suffix="x") == str(h["fname_nopfx"]) == "g1.fna.gz.w.21.spacing.sufx.10.hll"
+    for n in cli["names"]:
+        assert hostlib.make_fname(host, str(n), 10, 31, prefix="sk") == str(cli["hllname_" + str(n)])
+
+
+def test_hll_container_roundtrip(host, golden_dir, tmp_path):
+    h = np.load(os.path.join(golden_dir, "hll_payload.npz"))
+    for name, p, est, jest in (("fresh_p10", 10, 2, 2), ("fresh_p14", 14, 2, 2), ("calc_p10", 10, 2, 3)):
+        want = h[name].tobytes()
+        regs = np.ascontiguousarray(h[name + "_regs"])
+        value = float(np.frombuffer(want[20:28], dtype=np.float64)[0])
+        path = str(tmp_path / (name + ".hll"))
+        assert host.db200h_write_hll(path.encode(), regs.ctypes.data, p, est, jest, value) == 0
+        assert gzip.open(path, "rb").read() == want            # identical decompressed payload
+        # and a file written by the reference (here: its payload re-gzipped) reads back
+        ref_path = str(tmp_path / (name + ".ref.hll"))
+        with gzip.open(ref_path, "wb") as f:
+            f.write(want)
+        back = np.zeros(1 << p, np.uint8); hdr = np.zeros(5, np.uint32)
+        import ctypes as C
+        v = C.c_double()
+        assert host.db200h_read_hll(ref_path.encode(), back.ctypes.data, back.size, hdr.ctypes.data, C.byref(v)) == 0
+        np.testing.assert_array_equal(back, regs)
+        assert list(hdr) == [int(value >= 0), est, jest, 1, p] and (v.value == value)
+
+
+def test_fasta_reader_matches_kseq(host, cli, port, tmp_path):
+    """Records parsed by the host reader, sketched by the oracle, must give the registers the reference's kseq-fed
+    sketch_core wrote (multi-line, multi-record, gz, CRLF, FASTQ, lower case, N runs)."""
+    names = hostlib.materialise_inputs(cli, str(tmp_path))
+    for n in names:
+        recs = hostlib.read_records(host, str(tmp_path / n))
+        assert all(b"\n" not in r and b"\r" not in r and b">" not in r for r in recs)
+        want = cli["hll_" + n].tobytes()
+        np.testing.assert_array_equal(port.sketch(recs, 31, 10, True), np.frombuffer(want[28:], dtype=np.uint8), err_msg=n)
+    assert len(hostlib.read_records(host, str(tmp_path / "c.fa.gz"))) == 3
+    assert len(hostlib.read_records(host, str(tmp_path / "e.fq"))) == 160
+
+
+def _parse_ut(text: bytes, skip_header: int):
+    rows = text.decode().strip("\n").split("\n")[skip_header:]
+    vals = []
+    for r in rows:
+        vals += [float(x) for x in re.split(r"\t", r)[1:] if x not in ("-", "")]
+    return np.array(vals, dtype=np.float32)
+
+
+def test_symmetric_formats_byte_exact(host, cli):
+    names = [str(x) for x in cli["names"]]
+    n = len(names)
+    raw = cli["bin_mash_dist"].tobytes()
+    assert raw[0] == 0 and int(np.frombuffer(raw[1:9], dtype=np.uint64)[0]) == n          # distmat header
+    packed = np.frombuffer(raw[9:], dtype=np.float32)
+    assert packed.size == n * (n - 1) // 2
+    # PHYLIP from the binary values must reproduce the reference's text byte for byte
+    assert hostlib.format_symmetric(host, names, packed, 2) == cli["phylip_mash_dist"].tobytes()
+    # upper-triangular TSV: the presketched run printed the same Mash values under the .hll names
+    hnames = [str(cli["hllname_" + x]) for x in names]
+    assert hostlib.format_symmetric(host, hnames, packed, 0) == cli["presketched_tsv_mash_dist"].tobytes()
+    # the other TSV outputs: re-format the 6-digit values parsed from the reference's own text
+    for run, fmt, skip in (("tsv_ji", 0, 1), ("tsv_sizes_orig", 0, 1), ("tsv_symcont_k21_p12", 0, 1)):
+        want = cli[run + "_dist"].tobytes()
+        assert hostlib.format_symmetric(host, names, _parse_ut(want, skip), fmt) == want, run
+    # FULL_TSV (including the reference's "#Names<first name>" header quirk)
+    want = cli["full_jmle_dist"].tobytes()
+    rows = want.decode().strip("\n").split("\n")[1:]
+    full = np.array([[float(x) for x in r.split("\t")[1:]] for r in rows], dtype=np.float32)
+    iu = np.triu_indices(n, 1)
+    assert hostlib.format_symmetric(host, names, full[iu], 3, lower=full.T[iu]) == want
+    assert want.startswith(b"#Namesa.fa\tb.fa")
+    assert cli["bin_mash_labels"].tobytes() == ("\n".join(names) + "\n").encode()
+
+
+def test_sizes_and_rect_formats(host, cli):
+    names = [str(x) for x in cli["names"]]
+    want = cli["tsv_ji_sizes"].tobytes()
+    card = [float(l.split(b"\t")[1]) + 0.75 for l in want.strip().split(b"\n")[1:]]      # size_t(card) truncates
+    assert hostlib.format_sizes(host, names, card) == want
+    rect = cli["rect_tsv_cont_dist"].tobytes().strip(b"\n").split(b"\n")
+    for line in rect:
+        f = line.split(b"\t")
+        assert hostlib.format_rect_row(host, f[0].decode(), [float(x) for x in f[1:]]) == line + b"\n"
+    raw = np.frombuffer(cli["rect_bin_ji_dist"].tobytes(), dtype=np.float32)
+    assert raw.size == 2 * 4                                                              # nq x nr floats, no header
