@@ -156,6 +156,24 @@ def load_traffic(kind):
         return None
 
 
+def usable_cores():
+    """Host threads this process can really use: the affinity mask capped by the cgroup CPU quota (on the pool's GPU boxes
+    the container sees 128 logical CPUs but cpu.max grants 16 CPUs of time — oversubscribing it collapses OpenMP throughput)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            n = min(n, max(1, int(math.ceil(int(q) / int(per)))))
+    except Exception:
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read()); per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                n = min(n, max(1, int(math.ceil(q / per))))
+        except Exception:
+            pass
+    return n
+
+
 def dist_n_for(world):
     return int(round(N_DIST_1GPU * math.sqrt(world)))
 
@@ -224,7 +242,7 @@ def run_reference(args):
     if rank != 0:
         return 0
     chk, kind, desc = reference_checker()
-    threads = (chk.max_threads() if kind == "reference" else 1)
+    threads = (min(chk.max_threads(), usable_cores()) if kind == "reference" else 1)
     from dashing_b200 import synth
     n = dist_n_for(args.gpus)
     if args.workload == "sketch":
@@ -468,7 +486,7 @@ def run_gpu(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             chk, kind, desc = reference_checker()
-            threads = chk.max_threads() if kind == "reference" else 1
+            threads = min(chk.max_threads(), usable_cores()) if kind == "reference" else 1
             if "dist" in results:
                 n = results["dist"]["config"]["n_sketches"]
                 v, pairs, rows, dt = cpu_dist_sample(chk, kind, extra["dist"], n, 12.0, threads)

@@ -393,7 +393,7 @@ static int plan_run(db200_dist_plan *pl, const db200_dist_params *prm, int rect,
     a.nr = nr; a.nq = nq; a.qbase = pl->qbase;
     a.ksinv = (double)(float)(1. / prm->k);  // const float ksinv = 1./k, src/sketch_and_cmp.h:797
     a.p = pl->p; a.gmin = pl->gmin; a.gmax = pl->gmax; a.K = pl->K;
-    a.estim = prm->estim; a.rtype = prm->result_type; a.rect = rect;
+    a.estim = prm->estim; a.rtype = prm->result_type; a.rect = rect; a.one = 1;
     if (!joint) {
         // shared memory: S stages of 8 KiB + K x 2 KiB threshold counts + barriers; aim for two CTAs per SM
         const size_t gbytes = (size_t)std::max(pl->K, 1) * DT * DT * 2;

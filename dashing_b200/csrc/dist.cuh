@@ -191,6 +191,7 @@ struct DistArgs {
     int estim, rtype;
     int rect;                         // 0 symmetric, 1 rectangular (A = queries, B = references)
     int stages;
+    int one;                          // 1 — a runtime value so that ptxas keeps `popc * one + acc` as an IMAD (FMA pipe)
 };
 
 // Pair histogram accessor over the tile's threshold counts in shared memory (uint16, see wrap rule).
@@ -242,15 +243,16 @@ __global__ void __launch_bounds__(DIST_THREADS, 2) dist_kernel(const __grid_cons
         // ---------------- TMA producer ----------------
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+            int s = 0, t = lo - a.gmin, wb = 0;
+            uint32_t ph = 0;
             for (int it = 0; it < iters; ++it) {
-                const int s = it % S;
-                const uint32_t ph = (uint32_t)(it / S) & 1u;
                 mbar_wait(empty0 + 8 * s, ph ^ 1u);
-                const int t = lo - a.gmin + it / nbox, wb = it % nbox;
                 const uint32_t dst = smem_u32(stage_mem + (size_t)s * STAGE_BYTES);
                 mbar_expect_tx(full0 + 8 * s, STAGE_BYTES);
                 tma_load_3d(dst, &tmap, wb * 32, (int)rowA0, t, full0 + 8 * s);
                 tma_load_3d(dst + BOX_BYTES, &tmap, wb * 32, (int)rowB0, t, full0 + 8 * s);
+                if (++s == S) { s = 0; ph ^= 1u; }
+                if (++wb == nbox) { wb = 0; ++t; }
             }
         }
     } else {
@@ -282,12 +284,20 @@ __global__ void __launch_bounds__(DIST_THREADS, 2) dist_kernel(const __grid_cons
         DB200_CSA(c4, o, o, x1.z | y1.z, x1.w | y1.w);                                            \
         DB200_CSA(d2, t, t, c3, c4);                                                              \
         DB200_CSA(e, f, f, d1, d2);                                                               \
-        acc += 8u * (uint32_t)__popc(e);                                                          \
+        acc = (uint32_t)__popc(e) * eight + acc;                                                  \
     } while (0)
-#define DB200_POP4(p, q) (__popc(p.x | q.x) + __popc(p.y | q.y) + __popc(p.z | q.z) + __popc(p.w | q.w))
+        // accumulate with IMAD (x * one + acc, `one` a runtime 1): keeps the adds off the ALU pipe
+#define DB200_POP4(acc, p, q)                                                    \
+    do {                                                                         \
+        acc = (uint32_t)__popc(p.x | q.x) * one + acc;                           \
+        acc = (uint32_t)__popc(p.y | q.y) * one + acc;                           \
+        acc = (uint32_t)__popc(p.z | q.z) * one + acc;                           \
+        acc = (uint32_t)__popc(p.w | q.w) * one + acc;                           \
+    } while (0)
+        const uint32_t one = (uint32_t)a.one, eight = one << 3;
+        int s = 0, wb = 0, tl = 0;
+        uint32_t ph = 0;
         for (int it = 0; it < iters; ++it) {
-            const int s = it % S;
-            const uint32_t ph = (uint32_t)(it / S) & 1u;
             mbar_wait(full0 + 8 * s, ph);
             const uint8_t *A = stage_mem + (size_t)s * STAGE_BYTES, *B = A + BOX_BYTES;
             const uint8_t *a0p = A + ti * 128, *a1p = A + (ti + 16) * 128;
@@ -300,10 +310,10 @@ __global__ void __launch_bounds__(DIST_THREADS, 2) dist_kernel(const __grid_cons
                 const uint4 a1 = *reinterpret_cast<const uint4 *>(a1p + oa);
                 const uint4 b0 = *reinterpret_cast<const uint4 *>(b0p + ob);
                 const uint4 b1 = *reinterpret_cast<const uint4 *>(b1p + ob);
-                acc00 += DB200_POP4(a0, b0);
-                acc01 += DB200_POP4(a0, b1);
-                acc10 += DB200_POP4(a1, b0);
-                acc11 += DB200_POP4(a1, b1);
+                DB200_POP4(acc00, a0, b0);
+                DB200_POP4(acc01, a0, b1);
+                DB200_POP4(acc10, a1, b0);
+                DB200_POP4(acc11, a1, b1);
             }
             // chunks 4-7: carry-save adders
 #pragma unroll
@@ -320,8 +330,10 @@ __global__ void __launch_bounds__(DIST_THREADS, 2) dist_kernel(const __grid_cons
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(empty0 + 8 * s);
-            if ((it + 1) % nbox == 0) {
-                uint16_t *g = G + (size_t)(it / nbox) * (DT * DT);
+            if (++s == S) { s = 0; ph ^= 1u; }
+            if (++wb == nbox) {
+                wb = 0;
+                uint16_t *g = G + (size_t)(tl++) * (DT * DT);
                 g[ti * DT + tj] = (uint16_t)(acc00 + __popc(o00) + 2 * __popc(t00) + 4 * __popc(f00));
                 g[ti * DT + tj + 16] = (uint16_t)(acc01 + __popc(o01) + 2 * __popc(t01) + 4 * __popc(f01));
                 g[(ti + 16) * DT + tj] = (uint16_t)(acc10 + __popc(o10) + 2 * __popc(t10) + 4 * __popc(f10));
@@ -414,11 +426,10 @@ __global__ void __launch_bounds__(DIST_THREADS, 1) dist_jmle_kernel(const __grid
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmapA) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmapB) : "memory");
+            int s = 0, t = lo - a.gmin, wb = 0;                          // t = plane of threshold k = lo + 1 + (stage / nbox)
+            uint32_t ph = 0;
             for (int it = 0; it < iters; ++it) {
-                const int s = it % S;
-                const uint32_t ph = (uint32_t)(it / S) & 1u;
                 mbar_wait(empty0 + 8 * s, ph ^ 1u);
-                const int t = lo - a.gmin + it / nbox, wb = it % nbox;   // plane of threshold k = lo + 1 + it/nbox
                 const uint32_t dst = smem_u32(stage_mem + (size_t)s * JSTAGE_BYTES);
                 mbar_expect_tx(full0 + 8 * s, JSTAGE_BYTES);
                 // plane t+1 beyond the last stored threshold is out of bounds -> zero fill == "no register that large"
@@ -426,15 +437,18 @@ __global__ void __launch_bounds__(DIST_THREADS, 1) dist_jmle_kernel(const __grid
                 tma_load_3d(dst + JBOX_A, &tmapA, wb * 32, (int)rowA0, t + 1, full0 + 8 * s);
                 tma_load_3d(dst + 2 * JBOX_A, &tmapB, wb * 32, (int)rowB0, t, full0 + 8 * s);
                 tma_load_3d(dst + 2 * JBOX_A + JBOX_B, &tmapB, wb * 32, (int)rowB0, t + 1, full0 + 8 * s);
+                if (++s == S) { s = 0; ph ^= 1u; }
+                if (++wb == nbox) { wb = 0; ++t; }
             }
         }
     } else {
         const uint32_t ti = threadIdx.x >> 4, tj = threadIdx.x & 15;   // A row ti, B rows {tj, tj+16}
         const uint32_t swA = (ti & 7) << 4, swB = (tj & 7) << 4;
         uint32_t u0 = 0, u1 = 0, x0 = 0, x1 = 0, y0 = 0, y1 = 0;
+        int s = 0, wb = 0;
+        size_t tl = 0;
+        uint32_t ph = 0;
         for (int it = 0; it < iters; ++it) {
-            const int s = it % S;
-            const uint32_t ph = (uint32_t)(it / S) & 1u;
             mbar_wait(full0 + 8 * s, ph);
             const uint8_t *A0 = stage_mem + (size_t)s * JSTAGE_BYTES, *A1 = A0 + JBOX_A, *B0 = A0 + 2 * JBOX_A, *B1 = B0 + JBOX_B;
 #pragma unroll
@@ -450,14 +464,16 @@ __global__ void __launch_bounds__(DIST_THREADS, 1) dist_jmle_kernel(const __grid
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(empty0 + 8 * s);
-            if ((it + 1) % nbox == 0) {
-                const size_t tl = (size_t)(it / nbox);
+            if (++s == S) { s = 0; ph ^= 1u; }
+            if (++wb == nbox) {
+                wb = 0;
                 uint16_t *gu = G + tl * JPAIRS, *gx = G + ((size_t)Kcap + tl) * JPAIRS, *gy = G + ((size_t)2 * Kcap + tl) * JPAIRS;
                 const uint32_t p0 = ti * DT + tj, p1 = p0 + 16;
                 gu[p0] = (uint16_t)u0; gu[p1] = (uint16_t)u1;
                 gx[p0] = (uint16_t)x0; gx[p1] = (uint16_t)x1;
                 gy[p0] = (uint16_t)y0; gy[p1] = (uint16_t)y1;
                 u0 = u1 = x0 = x1 = y0 = y1 = 0;
+                ++tl;
             }
         }
     }
