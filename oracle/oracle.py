@@ -50,6 +50,21 @@ def _cpu_flags() -> set:
     return set()
 
 
+@lru_cache(maxsize=None)
+def usable_cores() -> int:
+    """Affinity mask capped by the cgroup CPU quota (the GPU boxes expose 128 logical CPUs but grant 16 CPUs of time;
+    running 128 OpenMP threads against that quota is ~10x slower than running 16)."""
+    import math
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            n = min(n, max(1, math.ceil(int(q) / int(per))))
+    except Exception:
+        pass
+    return n
+
+
 def ref_available() -> bool:
     return any(os.path.exists(os.path.join(REF_DIR, n)) for n in ("libdashing_ref_avx2.so", "libdashing_ref_avx512.so"))
 
@@ -266,7 +281,7 @@ class Ref(_Common):
         ng = len(genome_rec_begin) - 1
         regs = np.zeros((ng, 1 << p), dtype=np.uint8)
         grb = np.ascontiguousarray(genome_rec_begin, dtype=np.uint64)
-        self.l.dref_sketch_many(_ptr(bases, u8p), _ptr(offs, u64p), _ptr(grb, u64p), ng, k, p, int(canon), nthreads,
+        self.l.dref_sketch_many(_ptr(bases, u8p), _ptr(offs, u64p), _ptr(grb, u64p), ng, k, p, int(canon), nthreads or usable_cores(),
                                 _ptr(regs, u8p))
         return regs
 
@@ -317,7 +332,7 @@ class Ref(_Common):
         if out is None:
             out = np.zeros(n * (n - 1) // 2, dtype=np.float32)
         self.l.dref_dist_rows(_ptr(regs2d, u8p), n, p, k, estim, jestim, rtype, order, row_begin,
-                              n if row_end is None else row_end, nthreads, _ptr(out, f32p))
+                              n if row_end is None else row_end, nthreads or usable_cores(), _ptr(out, f32p))
         return out
 
     def dist_symmetric(self, regs2d, p, **kw):
@@ -332,7 +347,7 @@ class Ref(_Common):
         h, n = hset
         tri = lambda r: r * (2 * n - r - 1) // 2
         out = np.zeros(max(tri(min(row_end, n)) - tri(row_begin), 1), dtype=np.float32)
-        self.l.dref_set_dist_rows(C.c_void_p(h), k, rtype, order, row_begin, row_end, nthreads, _ptr(out, f32p))
+        self.l.dref_set_dist_rows(C.c_void_p(h), k, rtype, order, row_begin, row_end, nthreads or usable_cores(), _ptr(out, f32p))
         return out
 
     def set_free(self, hset):
@@ -343,7 +358,7 @@ class Ref(_Common):
         qrys = np.ascontiguousarray(qrys, dtype=np.uint8)
         out = np.zeros((qrys.shape[0], refs.shape[0]), dtype=np.float32)
         self.l.dref_dist_rect(_ptr(refs, u8p), refs.shape[0], _ptr(qrys, u8p), qrys.shape[0], p, k, estim, jestim, rtype,
-                              nthreads, _ptr(out, f32p))
+                              nthreads or usable_cores(), _ptr(out, f32p))
         return out
 
     def hll_write(self, path, regs, p, estim=2, jestim=2, calculated=False):
