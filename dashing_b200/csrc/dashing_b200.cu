@@ -258,7 +258,7 @@ struct db200_dist_plan {
     int p = 0, estim = -1, gmin = 0, gmax = 0, K = 0;
     bool ready = false;
     CUtensorMap tmap, tmap16;   // boxes of 32 / 16 sketches
-    db200::DevBuf planes, counts, card, smin, smax, pmin, pmax, minmax, tiles;
+    db200::DevBuf planes, counts, card, smin, smax, pmin, pmax, minmax, tiles, lists, sthr, pthr;
     // tile-list cache key
     int tl_rect = -1, tl_ta = 0; uint64_t tl_rb = 0, tl_re = 0, tl_nr = 0, tl_nq = 0, tl_n = 0; uint64_t ntiles = 0;
     uint64_t last_pairs = 0, last_tiles = 0;
@@ -303,6 +303,10 @@ static int plan_prepare(db200_dist_plan *pl, const uint8_t *d_regs, uint64_t nro
     DB200_TRY(pl->smax.reserve(nrows));
     DB200_TRY(pl->pmin.reserve(npan * 4));
     DB200_TRY(pl->pmax.reserve(npan * 4));
+    DB200_TRY(pl->pthr.reserve(npan * 4));
+    DB200_TRY(pl->lists.reserve(nrows * SPARSE_C * 4));
+    DB200_TRY(pl->sthr.reserve(nrows));
+    DB200_CUDA(cudaMemsetAsync(pl->pthr.ptr, 0, npan * 4, stream));
     DB200_CUDA(cudaMemsetAsync(pl->pmin.ptr, 0xFF, npan * 4, stream));
     DB200_CUDA(cudaMemsetAsync(pl->pmax.ptr, 0, npan * 4, stream));
     if (n1 + n2 != nrows || pl->K == 0) {  // padding rows (or the K==0 dummy plane) must read as "below every threshold"
@@ -310,6 +314,7 @@ static int plan_prepare(db200_dist_plan *pl, const uint8_t *d_regs, uint64_t nro
         DB200_CUDA(cudaMemsetAsync(pl->smin.ptr, 0, nrows, stream));
         DB200_CUDA(cudaMemsetAsync(pl->smax.ptr, 0, nrows, stream));
         DB200_CUDA(cudaMemsetAsync(pl->card.ptr, 0, nrows * 8, stream));
+        DB200_CUDA(cudaMemsetAsync(pl->lists.ptr, 0, nrows * SPARSE_C * 4, stream));
     }
     DB200_CUDA(cudaMemsetAsync(pl->counts.ptr, 0, nrows * 64 * 4, stream));
     for (int seg = 0; seg < 2; ++seg) {
@@ -317,7 +322,8 @@ static int plan_prepare(db200_dist_plan *pl, const uint8_t *d_regs, uint64_t nro
         if (!cnt) continue;
         if (pl->K > 0) {
             planes_kernel<<<(unsigned)cnt, 128, 0, stream>>>(reinterpret_cast<const uint32_t *>(d_regs), nrows, r0, p, pl->gmin, pl->K,
-                                                            pl->planes.as<uint32_t>(), pl->counts.as<uint32_t>());
+                                                            pl->planes.as<uint32_t>(), pl->counts.as<uint32_t>(), pl->lists.as<uint32_t>(),
+                                                            pl->sthr.as<uint8_t>(), pl->pthr.as<uint32_t>());
             DB200_LAUNCHED();
         }
         card_kernel<<<(unsigned)((cnt + 127) / 128), 128, 0, stream>>>(pl->counts.as<uint32_t>(), r0, cnt, p, pl->gmin, pl->gmax, estim,
@@ -387,6 +393,7 @@ static int plan_run(db200_dist_plan *pl, const db200_dist_params *prm, int rect,
     a.smin = pl->smin.as<uint8_t>(); a.smax = pl->smax.as<uint8_t>();
     a.pmin = pl->pmin.as<uint32_t>(); a.pmax = pl->pmax.as<uint32_t>();
     a.card = pl->card.as<double>();
+    a.counts = pl->counts.as<uint32_t>(); a.lists = pl->lists.as<uint32_t>(); a.pthr = pl->pthr.as<uint32_t>();
     a.out = d_out;
     a.n = pl->nrows; a.row_begin = rb; a.row_end = re;
     a.out_base = rect ? 0 : (rb * (2 * pl->nrows - rb - 1)) / 2;
@@ -400,7 +407,7 @@ static int plan_run(db200_dist_plan *pl, const db200_dist_params *prm, int rect,
         int S = 6;
         const size_t budget2 = 113 << 10, budget1 = 226 << 10;
         if (gbytes + (size_t)S * STAGE_BYTES + 1024 > budget2) S = (int)std::min<size_t>(12, (budget1 - gbytes - 1024) / STAGE_BYTES);
-        if (S < 2) { set_error("dist: %d live thresholds do not fit in shared memory", pl->K); return DB200_EUNSUPPORTED; }
+        if (S < 4) { set_error("dist: %d live thresholds do not fit in shared memory", pl->K); return DB200_EUNSUPPORTED; }   // stage buffers double as sparse-tail storage (29 KB)
         a.stages = S;
         const size_t smem = (size_t)S * STAGE_BYTES + gbytes + 2 * S * 8;
         DB200_CUDA(cudaFuncSetAttribute(dist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 << 10));
@@ -408,7 +415,7 @@ static int plan_run(db200_dist_plan *pl, const db200_dist_params *prm, int rect,
     } else {
         const size_t gbytes = (size_t)3 * std::max(pl->K, 1) * JPAIRS * 2;
         const size_t budget1 = 226 << 10;
-        const int S = (int)std::min<size_t>(6, (budget1 - gbytes - 1024) / JSTAGE_BYTES);
+        const int S = (int)std::min<size_t>(6, (budget1 - gbytes - 1024) / JSTAGE_BYTES);   // stage buffers double as sparse-tail storage (22 KB)
         if (S < 2) { set_error("dist (joint MLE): %d live thresholds do not fit in shared memory", pl->K); return DB200_EUNSUPPORTED; }
         a.stages = S;
         const size_t smem = (size_t)S * JSTAGE_BYTES + gbytes + 2 * S * 8;

@@ -32,6 +32,8 @@ constexpr int DIST_CONSUMERS = 256;    // 8 consumer warps
 constexpr int DIST_THREADS = DIST_CONSUMERS + 32;  // + 1 TMA producer warp
 constexpr int BOX_BYTES = DT * 128;    // 32 sketches x 32 words
 constexpr int STAGE_BYTES = 2 * BOX_BYTES;
+constexpr int SPARSE_C = 64;           // a sketch's "sparse tail" = its registers >= T_s, where T_s is the smallest
+                                       // threshold with at most SPARSE_C registers at or above it
 
 // ---------------------------------------------------------------------------------------------
 // global register range (min / max over the whole matrix)
@@ -57,8 +59,11 @@ __global__ void __launch_bounds__(256) range_kernel(const uint4 *__restrict__ re
 // counts[s][t] = #{ registers of sketch s >= gmin + 1 + t }.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) planes_kernel(const uint32_t *__restrict__ regs32, uint64_t n, uint64_t row0, int p, int gmin, int K,
-                                                     uint32_t *__restrict__ planes, uint32_t *__restrict__ counts /*[n][64]*/) {
+                                                     uint32_t *__restrict__ planes, uint32_t *__restrict__ counts /*[n][64]*/,
+                                                     uint32_t *__restrict__ lists /*[n][SPARSE_C]*/, uint8_t *__restrict__ sthr,
+                                                     uint32_t *__restrict__ pthr) {
     __shared__ uint32_t cnt[64];
+    __shared__ int s_T;
     const uint64_t s = row0 + blockIdx.x;
     const uint32_t m = 1u << p, W = m >> 5, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x < 64) cnt[threadIdx.x] = 0;
@@ -87,6 +92,42 @@ __global__ void __launch_bounds__(128) planes_kernel(const uint32_t *__restrict_
     }
     __syncthreads();
     if (threadIdx.x < 64) counts[s * 64 + threadIdx.x] = threadIdx.x < (uint32_t)K ? cnt[threadIdx.x] : 0u;
+    // sparse tail: T_s = smallest threshold with <= SPARSE_C registers at or above it (gmax + 1 if there is none)
+    if (threadIdx.x == 0) {
+        int t = 0;
+        while (t < K && cnt[t] > (uint32_t)SPARSE_C) ++t;
+        s_T = gmin + 1 + t;
+        sthr[s] = (uint8_t)s_T;
+        atomicMax(pthr + s / DT, (uint32_t)s_T);
+    }
+    __syncthreads();
+    if (warp == 0) {
+        // the registers >= T_s as (index << 8 | value), in index order, zero padded: <= SPARSE_C of them by construction
+        const uint32_t T4 = (uint32_t)s_T * 0x01010101u;
+        uint32_t *dst = lists + s * SPARSE_C;
+        uint32_t total = 0;
+        for (uint32_t w0 = 0; w0 < (m >> 2); w0 += 32) {
+            const uint32_t x = __ldg(src + w0 + lane);
+            const uint32_t ge = __vcmpgeu4(x, T4) & 0x01010101u;
+            if (!__any_sync(0xFFFFFFFFu, ge != 0u)) continue;
+            const uint32_t c = (uint32_t)__popc(ge);
+            uint32_t incl = c;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+                if (lane >= (uint32_t)off) incl += v;
+            }
+            uint32_t pos = total + incl - c;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if ((ge >> (8 * j)) & 1u) {
+                    if (pos < (uint32_t)SPARSE_C) dst[pos] = (((w0 + lane) * 4 + j) << 8) | ((x >> (8 * j)) & 0xFFu);
+                    ++pos;
+                }
+            total += __shfl_sync(0xFFFFFFFFu, incl, 31);
+        }
+        for (uint32_t i = total + lane; i < (uint32_t)SPARSE_C; i += 32) dst[i] = 0u;
+    }
 }
 
 // Histogram accessor over per-sketch threshold counts: G(k) = #{reg >= k}.
@@ -181,6 +222,9 @@ struct DistArgs {
     const uint8_t *smin, *smax;       // per sketch
     const uint32_t *pmin, *pmax;      // per 32-sketch panel
     const double *card;               // per sketch (estimator `estim`)
+    const uint32_t *counts;           // per sketch threshold counts [n][64]
+    const uint32_t *lists;            // per sketch sparse tail [n][SPARSE_C]
+    const uint32_t *pthr;             // per panel: max over its sketches of the sparse-tail threshold T_s
     float *out;
     uint64_t n;                       // sketches in the plane tensor
     uint64_t row_begin, row_end;      // symmetric: rows computed; rect: unused
@@ -228,9 +272,13 @@ __global__ void __launch_bounds__(DIST_THREADS, 2) dist_kernel(const __grid_cons
     const uint32_t panA = (uint32_t)(rowA0 / DT), panB = tile.b;
     const int lo = (int)min(a.pmin[panA], a.pmin[panB]);
     const int hi = (int)max(a.pmax[panA], a.pmax[panB]);
-    const int Kt = hi - lo;
+    // Thresholds lo+1 .. Td-1 are counted densely from the bit-planes.  From Td on every sketch of the tile has at most
+    // SPARSE_C registers at or above the threshold, and G(k) = #a(k) + #b(k) - #{i : a_i >= k and b_i >= k} is obtained by
+    // merging the two sorted sparse tails — no plane traffic, no POPC.
+    const int Tt = (int)max(a.pthr[panA], a.pthr[panB]);
+    const int Td = min(max(Tt, lo + 1), hi + 1);
     const int W = 1 << (a.p - 5), nbox = W >> 5;
-    const int iters = Kt * nbox;
+    const int iters = (Td - 1 - lo) * nbox;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, DIST_CONSUMERS / 32); }
@@ -348,8 +396,27 @@ __global__ void __launch_bounds__(DIST_THREADS, 2) dist_kernel(const __grid_cons
     }
     __syncthreads();
 
-    // ---------------- estimator + emission, one pair per thread at a time ----------------
+    // ---------------- sparse tails of the 64 sketches of the tile -> shared memory (re-using the stage buffers) --------
     const uint32_t m = 1u << a.p;
+    const int ns = hi - Td + 1;                                       // sparse thresholds Td..hi
+    uint32_t *L = reinterpret_cast<uint32_t *>(stage_mem);             // [2*DT][SPARSE_C]
+    uint32_t *CN = L + 2 * DT * SPARSE_C;                              // [2*DT][ns]: #{reg >= Td + kk}
+    if (ns > 0) {
+        for (uint32_t e = threadIdx.x; e < 2 * DT * SPARSE_C; e += DIST_THREADS) {
+            const uint32_t row = e / SPARSE_C;
+            const uint64_t sk = row < DT ? rowA0 + row : rowB0 + (row - DT);
+            L[e] = sk < a.n ? a.lists[sk * SPARSE_C + (e % SPARSE_C)] : 0u;
+        }
+        for (uint32_t e = threadIdx.x; e < (uint32_t)(2 * DT * ns); e += DIST_THREADS) {
+            const uint32_t row = e / ns;
+            const int k = Td + (int)(e % ns);
+            const uint64_t sk = row < DT ? rowA0 + row : rowB0 + (row - DT);
+            CN[e] = (sk < a.n && k <= a.gmax) ? (k <= a.gmin ? m : a.counts[sk * 64 + (k - a.gmin - 1)]) : 0u;
+        }
+    }
+    __syncthreads();
+
+    // ---------------- estimator + emission, one pair per thread at a time ----------------
     for (uint32_t pair = threadIdx.x; pair < DT * DT; pair += DIST_THREADS) {
         const uint32_t il = pair >> 5, jl = pair & 31;
         const uint64_t i = rowA0 + il, j = rowB0 + jl;
@@ -360,6 +427,24 @@ __global__ void __launch_bounds__(DIST_THREADS, 2) dist_kernel(const __grid_cons
         } else {
             if (i >= j || j >= a.n || i < a.row_begin || i >= a.row_end) continue;
             oidx = (i * (2 * a.n - i - 1)) / 2 - a.out_base + (j - i - 1);
+        }
+        if (ns > 0) {
+            uint16_t *g = G + (size_t)(Td - lo - 1) * (DT * DT) + pair;
+            const uint32_t *ca = CN + il * ns, *cb = CN + (DT + jl) * ns;
+            for (int kk = 0; kk < ns; ++kk) g[kk * (DT * DT)] = (uint16_t)(ca[kk] + cb[kk]);
+            // merge the two index-sorted tails; a register present in both with min value mn was counted twice for k <= mn
+            const uint32_t *la = L + il * SPARSE_C, *lb = L + (DT + jl) * SPARSE_C;
+            int ia = 0, ib = 0;
+            uint32_t ea = la[0], eb = lb[0];
+            while (ea != 0u && eb != 0u) {
+                const uint32_t xa = ea >> 8, xb = eb >> 8;
+                if (xa == xb) {
+                    const int mn = (int)min(ea & 0xFFu, eb & 0xFFu);
+                    for (int k = Td; k <= mn; ++k) g[(k - Td) * (DT * DT)] -= 1;
+                }
+                if (xa <= xb) ea = ++ia < SPARSE_C ? la[ia] : 0u;
+                if (xb <= xa) eb = ++ib < SPARSE_C ? lb[ib] : 0u;
+            }
         }
         const int kmin_pair = max((int)a.smin[i], (int)a.smin[j]);
         const int kmax_pair = max((int)a.smax[i], (int)a.smax[j]);
@@ -411,9 +496,11 @@ __global__ void __launch_bounds__(DIST_THREADS, 1) dist_jmle_kernel(const __grid
     const uint32_t panA = (uint32_t)(rowA0 / DT), panB = tile.b;
     const int lo = (int)min(a.pmin[panA], a.pmin[panB]);
     const int hi = (int)max(a.pmax[panA], a.pmax[panB]);
-    const int Kt = hi - lo;
+    // dense thresholds lo+1 .. Td-1 from the planes, sparse thresholds Td .. hi from the merged tails (see dist_kernel)
+    const int Tt = (int)max(a.pthr[panA], a.pthr[panB]);
+    const int Td = min(max(Tt, lo + 1), hi + 1);
     const int W = 1 << (a.p - 5), nbox = W >> 5;
-    const int iters = Kt * nbox;
+    const int iters = (Td - 1 - lo) * nbox;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, DIST_CONSUMERS / 32); }
@@ -481,6 +568,24 @@ __global__ void __launch_bounds__(DIST_THREADS, 1) dist_jmle_kernel(const __grid
 
     const uint32_t m = 1u << a.p;
     const int q = 64 - a.p;
+    const int ns = hi - Td + 1;                                       // sparse thresholds Td..hi
+    uint32_t *L = reinterpret_cast<uint32_t *>(stage_mem);             // [JT + DT][SPARSE_C]
+    uint32_t *CN = L + (JT + DT) * SPARSE_C;                           // [JT + DT][ns + 1]: #{reg >= Td + kk}
+    if (ns > 0) {
+        for (uint32_t e = threadIdx.x; e < (JT + DT) * SPARSE_C; e += DIST_THREADS) {
+            const uint32_t row = e / SPARSE_C;
+            const uint64_t sk = row < JT ? rowA0 + row : rowB0 + (row - JT);
+            L[e] = sk < a.n ? a.lists[sk * SPARSE_C + (e % SPARSE_C)] : 0u;
+        }
+        for (uint32_t e = threadIdx.x; e < (uint32_t)((JT + DT) * (ns + 1)); e += DIST_THREADS) {
+            const uint32_t row = e / (ns + 1);
+            const int k = Td + (int)(e % (ns + 1));
+            const uint64_t sk = row < JT ? rowA0 + row : rowB0 + (row - JT);
+            CN[e] = (sk < a.n && k <= a.gmax) ? (k <= a.gmin ? m : a.counts[sk * 64 + (k - a.gmin - 1)]) : 0u;
+        }
+    }
+    __syncthreads();
+
     for (uint32_t pair = threadIdx.x; pair < (uint32_t)JPAIRS; pair += DIST_THREADS) {
         const uint32_t il = pair >> 5, jl = pair & 31;
         const uint64_t i = rowA0 + il, j = rowB0 + jl;
@@ -491,6 +596,33 @@ __global__ void __launch_bounds__(DIST_THREADS, 1) dist_jmle_kernel(const __grid
         } else {
             if (i >= j || j >= a.n || i < a.row_begin || i >= a.row_end) continue;
             oidx = (i * (2 * a.n - i - 1)) / 2 - a.out_base + (j - i - 1);
+        }
+        if (ns > 0) {
+            // G_U(k) = #a(k) + #b(k)   - #{a_i >= k,   b_i >= k  }
+            // G_X(k) = #a(k) + #b(k+1) - #{a_i >= k,   b_i >= k+1}      (histogram of max(a, b-1))
+            // G_Y(k) = #a(k+1) + #b(k) - #{a_i >= k+1, b_i >= k  }      (histogram of max(a-1, b))
+            uint16_t *gu = G + (size_t)(Td - lo - 1) * JPAIRS + pair;
+            uint16_t *gx = gu + (size_t)Kcap * JPAIRS, *gy = gx + (size_t)Kcap * JPAIRS;
+            const uint32_t *ca = CN + il * (ns + 1), *cb = CN + (JT + jl) * (ns + 1);
+            for (int kk = 0; kk < ns; ++kk) {
+                gu[kk * JPAIRS] = (uint16_t)(ca[kk] + cb[kk]);
+                gx[kk * JPAIRS] = (uint16_t)(ca[kk] + cb[kk + 1]);
+                gy[kk * JPAIRS] = (uint16_t)(ca[kk + 1] + cb[kk]);
+            }
+            const uint32_t *la = L + il * SPARSE_C, *lb = L + (JT + jl) * SPARSE_C;
+            int ia = 0, ib = 0;
+            uint32_t ea = la[0], eb = lb[0];
+            while (ea != 0u && eb != 0u) {
+                const uint32_t xa = ea >> 8, xb = eb >> 8;
+                if (xa == xb) {
+                    const int va = (int)(ea & 0xFFu), vb = (int)(eb & 0xFFu);
+                    for (int k = Td; k <= min(va, vb); ++k) gu[(k - Td) * JPAIRS] -= 1;
+                    for (int k = Td; k <= min(va, vb - 1); ++k) gx[(k - Td) * JPAIRS] -= 1;
+                    for (int k = Td; k <= min(va - 1, vb); ++k) gy[(k - Td) * JPAIRS] -= 1;
+                }
+                if (xa <= xb) ea = ++ia < SPARSE_C ? la[ia] : 0u;
+                if (xb <= xa) eb = ++ib < SPARSE_C ? lb[ib] : 0u;
+            }
         }
         const int amin = a.smin[i], amax = a.smax[i], bmin = a.smin[j], bmax = a.smax[j];
         // union histogram -> cABX (always the MLE, hll.h:658)
