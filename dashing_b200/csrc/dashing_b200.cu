@@ -269,7 +269,7 @@ namespace db200 {
 
 static int plan_prepare(db200_dist_plan *pl, const uint8_t *d_regs, uint64_t nrows, uint64_t n1, uint64_t qbase, uint64_t n2, int p,
                         int estim, cudaStream_t stream) {
-    if (p < 10 || p > 16) { set_error("dist: p=%d outside the GPU path's range [10,16]", p); return DB200_EUNSUPPORTED; }
+    if (p < 7 || p > 16) { set_error("dist: p=%d outside the GPU path's range [7,16]", p); return DB200_EUNSUPPORTED; }
     if (estim < 0 || estim > 2) { set_error("dist: unknown estimation method %d", estim); return DB200_EINVAL; }
     if (nrows == 0 || nrows > (1ull << 31) - 64) { set_error("dist: %llu sketches unsupported", (unsigned long long)nrows); return DB200_EINVAL; }
     PFN_encodeTiled enc = get_encode();
@@ -277,7 +277,7 @@ static int plan_prepare(db200_dist_plan *pl, const uint8_t *d_regs, uint64_t nro
     pl->ready = false;
     pl->nrows = nrows; pl->n1 = n1; pl->qbase = qbase; pl->n2 = n2; pl->p = p; pl->estim = estim;
     pl->tl_rect = -1;
-    const uint64_t m = 1ull << p, W = m >> 5, npan = (nrows + DT - 1) / DT;
+    const uint64_t m = 1ull << p, W = std::max<uint64_t>(m >> 5, 32), npan = (nrows + DT - 1) / DT;
     DB200_TRY(pl->minmax.reserve(8));
     DB200_CUDA(cudaMemsetAsync(pl->minmax.ptr, 0xFF, 4, stream));
     DB200_CUDA(cudaMemsetAsync(pl->minmax.as<uint8_t>() + 4, 0, 4, stream));
@@ -403,7 +403,7 @@ static int plan_run(db200_dist_plan *pl, const db200_dist_params *prm, int rect,
     a.estim = prm->estim; a.rtype = prm->result_type; a.rect = rect; a.one = 1;
     if (!joint) {
         // shared memory: S stages of 8 KiB + K x 2 KiB threshold counts + barriers; aim for two CTAs per SM
-        const size_t gbytes = (size_t)std::max(pl->K, 1) * DT * DT * 2;
+        const size_t gbytes = (size_t)(pl->K + 1) * DT * DT * 2;   // bins lo..hi of a tile: at most K + 1
         int S = 6;
         const size_t budget2 = 113 << 10, budget1 = 226 << 10;
         if (gbytes + (size_t)S * STAGE_BYTES + 1024 > budget2) S = (int)std::min<size_t>(12, (budget1 - gbytes - 1024) / STAGE_BYTES);
@@ -676,7 +676,7 @@ int db200_dist_symmetric_rows(int device, const uint8_t *regs, uint64_t n, const
     auto tri = [n](uint64_t r) { return (r * (2 * n - r - 1)) / 2; };
     const uint64_t npairs = tri(row_end) - tri(row_begin);
     if (npairs && !out) { set_error("null output"); return DB200_EINVAL; }
-    if (prm->p < 10 || prm->p > 16) { set_error("dist: p=%d outside the GPU path's range [10,16]", prm->p); return DB200_EUNSUPPORTED; }
+    if (prm->p < 7 || prm->p > 16) { set_error("dist: p=%d outside the GPU path's range [7,16]", prm->p); return DB200_EUNSUPPORTED; }
     DB200_TRY(hc.regs.reserve(n * m));
     DB200_TRY(hc.out.reserve(std::max<uint64_t>(npairs, 1) * 4));
     DB200_CUDA(cudaMemcpyAsync(hc.regs.ptr, regs, n * m, cudaMemcpyHostToDevice, hc.stream));
@@ -696,7 +696,7 @@ int db200_dist_rect(int device, const uint8_t *ref_regs, uint64_t nr, const uint
     if (!prm || ((!ref_regs || !qry_regs || !out) && nr && nq)) { set_error("db200_dist_rect: null argument"); return DB200_EINVAL; }
     DB200_TRY(check_device(device));
     if (nr == 0 || nq == 0) return DB200_OK;
-    if (prm->p < 10 || prm->p > 16) { set_error("dist: p=%d outside the GPU path's range [10,16]", prm->p); return DB200_EUNSUPPORTED; }
+    if (prm->p < 7 || prm->p > 16) { set_error("dist: p=%d outside the GPU path's range [7,16]", prm->p); return DB200_EUNSUPPORTED; }
     HostCtx &hc = host_ctx(device);
     std::lock_guard<std::mutex> lk(hc.mu);
     DB200_TRY(hc.init(device));

@@ -65,14 +65,19 @@ __global__ void __launch_bounds__(128) planes_kernel(const uint32_t *__restrict_
     __shared__ uint32_t cnt[64];
     __shared__ int s_T;
     const uint64_t s = row0 + blockIdx.x;
-    const uint32_t m = 1u << p, W = m >> 5, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // plane rows are at least 32 words (one TMA box) wide: for p < 10 the tail is zero = "below every threshold"
+    const uint32_t m = 1u << p, W = max(m >> 5, 32u), lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t nwords = m >> 2, ngroups = max(m >> 10, 1u);
     if (threadIdx.x < 64) cnt[threadIdx.x] = 0;
     __syncthreads();
     const uint32_t *src = regs32 + s * (m >> 2);
-    for (uint32_t g = warp; g < (m >> 10); g += 4) {
+    for (uint32_t g = warp; g < ngroups; g += 4) {
         uint32_t x[8];
 #pragma unroll
-        for (int gg = 0; gg < 8; ++gg) x[gg] = __ldg(src + g * 256 + gg * 32 + lane);
+        for (int gg = 0; gg < 8; ++gg) {
+            const uint32_t wi = g * 256 + gg * 32 + lane;
+            x[gg] = wi < nwords ? __ldg(src + wi) : 0u;
+        }
         for (int t = 0; t < K; ++t) {
             const uint32_t k4 = (uint32_t)(gmin + 1 + t) * 0x01010101u;
             uint32_t kept = 0;
@@ -106,8 +111,8 @@ __global__ void __launch_bounds__(128) planes_kernel(const uint32_t *__restrict_
         const uint32_t T4 = (uint32_t)s_T * 0x01010101u;
         uint32_t *dst = lists + s * SPARSE_C;
         uint32_t total = 0;
-        for (uint32_t w0 = 0; w0 < (m >> 2); w0 += 32) {
-            const uint32_t x = __ldg(src + w0 + lane);
+        for (uint32_t w0 = 0; w0 < nwords; w0 += 32) {
+            const uint32_t x = w0 + lane < nwords ? __ldg(src + w0 + lane) : 0u;
             const uint32_t ge = __vcmpgeu4(x, T4) & 0x01010101u;
             if (!__any_sync(0xFFFFFFFFu, ge != 0u)) continue;
             const uint32_t c = (uint32_t)__popc(ge);
@@ -257,12 +262,42 @@ struct PairCounts {
     __device__ __forceinline__ uint32_t operator()(int k) const { return G(k) - G(k + 1); }
 };
 
+// Pair histogram with the bin counts themselves in shared memory (dist_kernel converts its threshold counts in place
+// before the estimator runs: one LDS per bin instead of two plus range logic).  Slot s holds bin lo + s, s = 0..hi-lo.
+struct PairHist {
+    const uint16_t *c;   // &C[0][pair]
+    uint32_t m;
+    int lo, hi;
+    int fullk;           // bin holding all 2^16 registers (stored as 0), or -1
+    __device__ __forceinline__ uint32_t operator()(int k) const {
+        const unsigned s = (unsigned)(k - lo);
+        if (s > (unsigned)(hi - lo)) return 0u;
+        return k == fullk ? m : (uint32_t)c[s * (DT * DT)];
+    }
+};
+
+// a / b for finite, normal, positive b: reciprocal seed + two Newton steps + one correction (<= 1 ulp), no special-case
+// path.  The estimator's denominators (x' + 1 - h, with h in (0,1]) always qualify.
+__device__ __forceinline__ double fast_div(double a, double b) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+    double e = fma(-b, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-b, r, 1.0);
+    r = fma(r, e, r);
+    double q = a * r;
+    const double rem = fma(-b, q, a);
+    return fma(rem, r, q);
+}
+
+struct NewtonDiv { __device__ __forceinline__ static double div(double a, double b) { return fast_div(a, b); } };
+
 __global__ void __launch_bounds__(DIST_THREADS, 2) dist_kernel(const __grid_constant__ CUtensorMap tmap, const DistArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int S = a.stages;
     uint8_t *stage_mem = smem;                                             // S x {A box, B box}
     uint16_t *G = reinterpret_cast<uint16_t *>(smem + (size_t)S * STAGE_BYTES);  // [K][1024]
-    const int Kcap = a.K > 0 ? a.K : 1;
+    const int Kcap = a.K + 1;   // slots for bins lo .. hi of the tile (slot 0 is filled when counts become bins)
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)S * STAGE_BYTES + (size_t)Kcap * DT * DT * 2);
     const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + S);
 
@@ -277,7 +312,7 @@ __global__ void __launch_bounds__(DIST_THREADS, 2) dist_kernel(const __grid_cons
     // merging the two sorted sparse tails — no plane traffic, no POPC.
     const int Tt = (int)max(a.pthr[panA], a.pthr[panB]);
     const int Td = min(max(Tt, lo + 1), hi + 1);
-    const int W = 1 << (a.p - 5), nbox = W >> 5;
+    const int W = max(1 << (a.p - 5), 32), nbox = W >> 5;
     const int iters = (Td - 1 - lo) * nbox;
 
     if (threadIdx.x == 0) {
@@ -343,7 +378,7 @@ __global__ void __launch_bounds__(DIST_THREADS, 2) dist_kernel(const __grid_cons
         acc = (uint32_t)__popc(p.w | q.w) * one + acc;                           \
     } while (0)
         const uint32_t one = (uint32_t)a.one, eight = one << 3;
-        int s = 0, wb = 0, tl = 0;
+        int s = 0, wb = 0, tl = 1;      // threshold lo + tl -> slot tl
         uint32_t ph = 0;
         for (int it = 0; it < iters; ++it) {
             mbar_wait(full0 + 8 * s, ph);
@@ -429,7 +464,7 @@ __global__ void __launch_bounds__(DIST_THREADS, 2) dist_kernel(const __grid_cons
             oidx = (i * (2 * a.n - i - 1)) / 2 - a.out_base + (j - i - 1);
         }
         if (ns > 0) {
-            uint16_t *g = G + (size_t)(Td - lo - 1) * (DT * DT) + pair;
+            uint16_t *g = G + (size_t)(Td - lo) * (DT * DT) + pair;
             const uint32_t *ca = CN + il * ns, *cb = CN + (DT + jl) * ns;
             for (int kk = 0; kk < ns; ++kk) g[kk * (DT * DT)] = (uint16_t)(ca[kk] + cb[kk]);
             // merge the two index-sorted tails; a register present in both with min value mn was counted twice for k <= mn
@@ -448,8 +483,25 @@ __global__ void __launch_bounds__(DIST_THREADS, 2) dist_kernel(const __grid_cons
         }
         const int kmin_pair = max((int)a.smin[i], (int)a.smin[j]);
         const int kmax_pair = max((int)a.smax[i], (int)a.smax[j]);
-        PairCounts c{G + pair, m, lo, hi, kmax_pair, DT * DT, 64};
-        const double us = calculate_estimate(c, a.estim, a.p, kmin_pair, kmax_pair);
+        // threshold counts G(k) (slots 1..hi-lo) -> bin counts c(k) = G(k) - G(k+1) in place, slot 0 = bin lo
+        int fullk = -1;
+        {
+            uint16_t *col = G + pair;
+            uint32_t gk = m;                                    // G(lo) = 2^p
+            for (int k = lo; k <= hi; ++k) {
+                uint32_t gn = 0u;                               // G(hi + 1) = 0
+                if (k < hi) {
+                    gn = col[(k + 1 - lo) * (DT * DT)];
+                    if (gn == 0u && k + 1 <= kmax_pair) gn = m;  // counts are stored mod 2^16 (only p == 16 can wrap)
+                }
+                const uint32_t ck = gk - gn;
+                if (ck > 0xFFFFu) fullk = k;
+                col[(k - lo) * (DT * DT)] = (uint16_t)ck;
+                gk = gn;
+            }
+        }
+        PairHist c{G + pair, m, lo, hi, fullk};
+        const double us = calculate_estimate<PairHist, NewtonDiv>(c, a.estim, a.p, kmin_pair, kmax_pair);
         // non-joint path is symmetric in its operands (IEEE addition commutes): lhs = A, rhs = B
         const double cl = a.card[i], cr = a.card[j];
         // jaccard_index, hll.h:1179-1182
@@ -499,7 +551,7 @@ __global__ void __launch_bounds__(DIST_THREADS, 1) dist_jmle_kernel(const __grid
     // dense thresholds lo+1 .. Td-1 from the planes, sparse thresholds Td .. hi from the merged tails (see dist_kernel)
     const int Tt = (int)max(a.pthr[panA], a.pthr[panB]);
     const int Td = min(max(Tt, lo + 1), hi + 1);
-    const int W = 1 << (a.p - 5), nbox = W >> 5;
+    const int W = max(1 << (a.p - 5), 32), nbox = W >> 5;
     const int iters = (Td - 1 - lo) * nbox;
 
     if (threadIdx.x == 0) {
