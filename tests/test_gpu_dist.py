@@ -119,3 +119,22 @@ def test_unsupported_is_loud(gpu):
     with pytest.raises(gpu.Db200Error) as ei:
         gpu.dist_symmetric(regs, 17)
     assert ei.value.code == gpu.EUNSUPPORTED
+
+
+def test_large_matrix_indexing(gpu, checker):
+    """20,011 sketches (2.0e8 pairs, 800 MB of output): 64-bit distmat offsets, ragged last panel, row shards far into the
+    triangle, all checked on samples against the oracle."""
+    p, n = 10, 20011
+    regs = synth.registers(424242, n, p, card=3e5, group=64)
+    out = gpu.dist_symmetric(regs, p, k=31, result_type=0)
+    assert out.size == n * (n - 1) // 2 and np.isfinite(out).all()
+    idx = lambda i, j: i * (2 * n - i - 1) // 2 + j - i - 1
+    rng = np.random.default_rng(9)
+    samples = [(0, 1), (0, n - 1), (n - 2, n - 1), (31, 32), (19999, 20010), (12345, 20000)]
+    samples += [tuple(sorted(map(int, rng.choice(n, 2, replace=False)))) for _ in range(150)]
+    for i, j in samples:
+        assert_close(out[idx(i, j)], checker.pair(regs[i], regs[j], p, rtype=0, k=31), what=f"pair {i},{j}")
+    # a row shard deep in the triangle equals the corresponding slice of the full result
+    rb, re_ = 17000, 17777
+    shard = gpu.dist_symmetric(regs, p, k=31, result_type=0, row_begin=rb, row_end=re_)
+    np.testing.assert_array_equal(shard, out[idx(rb, rb + 1): idx(re_, re_ + 1) if re_ < n - 1 else out.size])
