@@ -258,9 +258,12 @@ struct db200_dist_plan {
     int p = 0, estim = -1, gmin = 0, gmax = 0, K = 0;
     bool ready = false;
     CUtensorMap tmap, tmap16;   // boxes of 32 / 16 sketches
-    db200::DevBuf planes, counts, card, smin, smax, pmin, pmax, minmax, tiles, lists, sthr, pthr;
+    static constexpr int NSLOT = 4;   // independent tile lists, so that row blocks of one request can be in flight together
+    db200::DevBuf planes, counts, card, smin, smax, pmin, pmax, minmax, lists, sthr, pthr;
+    db200::DevBuf tiles[NSLOT];
+    std::vector<db200::DistTile> host_tiles[NSLOT];
     // tile-list cache key
-    int tl_rect = -1, tl_ta = 0; uint64_t tl_rb = 0, tl_re = 0, tl_nr = 0, tl_nq = 0, tl_n = 0; uint64_t ntiles = 0;
+    struct TileKey { int rect = -1, ta = 0; uint64_t rb = 0, re = 0, nr = 0, nq = 0, n = 0, ntiles = 0; } tl[NSLOT];
     uint64_t last_pairs = 0, last_tiles = 0;
     std::mutex mu;
 };
@@ -276,7 +279,7 @@ static int plan_prepare(db200_dist_plan *pl, const uint8_t *d_regs, uint64_t nro
     if (!enc) { set_error("cuTensorMapEncodeTiled not available from the driver"); return DB200_ECUDA; }
     pl->ready = false;
     pl->nrows = nrows; pl->n1 = n1; pl->qbase = qbase; pl->n2 = n2; pl->p = p; pl->estim = estim;
-    pl->tl_rect = -1;
+    // tile lists depend only on (n, row range, mode), not on the register data: they stay cached across prepares
     const uint64_t m = 1ull << p, W = std::max<uint64_t>(m >> 5, 32), npan = (nrows + DT - 1) / DT;
     DB200_TRY(pl->minmax.reserve(8));
     DB200_CUDA(cudaMemsetAsync(pl->minmax.ptr, 0xFF, 4, stream));
@@ -348,11 +351,13 @@ static int plan_prepare(db200_dist_plan *pl, const uint8_t *d_regs, uint64_t nro
     return DB200_OK;
 }
 
-static int plan_tiles(db200_dist_plan *pl, int rect, int ta, uint64_t rb, uint64_t re, uint64_t nr, uint64_t nq, cudaStream_t stream) {
-    if (pl->tl_rect == rect && pl->tl_ta == ta && pl->tl_rb == rb && pl->tl_re == re && pl->tl_nr == nr && pl->tl_nq == nq && pl->tl_n == pl->nrows) return DB200_OK;
+static int plan_tiles(db200_dist_plan *pl, int slot, int rect, int ta, uint64_t rb, uint64_t re, uint64_t nr, uint64_t nq, cudaStream_t stream) {
+    auto &key = pl->tl[slot];
+    if (key.rect == rect && key.ta == ta && key.rb == rb && key.re == re && key.nr == nr && key.nq == nq && key.n == pl->nrows) return DB200_OK;
     // A panels have `ta` rows (32, or 16 for the joint-MLE kernel), B panels DT = 32.  Tiles are ordered in
     // super-rows of A panels: concurrent CTAs share their A panels and sweep the B panels together (L2 reuse).
-    std::vector<DistTile> tiles;
+    std::vector<DistTile> &tiles = pl->host_tiles[slot];
+    tiles.clear();
     const uint32_t f = (uint32_t)(DT / ta);          // A panels per B panel
     const uint32_t SR = 8 * f;
     if (!rect) {
@@ -368,28 +373,29 @@ static int plan_tiles(db200_dist_plan *pl, int rect, int ta, uint64_t rb, uint64
             for (uint32_t b = 0; b < nb; ++b)
                 for (uint32_t a = sr; a < std::min(sr + SR, na); ++a) tiles.push_back(DistTile{a, b});
     }
-    pl->ntiles = tiles.size();
+    key.ntiles = tiles.size();
     if (!tiles.empty()) {
-        DB200_TRY(pl->tiles.reserve(tiles.size() * sizeof(DistTile)));
-        DB200_CUDA(cudaMemcpyAsync(pl->tiles.ptr, tiles.data(), tiles.size() * sizeof(DistTile), cudaMemcpyHostToDevice, stream));
-        DB200_CUDA(cudaStreamSynchronize(stream));  // `tiles` is pageable host memory about to go out of scope
+        DB200_TRY(pl->tiles[slot].reserve(tiles.size() * sizeof(DistTile)));
+        // pageable source: the runtime stages it before returning; host_tiles[slot] also stays alive in the plan
+        DB200_CUDA(cudaMemcpyAsync(pl->tiles[slot].ptr, tiles.data(), tiles.size() * sizeof(DistTile), cudaMemcpyHostToDevice, stream));
     }
-    pl->tl_rect = rect; pl->tl_ta = ta; pl->tl_rb = rb; pl->tl_re = re; pl->tl_nr = nr; pl->tl_nq = nq; pl->tl_n = pl->nrows;
+    key.rect = rect; key.ta = ta; key.rb = rb; key.re = re; key.nr = nr; key.nq = nq; key.n = pl->nrows;
     return DB200_OK;
 }
 
 static int plan_run(db200_dist_plan *pl, const db200_dist_params *prm, int rect, uint64_t rb, uint64_t re, uint64_t nr, uint64_t nq,
-                    float *d_out, cudaStream_t stream) {
+                    float *d_out, cudaStream_t stream, int slot = 0) {
     if (!pl->ready) { set_error("dist plan not prepared"); return DB200_EINVAL; }
     if (prm->p != pl->p || prm->estim != pl->estim) { set_error("dist params (p=%d, estim=%d) differ from the prepared plan (p=%d, estim=%d)", prm->p, prm->estim, pl->p, pl->estim); return DB200_EINVAL; }
     if (prm->result_type < 0 || prm->result_type > 8) { set_error("dist: unknown result type %d", prm->result_type); return DB200_EINVAL; }
     if (prm->k < 1) { set_error("dist: k must be positive"); return DB200_EINVAL; }
     const bool joint = prm->jestim == DB200_ERTL_JOINT_MLE;
-    DB200_TRY(plan_tiles(pl, rect, joint ? JT : DT, rb, re, nr, nq, stream));
-    pl->last_tiles = pl->ntiles;
-    if (pl->ntiles == 0) { pl->last_pairs = 0; return DB200_OK; }
+    DB200_TRY(plan_tiles(pl, slot, rect, joint ? JT : DT, rb, re, nr, nq, stream));
+    const uint64_t ntiles = pl->tl[slot].ntiles;
+    pl->last_tiles = ntiles;
+    if (ntiles == 0) { pl->last_pairs = 0; return DB200_OK; }
     DistArgs a;
-    a.tiles = pl->tiles.as<DistTile>();
+    a.tiles = pl->tiles[slot].as<DistTile>();
     a.smin = pl->smin.as<uint8_t>(); a.smax = pl->smax.as<uint8_t>();
     a.pmin = pl->pmin.as<uint32_t>(); a.pmax = pl->pmax.as<uint32_t>();
     a.card = pl->card.as<double>();
@@ -411,7 +417,7 @@ static int plan_run(db200_dist_plan *pl, const db200_dist_params *prm, int rect,
         a.stages = S;
         const size_t smem = (size_t)S * STAGE_BYTES + gbytes + 2 * S * 8;
         DB200_CUDA(cudaFuncSetAttribute(dist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 << 10));
-        dist_kernel<<<(unsigned)pl->ntiles, DIST_THREADS, smem, stream>>>(pl->tmap, a);
+        dist_kernel<<<(unsigned)ntiles, DIST_THREADS, smem, stream>>>(pl->tmap, a);
     } else {
         const size_t gbytes = (size_t)3 * std::max(pl->K, 1) * JPAIRS * 2;
         const size_t budget1 = 226 << 10;
@@ -421,7 +427,7 @@ static int plan_run(db200_dist_plan *pl, const db200_dist_params *prm, int rect,
         const size_t smem = (size_t)S * JSTAGE_BYTES + gbytes + 2 * S * 8;
         const int lhs_is_b = rect ? 1 : (prm->order == DB200_ORDER_COL_FIRST ? 1 : 0);
         DB200_CUDA(cudaFuncSetAttribute(dist_jmle_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 << 10));
-        dist_jmle_kernel<<<(unsigned)pl->ntiles, DIST_THREADS, smem, stream>>>(pl->tmap16, pl->tmap, a, lhs_is_b);
+        dist_jmle_kernel<<<(unsigned)ntiles, DIST_THREADS, smem, stream>>>(pl->tmap16, pl->tmap, a, lhs_is_b);
     }
     DB200_LAUNCHED();
     DB200_CUDA(cudaGetLastError());
@@ -437,13 +443,18 @@ static int plan_run(db200_dist_plan *pl, const db200_dist_params *prm, int rect,
 // Default per-device resources for the host-pointer entry points.
 struct HostCtx {
     std::mutex mu;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, cstream = nullptr;
+    cudaEvent_t blk_done[db200_dist_plan::NSLOT] = {nullptr, nullptr, nullptr, nullptr};
     DevBuf regs, out, cards;
     Uploader up;
     std::unique_ptr<db200_dist_plan> plan;
     std::unique_ptr<db200_packed_genomes> store;   // reused by db200_sketch_batch
     int init(int device) {
         if (!stream) DB200_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        if (!cstream) {
+            DB200_CUDA(cudaStreamCreateWithFlags(&cstream, cudaStreamNonBlocking));
+            for (auto &e : blk_done) DB200_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        }
         if (!plan) { plan.reset(new db200_dist_plan); plan->device = device; }
         if (!store) store.reset(new db200_packed_genomes);
         return DB200_OK;
@@ -681,9 +692,27 @@ int db200_dist_symmetric_rows(int device, const uint8_t *regs, uint64_t n, const
     DB200_TRY(hc.out.reserve(std::max<uint64_t>(npairs, 1) * 4));
     DB200_CUDA(cudaMemcpyAsync(hc.regs.ptr, regs, n * m, cudaMemcpyHostToDevice, hc.stream));
     DB200_TRY(plan_prepare(hc.plan.get(), hc.regs.as<uint8_t>(), n, n, 0, 0, prm->p, prm->estim, hc.stream));
-    DB200_TRY(plan_run(hc.plan.get(), prm, 0, row_begin, row_end, 0, 0, hc.out.as<float>(), hc.stream));
-    DB200_CUDA(cudaMemcpyAsync(out, hc.out.ptr, npairs * 4, cudaMemcpyDeviceToHost, hc.stream));
+    // Row blocks (equal pair counts, up to NSLOT of them): block b's device->host copy runs on the copy stream while block
+    // b+1 computes, so only the last block's transfer is exposed.
+    const int nblk = npairs >= (uint64_t(4) << 20) ? db200_dist_plan::NSLOT : 1;
+    uint64_t rb = row_begin;
+    for (int b = 0; b < nblk; ++b) {
+        uint64_t re = row_end;
+        if (b + 1 < nblk) {
+            const uint64_t target = tri(row_begin) + npairs * (uint64_t)(b + 1) / (uint64_t)nblk;
+            re = rb;
+            while (re < row_end && tri(re) < target) ++re;       // block boundaries are whole rows
+        }
+        if (re == rb) continue;
+        const uint64_t off = tri(rb) - tri(row_begin), cnt = tri(re) - tri(rb);
+        DB200_TRY(plan_run(hc.plan.get(), prm, 0, rb, re, 0, 0, hc.out.as<float>() + off, hc.stream, b));
+        DB200_CUDA(cudaEventRecord(hc.blk_done[b], hc.stream));
+        DB200_CUDA(cudaStreamWaitEvent(hc.cstream, hc.blk_done[b], 0));
+        if (cnt) DB200_CUDA(cudaMemcpyAsync(out + off, hc.out.as<float>() + off, cnt * 4, cudaMemcpyDeviceToHost, hc.cstream));
+        rb = re;
+    }
     DB200_CUDA(cudaStreamSynchronize(hc.stream));
+    DB200_CUDA(cudaStreamSynchronize(hc.cstream));
     return DB200_OK;
 }
 
