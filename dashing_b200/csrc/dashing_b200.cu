@@ -193,6 +193,7 @@ static int sketch_packed_impl(const db200_packed_genomes *pg, int p, int canon, 
     kc.rc_mul_lo = rcshift < 32 ? (1u << rcshift) : 0u;
     kc.rc_mul_hi = rcshift >= 32 ? (1u << (rcshift - 32)) : 0u;
     kc.rho_mul = 1u << p; kc.rho_add = 1u << (p - 1);
+    kc.neg_2p20 = 0u - (1u << 20); kc.c1087_2p20 = 1087u << 20;
     int occ = 1;
     const unsigned sms = (unsigned)g_num_sms(pg->device);
 #define DB200_SKETCH_LAUNCH(MODE, KC, CANON)                                                                                  \

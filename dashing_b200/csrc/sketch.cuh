@@ -88,6 +88,8 @@ struct SketchConsts {
     uint32_t rc_mul_hi; // 2^(rcshift-32)   if rcshift >= 32 else 0
     uint32_t rho_mul;   // 2^p
     uint32_t rho_add;   // 2^(p-1)
+    uint32_t neg_2p20;  // -(2^20)
+    uint32_t c1087_2p20; // 1087 << 20
 };
 
 // r = a * c + add (64-bit a, 32-bit c): IMAD.WIDE.U32 + IMAD
@@ -206,6 +208,7 @@ __global__ void __launch_bounds__(SK_THREADS) sketch_kernel(const uint4 *__restr
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint64_t ones = ((uint64_t)kc.neg1 << 32) | kc.neg1;
     const int idx_shift = 32 - p;   // p <= 24
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(sregs);
     constexpr uint32_t NWARPS = SK_THREADS / 32;
 
     // one base: roll the forward and reverse-complement k-mers
@@ -243,7 +246,6 @@ __global__ void __launch_bounds__(SK_THREADS) sketch_kernel(const uint4 *__restr
             for (uint32_t w = threadIdx.x; w < m / 4; w += SK_THREADS) reinterpret_cast<uint32_t *>(sregs)[w] = g32[w];
         }
         __syncthreads();
-        uint32_t *r32 = reinterpret_cast<uint32_t *>(sregs);
         uint8_t *r8 = MODE == 1 ? sregs : greg;
 
         const uint64_t blk_lo = item.pos_begin >> 6, blk_hi = (item.pos_end + 63) >> 6;
@@ -289,14 +291,25 @@ __global__ void __launch_bounds__(SK_THREADS) sketch_kernel(const uint4 *__restr
                         const uint64_t h = wang64(x, ones);
                         const uint32_t hlo = (uint32_t)h, hhi = (uint32_t)(h >> 32);
                         const uint32_t idx = hhi >> idx_shift;
-                        // rho = clz(((h << 1) | 1) << (p - 1)) + 1   (hll.h:830): leading zeros of the low 64-p bits
+                        // rho = clz(((h << 1) | 1) << (p - 1)) + 1 (hll.h:830) = 64 - floor(log2 T), T = (h << p) | 2^(p-1) != 0.
+                        // One u64 -> f64 conversion (round toward zero, so the exponent is exact) replaces clz of a 64-bit
+                        // value with its rare "upper word is zero" branch.
+                        const uint32_t tlo = hlo * kc.rho_mul + kc.rho_add;
                         const uint32_t thi = __funnelshift_l(hlo, hhi, p);
-                        uint32_t rho = (uint32_t)__clz((int)thi) + 1u;
-                        if (__builtin_expect(thi == 0u, 0)) rho = 33u + (uint32_t)__clz((int)(hlo * kc.rho_mul + kc.rho_add));
+                        const double dT = __ull2double_rz(((uint64_t)thi << 32) | tlo);
+                        const uint32_t ehi = (uint32_t)__double2hiint(dT);   // biased exponent in bits 20..30
                         const bool emit = (e16 >> i) & 1u;
                         if (MODE == 0) {
-                            if (emit && r32[idx] < rho) atomicMax(r32 + idx, rho);
+                            // staged registers are addressed in the shared window directly: no generic-address setup per k-mer
+                            const uint32_t addr = sbase + idx * 4u;
+                            uint32_t cur;
+                            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(cur) : "r"(addr));
+                            // cur < rho  <=>  exponent < 1087 - cur  <=>  ehi < (1087 - cur) << 20   (one IMAD, one compare)
+                            if (emit && ehi < cur * kc.neg_2p20 + kc.c1087_2p20)
+                                asm volatile("{\n\t.reg .u32 t;\n\tshr.u32 t, %1, 20;\n\tsub.u32 t, 1087, t;\n\t"   // rho, only on the rare path
+                                             "red.shared.max.u32 [%0], t;\n\t}" ::"r"(addr), "r"(ehi) : "memory");
                         } else {
+                            const uint32_t rho = 1087u - (ehi >> 20);
                             const bool upd = emit && r8[idx] < rho;
                             if (__any_sync(0xFFFFFFFFu, upd)) {
                                 if (upd) byte_max(reinterpret_cast<uint32_t *>(r8) + (idx >> 2), (idx & 3u) * 8u, rho);
