@@ -45,6 +45,8 @@ struct db200_packed_genomes {
     int device = 0, k = 0;
     uint64_t nbases = 0, nblk = 0, ngenomes = 0, kmers = 0;
     uint32_t nitems = 0;
+    std::vector<uint32_t> group_item_begin;   // items of genome group g: [group_item_begin[g], group_item_begin[g+1])
+    std::vector<uint64_t> group_end;          // one past the last base of group g
     db200::DevBuf bases2, nb, st, items, counter, starts;
 };
 
@@ -55,16 +57,25 @@ struct Uploader {
     DevBuf stage[2];
     cudaStream_t cs = nullptr;
     cudaEvent_t copied[2] = {nullptr, nullptr}, packed[2] = {nullptr, nullptr};
+    static constexpr int NGROUP = 4;
+    cudaStream_t ss = nullptr;                 // sketch stream: group g is sketched while later groups are still uploading
+    cudaEvent_t group_packed[NGROUP] = {nullptr, nullptr, nullptr, nullptr};
     int init() {
         if (cs) return DB200_OK;
         DB200_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+        DB200_CUDA(cudaStreamCreateWithFlags(&ss, cudaStreamNonBlocking));
         for (int i = 0; i < 2; ++i) {
             DB200_CUDA(cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming));
             DB200_CUDA(cudaEventCreateWithFlags(&packed[i], cudaEventDisableTiming));
         }
+        for (auto &e : group_packed) DB200_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         return DB200_OK;
     }
 };
+// When given to pack_genomes_impl, every genome group is sketched as soon as its last chunk has been packed.
+struct PipelinedSketch { int p, canon; uint8_t *d_regs; };
+static int sketch_launch(const db200_packed_genomes *pg, int p, int canon, uint8_t *d_regs, cudaStream_t stream, uint32_t item_begin,
+                         uint32_t item_count, int counter_idx);
 } // namespace db200
 
 namespace db200 {
@@ -81,7 +92,7 @@ static uint64_t count_kmers(const uint64_t *rec_offsets, uint64_t nrecords, int 
 
 static int pack_genomes_impl(int device, const char *bases, const uint64_t *rec_offsets, uint64_t nrecords,
                              const uint64_t *genome_rec_begin, uint64_t ngenomes, int k, db200_packed_genomes *pg,
-                             Uploader &up, cudaStream_t stream) {
+                             Uploader &up, cudaStream_t stream, const PipelinedSketch *ps = nullptr) {
     const uint64_t base0 = nrecords ? rec_offsets[0] : 0;
     const uint64_t T = nrecords ? rec_offsets[nrecords] - base0 : 0;
     pg->device = device; pg->k = k; pg->nbases = T; pg->ngenomes = ngenomes;
@@ -90,13 +101,70 @@ static int pack_genomes_impl(int device, const char *bases, const uint64_t *rec_
     DB200_TRY(pg->bases2.reserve(pg->nblk * 16));
     DB200_TRY(pg->nb.reserve(pg->nblk * 8));
     DB200_TRY(pg->st.reserve(pg->nblk * 8));
-    DB200_TRY(pg->counter.reserve(16));
+    DB200_TRY(pg->counter.reserve(64));
     DB200_CUDA(cudaMemsetAsync(pg->st.ptr, 0, pg->nblk * 8, stream));
     // the pack kernel writes whole 16-base groups; only the tail of the last block and the guard block need zeroing
     const uint64_t full_blk = T / 64;
     DB200_CUDA(cudaMemsetAsync(pg->nb.as<uint64_t>() + full_blk, 0, (pg->nblk - full_blk) * 8, stream));
     DB200_CUDA(cudaMemsetAsync(pg->bases2.as<uint4>() + full_blk, 0, (pg->nblk - full_blk) * 16, stream));
 
+    // record starts
+    std::vector<uint64_t> starts;
+    starts.reserve(nrecords);
+    for (uint64_t r = 0; r < nrecords; ++r) {
+        const uint64_t pos = rec_offsets[r] - base0;
+        if (pos < T && rec_offsets[r + 1] > rec_offsets[r]) starts.push_back(pos);
+    }
+    if (!starts.empty()) {
+        DB200_TRY(pg->starts.reserve(starts.size() * 8));
+        DB200_CUDA(cudaMemcpyAsync(pg->starts.ptr, starts.data(), starts.size() * 8, cudaMemcpyHostToDevice, stream));
+        mark_starts_kernel<<<(unsigned)((starts.size() + 255) / 256), 256, 0, stream>>>(pg->starts.as<uint64_t>(), starts.size(), pg->st.as<uint32_t>());
+        DB200_LAUNCHED();
+    }
+    // work items: every genome is cut into equal chunks of ~1 Mbase (at least ~16 items per SM overall).  Genomes form up to
+    // NGROUP contiguous groups of similar size (the unit of upload/compute overlap); inside a group items are ordered
+    // chunk-major so that by the time chunk c+1 of a genome starts, chunk c has been merged into HBM and seeds the staged
+    // registers (fewer updates).
+    std::vector<SketchItem> items;
+    pg->group_item_begin.assign(1, 0u);
+    pg->group_end.clear();
+    {
+        const uint64_t target_items = (uint64_t)g_num_sms(device) * 16;
+        uint64_t chunk = T / std::max<uint64_t>(target_items, 1);
+        chunk = std::min<uint64_t>(std::max<uint64_t>(chunk, 1ull << 16), 1ull << 20);
+        const int ngroups = ps ? Uploader::NGROUP : 1;
+        uint64_t g0 = 0;
+        for (int grp = 0; grp < ngroups && g0 < ngenomes; ++grp) {
+            uint64_t g1 = ngenomes;
+            if (grp + 1 < ngroups) {
+                const uint64_t want = T * (uint64_t)(grp + 1) / (uint64_t)ngroups;
+                g1 = g0 + 1;
+                while (g1 < ngenomes && rec_offsets[genome_rec_begin[g1]] - base0 < want) ++g1;
+            }
+            std::vector<std::pair<uint32_t, SketchItem>> tmp;
+            for (uint64_t g = g0; g < g1; ++g) {
+                const uint64_t gs = rec_offsets[genome_rec_begin[g]] - base0, ge = rec_offsets[genome_rec_begin[g + 1]] - base0;
+                if (ge <= gs) continue;
+                const uint64_t nch = (ge - gs + chunk - 1) / chunk;
+                const uint64_t step = (((ge - gs + nch - 1) / nch) + 63) & ~63ull;
+                uint32_t ci = 0;
+                for (uint64_t s = gs; s < ge; s += step, ++ci) tmp.push_back({ci, SketchItem{s, std::min(ge, s + step), (uint32_t)g, 0}});
+            }
+            std::stable_sort(tmp.begin(), tmp.end(), [](const auto &a, const auto &b) { return a.first < b.first; });
+            for (auto &t : tmp) items.push_back(t.second);
+            pg->group_item_begin.push_back((uint32_t)items.size());
+            pg->group_end.push_back(rec_offsets[genome_rec_begin[g1]] - base0);
+            g0 = g1;
+        }
+    }
+    pg->nitems = (uint32_t)items.size();
+    if (!items.empty()) {
+        DB200_TRY(pg->items.reserve(items.size() * sizeof(SketchItem)));
+        DB200_CUDA(cudaMemcpyAsync(pg->items.ptr, items.data(), items.size() * sizeof(SketchItem), cudaMemcpyHostToDevice, stream));
+    }
+    DB200_CUDA(cudaMemsetAsync(pg->counter.ptr, 0, 64, stream));
+    if (ps) DB200_CUDA(cudaMemsetAsync(ps->d_regs, 0, ngenomes << ps->p, stream));
+    size_t next_group = 0;
     // ASCII upload in 64-base-aligned chunks through two device staging buffers; the pack kernel of
     // chunk c overlaps the H2D copy of chunk c+1.
     const uint64_t CH = 64ull << 20;
@@ -131,60 +199,32 @@ static int pack_genomes_impl(int device, const char *bases, const uint64_t *rec_
                                                                           pg->nb.as<uint16_t>() + off / 16, ngroups);
         DB200_LAUNCHED();
         if (!on_dev) DB200_CUDA(cudaEventRecord(up.packed[b], stream));
+        // genome groups whose last base is now packed start sketching on their own stream
+        while (ps && next_group < pg->group_end.size() && pg->group_end[next_group] <= off + len) {
+            const uint32_t ib = pg->group_item_begin[next_group], ie = pg->group_item_begin[next_group + 1];
+            if (ie > ib) {
+                DB200_TRY(up.init());
+                DB200_CUDA(cudaEventRecord(up.group_packed[next_group], stream));
+                DB200_CUDA(cudaStreamWaitEvent(up.ss, up.group_packed[next_group], 0));
+                DB200_TRY(sketch_launch(pg, ps->p, ps->canon, ps->d_regs, up.ss, ib, ie - ib, (int)next_group));
+            }
+            ++next_group;
+        }
     }
     DB200_CUDA(cudaGetLastError());
+    if (ps && up.ss) {
+        const cudaError_t es = cudaStreamSynchronize(up.ss);
+        if (es != cudaSuccess) { set_error("sketch (pipelined): %s", cudaGetErrorString(es)); return DB200_ECUDA; }
+    }
 
-    // record starts
-    std::vector<uint64_t> starts;
-    starts.reserve(nrecords);
-    for (uint64_t r = 0; r < nrecords; ++r) {
-        const uint64_t pos = rec_offsets[r] - base0;
-        if (pos < T && rec_offsets[r + 1] > rec_offsets[r]) starts.push_back(pos);
-    }
-    if (!starts.empty()) {
-        DB200_TRY(pg->starts.reserve(starts.size() * 8));
-        DB200_CUDA(cudaMemcpyAsync(pg->starts.ptr, starts.data(), starts.size() * 8, cudaMemcpyHostToDevice, stream));
-        mark_starts_kernel<<<(unsigned)((starts.size() + 255) / 256), 256, 0, stream>>>(pg->starts.as<uint64_t>(), starts.size(), pg->st.as<uint32_t>());
-        DB200_LAUNCHED();
-    }
-    // work items: every genome is cut into equal chunks of ~1 Mbase (at least ~16 items per SM overall); items are
-    // ordered chunk-major so that by the time chunk c+1 of a genome starts, chunk c has been merged into HBM and
-    // seeds the staged registers (fewer updates).
-    std::vector<SketchItem> items;
-    {
-        const uint64_t target_items = (uint64_t)g_num_sms(device) * 16;
-        uint64_t chunk = T / std::max<uint64_t>(target_items, 1);
-        chunk = std::min<uint64_t>(std::max<uint64_t>(chunk, 1ull << 16), 1ull << 20);
-        std::vector<std::pair<uint32_t, SketchItem>> tmp;
-        for (uint64_t g = 0; g < ngenomes; ++g) {
-            const uint64_t gs = rec_offsets[genome_rec_begin[g]] - base0, ge = rec_offsets[genome_rec_begin[g + 1]] - base0;
-            if (ge <= gs) continue;
-            const uint64_t nch = (ge - gs + chunk - 1) / chunk;
-            const uint64_t step = (((ge - gs + nch - 1) / nch) + 63) & ~63ull;
-            uint32_t ci = 0;
-            for (uint64_t s = gs; s < ge; s += step, ++ci) tmp.push_back({ci, SketchItem{s, std::min(ge, s + step), (uint32_t)g, 0}});
-        }
-        std::stable_sort(tmp.begin(), tmp.end(), [](const auto &a, const auto &b) { return a.first < b.first; });
-        items.reserve(tmp.size());
-        for (auto &t : tmp) items.push_back(t.second);
-    }
-    pg->nitems = (uint32_t)items.size();
-    if (!items.empty()) {
-        DB200_TRY(pg->items.reserve(items.size() * sizeof(SketchItem)));
-        DB200_CUDA(cudaMemcpyAsync(pg->items.ptr, items.data(), items.size() * sizeof(SketchItem), cudaMemcpyHostToDevice, stream));
-    }
     const cudaError_t e = cudaStreamSynchronize(stream);  // the host vectors above go out of scope
     if (e != cudaSuccess) { set_error("pack_genomes: %s", cudaGetErrorString(e)); return DB200_ECUDA; }
     return DB200_OK;
 }
 
-static int sketch_packed_impl(const db200_packed_genomes *pg, int p, int canon, uint8_t *d_regs, cudaStream_t stream) {
-    if (p < 7 || p > 24) { set_error("sketch: p=%d outside the GPU path's range [7,24]", p); return DB200_EUNSUPPORTED; }
-    if (pg->k < 1 || pg->k > 32) { set_error("sketch: k=%d outside [1,32]", pg->k); return DB200_EUNSUPPORTED; }
+static int sketch_launch(const db200_packed_genomes *pg, int p, int canon, uint8_t *d_regs, cudaStream_t stream, uint32_t item_begin,
+                         uint32_t item_count, int counter_idx) {
     const uint64_t m = 1ull << p;
-    DB200_CUDA(cudaMemsetAsync(d_regs, 0, pg->ngenomes * m, stream));
-    if (pg->nitems == 0) return DB200_OK;
-    DB200_CUDA(cudaMemsetAsync(pg->counter.ptr, 0, 4, stream));
     const int mode = (m * 4 <= (128u << 10)) ? 0 : (m <= (128u << 10)) ? 1 : 2;
     const size_t smem = mode == 0 ? m * 4 : mode == 1 ? m : 0;
     const int k = pg->k, kclass = k <= 16 ? 0 : (k < 32 ? 1 : 2), rcshift = 2 * (k - 1);
@@ -201,10 +241,10 @@ static int sketch_packed_impl(const db200_packed_genomes *pg, int p, int canon, 
         auto kern = sketch_kernel<MODE, KC, CANON>;                                                                           \
         if (smem) DB200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 << 10));             \
         DB200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, SK_THREADS, smem));                              \
-        const unsigned grid = (unsigned)std::min<uint64_t>(pg->nitems, (uint64_t)sms * std::max(occ, 1));                     \
+        const unsigned grid = (unsigned)std::min<uint64_t>(item_count, (uint64_t)sms * std::max(occ, 1));                     \
         kern<<<grid, SK_THREADS, smem, stream>>>(pg->bases2.as<uint4>(), pg->nb.as<uint64_t>(), pg->st.as<uint64_t>(),        \
-                                                 pg->items.as<SketchItem>(), pg->nitems, pg->nblk - 1, k, p, d_regs,          \
-                                                 pg->counter.as<uint32_t>(), kc);                                             \
+                                                 pg->items.as<SketchItem>() + item_begin, item_count, pg->nblk - 1, k, p, d_regs, \
+                                                 pg->counter.as<uint32_t>() + counter_idx, kc);                               \
     } while (0)
 #define DB200_SKETCH_KC(MODE, CANON)                                        \
     do {                                                                    \
@@ -226,6 +266,15 @@ static int sketch_packed_impl(const db200_packed_genomes *pg, int p, int canon, 
     DB200_LAUNCHED();
     DB200_CUDA(cudaGetLastError());
     return DB200_OK;
+}
+
+static int sketch_packed_impl(const db200_packed_genomes *pg, int p, int canon, uint8_t *d_regs, cudaStream_t stream) {
+    if (p < 7 || p > 24) { set_error("sketch: p=%d outside the GPU path's range [7,24]", p); return DB200_EUNSUPPORTED; }
+    if (pg->k < 1 || pg->k > 32) { set_error("sketch: k=%d outside [1,32]", pg->k); return DB200_EUNSUPPORTED; }
+    DB200_CUDA(cudaMemsetAsync(d_regs, 0, pg->ngenomes << p, stream));
+    if (pg->nitems == 0) return DB200_OK;
+    DB200_CUDA(cudaMemsetAsync(pg->counter.ptr, 0, 64, stream));
+    return sketch_launch(pg, p, canon, d_regs, stream, 0, pg->nitems, 0);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -544,10 +593,11 @@ int db200_sketch_batch(int device, int p, int k, int canon, const char *bases, c
     std::lock_guard<std::mutex> lk(hc.mu);
     DB200_TRY(hc.init(device));
     db200_packed_genomes *pg = hc.store.get();   // device buffers persist across calls
-    DB200_TRY(pack_genomes_impl(device, bases, rec_offsets, nrecords, genome_rec_begin, ngenomes, k, pg, hc.up, hc.stream));
     const uint64_t bytes = ngenomes << p;
     DB200_TRY(hc.regs.reserve(std::max<uint64_t>(bytes, 16)));
-    DB200_TRY(sketch_packed_impl(pg, p, canon, hc.regs.as<uint8_t>(), hc.stream));
+    DB200_TRY(hc.up.init());
+    const PipelinedSketch ps{p, canon, hc.regs.as<uint8_t>()};   // each genome group is sketched while the next ones upload
+    DB200_TRY(pack_genomes_impl(device, bases, rec_offsets, nrecords, genome_rec_begin, ngenomes, k, pg, hc.up, hc.stream, &ps));
     DB200_CUDA(cudaMemcpyAsync(registers_out, hc.regs.ptr, bytes, cudaMemcpyDeviceToHost, hc.stream));
     DB200_CUDA(cudaStreamSynchronize(hc.stream));
     return DB200_OK;
