@@ -322,7 +322,7 @@ namespace db200 {
 
 static int plan_prepare(db200_dist_plan *pl, const uint8_t *d_regs, uint64_t nrows, uint64_t n1, uint64_t qbase, uint64_t n2, int p,
                         int estim, cudaStream_t stream) {
-    if (p < 7 || p > 16) { set_error("dist: p=%d outside the GPU path's range [7,16]", p); return DB200_EUNSUPPORTED; }
+    if (p < 7 || p > 20) { set_error("dist: p=%d outside the GPU path's range [7,20]", p); return DB200_EUNSUPPORTED; }
     if (estim < 0 || estim > 2) { set_error("dist: unknown estimation method %d", estim); return DB200_EINVAL; }
     if (nrows == 0 || nrows > (1ull << 31) - 64) { set_error("dist: %llu sketches unsupported", (unsigned long long)nrows); return DB200_EINVAL; }
     PFN_encodeTiled enc = get_encode();
@@ -457,27 +457,40 @@ static int plan_run(db200_dist_plan *pl, const db200_dist_params *prm, int rect,
     a.ksinv = (double)(float)(1. / prm->k);  // const float ksinv = 1./k, src/sketch_and_cmp.h:797
     a.p = pl->p; a.gmin = pl->gmin; a.gmax = pl->gmax; a.K = pl->K;
     a.estim = prm->estim; a.rtype = prm->result_type; a.rect = rect; a.one = 1;
+    const bool wide = pl->p > 16;                  // threshold counts above 2^16: 32-bit count storage
+    const size_t gsz = wide ? 4 : 2;
     if (!joint) {
-        // shared memory: S stages of 8 KiB + K x 2 KiB threshold counts + barriers; aim for two CTAs per SM
-        const size_t gbytes = (size_t)(pl->K + 1) * DT * DT * 2;   // bins lo..hi of a tile: at most K + 1
+        // shared memory: S stages of 8 KiB + (K + 1) x 1024 counts + barriers; aim for two CTAs per SM
+        const size_t gbytes = (size_t)(pl->K + 1) * DT * DT * gsz;   // bins lo..hi of a tile: at most K + 1
         int S = 6;
         const size_t budget2 = 113 << 10, budget1 = 226 << 10;
+        if (gbytes + 4 * STAGE_BYTES + 1024 > budget1) { set_error("dist: %d live thresholds do not fit in shared memory at p=%d", pl->K, pl->p); return DB200_EUNSUPPORTED; }
         if (gbytes + (size_t)S * STAGE_BYTES + 1024 > budget2) S = (int)std::min<size_t>(12, (budget1 - gbytes - 1024) / STAGE_BYTES);
         if (S < 4) { set_error("dist: %d live thresholds do not fit in shared memory", pl->K); return DB200_EUNSUPPORTED; }   // stage buffers double as sparse-tail storage (29 KB)
         a.stages = S;
         const size_t smem = (size_t)S * STAGE_BYTES + gbytes + 2 * S * 8;
-        DB200_CUDA(cudaFuncSetAttribute(dist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 << 10));
-        dist_kernel<<<(unsigned)ntiles, DIST_THREADS, smem, stream>>>(pl->tmap, a);
+        if (wide) {
+            DB200_CUDA(cudaFuncSetAttribute(dist_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 << 10));
+            dist_kernel<uint32_t><<<(unsigned)ntiles, DIST_THREADS, smem, stream>>>(pl->tmap, a);
+        } else {
+            DB200_CUDA(cudaFuncSetAttribute(dist_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 << 10));
+            dist_kernel<uint16_t><<<(unsigned)ntiles, DIST_THREADS, smem, stream>>>(pl->tmap, a);
+        }
     } else {
-        const size_t gbytes = (size_t)3 * std::max(pl->K, 1) * JPAIRS * 2;
+        const size_t gbytes = (size_t)3 * std::max(pl->K, 1) * JPAIRS * gsz;
         const size_t budget1 = 226 << 10;
+        if (gbytes + 2 * JSTAGE_BYTES + 1024 > budget1) { set_error("dist (joint MLE): %d live thresholds do not fit in shared memory at p=%d", pl->K, pl->p); return DB200_EUNSUPPORTED; }
         const int S = (int)std::min<size_t>(6, (budget1 - gbytes - 1024) / JSTAGE_BYTES);   // stage buffers double as sparse-tail storage (22 KB)
-        if (S < 2) { set_error("dist (joint MLE): %d live thresholds do not fit in shared memory", pl->K); return DB200_EUNSUPPORTED; }
         a.stages = S;
         const size_t smem = (size_t)S * JSTAGE_BYTES + gbytes + 2 * S * 8;
         const int lhs_is_b = rect ? 1 : (prm->order == DB200_ORDER_COL_FIRST ? 1 : 0);
-        DB200_CUDA(cudaFuncSetAttribute(dist_jmle_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 << 10));
-        dist_jmle_kernel<<<(unsigned)ntiles, DIST_THREADS, smem, stream>>>(pl->tmap16, pl->tmap, a, lhs_is_b);
+        if (wide) {
+            DB200_CUDA(cudaFuncSetAttribute(dist_jmle_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 << 10));
+            dist_jmle_kernel<uint32_t><<<(unsigned)ntiles, DIST_THREADS, smem, stream>>>(pl->tmap16, pl->tmap, a, lhs_is_b);
+        } else {
+            DB200_CUDA(cudaFuncSetAttribute(dist_jmle_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 << 10));
+            dist_jmle_kernel<uint16_t><<<(unsigned)ntiles, DIST_THREADS, smem, stream>>>(pl->tmap16, pl->tmap, a, lhs_is_b);
+        }
     }
     DB200_LAUNCHED();
     DB200_CUDA(cudaGetLastError());
@@ -738,7 +751,7 @@ int db200_dist_symmetric_rows(int device, const uint8_t *regs, uint64_t n, const
     auto tri = [n](uint64_t r) { return (r * (2 * n - r - 1)) / 2; };
     const uint64_t npairs = tri(row_end) - tri(row_begin);
     if (npairs && !out) { set_error("null output"); return DB200_EINVAL; }
-    if (prm->p < 7 || prm->p > 16) { set_error("dist: p=%d outside the GPU path's range [7,16]", prm->p); return DB200_EUNSUPPORTED; }
+    if (prm->p < 7 || prm->p > 20) { set_error("dist: p=%d outside the GPU path's range [7,20]", prm->p); return DB200_EUNSUPPORTED; }
     DB200_TRY(hc.regs.reserve(n * m));
     DB200_TRY(hc.out.reserve(std::max<uint64_t>(npairs, 1) * 4));
     DB200_CUDA(cudaMemcpyAsync(hc.regs.ptr, regs, n * m, cudaMemcpyHostToDevice, hc.stream));
@@ -776,7 +789,7 @@ int db200_dist_rect(int device, const uint8_t *ref_regs, uint64_t nr, const uint
     if (!prm || ((!ref_regs || !qry_regs || !out) && nr && nq)) { set_error("db200_dist_rect: null argument"); return DB200_EINVAL; }
     DB200_TRY(check_device(device));
     if (nr == 0 || nq == 0) return DB200_OK;
-    if (prm->p < 7 || prm->p > 16) { set_error("dist: p=%d outside the GPU path's range [7,16]", prm->p); return DB200_EUNSUPPORTED; }
+    if (prm->p < 7 || prm->p > 20) { set_error("dist: p=%d outside the GPU path's range [7,20]", prm->p); return DB200_EUNSUPPORTED; }
     HostCtx &hc = host_ctx(device);
     std::lock_guard<std::mutex> lk(hc.mu);
     DB200_TRY(hc.init(device));

@@ -260,8 +260,9 @@ struct DistArgs {
 };
 
 // Pair histogram accessor over the tile's threshold counts in shared memory (uint16, see wrap rule).
+template <typename GT>
 struct PairCounts {
-    const uint16_t *g;   // &G[0][pair]
+    const GT *g;         // &G[0][pair]
     uint32_t m;
     int lo, hi;          // tile value range: thresholds lo+1..hi are stored
     int kmax_pair;       // upper bound on the histogram's largest value (for the 2^16 wrap rule)
@@ -272,16 +273,17 @@ struct PairCounts {
         if (k <= lo) return m;
         if (k > hi) return 0u;
         const uint32_t v = g[(k - lo - 1) * stride];
-        // counts are stored mod 2^16; 0 inside the pair's live range can only mean 2^16 (p == 16)
-        return (v == 0u && k <= kmax_pair) ? m : v;
+        // uint16 counts are stored mod 2^16; 0 inside the pair's live range can only mean 2^16 (p == 16)
+        return (sizeof(GT) == 2 && v == 0u && k <= kmax_pair) ? m : v;
     }
     __device__ __forceinline__ uint32_t operator()(int k) const { return G(k) - G(k + 1); }
 };
 
 // Pair histogram with the bin counts themselves in shared memory (dist_kernel converts its threshold counts in place
 // before the estimator runs: one LDS per bin instead of two plus range logic).  Slot s holds bin lo + s, s = 0..hi-lo.
+template <typename GT>
 struct PairHist {
-    const uint16_t *c;   // &C[0][pair]
+    const GT *c;         // &C[0][pair]
     uint32_t m;
     int lo, hi;
     int fullk;           // bin holding all 2^16 registers (stored as 0), or -1
@@ -308,13 +310,15 @@ __device__ __forceinline__ double fast_div(double a, double b) {
 
 struct NewtonDiv { __device__ __forceinline__ static double div(double a, double b) { return fast_div(a, b); } };
 
+// GT: uint16_t for p <= 16 (two CTAs per SM), uint32_t above (counts no longer fit 16 bits)
+template <typename GT>
 __global__ void __launch_bounds__(DIST_THREADS, 2) dist_kernel(const __grid_constant__ CUtensorMap tmap, const DistArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int S = a.stages;
     uint8_t *stage_mem = smem;                                             // S x {A box, B box}
-    uint16_t *G = reinterpret_cast<uint16_t *>(smem + (size_t)S * STAGE_BYTES);  // [K][1024]
+    GT *G = reinterpret_cast<GT *>(smem + (size_t)S * STAGE_BYTES);  // [K + 1][1024]
     const int Kcap = a.K + 1;   // slots for bins lo .. hi of the tile (slot 0 is filled when counts become bins)
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)S * STAGE_BYTES + (size_t)Kcap * DT * DT * 2);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)S * STAGE_BYTES + (size_t)Kcap * DT * DT * sizeof(GT));
     const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + S);
 
     const DistTile tile = a.tiles[blockIdx.x];
@@ -432,11 +436,11 @@ __global__ void __launch_bounds__(DIST_THREADS, 2) dist_kernel(const __grid_cons
             if (++s == S) { s = 0; ph ^= 1u; }
             if (++wb == nbox) {
                 wb = 0;
-                uint16_t *g = G + (size_t)(tl++) * (DT * DT);
-                g[ti * DT + tj] = (uint16_t)(acc00 + __popc(o00) + 2 * __popc(t00) + 4 * __popc(f00));
-                g[ti * DT + tj + 16] = (uint16_t)(acc01 + __popc(o01) + 2 * __popc(t01) + 4 * __popc(f01));
-                g[(ti + 16) * DT + tj] = (uint16_t)(acc10 + __popc(o10) + 2 * __popc(t10) + 4 * __popc(f10));
-                g[(ti + 16) * DT + tj + 16] = (uint16_t)(acc11 + __popc(o11) + 2 * __popc(t11) + 4 * __popc(f11));
+                GT *g = G + (size_t)(tl++) * (DT * DT);
+                g[ti * DT + tj] = (GT)(acc00 + __popc(o00) + 2 * __popc(t00) + 4 * __popc(f00));
+                g[ti * DT + tj + 16] = (GT)(acc01 + __popc(o01) + 2 * __popc(t01) + 4 * __popc(f01));
+                g[(ti + 16) * DT + tj] = (GT)(acc10 + __popc(o10) + 2 * __popc(t10) + 4 * __popc(f10));
+                g[(ti + 16) * DT + tj + 16] = (GT)(acc11 + __popc(o11) + 2 * __popc(t11) + 4 * __popc(f11));
                 acc00 = acc01 = acc10 = acc11 = 0;
                 o00 = o01 = o10 = o11 = t00 = t01 = t10 = t11 = f00 = f01 = f10 = f11 = 0;
             }
@@ -488,9 +492,9 @@ __global__ void __launch_bounds__(DIST_THREADS, 2) dist_kernel(const __grid_cons
             oidx = (i * (2 * a.n - i - 1)) / 2 - a.out_base + (j - i - 1);
         }
         if (ns > 0) {
-            uint16_t *g = G + (size_t)(Td - lo) * (DT * DT) + pair;
+            GT *g = G + (size_t)(Td - lo) * (DT * DT) + pair;
             const uint32_t *ca = CN + il * ns, *cb = CN + (DT + jl) * ns;
-            for (int kk = 0; kk < ns; ++kk) g[kk * (DT * DT)] = (uint16_t)(ca[kk] + cb[kk]);
+            for (int kk = 0; kk < ns; ++kk) g[kk * (DT * DT)] = (GT)(ca[kk] + cb[kk]);
             // merge the two index-sorted tails; a register present in both with min value mn was counted twice for k <= mn
             const uint32_t *la = L + il * SPARSE_C, *lb = L + (DT + jl) * SPARSE_C;
             int ia = 0, ib = 0;
@@ -510,22 +514,22 @@ __global__ void __launch_bounds__(DIST_THREADS, 2) dist_kernel(const __grid_cons
         // threshold counts G(k) (slots 1..hi-lo) -> bin counts c(k) = G(k) - G(k+1) in place, slot 0 = bin lo
         int fullk = -1;
         {
-            uint16_t *col = G + pair;
+            GT *col = G + pair;
             uint32_t gk = m;                                    // G(lo) = 2^p
             for (int k = lo; k <= hi; ++k) {
                 uint32_t gn = 0u;                               // G(hi + 1) = 0
                 if (k < hi) {
                     gn = col[(k + 1 - lo) * (DT * DT)];
-                    if (gn == 0u && k + 1 <= kmax_pair) gn = m;  // counts are stored mod 2^16 (only p == 16 can wrap)
+                    if (sizeof(GT) == 2 && gn == 0u && k + 1 <= kmax_pair) gn = m;  // uint16 counts are stored mod 2^16 (only p == 16 can wrap)
                 }
                 const uint32_t ck = gk - gn;
-                if (ck > 0xFFFFu) fullk = k;
-                col[(k - lo) * (DT * DT)] = (uint16_t)ck;
+                if (sizeof(GT) == 2 && ck > 0xFFFFu) fullk = k;
+                col[(k - lo) * (DT * DT)] = (GT)ck;
                 gk = gn;
             }
         }
-        PairHist c{G + pair, m, lo, hi, fullk};
-        const double us = calculate_estimate<PairHist, NewtonDiv>(c, a.estim, a.p, kmin_pair, kmax_pair);
+        PairHist<GT> c{G + pair, m, lo, hi, fullk};
+        const double us = calculate_estimate<PairHist<GT>, NewtonDiv>(c, a.estim, a.p, kmin_pair, kmax_pair);
         // non-joint path is symmetric in its operands (IEEE addition commutes): lhs = A, rhs = B
         const double cl = a.card[i], cr = a.card[j];
         // jaccard_index, hll.h:1179-1182
@@ -555,15 +559,16 @@ constexpr int JBOX_A = JT * 128, JBOX_B = DT * 128;
 constexpr int JSTAGE_BYTES = 2 * (JBOX_A + JBOX_B);    // A_k, A_{k+1}, B_k, B_{k+1}
 constexpr int JPAIRS = JT * DT;
 
+template <typename GT>
 __global__ void __launch_bounds__(DIST_THREADS, 1) dist_jmle_kernel(const __grid_constant__ CUtensorMap tmapA,
                                                                     const __grid_constant__ CUtensorMap tmapB, const DistArgs a,
                                                                     const int lhs_is_b) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int S = a.stages;
     uint8_t *stage_mem = smem;
-    uint16_t *G = reinterpret_cast<uint16_t *>(smem + (size_t)S * JSTAGE_BYTES);  // [3][K][512]
+    GT *G = reinterpret_cast<GT *>(smem + (size_t)S * JSTAGE_BYTES);  // [3][K][512]
     const int Kcap = a.K > 0 ? a.K : 1;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)S * JSTAGE_BYTES + (size_t)3 * Kcap * JPAIRS * 2);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)S * JSTAGE_BYTES + (size_t)3 * Kcap * JPAIRS * sizeof(GT));
     const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + S);
 
     const DistTile tile = a.tiles[blockIdx.x];          // tile.a counts 16-row half panels
@@ -630,11 +635,11 @@ __global__ void __launch_bounds__(DIST_THREADS, 1) dist_jmle_kernel(const __grid
             if (++s == S) { s = 0; ph ^= 1u; }
             if (++wb == nbox) {
                 wb = 0;
-                uint16_t *gu = G + tl * JPAIRS, *gx = G + ((size_t)Kcap + tl) * JPAIRS, *gy = G + ((size_t)2 * Kcap + tl) * JPAIRS;
+                GT *gu = G + tl * JPAIRS, *gx = G + ((size_t)Kcap + tl) * JPAIRS, *gy = G + ((size_t)2 * Kcap + tl) * JPAIRS;
                 const uint32_t p0 = ti * DT + tj, p1 = p0 + 16;
-                gu[p0] = (uint16_t)u0; gu[p1] = (uint16_t)u1;
-                gx[p0] = (uint16_t)x0; gx[p1] = (uint16_t)x1;
-                gy[p0] = (uint16_t)y0; gy[p1] = (uint16_t)y1;
+                gu[p0] = (GT)u0; gu[p1] = (GT)u1;
+                gx[p0] = (GT)x0; gx[p1] = (GT)x1;
+                gy[p0] = (GT)y0; gy[p1] = (GT)y1;
                 u0 = u1 = x0 = x1 = y0 = y1 = 0;
                 ++tl;
             }
@@ -683,13 +688,13 @@ __global__ void __launch_bounds__(DIST_THREADS, 1) dist_jmle_kernel(const __grid
             // G_U(k) = #a(k) + #b(k)   - #{a_i >= k,   b_i >= k  }
             // G_X(k) = #a(k) + #b(k+1) - #{a_i >= k,   b_i >= k+1}      (histogram of max(a, b-1))
             // G_Y(k) = #a(k+1) + #b(k) - #{a_i >= k+1, b_i >= k  }      (histogram of max(a-1, b))
-            uint16_t *gu = G + (size_t)(Td - lo - 1) * JPAIRS + pair;
-            uint16_t *gx = gu + (size_t)Kcap * JPAIRS, *gy = gx + (size_t)Kcap * JPAIRS;
+            GT *gu = G + (size_t)(Td - lo - 1) * JPAIRS + pair;
+            GT *gx = gu + (size_t)Kcap * JPAIRS, *gy = gx + (size_t)Kcap * JPAIRS;
             const uint32_t *ca = CN + il * (ns + 1), *cb = CN + (JT + jl) * (ns + 1);
             for (int kk = 0; kk < ns; ++kk) {
-                gu[kk * JPAIRS] = (uint16_t)(ca[kk] + cb[kk]);
-                gx[kk * JPAIRS] = (uint16_t)(ca[kk] + cb[kk + 1]);
-                gy[kk * JPAIRS] = (uint16_t)(ca[kk + 1] + cb[kk]);
+                gu[kk * JPAIRS] = (GT)(ca[kk] + cb[kk]);
+                gx[kk * JPAIRS] = (GT)(ca[kk] + cb[kk + 1]);
+                gy[kk * JPAIRS] = (GT)(ca[kk + 1] + cb[kk]);
             }
             const uint32_t *la = L + il * SPARSE_C, *lb = L + (JT + jl) * SPARSE_C;
             int ia = 0, ib = 0;
@@ -708,11 +713,11 @@ __global__ void __launch_bounds__(DIST_THREADS, 1) dist_jmle_kernel(const __grid
         }
         const int amin = a.smin[i], amax = a.smax[i], bmin = a.smin[j], bmax = a.smax[j];
         // union histogram -> cABX (always the MLE, hll.h:658)
-        PairCounts cu{G + pair, m, lo, hi, max(amax, bmax), JPAIRS, 64};
+        PairCounts<GT> cu{G + pair, m, lo, hi, max(amax, bmax), JPAIRS, 64};
         const double cABX = ertl_mle(cu, a.p, q, max(amin, bmin), max(amax, bmax));
         // tile families: X = max(A, B-1), Y = max(A-1, B); bins above q-1 fold into bin q (hll.h:660-674)
-        PairCounts cx{G + (size_t)Kcap * JPAIRS + pair, m, lo, hi, max(amax, bmax - 1), JPAIRS, q};
-        PairCounts cy{G + (size_t)2 * Kcap * JPAIRS + pair, m, lo, hi, max(amax - 1, bmax), JPAIRS, q};
+        PairCounts<GT> cx{G + (size_t)Kcap * JPAIRS + pair, m, lo, hi, max(amax, bmax - 1), JPAIRS, q};
+        PairCounts<GT> cy{G + (size_t)2 * Kcap * JPAIRS + pair, m, lo, hi, max(amax - 1, bmax), JPAIRS, q};
         const double eX = ertl_mle(cx, a.p, q - 1, max(amin, bmin - 1) < 0 ? 0 : max(amin, bmin - 1), max(amax, bmax - 1));
         const double eY = ertl_mle(cy, a.p, q - 1, max(amin - 1, bmin) < 0 ? 0 : max(amin - 1, bmin), max(amax - 1, bmax));
         // lhs / rhs of result_cmp: lhs = A (row sketch) unless lhs_is_b

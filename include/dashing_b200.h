@@ -72,7 +72,7 @@ enum db200_emission {
 enum db200_order { DB200_ORDER_ROW_FIRST = 0 /* cmp(s[i], s[j]) */, DB200_ORDER_COL_FIRST = 1 /* cmp(s[j], s[i]) */ };
 
 typedef struct db200_dist_params {
-    int32_t p;           /* log2 registers per sketch; GPU path: 7 <= p <= 16 */
+    int32_t p;           /* log2 registers per sketch; GPU path: 7 <= p <= 20 */
     int32_t k;           /* k-mer length (only enters Mash/containment distances through ksinv = (float)(1./k)) */
     int32_t estim;       /* enum db200_estim: estimator behind creport() and the union estimate */
     int32_t jestim;      /* DB200_ERTL_JOINT_MLE or anything else for the union path */
