@@ -464,10 +464,10 @@ static int plan_run(db200_dist_plan *pl, const db200_dist_params *prm, int rect,
         const size_t gbytes = (size_t)(pl->K + 1) * DT * DT * gsz;   // bins lo..hi of a tile: at most K + 1
         int S = 6;
         const size_t budget2 = 113 << 10, budget1 = 226 << 10;
-        if (gbytes + 4 * STAGE_BYTES + 1024 > budget1) { set_error("dist: %d live thresholds do not fit in shared memory at p=%d", pl->K, pl->p); return DB200_EUNSUPPORTED; }
+        if (gbytes + 2 * STAGE_BYTES + 1024 > budget1) { set_error("dist: %d live thresholds do not fit in shared memory at p=%d", pl->K, pl->p); return DB200_EUNSUPPORTED; }
         if (gbytes + (size_t)S * STAGE_BYTES + 1024 > budget2) S = (int)std::min<size_t>(12, (budget1 - gbytes - 1024) / STAGE_BYTES);
-        if (S < 4) { set_error("dist: %d live thresholds do not fit in shared memory", pl->K); return DB200_EUNSUPPORTED; }   // stage buffers double as sparse-tail storage (29 KB)
         a.stages = S;
+        a.sparse = S >= 4;   // the stage buffers double as sparse-tail storage (29 KB); with fewer stages every threshold is dense
         const size_t smem = (size_t)S * STAGE_BYTES + gbytes + 2 * S * 8;
         if (wide) {
             DB200_CUDA(cudaFuncSetAttribute(dist_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 << 10));
@@ -482,6 +482,7 @@ static int plan_run(db200_dist_plan *pl, const db200_dist_params *prm, int rect,
         if (gbytes + 2 * JSTAGE_BYTES + 1024 > budget1) { set_error("dist (joint MLE): %d live thresholds do not fit in shared memory at p=%d", pl->K, pl->p); return DB200_EUNSUPPORTED; }
         const int S = (int)std::min<size_t>(6, (budget1 - gbytes - 1024) / JSTAGE_BYTES);   // stage buffers double as sparse-tail storage (22 KB)
         a.stages = S;
+        a.sparse = 1;      // 2 joint stages (24 KB) already hold the 22 KB of staged tails
         const size_t smem = (size_t)S * JSTAGE_BYTES + gbytes + 2 * S * 8;
         const int lhs_is_b = rect ? 1 : (prm->order == DB200_ORDER_COL_FIRST ? 1 : 0);
         if (wide) {

@@ -256,6 +256,7 @@ struct DistArgs {
     int estim, rtype;
     int rect;                         // 0 symmetric, 1 rectangular (A = queries, B = references)
     int stages;
+    int sparse;                       // 0: shared memory too tight to stage the sparse tails -> every live threshold is swept densely
     int one;                          // 1 — a runtime value so that ptxas keeps `popc * one + acc` as an IMAD (FMA pipe)
 };
 
@@ -330,7 +331,7 @@ __global__ void __launch_bounds__(DIST_THREADS, 2) dist_kernel(const __grid_cons
     // Thresholds lo+1 .. Td-1 are counted densely from the bit-planes.  From Td on every sketch of the tile has at most
     // SPARSE_C registers at or above the threshold, and G(k) = #a(k) + #b(k) - #{i : a_i >= k and b_i >= k} is obtained by
     // merging the two sorted sparse tails — no plane traffic, no POPC.
-    const int Tt = (int)max(a.pthr[panA], a.pthr[panB]);
+    const int Tt = a.sparse ? (int)max(a.pthr[panA], a.pthr[panB]) : 255;
     const int Td = min(max(Tt, lo + 1), hi + 1);
     const int W = max(1 << (a.p - 5), 32), nbox = W >> 5;
     const int iters = (Td - 1 - lo) * nbox;
@@ -578,7 +579,7 @@ __global__ void __launch_bounds__(DIST_THREADS, 1) dist_jmle_kernel(const __grid
     const int lo = (int)min(a.pmin[panA], a.pmin[panB]);
     const int hi = (int)max(a.pmax[panA], a.pmax[panB]);
     // dense thresholds lo+1 .. Td-1 from the planes, sparse thresholds Td .. hi from the merged tails (see dist_kernel)
-    const int Tt = (int)max(a.pthr[panA], a.pthr[panB]);
+    const int Tt = a.sparse ? (int)max(a.pthr[panA], a.pthr[panB]) : 255;
     const int Td = min(max(Tt, lo + 1), hi + 1);
     const int W = max(1 << (a.p - 5), 32), nbox = W >> 5;
     const int iters = (Td - 1 - lo) * nbox;
