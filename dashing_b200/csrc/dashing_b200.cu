@@ -309,7 +309,7 @@ struct db200_dist_plan {
     bool ready = false;
     CUtensorMap tmap, tmap16;   // boxes of 32 / 16 sketches
     static constexpr int NSLOT = 4;   // independent tile lists, so that row blocks of one request can be in flight together
-    db200::DevBuf planes, counts, card, smin, smax, pmin, pmax, minmax, lists, sthr, pthr;
+    db200::DevBuf planes, counts, card, smin, smax, pmin, pmax, minmax, lists, sthr, pthr, llists, ptl;
     db200::DevBuf tiles[NSLOT];
     std::vector<db200::DistTile> host_tiles[NSLOT];
     // tile-list cache key
@@ -360,6 +360,9 @@ static int plan_prepare(db200_dist_plan *pl, const uint8_t *d_regs, uint64_t nro
     DB200_TRY(pl->lists.reserve(nrows * SPARSE_C * 4));
     DB200_TRY(pl->sthr.reserve(nrows));
     DB200_CUDA(cudaMemsetAsync(pl->pthr.ptr, 0, npan * 4, stream));
+    DB200_TRY(pl->ptl.reserve(npan * 4));
+    DB200_TRY(pl->llists.reserve(nrows * SPARSE_C * 4));
+    DB200_CUDA(cudaMemsetAsync(pl->ptl.ptr, 0xFF, npan * 4, stream));
     DB200_CUDA(cudaMemsetAsync(pl->pmin.ptr, 0xFF, npan * 4, stream));
     DB200_CUDA(cudaMemsetAsync(pl->pmax.ptr, 0, npan * 4, stream));
     if (n1 + n2 != nrows || pl->K == 0) {  // padding rows (or the K==0 dummy plane) must read as "below every threshold"
@@ -368,6 +371,7 @@ static int plan_prepare(db200_dist_plan *pl, const uint8_t *d_regs, uint64_t nro
         DB200_CUDA(cudaMemsetAsync(pl->smax.ptr, 0, nrows, stream));
         DB200_CUDA(cudaMemsetAsync(pl->card.ptr, 0, nrows * 8, stream));
         DB200_CUDA(cudaMemsetAsync(pl->lists.ptr, 0, nrows * SPARSE_C * 4, stream));
+        DB200_CUDA(cudaMemsetAsync(pl->llists.ptr, 0, nrows * SPARSE_C * 4, stream));
     }
     DB200_CUDA(cudaMemsetAsync(pl->counts.ptr, 0, nrows * 64 * 4, stream));
     for (int seg = 0; seg < 2; ++seg) {
@@ -376,7 +380,8 @@ static int plan_prepare(db200_dist_plan *pl, const uint8_t *d_regs, uint64_t nro
         if (pl->K > 0) {
             planes_kernel<<<(unsigned)cnt, 128, 0, stream>>>(reinterpret_cast<const uint32_t *>(d_regs), nrows, r0, p, pl->gmin, pl->K,
                                                             pl->planes.as<uint32_t>(), pl->counts.as<uint32_t>(), pl->lists.as<uint32_t>(),
-                                                            pl->sthr.as<uint8_t>(), pl->pthr.as<uint32_t>());
+                                                            pl->sthr.as<uint8_t>(), pl->pthr.as<uint32_t>(), pl->llists.as<uint32_t>(),
+                                                            pl->ptl.as<uint32_t>());
             DB200_LAUNCHED();
         }
         card_kernel<<<(unsigned)((cnt + 127) / 128), 128, 0, stream>>>(pl->counts.as<uint32_t>(), r0, cnt, p, pl->gmin, pl->gmax, estim,
@@ -450,6 +455,7 @@ static int plan_run(db200_dist_plan *pl, const db200_dist_params *prm, int rect,
     a.pmin = pl->pmin.as<uint32_t>(); a.pmax = pl->pmax.as<uint32_t>();
     a.card = pl->card.as<double>();
     a.counts = pl->counts.as<uint32_t>(); a.lists = pl->lists.as<uint32_t>(); a.pthr = pl->pthr.as<uint32_t>();
+    a.llists = pl->llists.as<uint32_t>(); a.ptl = pl->ptl.as<uint32_t>(); a.low = 0;
     a.out = d_out;
     a.n = pl->nrows; a.row_begin = rb; a.row_end = re;
     a.out_base = rect ? 0 : (rb * (2 * pl->nrows - rb - 1)) / 2;
@@ -468,6 +474,7 @@ static int plan_run(db200_dist_plan *pl, const db200_dist_params *prm, int rect,
         if (gbytes + (size_t)S * STAGE_BYTES + 1024 > budget2) S = (int)std::min<size_t>(12, (budget1 - gbytes - 1024) / STAGE_BYTES);
         a.stages = S;
         a.sparse = S >= 4;   // the stage buffers double as sparse-tail storage (29 KB); with fewer stages every threshold is dense
+        a.low = S >= 6;      // ... plus 16 KB for the low tails
         const size_t smem = (size_t)S * STAGE_BYTES + gbytes + 2 * S * 8;
         if (wide) {
             DB200_CUDA(cudaFuncSetAttribute(dist_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 << 10));

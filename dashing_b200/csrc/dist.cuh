@@ -61,9 +61,10 @@ __global__ void __launch_bounds__(256) range_kernel(const uint4 *__restrict__ re
 __global__ void __launch_bounds__(128) planes_kernel(const uint32_t *__restrict__ regs32, uint64_t n, uint64_t row0, int p, int gmin, int K,
                                                      uint32_t *__restrict__ planes, uint32_t *__restrict__ counts /*[n][64]*/,
                                                      uint32_t *__restrict__ lists /*[n][SPARSE_C]*/, uint8_t *__restrict__ sthr,
-                                                     uint32_t *__restrict__ pthr) {
+                                                     uint32_t *__restrict__ pthr, uint32_t *__restrict__ llists /*[n][SPARSE_C]*/,
+                                                     uint32_t *__restrict__ ptl) {
     __shared__ uint32_t cnt[64];
-    __shared__ int s_T;
+    __shared__ int s_T, s_TL;
     const uint64_t s = row0 + blockIdx.x;
     // plane rows are at least 32 words (one TMA box) wide: for p < 10 the tail is zero = "below every threshold"
     const uint32_t m = 1u << p, W = max(m >> 5, 32u), lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -104,6 +105,11 @@ __global__ void __launch_bounds__(128) planes_kernel(const uint32_t *__restrict_
         s_T = gmin + 1 + t;
         sthr[s] = (uint8_t)s_T;
         atomicMax(pthr + s / DT, (uint32_t)s_T);
+        // low tail: TL_s = largest threshold with <= SPARSE_C registers BELOW it (gmin if there is none)
+        t = 0;
+        while (t < K && m - cnt[t] <= (uint32_t)SPARSE_C) ++t;
+        s_TL = gmin + t;
+        atomicMin(ptl + s / DT, (uint32_t)s_TL);
     }
     __syncthreads();
     if (warp == 0) {
@@ -127,6 +133,33 @@ __global__ void __launch_bounds__(128) planes_kernel(const uint32_t *__restrict_
             for (int j = 0; j < 4; ++j)
                 if ((ge >> (8 * j)) & 1u) {
                     if (pos < (uint32_t)SPARSE_C) dst[pos] = (((w0 + lane) * 4 + j) << 8) | ((x >> (8 * j)) & 0xFFu);
+                    ++pos;
+                }
+            total += __shfl_sync(0xFFFFFFFFu, incl, 31);
+        }
+        for (uint32_t i = total + lane; i < (uint32_t)SPARSE_C; i += 32) dst[i] = 0u;
+    } else if (warp == 1) {
+        // the registers < TL_s as (index << 8 | value + 1) — never zero —, index order, zero padded (<= SPARSE_C of them)
+        const uint32_t T4 = (uint32_t)s_TL * 0x01010101u;
+        uint32_t *dst = llists + s * SPARSE_C;
+        uint32_t total = 0;
+        for (uint32_t w0 = 0; w0 < nwords; w0 += 32) {
+            const bool in = w0 + lane < nwords;
+            const uint32_t x = in ? __ldg(src + w0 + lane) : 0xFFFFFFFFu;
+            const uint32_t lt = __vcmpltu4(x, T4) & 0x01010101u;
+            if (!__any_sync(0xFFFFFFFFu, lt != 0u)) continue;
+            const uint32_t c = (uint32_t)__popc(lt);
+            uint32_t incl = c;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+                if (lane >= (uint32_t)off) incl += v;
+            }
+            uint32_t pos = total + incl - c;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if ((lt >> (8 * j)) & 1u) {
+                    if (pos < (uint32_t)SPARSE_C) dst[pos] = (((w0 + lane) * 4 + j) << 8) | (((x >> (8 * j)) & 0xFFu) + 1u);
                     ++pos;
                 }
             total += __shfl_sync(0xFFFFFFFFu, incl, 31);
@@ -246,6 +279,8 @@ struct DistArgs {
     const uint32_t *counts;           // per sketch threshold counts [n][64]
     const uint32_t *lists;            // per sketch sparse tail [n][SPARSE_C]
     const uint32_t *pthr;             // per panel: max over its sketches of the sparse-tail threshold T_s
+    const uint32_t *llists;           // per sketch low tail [n][SPARSE_C]: registers below TL_s
+    const uint32_t *ptl;              // per panel: min over its sketches of TL_s
     float *out;
     uint64_t n;                       // sketches in the plane tensor
     uint64_t row_begin, row_end;      // symmetric: rows computed; rect: unused
@@ -256,6 +291,7 @@ struct DistArgs {
     int estim, rtype;
     int rect;                         // 0 symmetric, 1 rectangular (A = queries, B = references)
     int stages;
+    int low;                          // 1: low tails are staged too (needs 45 KB of stage buffers)
     int sparse;                       // 0: shared memory too tight to stage the sparse tails -> every live threshold is swept densely
     int one;                          // 1 — a runtime value so that ptxas keeps `popc * one + acc` as an IMAD (FMA pipe)
 };
@@ -333,8 +369,12 @@ __global__ void __launch_bounds__(DIST_THREADS, 2) dist_kernel(const __grid_cons
     // merging the two sorted sparse tails — no plane traffic, no POPC.
     const int Tt = a.sparse ? (int)max(a.pthr[panA], a.pthr[panB]) : 255;
     const int Td = min(max(Tt, lo + 1), hi + 1);
+    // Symmetrically, for the lowest thresholds almost every register is at or above k: while every sketch of the tile has at
+    // most SPARSE_C registers below k (k <= TLe), G(k) = 2^p - #{i : a_i < k and b_i < k} comes from merging the low tails.
+    const int TLe = (a.sparse && a.low) ? min((int)min(a.ptl[panA], a.ptl[panB]), Td - 1) : lo;
+    const int kd0 = max(lo, TLe) + 1;                      // first densely swept threshold
     const int W = max(1 << (a.p - 5), 32), nbox = W >> 5;
-    const int iters = (Td - 1 - lo) * nbox;
+    const int iters = max(Td - kd0, 0) * nbox;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, DIST_CONSUMERS / 32); }
@@ -347,7 +387,7 @@ __global__ void __launch_bounds__(DIST_THREADS, 2) dist_kernel(const __grid_cons
         // ---------------- TMA producer ----------------
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
-            int s = 0, t = lo - a.gmin, wb = 0;
+            int s = 0, t = kd0 - a.gmin - 1, wb = 0;
             uint32_t ph = 0;
             for (int it = 0; it < iters; ++it) {
                 mbar_wait_relaxed(empty0 + 8 * s, ph ^ 1u);
@@ -399,7 +439,7 @@ __global__ void __launch_bounds__(DIST_THREADS, 2) dist_kernel(const __grid_cons
         acc = (uint32_t)__popc(p.w | q.w) * one + acc;                           \
     } while (0)
         const uint32_t one = (uint32_t)a.one, eight = one << 3;
-        int s = 0, wb = 0, tl = 1;      // threshold lo + tl -> slot tl
+        int s = 0, wb = 0, tl = kd0 - lo;      // threshold lo + tl -> slot tl
         uint32_t ph = 0;
         for (int it = 0; it < iters; ++it) {
             mbar_wait(full0 + 8 * s, ph);
@@ -457,6 +497,15 @@ __global__ void __launch_bounds__(DIST_THREADS, 2) dist_kernel(const __grid_cons
     const int ns = hi - Td + 1;                                       // sparse thresholds Td..hi
     uint32_t *L = reinterpret_cast<uint32_t *>(stage_mem);             // [2*DT][SPARSE_C]
     uint32_t *CN = L + 2 * DT * SPARSE_C;                              // [2*DT][ns]: #{reg >= Td + kk}
+    uint32_t *LL = L + 2 * DT * (SPARSE_C + 52);                       // [2*DT][SPARSE_C] low tails (a.low only)
+    const int nl = kd0 - 1 - lo;                                       // low-sparse thresholds lo+1 .. kd0-1
+    if (nl > 0) {
+        for (uint32_t e = threadIdx.x; e < 2 * DT * SPARSE_C; e += DIST_THREADS) {
+            const uint32_t row = e / SPARSE_C;
+            const uint64_t sk = row < DT ? rowA0 + row : rowB0 + (row - DT);
+            LL[e] = sk < a.n ? a.llists[sk * SPARSE_C + (e % SPARSE_C)] : 0u;
+        }
+    }
     if (ns > 0) {
         // one warp per sketch: keep only the entries >= Td (Td >= the sketch's own T_s), order preserved, zero terminated
         static_assert(SPARSE_C == 64, "compaction below assumes two entries per lane");
@@ -491,6 +540,23 @@ __global__ void __launch_bounds__(DIST_THREADS, 2) dist_kernel(const __grid_cons
         } else {
             if (i >= j || j >= a.n || i < a.row_begin || i >= a.row_end) continue;
             oidx = (i * (2 * a.n - i - 1)) / 2 - a.out_base + (j - i - 1);
+        }
+        if (nl > 0) {
+            // thresholds lo+1 .. kd0-1: start from 2^p and take out the registers that are below k in both sketches
+            GT *g = G + (size_t)(DT * DT) + pair;                  // slot of threshold lo + 1
+            for (int kk = 0; kk < nl; ++kk) g[kk * (DT * DT)] = (GT)m;
+            const uint32_t *la = LL + il * SPARSE_C, *lb = LL + (DT + jl) * SPARSE_C;
+            int ia = 0, ib = 0;
+            uint32_t ea = la[0], eb = lb[0];
+            while (ea != 0u && eb != 0u) {
+                const uint32_t xa = ea >> 8, xb = eb >> 8;
+                if (xa == xb) {
+                    const int mx = (int)max(ea & 0xFFu, eb & 0xFFu) - 1;   // values are stored + 1
+                    for (int k = max(mx, lo) + 1; k < kd0; ++k) g[(k - lo - 1) * (DT * DT)] -= 1;
+                }
+                if (xa <= xb) ea = ++ia < SPARSE_C ? la[ia] : 0u;
+                if (xb <= xa) eb = ++ib < SPARSE_C ? lb[ib] : 0u;
+            }
         }
         if (ns > 0) {
             GT *g = G + (size_t)(Td - lo) * (DT * DT) + pair;
