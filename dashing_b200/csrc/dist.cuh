@@ -345,6 +345,27 @@ __device__ __forceinline__ double fast_div(double a, double b) {
     return fma(rem, r, q);
 }
 
+// Carry-save adder over three bit-vectors: h = majority (carry), l = parity (sum); two LOP3.
+#define DB200_CSA(h, l, a, b, c)                                        \
+    do {                                                                \
+        const uint32_t u__ = (a), v__ = (b), w__ = (c);                 \
+        asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(h) : "r"(u__), "r"(v__), "r"(w__)); /* majority */ \
+        asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(l) : "r"(u__), "r"(v__), "r"(w__)); /* parity   */ \
+    } while (0)
+// 8 OR-words (two 16-byte chunks of A row `x` and B row `y`) -> planes (o,t,f) + 8 * popc(eights)
+#define DB200_HS8(acc, o, t, f, x0, x1, y0, y1)                                                   \
+    do {                                                                                          \
+        uint32_t c1, c2, c3, c4, d1, d2, e;                                                       \
+        DB200_CSA(c1, o, o, x0.x | y0.x, x0.y | y0.y);                                            \
+        DB200_CSA(c2, o, o, x0.z | y0.z, x0.w | y0.w);                                            \
+        DB200_CSA(d1, t, t, c1, c2);                                                              \
+        DB200_CSA(c3, o, o, x1.x | y1.x, x1.y | y1.y);                                            \
+        DB200_CSA(c4, o, o, x1.z | y1.z, x1.w | y1.w);                                            \
+        DB200_CSA(d2, t, t, c3, c4);                                                              \
+        DB200_CSA(e, f, f, d1, d2);                                                               \
+        acc = (uint32_t)__popc(e) * eight + acc;                                                  \
+    } while (0)
+
 struct NewtonDiv { __device__ __forceinline__ static double div(double a, double b) { return fast_div(a, b); } };
 
 // GT: uint16_t for p <= 16 (two CTAs per SM), uint32_t above (counts no longer fit 16 bits)
@@ -411,25 +432,6 @@ __global__ void __launch_bounds__(DIST_THREADS, 2) dist_kernel(const __grid_cons
         uint32_t o00 = 0, o01 = 0, o10 = 0, o11 = 0;   // weight-1 planes
         uint32_t t00 = 0, t01 = 0, t10 = 0, t11 = 0;   // weight-2 planes
         uint32_t f00 = 0, f01 = 0, f10 = 0, f11 = 0;   // weight-4 planes
-#define DB200_CSA(h, l, a, b, c)                                        \
-    do {                                                                \
-        const uint32_t u__ = (a), v__ = (b), w__ = (c);                 \
-        asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(h) : "r"(u__), "r"(v__), "r"(w__)); /* majority */ \
-        asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(l) : "r"(u__), "r"(v__), "r"(w__)); /* parity   */ \
-    } while (0)
-        // 8 OR-words (two 16-byte chunks of A row `x` and B row `y`) -> planes (o,t,f) + 8 * popc(eights)
-#define DB200_HS8(acc, o, t, f, x0, x1, y0, y1)                                                   \
-    do {                                                                                          \
-        uint32_t c1, c2, c3, c4, d1, d2, e;                                                       \
-        DB200_CSA(c1, o, o, x0.x | y0.x, x0.y | y0.y);                                            \
-        DB200_CSA(c2, o, o, x0.z | y0.z, x0.w | y0.w);                                            \
-        DB200_CSA(d1, t, t, c1, c2);                                                              \
-        DB200_CSA(c3, o, o, x1.x | y1.x, x1.y | y1.y);                                            \
-        DB200_CSA(c4, o, o, x1.z | y1.z, x1.w | y1.w);                                            \
-        DB200_CSA(d2, t, t, c3, c4);                                                              \
-        DB200_CSA(e, f, f, d1, d2);                                                               \
-        acc = (uint32_t)__popc(e) * eight + acc;                                                  \
-    } while (0)
         // accumulate with IMAD (x * one + acc, `one` a runtime 1): keeps the adds off the ALU pipe
 #define DB200_POP4(acc, p, q)                                                    \
     do {                                                                         \
@@ -487,8 +489,6 @@ __global__ void __launch_bounds__(DIST_THREADS, 2) dist_kernel(const __grid_cons
             }
         }
 #undef DB200_POP4
-#undef DB200_HS8
-#undef DB200_CSA
     }
     __syncthreads();
 
@@ -680,22 +680,45 @@ __global__ void __launch_bounds__(DIST_THREADS, 1) dist_jmle_kernel(const __grid
         const uint32_t ti = threadIdx.x >> 4, tj = threadIdx.x & 15;   // A row ti, B rows {tj, tj+16}
         const uint32_t swA = (ti & 7) << 4, swB = (tj & 7) << 4;
         uint32_t u0 = 0, u1 = 0, x0 = 0, x1 = 0, y0 = 0, y1 = 0;
+        // carry-save planes (weight 1, 2, 4) per (pair, family): half of every box is counted on the ALU pipe (see dist_kernel)
+        uint32_t ou0 = 0, ou1 = 0, ox0 = 0, ox1 = 0, oy0 = 0, oy1 = 0;
+        uint32_t tu0 = 0, tu1 = 0, tx0 = 0, tx1 = 0, ty0 = 0, ty1 = 0;
+        uint32_t fu0 = 0, fu1 = 0, fx0 = 0, fx1 = 0, fy0 = 0, fy1 = 0;
+        const uint32_t eight = 8u * (uint32_t)a.one;
         int s = 0, wb = 0;
         size_t tl = 0;
         uint32_t ph = 0;
         for (int it = 0; it < iters; ++it) {
             mbar_wait(full0 + 8 * s, ph);
             const uint8_t *A0 = stage_mem + (size_t)s * JSTAGE_BYTES, *A1 = A0 + JBOX_A, *B0 = A0 + 2 * JBOX_A, *B1 = B0 + JBOX_B;
+#define DB200_POP4(p, q) (__popc(p.x | q.x) + __popc(p.y | q.y) + __popc(p.z | q.z) + __popc(p.w | q.w))
 #pragma unroll
-            for (uint32_t c = 0; c < 8; ++c) {
+            for (uint32_t c = 0; c < 4; ++c) {
                 const uint32_t oa = ti * 128 + ((c << 4) ^ swA), ob0 = tj * 128 + ((c << 4) ^ swB), ob1 = ob0 + 16 * 128;
                 const uint4 ak = *reinterpret_cast<const uint4 *>(A0 + oa), an = *reinterpret_cast<const uint4 *>(A1 + oa);
                 const uint4 bk0 = *reinterpret_cast<const uint4 *>(B0 + ob0), bn0 = *reinterpret_cast<const uint4 *>(B1 + ob0);
                 const uint4 bk1 = *reinterpret_cast<const uint4 *>(B0 + ob1), bn1 = *reinterpret_cast<const uint4 *>(B1 + ob1);
-#define DB200_POP4(p, q) (__popc(p.x | q.x) + __popc(p.y | q.y) + __popc(p.z | q.z) + __popc(p.w | q.w))
                 u0 += DB200_POP4(ak, bk0); x0 += DB200_POP4(ak, bn0); y0 += DB200_POP4(an, bk0);
                 u1 += DB200_POP4(ak, bk1); x1 += DB200_POP4(ak, bn1); y1 += DB200_POP4(an, bk1);
+            }
 #undef DB200_POP4
+#pragma unroll
+            for (uint32_t c = 4; c < 8; c += 2) {
+                const uint32_t oa = ti * 128 + ((c << 4) ^ swA), oa2 = ti * 128 + (((c + 1) << 4) ^ swA);
+                const uint32_t ob0 = tj * 128 + ((c << 4) ^ swB), ob02 = tj * 128 + (((c + 1) << 4) ^ swB);
+                const uint32_t ob1 = ob0 + 16 * 128, ob12 = ob02 + 16 * 128;
+                const uint4 ak = *reinterpret_cast<const uint4 *>(A0 + oa), ak2 = *reinterpret_cast<const uint4 *>(A0 + oa2);
+                const uint4 an = *reinterpret_cast<const uint4 *>(A1 + oa), an2 = *reinterpret_cast<const uint4 *>(A1 + oa2);
+                const uint4 bk0 = *reinterpret_cast<const uint4 *>(B0 + ob0), bk02 = *reinterpret_cast<const uint4 *>(B0 + ob02);
+                const uint4 bn0 = *reinterpret_cast<const uint4 *>(B1 + ob0), bn02 = *reinterpret_cast<const uint4 *>(B1 + ob02);
+                const uint4 bk1 = *reinterpret_cast<const uint4 *>(B0 + ob1), bk12 = *reinterpret_cast<const uint4 *>(B0 + ob12);
+                const uint4 bn1 = *reinterpret_cast<const uint4 *>(B1 + ob1), bn12 = *reinterpret_cast<const uint4 *>(B1 + ob12);
+                DB200_HS8(u0, ou0, tu0, fu0, ak, ak2, bk0, bk02);
+                DB200_HS8(x0, ox0, tx0, fx0, ak, ak2, bn0, bn02);
+                DB200_HS8(y0, oy0, ty0, fy0, an, an2, bk0, bk02);
+                DB200_HS8(u1, ou1, tu1, fu1, ak, ak2, bk1, bk12);
+                DB200_HS8(x1, ox1, tx1, fx1, ak, ak2, bn1, bn12);
+                DB200_HS8(y1, oy1, ty1, fy1, an, an2, bk1, bk12);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(empty0 + 8 * s);
@@ -704,10 +727,13 @@ __global__ void __launch_bounds__(DIST_THREADS, 1) dist_jmle_kernel(const __grid
                 wb = 0;
                 GT *gu = G + tl * JPAIRS, *gx = G + ((size_t)Kcap + tl) * JPAIRS, *gy = G + ((size_t)2 * Kcap + tl) * JPAIRS;
                 const uint32_t p0 = ti * DT + tj, p1 = p0 + 16;
-                gu[p0] = (GT)u0; gu[p1] = (GT)u1;
-                gx[p0] = (GT)x0; gx[p1] = (GT)x1;
-                gy[p0] = (GT)y0; gy[p1] = (GT)y1;
+#define DB200_FLUSH(acc, o, t, f) ((GT)((acc) + __popc(o) + 2 * __popc(t) + 4 * __popc(f)))
+                gu[p0] = DB200_FLUSH(u0, ou0, tu0, fu0); gu[p1] = DB200_FLUSH(u1, ou1, tu1, fu1);
+                gx[p0] = DB200_FLUSH(x0, ox0, tx0, fx0); gx[p1] = DB200_FLUSH(x1, ox1, tx1, fx1);
+                gy[p0] = DB200_FLUSH(y0, oy0, ty0, fy0); gy[p1] = DB200_FLUSH(y1, oy1, ty1, fy1);
+#undef DB200_FLUSH
                 u0 = u1 = x0 = x1 = y0 = y1 = 0;
+                ou0 = ou1 = ox0 = ox1 = oy0 = oy1 = tu0 = tu1 = tx0 = tx1 = ty0 = ty1 = fu0 = fu1 = fx0 = fx1 = fy0 = fy1 = 0;
                 ++tl;
             }
         }
