@@ -64,6 +64,9 @@ _SIGS = {
     "db200_dist_plan_prepare_dev": (C.c_int, [vp, vp, C.c_uint64, C.c_int, C.c_int, vp]),
     "db200_dist_plan_run_symmetric_dev": (C.c_int, [vp, C.POINTER(DistParams), C.c_uint64, C.c_uint64, vp, vp]),
     "db200_dist_plan_run_rect_dev": (C.c_int, [vp, C.POINTER(DistParams), C.c_uint64, C.c_uint64, vp, vp]),
+    "db200_dist_knn_symmetric": (C.c_int, [C.c_int, u8p, C.c_uint64, C.POINTER(DistParams), C.c_uint32, vp]),
+    "db200_dist_knn_rect": (C.c_int, [C.c_int, u8p, C.c_uint64, u8p, C.c_uint64, C.POINTER(DistParams), C.c_uint32, vp]),
+    "db200_dist_plan_run_knn_dev": (C.c_int, [vp, C.POINTER(DistParams), C.c_uint64, C.c_uint64, C.c_uint32, vp, vp]),
     "db200_dist_plan_cardinalities_dev": (C.c_int, [vp, C.POINTER(vp)]),
     "db200_kernel_launches": (C.c_uint64, []),
     "db200_dist_plan_last_run_info": (C.c_int, [vp, u64p, u64p, C.POINTER(C.c_int)]),
@@ -154,7 +157,7 @@ class Sketcher:
         return out
 
     def close(self):
-        if self.h:
+        if self.h and lib is not None:        # (module globals are gone at interpreter shutdown)
             lib.db200_sketcher_destroy(self.h)
             self.h = vp()
 
@@ -185,7 +188,7 @@ class PackedGenomes:
         _check(lib.db200_sketch_packed_dev(self.h, p, int(canon), vp(d_registers), vp(stream)))
 
     def close(self):
-        if self.h:
+        if self.h and lib is not None:        # (module globals are gone at interpreter shutdown)
             lib.db200_packed_genomes_free(self.h)
             self.h = vp()
 
@@ -224,6 +227,31 @@ def dist_rect(refs, qrys, p, k=31, estim=ERTL_MLE, jestim=ERTL_MLE, result_type=
     return out
 
 
+# db200_neighbor == the reference's validx_t = std::pair<float, uint32_t> (src/sketch_and_cmp.h:605)
+NEIGHBOR_DTYPE = np.dtype([("value", np.float32), ("index", np.uint32)])
+DIST_MEASURES = (MASH_DIST, FULL_MASH_DIST, CONTAINMENT_DIST, FULL_CONTAINMENT_DIST, SYMMETRIC_CONTAINMENT_DIST)
+
+
+def knn_symmetric(regs, p, nneighbors, k=31, estim=ERTL_MLE, jestim=ERTL_MLE, result_type=JI, order=ORDER_COL_FIRST,
+                  device=0) -> np.ndarray:
+    """-> structured array [n][nneighbors] of (value, index), best first (nndist_loop, src/sketch_and_cmp.h:712-783)."""
+    regs = _np(regs, np.uint8).reshape(-1, 1 << p)
+    out = np.zeros((regs.shape[0], nneighbors), dtype=NEIGHBOR_DTYPE)
+    prm = dist_params(p, k, estim, jestim, result_type, order)
+    _check(lib.db200_dist_knn_symmetric(device, regs.ctypes.data_as(u8p), regs.shape[0], C.byref(prm), nneighbors, vp(out.ctypes.data)))
+    return out
+
+
+def knn_rect(refs, qrys, p, nneighbors, k=31, estim=ERTL_MLE, jestim=ERTL_MLE, result_type=JI, device=0) -> np.ndarray:
+    refs = _np(refs, np.uint8).reshape(-1, 1 << p)
+    qrys = _np(qrys, np.uint8).reshape(-1, 1 << p)
+    out = np.zeros((qrys.shape[0], nneighbors), dtype=NEIGHBOR_DTYPE)
+    prm = dist_params(p, k, estim, jestim, result_type, ORDER_COL_FIRST)
+    _check(lib.db200_dist_knn_rect(device, refs.ctypes.data_as(u8p), refs.shape[0], qrys.ctypes.data_as(u8p), qrys.shape[0],
+                                   C.byref(prm), nneighbors, vp(out.ctypes.data)))
+    return out
+
+
 class DistPlan:
     """Device-resident all-pairs plan (threshold bit-planes + cardinalities) over a device register matrix."""
 
@@ -240,6 +268,9 @@ class DistPlan:
     def run_rect_dev(self, prm: DistParams, nr: int, nq: int, d_out: int, stream: int = 0):
         _check(lib.db200_dist_plan_run_rect_dev(self.h, C.byref(prm), nr, nq, vp(d_out), vp(stream)))
 
+    def run_knn_dev(self, prm: DistParams, nr: int, nq: int, nneighbors: int, d_out: int, stream: int = 0):
+        _check(lib.db200_dist_plan_run_knn_dev(self.h, C.byref(prm), nr, nq, nneighbors, vp(d_out), vp(stream)))
+
     def cardinalities_dev(self) -> int:
         ptr = vp()
         _check(lib.db200_dist_plan_cardinalities_dev(self.h, C.byref(ptr)))
@@ -251,7 +282,7 @@ class DistPlan:
         return pairs.value, tiles.value, thr.value
 
     def close(self):
-        if self.h:
+        if self.h and lib is not None:        # (module globals are gone at interpreter shutdown)
             lib.db200_dist_plan_destroy(self.h)
             self.h = vp()
 

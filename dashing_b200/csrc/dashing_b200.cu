@@ -311,6 +311,7 @@ struct db200_dist_plan {
     static constexpr int NSLOT = 4;   // independent tile lists, so that row blocks of one request can be in flight together
     db200::DevBuf planes, counts, card, smin, smax, pmin, pmax, minmax, lists, sthr, pthr, llists, ptl;
     db200::DevBuf tiles[NSLOT];
+    db200::DevBuf knn_vals, knn_keys;   // k-NN: one row block of all-pairs values, retained (value, index) keys
     std::vector<db200::DistTile> host_tiles[NSLOT];
     // tile-list cache key
     struct TileKey { int rect = -1, ta = 0; uint64_t rb = 0, re = 0, nr = 0, nq = 0, n = 0, ntiles = 0; } tl[NSLOT];
@@ -439,7 +440,7 @@ static int plan_tiles(db200_dist_plan *pl, int slot, int rect, int ta, uint64_t 
 }
 
 static int plan_run(db200_dist_plan *pl, const db200_dist_params *prm, int rect, uint64_t rb, uint64_t re, uint64_t nr, uint64_t nq,
-                    float *d_out, cudaStream_t stream, int slot = 0) {
+                    float *d_out, cudaStream_t stream, int slot = 0, bool ksinv_double = false) {
     if (!pl->ready) { set_error("dist plan not prepared"); return DB200_EINVAL; }
     if (prm->p != pl->p || prm->estim != pl->estim) { set_error("dist params (p=%d, estim=%d) differ from the prepared plan (p=%d, estim=%d)", prm->p, prm->estim, pl->p, pl->estim); return DB200_EINVAL; }
     if (prm->result_type < 0 || prm->result_type > 8) { set_error("dist: unknown result type %d", prm->result_type); return DB200_EINVAL; }
@@ -460,7 +461,8 @@ static int plan_run(db200_dist_plan *pl, const db200_dist_params *prm, int rect,
     a.n = pl->nrows; a.row_begin = rb; a.row_end = re;
     a.out_base = rect ? 0 : (rb * (2 * pl->nrows - rb - 1)) / 2;
     a.nr = nr; a.nq = nq; a.qbase = pl->qbase;
-    a.ksinv = (double)(float)(1. / prm->k);  // const float ksinv = 1./k, src/sketch_and_cmp.h:797
+    // const float ksinv = 1./k in dist_loop (src/sketch_and_cmp.h:797) but const double in nndist_loop (:729)
+    a.ksinv = ksinv_double ? 1. / prm->k : (double)(float)(1. / prm->k);
     a.p = pl->p; a.gmin = pl->gmin; a.gmax = pl->gmax; a.K = pl->K;
     a.estim = prm->estim; a.rtype = prm->result_type; a.rect = rect; a.one = 1;
     const bool wide = pl->p > 16;                  // threshold counts above 2^16: 32-bit count storage
@@ -511,12 +513,85 @@ static int plan_run(db200_dist_plan *pl, const db200_dist_params *prm, int rect,
     return DB200_OK;
 }
 
+// emt2nntype, src/dashing.h:268-280
+static bool is_similarity(int rtype) {
+    switch (rtype) {
+        case DB200_MASH_DIST: case DB200_FULL_MASH_DIST: case DB200_CONTAINMENT_DIST: case DB200_FULL_CONTAINMENT_DIST:
+        case DB200_SYMMETRIC_CONTAINMENT_DIST: return false;
+        default: return true;
+    }
+}
+
+// k nearest neighbours: the all-pairs values of one row block at a time go to plan scratch, a second kernel folds them
+// into the per-sketch retained sets, a third sorts and decodes.  nq == 0: symmetric.
+static int plan_knn(db200_dist_plan *pl, const db200_dist_params *prm, uint64_t nr, uint64_t nq, uint32_t nn, Neighbor *d_out,
+                    cudaStream_t stream) {
+    if (!pl->ready) { set_error("dist plan not prepared"); return DB200_EINVAL; }
+    if (nn < 1 || nn > 1024) { set_error("nearest neighbours: nneighbors=%u outside the GPU path's range [1,1024]", nn); return DB200_EUNSUPPORTED; }
+    if (prm->result_type < 0 || prm->result_type > 8) { set_error("dist: unknown result type %d", prm->result_type); return DB200_EINVAL; }
+    const int rect = nq != 0, sim = is_similarity(prm->result_type);
+    const uint64_t n = pl->nrows, rows = rect ? nq : n;
+    // all-pairs values held in HBM at a time (1 GiB of floats unless DB200_KNN_BLOCK_PAIRS says otherwise)
+    const char *benv = std::getenv("DB200_KNN_BLOCK_PAIRS");
+    const uint64_t bval = benv ? std::strtoull(benv, nullptr, 10) : 0;
+    const uint64_t budget = bval ? bval : (uint64_t)1 << 28;
+    DB200_TRY(pl->knn_keys.reserve(rows * nn * 8));
+    knn_init_kernel<<<(unsigned)std::min<uint64_t>((rows * nn + 255) / 256, 65535), 256, 0, stream>>>(pl->knn_keys.as<uint64_t>(), rows * nn, sim);
+    DB200_LAUNCHED();
+    KnnArgs ka{};
+    ka.keys = pl->knn_keys.as<uint64_t>(); ka.n = n; ka.nr = nr; ka.nn = nn; ka.sim = sim; ka.rect = rect;
+    const size_t smem = (size_t)KNN_WARPS * nn * 8;
+    uint64_t total_pairs = 0, total_tiles = 0;
+    if (!rect) {
+        auto tri = [n](uint64_t r) { return (r * (2 * n - r - 1)) / 2; };
+        for (uint64_t rb = 0; rb + 1 < n;) {
+            // as many whole panels of rows as fit the budget (at least one)
+            uint64_t re = std::min(n, (rb / DT + 1) * DT);
+            while (re < n && tri(std::min(n, re + DT)) - tri(rb) <= budget) re = std::min(n, re + DT);
+            const uint64_t npairs = tri(re) - tri(rb);
+            if (npairs) {
+                DB200_TRY(pl->knn_vals.reserve(npairs * 4));
+                DB200_TRY(plan_run(pl, prm, 0, rb, re, 0, 0, pl->knn_vals.as<float>(), stream, 0, true));
+                total_pairs += pl->last_pairs; total_tiles += pl->last_tiles;
+                ka.vals = pl->knn_vals.as<float>(); ka.rb = rb; ka.re = re;
+                knn_update_kernel<<<(unsigned)((n - rb + KNN_WARPS - 1) / KNN_WARPS), KNN_WARPS * 32, smem, stream>>>(ka);
+                DB200_LAUNCHED();
+            }
+            rb = re;
+        }
+    } else {
+        if (nr == 0) { set_error("nearest neighbours: no references"); return DB200_EINVAL; }
+        const uint64_t qbase0 = pl->qbase;
+        uint64_t qstep = std::max<uint64_t>(DT, budget / nr / DT * DT);
+        int rc = DB200_OK;
+        for (uint64_t q0 = 0; q0 < nq && rc == DB200_OK; q0 += qstep) {
+            const uint64_t qn = std::min(qstep, nq - q0);
+            rc = pl->knn_vals.reserve(qn * nr * 4);
+            if (rc != DB200_OK) break;
+            pl->qbase = qbase0 + q0;     // queries [q0, q0 + qn) of the plan as a rect run of their own (q0 % DT == 0)
+            rc = plan_run(pl, prm, 1, 0, 0, nr, qn, pl->knn_vals.as<float>(), stream, 0, true);
+            pl->qbase = qbase0;
+            if (rc != DB200_OK) break;
+            total_pairs += pl->last_pairs; total_tiles += pl->last_tiles;
+            ka.vals = pl->knn_vals.as<float>(); ka.q0 = q0; ka.nq = qn;
+            knn_update_kernel<<<(unsigned)((qn + KNN_WARPS - 1) / KNN_WARPS), KNN_WARPS * 32, smem, stream>>>(ka);
+            DB200_LAUNCHED();
+        }
+        if (rc != DB200_OK) return rc;
+    }
+    knn_sort_kernel<<<(unsigned)((rows + KNN_WARPS - 1) / KNN_WARPS), KNN_WARPS * 32, smem, stream>>>(pl->knn_keys.as<uint64_t>(), rows, nn, sim, d_out);
+    DB200_LAUNCHED();
+    DB200_CUDA(cudaGetLastError());
+    pl->last_pairs = total_pairs; pl->last_tiles = total_tiles;
+    return DB200_OK;
+}
+
 // Default per-device resources for the host-pointer entry points.
 struct HostCtx {
     std::mutex mu;
     cudaStream_t stream = nullptr, cstream = nullptr;
     cudaEvent_t blk_done[db200_dist_plan::NSLOT] = {nullptr, nullptr, nullptr, nullptr};
-    DevBuf regs, out, cards;
+    DevBuf regs, out, cards, nbrs;
     Uploader up;
     std::unique_ptr<db200_dist_plan> plan;
     std::unique_ptr<db200_packed_genomes> store;   // reused by db200_sketch_batch
@@ -730,6 +805,62 @@ int db200_dist_plan_run_rect_dev(db200_dist_plan *pl, const db200_dist_params *p
         return rc;
     }
     return plan_run(pl, prm, 1, 0, 0, nr, nq, d_out, (cudaStream_t)stream);
+}
+int db200_dist_plan_run_knn_dev(db200_dist_plan *pl, const db200_dist_params *prm, uint64_t nr, uint64_t nq, uint32_t nneighbors,
+                                db200_neighbor *d_out, void *stream) {
+    if (!pl || !prm || !d_out) { set_error("db200_dist_plan_run_knn_dev: null argument"); return DB200_EINVAL; }
+    DB200_TRY(check_device(pl->device));
+    std::lock_guard<std::mutex> lk(pl->mu);
+    static_assert(sizeof(Neighbor) == sizeof(db200_neighbor), "neighbour layout");
+    if (nq == 0) return plan_knn(pl, prm, 0, 0, nneighbors, reinterpret_cast<Neighbor *>(d_out), (cudaStream_t)stream);
+    if (pl->qbase == 0) {
+        if (nr % DT != 0 || nr + nq != pl->nrows) { set_error("rect run on a symmetric plan needs nr %% %d == 0 and nr + nq == n", DT); return DB200_EINVAL; }
+        pl->qbase = nr;
+        const int rc = plan_knn(pl, prm, nr, nq, nneighbors, reinterpret_cast<Neighbor *>(d_out), (cudaStream_t)stream);
+        pl->qbase = 0;
+        return rc;
+    }
+    return plan_knn(pl, prm, nr, nq, nneighbors, reinterpret_cast<Neighbor *>(d_out), (cudaStream_t)stream);
+}
+int db200_dist_knn_symmetric(int device, const uint8_t *regs, uint64_t n, const db200_dist_params *prm, uint32_t nneighbors,
+                             db200_neighbor *out) {
+    if (!prm || ((!regs || !out) && n)) { set_error("db200_dist_knn_symmetric: null argument"); return DB200_EINVAL; }
+    DB200_TRY(check_device(device));
+    if (n == 0) return DB200_OK;
+    if (prm->p < 7 || prm->p > 20) { set_error("dist: p=%d outside the GPU path's range [7,20]", prm->p); return DB200_EUNSUPPORTED; }
+    HostCtx &hc = host_ctx(device);
+    std::lock_guard<std::mutex> lk(hc.mu);
+    DB200_TRY(hc.init(device));
+    const uint64_t m = 1ull << prm->p;
+    DB200_TRY(hc.regs.reserve(n * m));
+    DB200_TRY(hc.nbrs.reserve(n * nneighbors * sizeof(db200_neighbor)));
+    DB200_CUDA(cudaMemcpyAsync(hc.regs.ptr, regs, n * m, cudaMemcpyHostToDevice, hc.stream));
+    DB200_TRY(plan_prepare(hc.plan.get(), hc.regs.as<uint8_t>(), n, n, 0, 0, prm->p, prm->estim, hc.stream));
+    DB200_TRY(plan_knn(hc.plan.get(), prm, 0, 0, nneighbors, hc.nbrs.as<Neighbor>(), hc.stream));
+    DB200_CUDA(cudaMemcpyAsync(out, hc.nbrs.ptr, n * nneighbors * sizeof(db200_neighbor), cudaMemcpyDeviceToHost, hc.stream));
+    DB200_CUDA(cudaStreamSynchronize(hc.stream));
+    return DB200_OK;
+}
+int db200_dist_knn_rect(int device, const uint8_t *ref_regs, uint64_t nr, const uint8_t *qry_regs, uint64_t nq, const db200_dist_params *prm,
+                        uint32_t nneighbors, db200_neighbor *out) {
+    if (!prm || ((!ref_regs || !qry_regs || !out) && nr && nq)) { set_error("db200_dist_knn_rect: null argument"); return DB200_EINVAL; }
+    DB200_TRY(check_device(device));
+    if (nr == 0 || nq == 0) return DB200_OK;
+    if (prm->p < 7 || prm->p > 20) { set_error("dist: p=%d outside the GPU path's range [7,20]", prm->p); return DB200_EUNSUPPORTED; }
+    HostCtx &hc = host_ctx(device);
+    std::lock_guard<std::mutex> lk(hc.mu);
+    DB200_TRY(hc.init(device));
+    const uint64_t m = 1ull << prm->p;
+    const uint64_t qbase = (nr + DT - 1) / DT * DT, nrows = qbase + nq;
+    DB200_TRY(hc.regs.reserve(nrows * m));
+    DB200_TRY(hc.nbrs.reserve(nq * nneighbors * sizeof(db200_neighbor)));
+    DB200_CUDA(cudaMemcpyAsync(hc.regs.ptr, ref_regs, nr * m, cudaMemcpyHostToDevice, hc.stream));
+    DB200_CUDA(cudaMemcpyAsync(hc.regs.as<uint8_t>() + qbase * m, qry_regs, nq * m, cudaMemcpyHostToDevice, hc.stream));
+    DB200_TRY(plan_prepare(hc.plan.get(), hc.regs.as<uint8_t>(), nrows, nr, qbase, nq, prm->p, prm->estim, hc.stream));
+    DB200_TRY(plan_knn(hc.plan.get(), prm, nr, nq, nneighbors, hc.nbrs.as<Neighbor>(), hc.stream));
+    DB200_CUDA(cudaMemcpyAsync(out, hc.nbrs.ptr, nq * nneighbors * sizeof(db200_neighbor), cudaMemcpyDeviceToHost, hc.stream));
+    DB200_CUDA(cudaStreamSynchronize(hc.stream));
+    return DB200_OK;
 }
 int db200_dist_plan_cardinalities_dev(db200_dist_plan *pl, const double **d_card) {
     if (!pl || !d_card || !pl->ready) { set_error("plan not prepared"); return DB200_EINVAL; }

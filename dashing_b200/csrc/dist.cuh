@@ -79,7 +79,14 @@ __global__ void __launch_bounds__(128) planes_kernel(const uint32_t *__restrict_
             const uint32_t wi = g * 256 + gg * 32 + lane;
             x[gg] = wi < nwords ? __ldg(src + wi) : 0u;
         }
-        for (int t = 0; t < K; ++t) {
+        // thresholds above the largest register of this group of 1024 have empty planes: no ballots for them
+        uint32_t mx4 = x[0];
+#pragma unroll
+        for (int gg = 1; gg < 8; ++gg) mx4 = __vmaxu4(mx4, x[gg]);
+        mx4 = max(max(mx4 & 0xFFu, (mx4 >> 8) & 0xFFu), max((mx4 >> 16) & 0xFFu, mx4 >> 24));
+        const int tl = min(K, max(0, (int)__reduce_max_sync(0xFFFFFFFFu, mx4) - gmin));
+        for (int t = tl; t < K; ++t) planes[((uint64_t)t * n + s) * W + g * 32 + lane] = 0u;
+        for (int t = 0; t < tl; ++t) {
             const uint32_t k4 = (uint32_t)(gmin + 1 + t) * 0x01010101u;
             uint32_t kept = 0;
 #pragma unroll
@@ -823,6 +830,148 @@ __global__ void __launch_bounds__(DIST_THREADS, 1) dist_jmle_kernel(const __grid
         const double t2 = 0. < h ? h : 0.;
         const double ji = t2 / (t0 + t1 + t2);   // hll.h:1175-1178
         a.out[oidx] = emit_value(a.rtype, ji, t0, t1, t2, a.ksinv);
+    }
+}
+
+// =============================================================================================
+// k nearest neighbours (perform_nns / lock_update / lockfree_update, src/sketch_and_cmp.h:605-697)
+// =============================================================================================
+// The reference keeps, per sketch, a heap of `nneighbors` (value, index) pairs, visits the other sketches and
+// replaces the heap top (the retained pair that sorts LAST under std::less / std::greater on the pair) whenever the
+// new value is STRICTLY better than the top's value; the rows are sorted at the end.  With one thread (and always in
+// the -Q/-F mode) the visiting order is ascending index, which fixes which of several equal values at the cut survive;
+// with more threads the reference itself is schedule dependent there.  This kernel replays the ascending order.
+//
+// A pair is held as one 64-bit key whose unsigned order is the final output order (smaller key = sorts first):
+//   distance measures   key =  (ord(value) << 32 | index)       ascending (value, index)      std::less
+//   similarity measures key = ~(ord(value) << 32 | index)       descending (value, index)     std::greater
+// ord() is the usual order-preserving float -> uint32 map (after -0 -> +0, so that equal floats tie on the index).
+__device__ __forceinline__ uint32_t nn_ord(float v) {
+    const uint32_t u = __float_as_uint(v + 0.0f);
+    return u ^ ((u >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+}
+__device__ __forceinline__ float nn_unord(uint32_t o) {
+    return __uint_as_float(o ^ ((o >> 31) ? 0x80000000u : 0xFFFFFFFFu));
+}
+__device__ __forceinline__ uint64_t nn_key(float v, uint32_t idx, int sim) {
+    const uint64_t k = ((uint64_t)nn_ord(v) << 32) | idx;
+    return sim ? ~k : k;
+}
+// empty slot: (+-FLT_MAX, uint32(-1)), src/sketch_and_cmp.h:652-653
+__device__ __forceinline__ uint64_t nn_empty(int sim) { return nn_key(sim ? -3.402823466e+38f : 3.402823466e+38f, 0xFFFFFFFFu, sim); }
+
+__global__ void knn_init_kernel(uint64_t *__restrict__ keys, uint64_t total, int sim) {
+    const uint64_t e = nn_empty(sim);
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) keys[i] = e;
+}
+
+struct KnnArgs {
+    const float *vals;        // symmetric: rows [rb, re) of the packed upper triangle, from vals[0]; rect: [nq_block][nr]
+    uint64_t *keys;           // [rows][nn] retained pairs (state across row blocks)
+    uint64_t n;               // symmetric: sketches; rect: unused
+    uint64_t rb, re;          // symmetric: rows held in vals
+    uint64_t nr;              // rect: references
+    uint64_t q0, nq;          // rect: first query of this block, queries in this block
+    uint32_t nn;
+    int sim, rect;
+};
+
+constexpr int KNN_WARPS = 4;
+
+// One warp per sketch (symmetric: every sketch r >= rb, which sees sources i in [rb, min(re, r)) — gathered down the
+// column — and then, if its own row is in the block, j in (r, n) — contiguous —; rect: one query, j in [0, nr)).
+__global__ void __launch_bounds__(KNN_WARPS * 32) knn_update_kernel(KnnArgs a) {
+    extern __shared__ uint64_t knn_smem[];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t w = (uint64_t)blockIdx.x * KNN_WARPS + warp;
+    uint64_t *S = knn_smem + (size_t)warp * a.nn;
+    uint64_t row;          // index into keys
+    if (a.rect) { if (w >= a.nq) return; row = a.q0 + w; }
+    else { row = a.rb + w; if (row >= a.n) return; }
+    uint64_t *gk = a.keys + row * a.nn;
+    for (uint32_t e = lane; e < a.nn; e += 32) S[e] = gk[e];
+    __syncwarp();
+    uint64_t wkey; uint32_t wpos;
+    auto find_worst = [&]() {
+        uint64_t bk = 0; uint32_t bp = 0;
+        for (uint32_t e = lane; e < a.nn; e += 32) { const uint64_t k = S[e]; if (k >= bk) { bk = k; bp = e; } }
+#pragma unroll
+        for (int off = 16; off; off >>= 1) {
+            const uint64_t ok = __shfl_xor_sync(0xFFFFFFFFu, bk, off);
+            const uint32_t op = __shfl_xor_sync(0xFFFFFFFFu, bp, off);
+            if (ok > bk || (ok == bk && op > bp)) { bk = ok; bp = op; }
+        }
+        wkey = bk; wpos = bp;
+    };
+    find_worst();
+    bool dirty = false;
+    auto consider = [&](float v, uint32_t idx, bool valid) {
+        // strictly better VALUE than the worst retained one (the index plays no part in admission)
+        const uint32_t hi = a.sim ? ~nn_ord(v) : nn_ord(v);
+        uint32_t mask = __ballot_sync(0xFFFFFFFFu, valid && v == v && hi < (uint32_t)(wkey >> 32));
+        while (mask) {
+            const int l = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const uint32_t hl = __shfl_sync(0xFFFFFFFFu, hi, l);
+            const uint32_t il = __shfl_sync(0xFFFFFFFFu, idx, l);
+            if (hl < (uint32_t)(wkey >> 32)) {
+                if (lane == 0) S[wpos] = ((uint64_t)hl << 32) | (a.sim ? ~il : il);
+                __syncwarp();
+                find_worst();
+                dirty = true;
+            }
+        }
+    };
+    if (a.rect) {
+        const float *src = a.vals + w * a.nr;
+        for (uint64_t j0 = 0; j0 < a.nr; j0 += 32) {
+            const uint64_t j = j0 + lane;
+            const bool ok = j < a.nr;
+            consider(ok ? __ldg(src + j) : 0.f, (uint32_t)j, ok);
+        }
+    } else {
+        const uint64_t n = a.n, r = row;
+        auto tri = [n](uint64_t i) { return (i * (2 * n - i - 1)) / 2; };
+        const uint64_t base = tri(a.rb);
+        const uint64_t iend = a.re < r ? a.re : r;
+        for (uint64_t i0 = a.rb; i0 < iend; i0 += 32) {
+            const uint64_t i = i0 + lane;
+            const bool ok = i < iend;
+            consider(ok ? __ldg(a.vals + (tri(i) - base + (r - i - 1))) : 0.f, (uint32_t)i, ok);
+        }
+        if (r < a.re) {
+            const float *src = a.vals + (tri(r) - base);
+            for (uint64_t j0 = r + 1; j0 < n; j0 += 32) {
+                const uint64_t j = j0 + lane;
+                const bool ok = j < n;
+                consider(ok ? __ldg(src + (j - r - 1)) : 0.f, (uint32_t)j, ok);
+            }
+        }
+    }
+    if (dirty) {
+        __syncwarp();
+        for (uint32_t e = lane; e < a.nn; e += 32) gk[e] = S[e];
+    }
+}
+
+struct Neighbor { float value; uint32_t index; };   // std::pair<float, uint32_t> (validx_t, src/sketch_and_cmp.h:605)
+
+// Final per-row sort (std::sort with std::less / std::greater, :692-696) by ranking, and decode to (value, index).
+__global__ void __launch_bounds__(KNN_WARPS * 32) knn_sort_kernel(const uint64_t *__restrict__ keys, uint64_t rows, uint32_t nn, int sim,
+                                                                 Neighbor *__restrict__ out) {
+    extern __shared__ uint64_t knn_smem[];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t row = (uint64_t)blockIdx.x * KNN_WARPS + warp;
+    if (row >= rows) return;
+    uint64_t *S = knn_smem + (size_t)warp * nn;
+    for (uint32_t e = lane; e < nn; e += 32) S[e] = keys[row * nn + e];
+    __syncwarp();
+    for (uint32_t e = lane; e < nn; e += 32) {
+        const uint64_t k = S[e];
+        uint32_t rank = 0;
+        for (uint32_t f = 0; f < nn; ++f) { const uint64_t o = S[f]; rank += (o < k) || (o == k && f < e); }
+        const uint64_t raw = sim ? ~k : k;
+        out[row * nn + rank] = Neighbor{nn_unord((uint32_t)(raw >> 32)), (uint32_t)raw};
     }
 }
 

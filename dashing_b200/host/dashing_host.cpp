@@ -332,6 +332,31 @@ void sketch_core(const SketchOptions &o, std::vector<std::string> paths) {
     sketch_paths(o, paths, todo, [&](size_t i, const uint8_t *regs) { write_hll(fnames[i], regs, o.p, 2, 2, -1.); });
 }
 
+// TSV table of nndist_loop (src/sketch_and_cmp.h:741-781): "<path>(\t<index>:<%g value>)*"; the index goes through
+// kstring's putw_(int), so the filler index uint32(-1) prints as -1.
+std::string format_neighbors(const std::vector<std::string> &names, size_t qoffset, const Neighbor *nb, size_t rows, unsigned nn) {
+    std::string s = "#File\tNeighbor ID:distance\t...\n";
+    char buf[64];
+    for (size_t i = 0; i < rows; ++i) {
+        s += names[i + qoffset];
+        for (unsigned j = 0; j < nn; ++j) {
+            const Neighbor &e = nb[i * nn + j];
+            std::snprintf(buf, sizeof buf, "\t%d:%g", (int)e.index, (double)e.value);
+            s += buf;
+        }
+        s += '\n';
+    }
+    return s;
+}
+
+// Binary table (:733-740): uint32 number of paths, uint32 neighbours per row, then the (float, uint32) pairs.
+void write_binary_neighbors(std::FILE *fp, uint32_t npaths, const Neighbor *nb, size_t rows, unsigned nn) {
+    const uint32_t hdr[2] = {npaths, nn};
+    static_assert(sizeof(Neighbor) == 8, "validx_t layout");
+    if (std::fwrite(hdr, sizeof(uint32_t), 2, fp) != 2 || std::fwrite(nb, sizeof(Neighbor), rows * nn, fp) != rows * nn)
+        throw Error("Failed to write neighbors to disk (binary)");
+}
+
 void dist_sketch_and_cmp(const DistOptions &o, std::vector<std::string> inpaths, size_t nq) {
     const size_t n = inpaths.size(), m = size_t(1) << o.p;
     if (nq > n) throw Error("more queries than paths");
@@ -372,7 +397,25 @@ void dist_sketch_and_cmp(const DistOptions &o, std::vector<std::string> inpaths,
     if (!pfp) throw Error("Could not open file at " + o.dist_path + " for writing.");
     db200_dist_params prm{o.p, o.k, o.estim, o.jestim, o.result_type, DB200_ORDER_ROW_FIRST};
     const bool joint = o.jestim == DB200_ERTL_JOINT_MLE;
-    if (nq) {
+    if (o.nneighbors) {
+        // nndist_loop (src/sketch_and_cmp.h:712-783): the all-pairs values never leave the GPU, only rows x nn pairs do
+        if (nq >= n) throw Error("Wrong number of query/references.");
+        const size_t rows = nq ? nq : n, possible = nq ? n - nq : n, qoffset = nq ? n - nq : 0;
+        unsigned nn = o.nneighbors;
+        if (nn > possible) {
+            std::fprintf(stderr, "Only reporting %zu rather than %u neighbors due to their being only that many sets.\n", possible, nn);
+            nn = (unsigned)possible;
+        }
+        std::vector<Neighbor> nb(rows * nn);
+        static_assert(sizeof(Neighbor) == sizeof(db200_neighbor), "neighbour layout");
+        prm.order = DB200_ORDER_COL_FIRST;                                     // func(sketches[j], h1), :670
+        if (nq) check(db200_dist_knn_rect(o.device, regs.data(), n - nq, regs.data() + (n - nq) * m, nq, &prm, nn, reinterpret_cast<db200_neighbor *>(nb.data())));
+        else check(db200_dist_knn_symmetric(o.device, regs.data(), n, &prm, nn, reinterpret_cast<db200_neighbor *>(nb.data())));
+        // The reference's emitters loop over ALL paths even in the -Q/-F mode, where only nq rows exist (an out-of-bounds
+        // read there); this writes the nq rows that do.
+        if (o.emit_fmt == BINARY) write_binary_neighbors(pfp, (uint32_t)n, nb.data(), rows, nn);
+        else { const std::string s = format_neighbors(inpaths, qoffset, nb.data(), rows, nn); std::fwrite(s.data(), 1, s.size(), pfp); }
+    } else if (nq) {
         if (nq >= n) throw Error("Wrong number of query/references.");
         const size_t nr = n - nq;
         std::vector<float> out(nr * nq);
@@ -417,8 +460,8 @@ void dist_sketch_and_cmp(const DistOptions &o, std::vector<std::string> inpaths,
 // CLI (hot subset of src/distmain.cpp:47-100 and src/dashing.cpp:307-337)
 // ---------------------------------------------------------------------------------------------------------------
 [[noreturn]] static void unsupported(const char *flag) {
-    throw Error(std::string("flag ") + flag + " selects a code path outside the B200 engine (spaced/windowed k-mers, count-min, non-HLL sketches, "
-                "nearest neighbours): run the reference binary for it");
+    throw Error(std::string("flag ") + flag + " selects a code path outside the B200 engine (spaced/windowed k-mers, count-min, non-HLL sketches): "
+                "run the reference binary for it");
 }
 
 int dist_main(int argc, char **argv) {
@@ -478,7 +521,10 @@ int dist_main(int argc, char **argv) {
             case 'w': unsupported("-w/--window-size");
             case 'y': unsupported("-y/--countmin");
             case '8': unsupported("-8/--use-bb-minhash");
-            case 143: unsupported("--nearest-neighbors");
+            case 143:                                                           // src/distmain.cpp:89-93
+                if (std::atoi(optarg) <= 0) throw Error("--nearest-neighbors needs a positive count");
+                o.nneighbors = (unsigned)std::atoi(optarg);
+                break;
             default: throw Error("unknown option; see the reference's `dashing dist` usage for the supported subset");
         }
     }
@@ -578,6 +624,22 @@ DB200H_API uint64_t db200h_format_symmetric(const char *names_nl, uint64_t n, co
     const char *p = names_nl;
     for (uint64_t i = 0; i < n; ++i) { const char *e = std::strchr(p, '\n'); names.emplace_back(p, e ? e - p : std::strlen(p)); p = e ? e + 1 : p + std::strlen(p); }
     const std::string s = db200h::format_symmetric(names, packed, (db200h::EmissionFormat)fmt, packed_lower);
+    if (s.size() <= cap) std::memcpy(out, s.data(), s.size());
+    return s.size();
+}
+// nearest-neighbour table: TSV into `out` (fmt 0) or the binary form (fmt 1: 8-byte header + pairs).  Returns bytes needed.
+DB200H_API uint64_t db200h_format_neighbors(const char *names_nl, uint64_t n, uint64_t qoffset, const void *nb, uint64_t rows, uint32_t nn, int fmt,
+                                            char *out, uint64_t cap) {
+    std::vector<std::string> names;
+    const char *p = names_nl;
+    for (uint64_t i = 0; i < n; ++i) { const char *e = std::strchr(p, '\n'); names.emplace_back(p, e ? e - p : std::strlen(p)); p = e ? e + 1 : p + std::strlen(p); }
+    std::string s;
+    if (fmt == 0) s = db200h::format_neighbors(names, qoffset, static_cast<const db200h::Neighbor *>(nb), rows, nn);
+    else {
+        const uint32_t hdr[2] = {(uint32_t)n, nn};
+        s.assign(reinterpret_cast<const char *>(hdr), 8);
+        s.append(static_cast<const char *>(nb), rows * nn * sizeof(db200h::Neighbor));
+    }
     if (s.size() <= cap) std::memcpy(out, s.data(), s.size());
     return s.size();
 }

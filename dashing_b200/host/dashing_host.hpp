@@ -63,6 +63,7 @@ struct DistOptions : SketchOptions {
     int estim = 2, jestim = 2, result_type = 1 /* JI */;
     EmissionFormat emit_fmt = UT_TSV;
     bool presketched = false, cache_sketches = false;
+    unsigned nneighbors = 0;                 // --nearest-neighbors (gargs.number_neighbors, src/dashing.h:255); 0 = all pairs
     std::string sizes_path, dist_path;       // empty -> stdout
 };
 // sketch_core<hll_t>, src/sketch_and_cmp.h:445-538: one .hll per input path
@@ -70,6 +71,10 @@ void sketch_core(const SketchOptions &o, std::vector<std::string> paths);
 // dist_sketch_and_cmp<hll_t> + dist_loop / partdist_loop, src/sketch_and_cmp.h:268-417, :785-880; src/dashing.h:660-712.
 // The last nq entries of inpaths are queries (rectangular mode).
 void dist_sketch_and_cmp(const DistOptions &o, std::vector<std::string> inpaths, size_t nq);
+// nndist_loop's two output forms (src/sketch_and_cmp.h:733-782): rows of `nn` (value, index) pairs, row i named names[i + qoffset]
+struct Neighbor { float value; uint32_t index; };
+std::string format_neighbors(const std::vector<std::string> &names, size_t qoffset, const Neighbor *nb, size_t rows, unsigned nn);
+void write_binary_neighbors(std::FILE *fp, uint32_t npaths, const Neighbor *nb, size_t rows, unsigned nn);
 // sketch_main / dist_main (src/dashing.cpp:294-409, src/distmain.cpp:28-204): the hot subset of the flags
 int sketch_main(int argc, char **argv);
 int dist_main(int argc, char **argv);

@@ -155,6 +155,27 @@ DB200_API int db200_dist_plan_run_symmetric_dev(db200_dist_plan *pl, const db200
 /* Rectangular: sketches [0,nr) of the prepared matrix are references, [nr, nr+nq) queries. */
 DB200_API int db200_dist_plan_run_rect_dev(db200_dist_plan *pl, const db200_dist_params *prm, uint64_t nr, uint64_t nq,
                                  float *d_out, void *stream);
+/* ---- S3b: k nearest neighbours (--nearest-neighbors; nndist_loop / perform_nns, src/sketch_and_cmp.h:642-783) ----
+ * Per sketch, the `nneighbors` best (value, index) pairs over all OTHER sketches (symmetric) or, per query, over all
+ * references (rect), best first: ascending for the distance measures (MASH_DIST, FULL_MASH_DIST, *CONTAINMENT_DIST),
+ * descending for the similarity measures (emt2nntype, src/dashing.h:268-280).  The all-pairs values stay in HBM; only
+ * n x nneighbors pairs come back.  db200_neighbor is layout-compatible with the reference's validx_t =
+ * std::pair<float, uint32_t> (:605).  Semantics are those of the reference run with one thread (and of its -Q/-F mode
+ * with any number of threads): sketches are visited in ascending index and a value replaces the current worst only if
+ * STRICTLY better, which decides which of several equal values at the cut survive; unused slots keep the reference's
+ * (+-FLT_MAX, UINT32_MAX) filler.  Values are result_cmp(..., ksinv = 1./k in double) as at :729 (the all-pairs paths
+ * round ksinv to float first), evaluated as cmp(sketches[j], sketches[i]) for j > i when prm->order is
+ * DB200_ORDER_COL_FIRST (what :670 does).  1 <= nneighbors <= 1024. */
+typedef struct db200_neighbor { float value; uint32_t index; } db200_neighbor;
+DB200_API int db200_dist_knn_symmetric(int device, const uint8_t *regs, uint64_t n, const db200_dist_params *prm, uint32_t nneighbors,
+                             db200_neighbor *out /* [n][nneighbors] */);
+DB200_API int db200_dist_knn_rect(int device, const uint8_t *ref_regs, uint64_t nr, const uint8_t *qry_regs, uint64_t nq,
+                        const db200_dist_params *prm, uint32_t nneighbors, db200_neighbor *out /* [nq][nneighbors] */);
+/* Device form on a prepared plan: nq == 0 -> symmetric over the plan's n sketches (nr ignored), else references
+ * [0,nr) and queries [nr, nr+nq) as in db200_dist_plan_run_rect_dev.  d_out: device db200_neighbor[rows][nneighbors]. */
+DB200_API int db200_dist_plan_run_knn_dev(db200_dist_plan *pl, const db200_dist_params *prm, uint64_t nr, uint64_t nq, uint32_t nneighbors,
+                                db200_neighbor *d_out, void *stream);
+
 /* Device pointer to the plan's per-sketch cardinalities (double[n]) — valid until the next prepare/destroy. */
 DB200_API int db200_dist_plan_cardinalities_dev(db200_dist_plan *pl, const double **d_card);
 /* Launch accounting for bench.py: kernels launched by this library since process start. */

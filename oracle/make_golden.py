@@ -149,6 +149,7 @@ def main():
     h["fname_nopfx"] = np.array(R.make_fname("g1.fna.gz", 10, 0, 21, 21, "", "x", ""))
     np.savez_compressed(os.path.join(OUT, "hll_payload.npz"), **h)
     make_cli_golden(R)
+    make_knn_golden(R)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 
@@ -182,6 +183,32 @@ def cli_inputs():
     return files
 
 
+def knn_inputs():
+    """p=10: the dist.npz set (value ties through the adversarial rows) + 96 small sketches in groups of 8, where most
+    pairs are unrelated (Jaccard exactly 0, Mash exactly 1: long runs of equal values at the cut)."""
+    p = 10
+    a = np.concatenate([synth.registers(7, 24, p, card=3e5), synth.adversarial_registers(3, p)])
+    b = synth.registers(21, 96, p, card=2e4, group=8)
+    return p, a, b
+
+
+KNN_CASES = [  # (input set, rtype, jestim, nneighbors, nq)
+    ("a", 0, 2, 5, 0), ("a", 1, 2, 5, 0), ("a", 1, 3, 7, 0), ("a", 2, 2, 3, 0), ("a", 7, 2, 4, 0), ("a", 8, 2, 64, 0),
+    ("b", 0, 2, 10, 0), ("b", 1, 2, 10, 0), ("b", 3, 2, 1, 0), ("b", 5, 3, 12, 0), ("b", 1, 2, 96, 0),
+    ("b", 0, 2, 6, 32), ("b", 1, 2, 6, 32), ("b", 6, 3, 9, 13), ("a", 1, 2, 40, 5),
+]
+
+
+def make_knn_golden(R):
+    """perform_nns of the reference (one thread: the deterministic visiting order) on seeded register sets."""
+    p, a, b = knn_inputs()
+    out = {"p": np.array(p), "k": np.array(21), "cases": np.array(json.dumps(KNN_CASES))}
+    for ci, (which, rtype, jestim, nn, nq) in enumerate(KNN_CASES):
+        regs = a if which == "a" else b
+        out[f"case{ci}"] = R.knn(regs, p, nn, k=21, jestim=jestim, rtype=rtype, nq=nq, nthreads=1)
+    np.savez_compressed(os.path.join(OUT, "knn.npz"), **out)
+
+
 def make_cli_golden(R):
     """Outputs of the reference's own drivers (sketch_core<hll_t>, dist_sketch_and_cmp<hll_t>) on the small inputs."""
     files = cli_inputs()
@@ -210,6 +237,10 @@ def make_cli_golden(R):
                 "rect_tsv_cont": dict(rtype=5, emit_fmt=0, nq=2),
                 "rect_bin_ji": dict(rtype=1, emit_fmt=1, nq=2),
                 "rect_phylip_mash_jmle": dict(rtype=0, emit_fmt=2, nq=3, jestim=3),
+                # --nearest-neighbors (nndist_loop); one thread = deterministic visiting and output order
+                "nn_tsv_mash": dict(rtype=0, emit_fmt=0, nneighbors=3),
+                "nn_bin_ji": dict(rtype=1, emit_fmt=1, nneighbors=2),
+                "nn_tsv_ji_all": dict(rtype=1, emit_fmt=0, nneighbors=50),
             }
             out["runs"] = np.array(list(runs))
             for rn, kw in runs.items():
@@ -230,4 +261,8 @@ def make_cli_golden(R):
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "knn":       # only the nearest-neighbour fixtures (knn.npz + cli.npz)
+        make_cli_golden(O.ref())
+        make_knn_golden(O.ref())
+    else:
+        main()

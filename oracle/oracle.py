@@ -27,6 +27,9 @@ f32p = C.POINTER(C.c_float)
 f64p = C.POINTER(C.c_double)
 
 
+NEIGHBOR_DTYPE = np.dtype([("value", np.float32), ("index", np.uint32)])   # validx_t, src/sketch_and_cmp.h:605
+
+
 def _ptr(a: np.ndarray, t):
     return a.ctypes.data_as(t)
 
@@ -139,6 +142,7 @@ class Port(_Common):
         l.orc_result_cmp.argtypes = [u8p, u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double]
         l.orc_dist_rows.argtypes = [u8p, C.c_uint64] + [C.c_int] * 6 + [C.c_uint64, C.c_uint64, f32p]
         l.orc_dist_rect.argtypes = [u8p, C.c_uint64, u8p, C.c_uint64] + [C.c_int] * 5 + [f32p]
+        l.orc_knn.argtypes = [u8p, C.c_uint64] + [C.c_int] * 5 + [C.c_uint64, C.c_uint32, C.c_void_p]
         l.orc_hll_payload.restype = C.c_uint64
         l.orc_hll_payload.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_double, u8p, C.c_uint64]
 
@@ -209,6 +213,15 @@ class Port(_Common):
                              _ptr(out, f32p))
         return out
 
+    def knn(self, regs2d, p, nn, k=31, estim=2, jestim=2, rtype=1, nq=0, nthreads=1):
+        """[rows][nn] (value, index), rows = nq or n; the last nq sketches are the queries when nq > 0."""
+        regs2d = np.ascontiguousarray(regs2d, dtype=np.uint8)
+        n = regs2d.shape[0]
+        out = np.zeros((nq if nq else n, nn), dtype=NEIGHBOR_DTYPE)
+        if self.l.orc_knn(_ptr(regs2d, u8p), n, p, k, estim, jestim, rtype, nq, nn, C.c_void_p(out.ctypes.data)):
+            raise RuntimeError("orc_knn failed")
+        return out
+
     def hll_payload(self, regs, p, estim=2, jestim=2, value=-1.0):
         out = np.zeros(28 + (1 << p), dtype=np.uint8)
         n = self.l.orc_hll_payload(_ptr(np.ascontiguousarray(regs), u8p), p, estim, jestim, value, _ptr(out, u8p), out.size)
@@ -251,6 +264,8 @@ class Ref(_Common):
         l.dref_set_create.argtypes = [u8p, C.c_uint64, C.c_int, C.c_int, C.c_int]
         l.dref_set_free.argtypes = [C.c_void_p]
         l.dref_set_dist_rows.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_int, f32p]
+        l.dref_knn.argtypes = [u8p, C.c_uint64] + [C.c_int] * 5 + [C.c_uint64, C.c_uint32, C.c_int, C.c_void_p]
+        l.dref_set_nneighbors.argtypes = [C.c_uint32]
         l.dref_cli_dist.argtypes = [C.c_int, C.POINTER(C.c_char_p)] + [C.c_int] * 10 + [C.c_char_p, C.c_char_p, C.c_int, C.c_char_p, C.c_char_p]
         l.dref_cli_sketch.argtypes = [C.c_int, C.POINTER(C.c_char_p)] + [C.c_int] * 4 + [C.c_char_p, C.c_char_p, C.c_int]
         l.dref_hll_write.argtypes = [C.c_char_p, u8p, C.c_int, C.c_int, C.c_int, C.c_int]
@@ -361,6 +376,14 @@ class Ref(_Common):
                               nthreads or usable_cores(), _ptr(out, f32p))
         return out
 
+    def knn(self, regs2d, p, nn, k=31, estim=2, jestim=2, rtype=1, nq=0, nthreads=1):
+        """The reference's perform_nns; nthreads=1 is the deterministic order."""
+        regs2d = np.ascontiguousarray(regs2d, dtype=np.uint8)
+        n = regs2d.shape[0]
+        out = np.zeros((nq if nq else n, nn), dtype=NEIGHBOR_DTYPE)
+        self.l.dref_knn(_ptr(regs2d, u8p), n, p, k, estim, jestim, rtype, nq, nn, nthreads, C.c_void_p(out.ctypes.data))
+        return out
+
     def hll_write(self, path, regs, p, estim=2, jestim=2, calculated=False):
         rc = self.l.dref_hll_write(os.fsencode(path), _ptr(np.ascontiguousarray(regs), u8p), p, estim, jestim,
                                    int(calculated))
@@ -377,9 +400,12 @@ class Ref(_Common):
         return regs[: 1 << p.value].copy(), p.value, e.value, j.value, v.value
 
     def cli_dist(self, paths, sizes_path, dist_path, nq=0, k=31, p=10, canon=True, estim=2, jestim=2, rtype=1, emit_fmt=0,
-                 presketched=False, nthreads=1, cache=False, prefix="", suffix=""):
+                 presketched=False, nthreads=1, cache=False, prefix="", suffix="", nneighbors=0):
         """The reference's dist_sketch_and_cmp<hll_t> (sizes file + distance output), paths in final order."""
         arr = (C.c_char_p * len(paths))(*[os.fsencode(p_) for p_ in paths])
+        self.l.dref_set_nneighbors(nneighbors)
+        if nneighbors:
+            emit_fmt |= 8          # NEAREST_NEIGHBOR_TABLE, src/enums.h:32; src/distmain.cpp:106-109
         rc = self.l.dref_cli_dist(len(paths), arr, nq, k, p, int(canon), estim, jestim, rtype, emit_fmt, int(presketched), nthreads,
                                   os.fsencode(sizes_path), os.fsencode(dist_path), int(cache), prefix.encode(), suffix.encode())
         if rc:

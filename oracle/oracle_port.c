@@ -333,9 +333,8 @@ ORC_API double orc_jaccard(const uint8_t *a, const uint8_t *b, int p, int estim,
 /* a15. result_cmp — src/dashing.h:568-592 with dist_index :154-156, containment_dist :163-165,
  * full_dist_index :172-174, full_containment_dist :181-183.  EmissionType numbering: src/enums.h:13-23.
  * lhs / rhs keep the operand order of the call site. */
-ORC_API float orc_result_cmp(const uint8_t *lhs, const uint8_t *rhs, int p, int estim, int jestim, int rtype, int k,
-                             double cL, double cR) {
-    const double ksinv = (double)(float)(1. / k); /* float ksinv promoted, src/sketch_and_cmp.h:797 */
+static float result_cmp_dks(const uint8_t *lhs, const uint8_t *rhs, int p, int estim, int jestim, int rtype, double ksinv,
+                            double cL, double cR) {
     double ret;
     if (rtype == 0 || rtype == 1 || rtype == 3) {
         ret = orc_jaccard(lhs, rhs, p, estim, jestim, cL, cR);
@@ -355,6 +354,12 @@ ORC_API float orc_result_cmp(const uint8_t *lhs, const uint8_t *rhs, int p, int 
         } /* rtype == 2 (SIZES): intersection size */
     }
     return (float)ret;
+}
+
+ORC_API float orc_result_cmp(const uint8_t *lhs, const uint8_t *rhs, int p, int estim, int jestim, int rtype, int k,
+                             double cL, double cR) {
+    /* float ksinv promoted, src/sketch_and_cmp.h:797 */
+    return result_cmp_dks(lhs, rhs, p, estim, jestim, rtype, (double)(float)(1. / k), cL, cR);
 }
 
 /* a16. symmetric all-pairs, packed upper triangle in distmat order (distmat/distmat.h:260-276).
@@ -390,6 +395,66 @@ ORC_API int orc_dist_rect(const uint8_t *ref_regs, uint64_t nr, const uint8_t *q
     free(cr); free(cq);
     return 0;
 }
+
+/* ---- k nearest neighbours: perform_nns + lock_update / lockfree_update (src/sketch_and_cmp.h:605-697) -------------
+ * The reference keeps a binary heap per sketch and replaces its top whenever a new value is strictly better than the
+ * top's value; the top of a std::less heap of pairs is the lexicographically largest (value, index), of a std::greater
+ * heap the smallest.  Only WHICH pair is evicted matters, so a linear scan for the extreme stands in for the heap.
+ * Visiting order: ascending index (the reference's order with one thread; its -Q/-F mode always).  Values: result_cmp
+ * with ksinv = 1./k in double (:729), as cmp(sketches[j], sketches[i]) for j > i (:670) / cmp(ref, query) (:686). */
+typedef struct { float v; uint32_t i; } orc_nb;
+
+static int nb_less(orc_nb a, orc_nb b) { return a.v < b.v || (!(b.v < a.v) && a.i < b.i); }   /* std::pair operator< */
+
+static void nb_update(orc_nb *heap, uint32_t nn, float val, uint32_t idx, int sim) {
+    /* heap "top": sim -> min under nb_less (std::greater heap), else max */
+    uint32_t top = 0;
+    for (uint32_t e = 1; e < nn; ++e)
+        if (sim ? nb_less(heap[e], heap[top]) : nb_less(heap[top], heap[e])) top = e;
+    if (sim ? (val > heap[top].v) : (val < heap[top].v)) { heap[top].v = val; heap[top].i = idx; }
+}
+
+static int nb_cmp_less(const void *a, const void *b) {
+    const orc_nb x = *(const orc_nb *)a, y = *(const orc_nb *)b;
+    return nb_less(x, y) ? -1 : (nb_less(y, x) ? 1 : 0);
+}
+static int nb_cmp_greater(const void *a, const void *b) { return nb_cmp_less(b, a); }
+
+static float result_cmp_dks(const uint8_t *lhs, const uint8_t *rhs, int p, int estim, int jestim, int rtype, double ksinv,
+                            double cL, double cR);
+
+/* regs: n sketches; nq > 0: the last nq are the queries and the first n - nq the references.  out: [rows][nn]. */
+ORC_API int orc_knn(const uint8_t *regs, uint64_t n, int p, int k, int estim, int jestim, int rtype, uint64_t nq, uint32_t nn,
+                    void *out_) {
+    orc_nb *out = (orc_nb *)out_;
+    const uint64_t m = 1ull << p, rows = nq ? nq : n;
+    /* emt2nntype, src/dashing.h:268-280 */
+    const int sim = !(rtype == 0 || rtype == 3 || rtype == 4 || rtype == 6 || rtype == 8);
+    const double ksinv = 1. / k;
+    double *card = (double *)malloc(sizeof(double) * (n ? n : 1));
+    if (!card) return 1;
+    for (uint64_t i = 0; i < n; ++i) card[i] = orc_cardinality(regs + i * m, p, estim);
+    for (uint64_t i = 0; i < rows * nn; ++i) { out[i].v = sim ? -3.402823466e+38f : 3.402823466e+38f; out[i].i = 0xFFFFFFFFu; }
+    if (nq == 0) {
+        for (uint64_t i = 0; i < n; ++i)
+            for (uint64_t j = i + 1; j < n; ++j) {
+                const float val = result_cmp_dks(regs + j * m, regs + i * m, p, estim, jestim, rtype, ksinv, card[j], card[i]);
+                nb_update(out + i * nn, nn, val, (uint32_t)j, sim);
+                nb_update(out + j * nn, nn, val, (uint32_t)i, sim);
+            }
+    } else {
+        const uint64_t nr = n - nq;
+        for (uint64_t q = 0; q < nq; ++q)
+            for (uint64_t j = 0; j < nr; ++j)
+                nb_update(out + q * nn, nn,
+                          result_cmp_dks(regs + j * m, regs + (nr + q) * m, p, estim, jestim, rtype, ksinv, card[j], card[nr + q]),
+                          (uint32_t)j, sim);
+    }
+    for (uint64_t r = 0; r < rows; ++r) qsort(out + r * nn, nn, sizeof(orc_nb), sim ? nb_cmp_greater : nb_cmp_less);
+    free(card);
+    return 0;
+}
+
 
 /* a7. decompressed .hll payload — hll.h:1039-1047: u32[4]{is_calculated, estim, jestim, 1}, u32 p,
  * f64 value, u8[2^p]; 28 + 2^p bytes, little-endian.  Returns bytes written (0 if cap too small). */

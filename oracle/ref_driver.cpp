@@ -242,6 +242,26 @@ int dref_dist_rect(const uint8_t *ref_regs, uint64_t nr, const uint8_t *qry_regs
     return 0;
 }
 
+// Nearest neighbours through the reference's own perform_nns (src/sketch_and_cmp.h:642-697), values as in nndist_loop
+// (:729-730: result_cmp with ksinv = 1./k in DOUBLE).  regs = all n sketches; nq > 0: the last nq are queries.
+// out: validx_t[rows][nn], rows = nq ? nq : n.  nthreads = 1 makes the symmetric mode deterministic.
+int dref_knn(const uint8_t *regs, uint64_t n, int p, int k, int estim, int jestim, int rtype, uint64_t nq, uint32_t nn,
+             int nthreads, void *out) {
+    static_assert(sizeof(validx_t) == 8, "validx_t layout");
+    if(nthreads <= 0) nthreads = omp_get_max_threads();
+    const int prev = omp_get_max_threads();
+    omp_set_num_threads(nthreads);
+    std::vector<hll_t> sk = make_sketches(regs, n, p, estim, jestim);
+    std::vector<std::string> inpaths(n);
+    const EmissionType rt = (EmissionType)rtype;
+    const double ksinv = 1. / k;
+    auto call_cmp = [rt, ksinv](const auto &x, const auto &y) {return result_cmp(x, y, rt, ksinv);};
+    perform_nns(static_cast<validx_t *>(out), sk.data(), inpaths, (unsigned)k, rt, (size_t)nq, (unsigned)nn,
+                emt2nntype(rt) == SIMILARITY_MEASURE, call_cmp);
+    omp_set_num_threads(prev);
+    return 0;
+}
+
 // .hll container via the reference's own writer/reader (gz).  A freshly sketched hll_t is written
 // with value_ = -1 ("not calculated"), as sketch_core does (src/sketch_and_cmp.h:522).
 int dref_hll_write(const char *path, const uint8_t *regs, int p, int estim, int jestim, int calculated) {
@@ -299,6 +319,10 @@ int dref_cli_dist(int npaths, const char **paths, int nq, int k, int p, int cano
     } catch(const std::exception &e) { std::fprintf(stderr, "dref_cli_dist: %s\n", e.what()); return 1; }
     return 0;
 }
+
+// --nearest-neighbors N (src/distmain.cpp:89-93, :106-109): N > 0 and emit_fmt | NEAREST_NEIGHBOR_TABLE (8) make
+// dist_sketch_and_cmp call nndist_loop instead of dist_loop (src/sketch_and_cmp.h:398-400).
+void dref_set_nneighbors(uint32_t n) { gargs.number_neighbors = n; }
 
 // `dashing sketch` for the HLL sketch type (src/dashing.cpp:374-394 -> sketch_core<hll_t>), paths in final order.
 int dref_cli_sketch(int npaths, const char **paths, int k, int p, int canon, int nthreads, const char *prefix, const char *suffix,

@@ -21,6 +21,8 @@ def load():
     l.db200h_format_sizes.argtypes = [C.c_char_p, C.c_uint64, C.c_void_p, C.c_char_p, C.c_uint64]
     l.db200h_format_rect_row.restype = C.c_uint64
     l.db200h_format_rect_row.argtypes = [C.c_char_p, C.c_void_p, C.c_uint64, C.c_char_p, C.c_uint64]
+    l.db200h_format_neighbors.restype = C.c_uint64
+    l.db200h_format_neighbors.argtypes = [C.c_char_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint32, C.c_int, C.c_char_p, C.c_uint64]
     l.db200h_read_records.restype = C.c_int64
     l.db200h_read_records.argtypes = [C.c_char_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
     return l
@@ -48,6 +50,17 @@ def format_sizes(l, names, card):
     cap = 1 << 20
     buf = C.create_string_buffer(cap)
     n = l.db200h_format_sizes("\n".join(names).encode() + b"\n", len(names), card.ctypes.data, buf, cap)
+    return buf.raw[:n]
+
+
+def format_neighbors(l, names, qoffset, nb, fmt):
+    """nb: structured array [rows][nn] of (value f32, index u32)."""
+    nb = np.ascontiguousarray(nb)
+    rows, nn = nb.shape
+    cap = 1 << 20
+    buf = C.create_string_buffer(cap)
+    n = l.db200h_format_neighbors("\n".join(names).encode() + b"\n", len(names), qoffset, nb.ctypes.data, rows, nn, fmt, buf, cap)
+    assert n <= cap
     return buf.raw[:n]
 
 
@@ -87,6 +100,9 @@ def assert_text_matches(got: bytes, want: bytes, rtol=2e-5, what=""):
         for x, y in zip(fa, fb):
             if x == y:
                 continue
+            if b":" in x and b":" in y:          # nearest-neighbour tables: "<index>:<value>"
+                (xi, x), (yi, y) = x.split(b":", 1), y.split(b":", 1)
+                assert xi == yi, f"{what}: neighbour index {xi!r} != {yi!r} in {a!r} vs {b!r}"
             assert _NUM.match(x.strip()) and _NUM.match(y.strip()), f"{what}: {x!r} != {y!r}"
             fx, fy = float(x), float(y)
             assert abs(fx - fy) <= rtol * max(abs(fx), abs(fy), 1e-30), f"{what}: {x!r} vs {y!r}"

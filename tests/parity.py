@@ -47,3 +47,29 @@ def unstable_size(intersection_want, scale, eps=1e-9):
     discontinuity at 0) is decided by rounding noise in the reference itself and is not compared."""
     s = np.asarray(intersection_want, dtype=np.float64)
     return ~(np.isfinite(s) & (np.abs(s) >= eps * scale))
+
+
+def assert_knn_close(got, want, rtol=RTOL, what=""):
+    """Nearest-neighbour tables [rows][nn] of (value, index).
+
+    Values: position by position within `rtol` (the filler +-FLT_MAX must match exactly).  Indices: equal wherever the
+    values around them are distinct beyond `rtol`; where several candidates are within `rtol` of each other the order
+    (and, at the cut, the membership) is decided by the last float bit, so an index mismatch at position j is accepted
+    only if the checker's row holds that index at a value within `rtol` of position j's, or does not hold it at all and
+    position j's value is within `rtol` of the row's last (worst retained) value."""
+    gv, gi = np.asarray(got["value"], dtype=np.float64), np.asarray(got["index"])
+    wv, wi = np.asarray(want["value"], dtype=np.float64), np.asarray(want["index"])
+    assert gv.shape == wv.shape, f"{what}: shape {gv.shape} vs {wv.shape}"
+    assert_close(gv, wv, rtol=rtol, what=what + " values")
+    bad_rows, bad_cols = np.nonzero(gi != wi)
+    for r, j in zip(bad_rows, bad_cols):
+        v = gv[r, j]
+        pos = np.nonzero(wi[r] == gi[r, j])[0]
+        near = lambda x: abs(x - v) <= rtol * max(abs(x), abs(v), 1.0)
+        if pos.size:
+            ok = near(wv[r, pos[0]])
+        else:
+            ok = near(wv[r, -1])
+        if not ok:
+            raise AssertionError(f"{what}: row {r} slot {j}: got ({v}, {gi[r, j]}), want ({wv[r, j]}, {wi[r, j]})\n"
+                                 f" got  {got[r]}\n want {want[r]}")

@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 
 import hostlib
-from parity import assert_close
+from parity import assert_close, assert_knn_close
 
 pytestmark = pytest.mark.gpu
 
@@ -56,6 +56,8 @@ def test_cli_dist_all_formats(gpu, cli, tmp_path):
             args.append("-J")
         if kw.get("estim") == 0:
             args.append("-E")
+        if kw.get("nneighbors"):
+            args += ["--nearest-neighbors", str(kw["nneighbors"])]
         if nq:
             (tmp_path / "refs.txt").write_text("\n".join(names[:-nq]) + "\n")
             (tmp_path / "qry.txt").write_text("\n".join(names[-nq:]) + "\n")
@@ -65,7 +67,12 @@ def test_cli_dist_all_formats(gpu, cli, tmp_path):
         run_cli(str(tmp_path), *args)
         assert (tmp_path / "sizes.txt").read_bytes() == cli[run + "_sizes"].tobytes(), f"{run}: sizes file"
         got, want = (tmp_path / "dist.out").read_bytes(), cli[run + "_dist"].tobytes()
-        if kw.get("emit_fmt") == 1:
+        if kw.get("nneighbors") and kw.get("emit_fmt") == 1:
+            dt = np.dtype([("value", np.float32), ("index", np.uint32)])
+            assert got[:8] == want[:8] and len(got) == len(want), run
+            nn = int(np.frombuffer(got[4:8], np.uint32)[0])
+            assert_knn_close(np.frombuffer(got[8:], dt).reshape(-1, nn), np.frombuffer(want[8:], dt).reshape(-1, nn), what=run)
+        elif kw.get("emit_fmt") == 1:
             hdr = 0 if nq else 9
             assert got[:hdr] == want[:hdr] and len(got) == len(want), run
             assert_close(np.frombuffer(got[hdr:], np.float32), np.frombuffer(want[hdr:], np.float32), what=run)

@@ -109,3 +109,28 @@ def test_sizes_and_rect_formats(host, cli):
         assert hostlib.format_rect_row(host, f[0].decode(), [float(x) for x in f[1:]]) == line + b"\n"
     raw = np.frombuffer(cli["rect_bin_ji_dist"].tobytes(), dtype=np.float32)
     assert raw.size == 2 * 4                                                              # nq x nr floats, no header
+
+
+def test_neighbor_formats_byte_exact(host, cli):
+    """nndist_loop's outputs (src/sketch_and_cmp.h:733-782) re-formatted from the values the reference printed / wrote."""
+    names = [str(x) for x in cli["names"]]
+    n = len(names)
+    dt = np.dtype([("value", np.float32), ("index", np.uint32)])
+    # binary table: uint32 n, uint32 nn, pairs
+    raw = cli["nn_bin_ji_dist"].tobytes()
+    hdr = np.frombuffer(raw[:8], dtype=np.uint32)
+    assert hdr[0] == n and hdr[1] == 2
+    nb = np.frombuffer(raw[8:], dtype=dt).reshape(n, 2)
+    assert hostlib.format_neighbors(host, names, 0, nb, 1) == raw
+    # TSV tables, including the (uint32(-1), -FLT_MAX) filler printed as "-1:-3.40282e+38"
+    for run in ("nn_tsv_mash", "nn_tsv_ji_all"):
+        want = cli[run + "_dist"].tobytes()
+        lines = want.decode().strip("\n").split("\n")
+        assert lines[0] == "#File\tNeighbor ID:distance\t..."
+        rows = []
+        for ln in lines[1:]:
+            f = ln.split("\t")
+            rows.append([(np.float32(x.split(":")[1]), np.uint32(int(x.split(":")[0]) & 0xFFFFFFFF)) for x in f[1:]])
+        nb = np.array(rows, dtype=dt)
+        assert hostlib.format_neighbors(host, names, 0, nb, 0) == want, run
+    assert b"\t-1:-3.40282e+38\n" in cli["nn_tsv_ji_all_dist"].tobytes()
