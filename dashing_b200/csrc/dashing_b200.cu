@@ -473,10 +473,12 @@ static int plan_run(db200_dist_plan *pl, const db200_dist_params *prm, int rect,
         int S = 6;
         const size_t budget2 = 113 << 10, budget1 = 226 << 10;
         if (gbytes + 2 * STAGE_BYTES + 1024 > budget1) { set_error("dist: %d live thresholds do not fit in shared memory at p=%d", pl->K, pl->p); return DB200_EUNSUPPORTED; }
+        // two CTAs per SM matter more than pipeline depth: drop to 5 or 4 stages before giving up the second CTA
+        while (S > 4 && gbytes + (size_t)S * STAGE_BYTES + 1024 > budget2) --S;
         if (gbytes + (size_t)S * STAGE_BYTES + 1024 > budget2) S = (int)std::min<size_t>(12, (budget1 - gbytes - 1024) / STAGE_BYTES);
         a.stages = S;
-        a.sparse = S >= 4;   // the stage buffers double as sparse-tail storage (29 KB); with fewer stages every threshold is dense
-        a.low = S >= 6;      // ... plus 16 KB for the low tails
+        a.sparse = S >= 4;   // the stage buffers double as sparse-tail storage (16 + 3.6 KB); with fewer stages every threshold is dense
+        a.low = S >= 5;      // ... plus 16 KB for the low tails
         const size_t smem = (size_t)S * STAGE_BYTES + gbytes + 2 * S * 8;
         if (wide) {
             DB200_CUDA(cudaFuncSetAttribute(dist_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 << 10));

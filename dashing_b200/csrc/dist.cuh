@@ -298,7 +298,7 @@ struct DistArgs {
     int estim, rtype;
     int rect;                         // 0 symmetric, 1 rectangular (A = queries, B = references)
     int stages;
-    int low;                          // 1: low tails are staged too (needs 45 KB of stage buffers)
+    int low;                          // 1: low tails are staged too (16 + 16 + 3.6 KB: needs 5 stage buffers; sparse alone 4)
     int sparse;                       // 0: shared memory too tight to stage the sparse tails -> every live threshold is swept densely
     int one;                          // 1 — a runtime value so that ptxas keeps `popc * one + acc` as an IMAD (FMA pipe)
 };
@@ -502,9 +502,10 @@ __global__ void __launch_bounds__(DIST_THREADS, 2) dist_kernel(const __grid_cons
     // ---------------- sparse tails of the 64 sketches of the tile -> shared memory (re-using the stage buffers) --------
     const uint32_t m = 1u << a.p;
     const int ns = hi - Td + 1;                                       // sparse thresholds Td..hi
-    uint32_t *L = reinterpret_cast<uint32_t *>(stage_mem);             // [2*DT][SPARSE_C]
-    uint32_t *CN = L + 2 * DT * SPARSE_C;                              // [2*DT][ns]: #{reg >= Td + kk}
-    uint32_t *LL = L + 2 * DT * (SPARSE_C + 52);                       // [2*DT][SPARSE_C] low tails (a.low only)
+    uint32_t *L = reinterpret_cast<uint32_t *>(stage_mem);             // [2*DT][SPARSE_C]                        16 KB
+    uint32_t *LL = L + 2 * DT * SPARSE_C;                              // [2*DT][SPARSE_C] low tails (a.low only)  16 KB
+    // [2*DT][ns]: #{reg >= Td + kk} — at most SPARSE_C for every threshold >= Td >= T_s, so a byte each (<= 3.6 KB)
+    uint8_t *CN = reinterpret_cast<uint8_t *>(L + (a.low ? 4 : 2) * DT * SPARSE_C);
     const int nl = kd0 - 1 - lo;                                       // low-sparse thresholds lo+1 .. kd0-1
     if (nl > 0) {
         for (uint32_t e = threadIdx.x; e < 2 * DT * SPARSE_C; e += DIST_THREADS) {
@@ -531,7 +532,7 @@ __global__ void __launch_bounds__(DIST_THREADS, 2) dist_kernel(const __grid_cons
             const uint32_t row = e / ns;
             const int k = Td + (int)(e % ns);
             const uint64_t sk = row < DT ? rowA0 + row : rowB0 + (row - DT);
-            CN[e] = (sk < a.n && k <= a.gmax) ? (k <= a.gmin ? m : a.counts[sk * 64 + (k - a.gmin - 1)]) : 0u;
+            CN[e] = (uint8_t)((sk < a.n && k <= a.gmax) ? a.counts[sk * 64 + (k - a.gmin - 1)] : 0u);   // k >= Td > gmin
         }
     }
     __syncthreads();
@@ -567,8 +568,8 @@ __global__ void __launch_bounds__(DIST_THREADS, 2) dist_kernel(const __grid_cons
         }
         if (ns > 0) {
             GT *g = G + (size_t)(Td - lo) * (DT * DT) + pair;
-            const uint32_t *ca = CN + il * ns, *cb = CN + (DT + jl) * ns;
-            for (int kk = 0; kk < ns; ++kk) g[kk * (DT * DT)] = (GT)(ca[kk] + cb[kk]);
+            const uint8_t *ca = CN + il * ns, *cb = CN + (DT + jl) * ns;
+            for (int kk = 0; kk < ns; ++kk) g[kk * (DT * DT)] = (GT)((uint32_t)ca[kk] + cb[kk]);
             // merge the two index-sorted tails; a register present in both with min value mn was counted twice for k <= mn
             const uint32_t *la = L + il * SPARSE_C, *lb = L + (DT + jl) * SPARSE_C;
             int ia = 0, ib = 0;

@@ -153,3 +153,27 @@ def test_wide_counts_full_value_range(gpu, checker):
     card = checker.cardinalities(regs, p, 2)
     ign = unstable_size(checker.dist_rows(regs, p, k=21, rtype=2), float(np.max(card[np.isfinite(card)])))
     assert_close(got, want, ignore=ign, what="p=17 full range")
+
+
+@pytest.mark.parametrize("vmax,label", [(31, "6 stages"), (34, "5 stages, both tails"), (38, "4 stages, sparse tails only"), (45, "one CTA per SM")])
+def test_live_threshold_count_selects_the_pipeline_shape(gpu, checker, vmax, label):
+    """The number of live thresholds K = gmax - gmin decides how much shared memory is left for the TMA ring and the
+    staged tails (plan_run): 2 CTAs/SM with 6, 5 or 4 stages, then 1 CTA/SM.  Same results in every shape — and at
+    100,000 real sketches K is about 35, so these are not corner cases."""
+    p = 14
+    regs = synth.registers(23, 40, p, card=3e6, group=8)
+    rng = np.random.default_rng(vmax)
+    regs = np.minimum(regs, vmax).astype(np.uint8)
+    # plant the extremes: a few empty registers (gmin = 0) and a few at vmax (gmax = vmax), plus a mid-range sprinkle
+    for s in range(regs.shape[0]):
+        idx = rng.choice(1 << p, size=40, replace=False)
+        regs[s, idx[:5]] = 0
+        regs[s, idx[5:8]] = vmax
+        regs[s, idx[8:]] = rng.integers(1, vmax + 1, size=32)
+    assert int(regs.min()) == 0 and int(regs.max()) == vmax
+    for jestim, rtype in ((2, 1), (2, 0), (3, 1)):
+        got = gpu.dist_symmetric(regs, p, k=21, jestim=jestim, result_type=rtype)
+        want = checker.dist_rows(regs, p, k=21, jestim=jestim, rtype=rtype)
+        card = checker.cardinalities(regs, p, 2)
+        ign = unstable_size(checker.dist_rows(regs, p, k=21, jestim=jestim, rtype=2), float(np.max(card)))
+        assert_close(got, want, ignore=ign, what=f"K={vmax} ({label}) j{jestim} r{rtype}")
