@@ -44,6 +44,7 @@ _SIGS = {
     "db200_last_error": (C.c_char_p, []),
     "db200_version": (C.c_int, []),
     "db200_device_count": (C.c_int, []),
+    "db200_warmup": (C.c_int, [C.c_int]),
     "db200_host_alloc": (C.c_int, [C.POINTER(vp), C.c_size_t]),
     "db200_host_free": (C.c_int, [vp]),
     "db200_sketcher_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, C.POINTER(vp)]),

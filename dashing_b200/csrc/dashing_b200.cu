@@ -632,6 +632,12 @@ int db200_device_count(void) {
     return n;
 }
 
+int db200_warmup(int device) {
+    DB200_TRY(check_device(device));
+    DB200_CUDA(cudaFree(nullptr));
+    return DB200_OK;
+}
+
 int db200_host_alloc(void **out, size_t bytes) {
     if (!out) { set_error("db200_host_alloc: null out"); return DB200_EINVAL; }
     DB200_TRY(check_device(0));

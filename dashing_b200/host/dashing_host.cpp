@@ -8,6 +8,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <future>
+#include <memory>
 #include <getopt.h>
 #include <sys/stat.h>
 #include <zlib.h>
@@ -19,6 +21,17 @@ namespace db200h {
 
 static void check(int rc) {
     if (rc != DB200_OK) throw Error(db200_last_error());
+}
+
+// DB200_TIMING=1: phase timings of the drivers on stderr (wall clock since the first call)
+static void phase(const char *what) {
+    static const bool on = std::getenv("DB200_TIMING") != nullptr;
+    if (!on) return;
+    static const double t0 = omp_get_wtime();
+    static double last = t0;
+    const double now = omp_get_wtime();
+    std::fprintf(stderr, "[db200 timing] %-28s +%8.3f ms  (t = %8.3f ms)\n", what, (now - last) * 1e3, (now - t0) * 1e3);
+    last = now;
 }
 
 static bool isfile(const std::string &p) {
@@ -130,6 +143,22 @@ void sort_paths_by_fsize(std::vector<std::string> &paths) {
 // FASTA / FASTQ
 // ---------------------------------------------------------------------------------------------------------------
 namespace {
+// Destination of sequence bytes: a growing std::string, or a caller-owned window that must not be overrun.
+struct SeqSink {
+    std::string *str = nullptr;
+    char *dst = nullptr;
+    size_t len = 0, cap = 0;
+    bool overflow = false;
+    void append(const char *s, size_t l) {
+        if (str) { str->append(s, l); len = str->size(); return; }
+        if (len + l > cap) { overflow = true; return; }
+        std::memcpy(dst + len, s, l);
+        len += l;
+    }
+    char back() const { return str ? str->back() : dst[len - 1]; }
+    void pop_back() { if (str) str->pop_back(); --len; }
+};
+
 struct LineReader {
     gzFile fp;
     std::vector<char> buf;
@@ -146,41 +175,67 @@ struct LineReader {
         pos = 0; end = n > 0 ? (size_t)n : 0;
         if (n <= 0) eof = true;
     }
-    // appends the rest of the current line (without the newline / trailing CR) to `out` (or discards it)
-    void line(std::string *out) {
+    // appends the rest of the current line (without the newline / trailing CR) to `out` (or discards it); `floor` is the
+    // sink length at the start of the record: kseq strips a trailing CR only while the record holds more than it
+    // (ks_getuntil2, bonsai/klib/kseq.h:140-141: `str->l > 1`)
+    size_t line(SeqSink *out, size_t floor = 0) {
+        size_t got = 0;
         for (;;) {
-            if (pos == end) { fill(); if (pos == end) return; }
+            if (pos == end) { fill(); if (pos == end) return got; }
             const char *s = buf.data() + pos;
             const char *nl = (const char *)std::memchr(s, '\n', end - pos);
             const size_t len = nl ? (size_t)(nl - s) : end - pos;
             if (out) out->append(s, len);
+            got += len;
             pos += len + (nl ? 1 : 0);
-            if (nl) { if (out && !out->empty() && out->back() == '\r') out->pop_back(); return; }
+            if (nl) {
+                if (out && !out->overflow && out->len > floor + 1 && out->back() == '\r') { out->pop_back(); --got; }
+                return got;
+            }
         }
     }
 };
-} // namespace
 
-void for_each_record(const std::string &file, const std::function<void(const char *, size_t)> &fn) {
+// kseq_read's record loop (bonsai/klib/kseq.h:177-218) over one file; record boundaries (sink lengths) go to `ends`.
+void parse_records(const std::string &file, SeqSink &sink, std::vector<uint64_t> &ends) {
     gzFile fp = gzopen(file.c_str(), "rb");
     if (!fp) throw Error("Could not open file at " + file + ". Abort!");
     gzbuffer(fp, 1 << 18);
     LineReader lr(fp);
-    std::string seq, tmp;
     int c;
-    while ((c = lr.peek()) != -1) {
+    while ((c = lr.peek()) != -1 && !sink.overflow) {
         if (c != '>' && c != '@') { lr.line(nullptr); continue; }   // skip to the next header
         lr.line(nullptr);                                          // name + comment
-        seq.clear();
-        while ((c = lr.peek()) != -1 && c != '>' && c != '+' && c != '@') lr.line(&seq);
+        const size_t rs = sink.len;
+        while ((c = lr.peek()) != -1 && c != '>' && c != '+' && c != '@') lr.line(&sink, rs);
         if (c == '+') {                                            // FASTQ: skip the '+' line and the qualities
             lr.line(nullptr);
-            size_t got = 0;
-            while (got < seq.size() && lr.peek() != -1) { tmp.clear(); lr.line(&tmp); got += tmp.size(); }
+            std::string qual;                                       // qual.l < seq.l, kseq.h:210
+            SeqSink qs;
+            qs.str = &qual;
+            while (qs.len < sink.len - rs && lr.peek() != -1) lr.line(&qs, 0);
         }
-        fn(seq.data(), seq.size());
+        ends.push_back(sink.len);
     }
     gzclose(fp);
+}
+} // namespace
+
+size_t parse_into_window(const std::string &file, char *dst, size_t cap, std::vector<uint64_t> &ends) {
+    SeqSink sk;
+    sk.dst = dst; sk.cap = cap;
+    parse_records(file, sk, ends);
+    return sk.overflow ? SIZE_MAX : sk.len;
+}
+
+void for_each_record(const std::string &file, const std::function<void(const char *, size_t)> &fn) {
+    std::string seq;
+    SeqSink sink;
+    sink.str = &seq;
+    std::vector<uint64_t> ends;
+    parse_records(file, sink, ends);
+    uint64_t b = 0;
+    for (uint64_t e : ends) { fn(seq.data() + b, e - b); b = e; }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -277,48 +332,156 @@ Genome load_genome(const std::string &path) {
     return g;
 }
 
-// Sketch a list of paths in batches through db200_sketch_batch; out[i] receives 2^p registers.
+// One input file of a batch: parsed straight into its window of the batch arena.
+struct FileSlot {
+    size_t genome = 0;          // index into the batch
+    std::string path;
+    size_t cap = 0, off = 0, used = 0;
+    std::vector<uint64_t> ends; // record ends, relative to `off`
+    bool redo = false;          // window too small (multi-member gzip, ...): the genome goes through load_genome instead
+};
+
+// Upper bound on the sequence bytes of a file: its size, or for gzip the ISIZE trailer (RFC 1952; wrong for multi-member
+// files such as bgzip output — those overflow their window and take the load_genome path).
+size_t file_capacity(const std::string &f) {
+    struct stat st;
+    if (::stat(f.c_str(), &st) != 0) throw Error("Could not open file at " + f + ". Abort!");
+    size_t cap = (size_t)st.st_size;
+    std::FILE *fp = std::fopen(f.c_str(), "rb");
+    if (!fp) throw Error("Could not open file at " + f + ". Abort!");
+    unsigned char magic[2] = {0, 0};
+    if (std::fread(magic, 1, 2, fp) == 2 && magic[0] == 0x1f && magic[1] == 0x8b && st.st_size >= 18) {
+        uint32_t isize = 0;
+        if (std::fseek(fp, -4, SEEK_END) == 0 && std::fread(&isize, 4, 1, fp) == 1) cap = isize;
+    }
+    std::fclose(fp);
+    return cap;
+}
+
+struct Batch {
+    std::vector<size_t> which;          // genome -> index into the caller's path list
+    std::vector<FileSlot> slots;
+    std::vector<uint64_t> rec_offs, grb;
+    std::vector<uint8_t> regs;
+    std::vector<size_t> redo;           // batch genomes to be re-read through load_genome
+    size_t bytes = 0;
+};
+
+// Sketch a list of paths through db200_sketch_batch.  Files are parsed in parallel straight into one reusable arena per
+// batch (no per-genome strings, no concatenation pass; the unused tail of a window becomes a record of 'N's, which holds
+// no k-mer), and the GPU call + register hand-off of batch b run on a helper thread while batch b+1 is being parsed.
 void sketch_paths(const SketchOptions &o, const std::vector<std::string> &paths, const std::vector<size_t> &which,
                   const std::function<void(size_t, const uint8_t *)> &sink) {
+    if (which.empty()) return;
     const size_t m = size_t(1) << o.p;
+    const int nt = std::max(1, o.nthreads);
+    // CUDA initialisation (seconds on a multi-GPU node) overlaps the parsing of the first batch
+    std::future<std::string> warm = std::async(std::launch::async, [&o] {   // (the error text is thread-local: carry it over)
+        return db200_warmup(o.device) == DB200_OK ? std::string() : std::string(db200_last_error());
+    });
+    std::unique_ptr<char[]> arena[2];
+    size_t arena_cap[2] = {0, 0};
+    std::future<void> inflight;
+    int cur = 0;
     size_t at = 0;
-    while (at < which.size()) {
-        // parse a batch of genomes in parallel (kseq + gz inflate are the host's job, as in the reference)
-        std::vector<Genome> gs;
-        size_t bytes = 0, b0 = at;
-        while (at < which.size() && (gs.empty() || bytes < o.batch_bytes)) {
-            const size_t chunk = std::min<size_t>(which.size() - at, std::max(1, o.nthreads));
-            std::vector<Genome> part(chunk);
+    auto finish = [&](std::future<void> &f) { if (f.valid()) f.get(); };
+    try {
+        while (at < which.size()) {
+            phase("batch begin");
+            auto bt = std::make_shared<Batch>();
+            // ---- batch layout from file sizes
+            while (at < which.size() && (bt->which.empty() || bt->bytes < o.batch_bytes)) {
+                for (auto &f : split_paths(paths[which[at]])) {
+                    FileSlot sl;
+                    sl.genome = bt->which.size(); sl.path = f; sl.cap = file_capacity(f); sl.off = bt->bytes;
+                    bt->bytes += (sl.cap + 63) & ~size_t(63);
+                    bt->slots.push_back(std::move(sl));
+                }
+                bt->which.push_back(which[at++]);
+            }
+            if (arena_cap[cur] < bt->bytes + 64) { arena[cur].reset(new char[bt->bytes + 64]); arena_cap[cur] = bt->bytes + 64; }
+            char *base = arena[cur].get();
+            // ---- parse (kseq + gz inflate are the host's job, as in the reference)
             std::string err;
-#pragma omp parallel for schedule(dynamic) num_threads(std::max(1, o.nthreads))
-            for (size_t i = 0; i < chunk; ++i) {
-                try { part[i] = load_genome(paths[which[at + i]]); }
-                catch (const std::exception &e) {
+#pragma omp parallel for schedule(dynamic) num_threads(nt)
+            for (size_t i = 0; i < bt->slots.size(); ++i) {
+                FileSlot &sl = bt->slots[i];
+                const size_t window = (i + 1 < bt->slots.size() ? bt->slots[i + 1].off : bt->bytes) - sl.off;
+                try {
+                    const size_t used = parse_into_window(sl.path, base + sl.off, sl.cap, sl.ends);
+                    if (used == SIZE_MAX) { sl.redo = true; sl.ends.clear(); sl.used = 0; }
+                    else sl.used = used;
+                } catch (const std::exception &e) {
 #pragma omp critical
                     err = e.what();
                 }
+                std::memset(base + sl.off + sl.used, 'N', window - sl.used);
             }
             if (!err.empty()) throw Error(err);
-            for (auto &g : part) { bytes += g.bases.size(); gs.push_back(std::move(g)); }
-            at += chunk;
+            phase("files parsed");
+            // ---- record table: the records of each file, then one filler record up to the next window
+            bt->rec_offs.assign(1, 0);
+            bt->grb.assign(1, 0);
+            std::vector<char> redo_genome(bt->which.size(), 0);
+            for (size_t i = 0; i < bt->slots.size(); ++i) {
+                const FileSlot &sl = bt->slots[i];
+                if (i && sl.genome != bt->slots[i - 1].genome)
+                    for (size_t g = bt->slots[i - 1].genome; g < sl.genome; ++g) bt->grb.push_back(bt->rec_offs.size() - 1);
+                for (uint64_t e : sl.ends) bt->rec_offs.push_back(sl.off + e);
+                const uint64_t wend = i + 1 < bt->slots.size() ? bt->slots[i + 1].off : bt->bytes;
+                if (wend > bt->rec_offs.back()) bt->rec_offs.push_back(wend);
+                if (sl.redo) redo_genome[sl.genome] = 1;
+            }
+            while (bt->grb.size() < bt->which.size() + 1) bt->grb.push_back(bt->rec_offs.size() - 1);
+            for (size_t g = 0; g < redo_genome.size(); ++g) if (redo_genome[g]) bt->redo.push_back(g);
+            bt->regs.resize(bt->which.size() * m);
+            // ---- previous batch must be through before its arena's twin is reused two batches later; hand this one over
+            finish(inflight);
+            if (warm.valid()) { const std::string werr = warm.get(); if (!werr.empty()) throw Error(werr); }
+            phase("previous batch done");
+            inflight = std::async(std::launch::async, [bt, base, m, nt, &o, &paths, &sink] {
+                check(db200_sketch_batch(o.device, o.p, o.k, o.canon, base, bt->rec_offs.data(), bt->rec_offs.size() - 1, bt->grb.data(),
+                                         bt->which.size(), bt->regs.data()));
+                if (!bt->redo.empty()) {
+                    // windows that were too small: the old route (private strings, one more call)
+                    std::string all;
+                    std::vector<uint64_t> ro{0}, gb{0};
+                    for (size_t g : bt->redo) {
+                        Genome gn = load_genome(paths[bt->which[g]]);
+                        const uint64_t b0 = all.size();
+                        all += gn.bases;
+                        for (size_t r = 1; r < gn.offs.size(); ++r) ro.push_back(b0 + gn.offs[r]);
+                        gb.push_back(ro.size() - 1);
+                    }
+                    std::vector<uint8_t> rr(bt->redo.size() * m);
+                    check(db200_sketch_batch(o.device, o.p, o.k, o.canon, all.data(), ro.data(), ro.size() - 1, gb.data(), bt->redo.size(), rr.data()));
+                    for (size_t j = 0; j < bt->redo.size(); ++j) std::memcpy(&bt->regs[bt->redo[j] * m], &rr[j * m], m);
+                }
+                std::string serr;
+#pragma omp parallel for schedule(dynamic) num_threads(nt)
+                for (size_t g = 0; g < bt->which.size(); ++g) {
+                    try { sink(bt->which[g], bt->regs.data() + g * m); }
+                    catch (const std::exception &e) {
+#pragma omp critical
+                        serr = e.what();
+                    }
+                }
+                if (!serr.empty()) throw Error(serr);
+            });
+            cur ^= 1;
         }
-        // one contiguous buffer + offsets
-        std::string all;
-        all.reserve(bytes);
-        std::vector<uint64_t> rec_offs{0}, grb{0};
-        for (auto &g : gs) {
-            const uint64_t base = all.size();
-            all += g.bases;
-            for (size_t r = 1; r < g.offs.size(); ++r) rec_offs.push_back(base + g.offs[r]);
-            grb.push_back(rec_offs.size() - 1);
-        }
-        std::vector<uint8_t> regs(gs.size() * m);
-        check(db200_sketch_batch(o.device, o.p, o.k, o.canon, all.data(), rec_offs.data(), rec_offs.size() - 1, grb.data(), gs.size(), regs.data()));
-        for (size_t i = 0; i < gs.size(); ++i) sink(which[b0 + i], regs.data() + i * m);
+        finish(inflight);
+        phase("last batch done");
+    } catch (...) {
+        if (inflight.valid()) { try { inflight.get(); } catch (...) {} }
+        if (warm.valid()) warm.wait();
+        throw;
     }
 }
 
 } // namespace
+
+size_t file_window(const std::string &f) { return file_capacity(f); }
 
 void sketch_core(const SketchOptions &o, std::vector<std::string> paths) {
     if (!o.avoid_sorting) sort_paths_by_fsize(paths);
@@ -383,6 +546,7 @@ void dist_sketch_and_cmp(const DistOptions &o, std::vector<std::string> inpaths,
         if (o.cache_sketches) write_hll(fnames[i], r, o.p, 2, 2, -1.);
     });
     // ---- phase B: sizes (:372-385)
+    phase("sketches ready");
     std::vector<double> card(n);
     check(db200_cardinalities(o.device, regs.data(), n, o.p, o.estim, card.data()));
     {
@@ -393,6 +557,7 @@ void dist_sketch_and_cmp(const DistOptions &o, std::vector<std::string> inpaths,
         if (fp != stdout) std::fclose(fp); else std::fflush(fp);
     }
     // ---- phase C: all pairs (:785-880, src/dashing.h:660-712)
+    phase("sizes written");
     std::FILE *pfp = o.dist_path.empty() ? stdout : std::fopen(o.dist_path.c_str(), "wb");
     if (!pfp) throw Error("Could not open file at " + o.dist_path + " for writing.");
     db200_dist_params prm{o.p, o.k, o.estim, o.jestim, o.result_type, DB200_ORDER_ROW_FIRST};
@@ -454,6 +619,7 @@ void dist_sketch_and_cmp(const DistOptions &o, std::vector<std::string> inpaths,
         }
     }
     if (pfp != stdout) std::fclose(pfp); else std::fflush(pfp);
+    phase("distances written");
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -580,6 +746,7 @@ int sketch_main(int argc, char **argv) {
 }
 
 int cli_main(int argc, char **argv) {
+    phase("start");
     try {
         if (argc < 2) throw Error("usage: dashing_b200 <sketch|dist|cmp> [options] (the hot subset of dashing's flags)");
         const std::string sub = argv[1];
@@ -659,14 +826,16 @@ DB200H_API uint64_t db200h_format_rect_row(const char *qname, const float *row, 
 // parses a FASTA/FASTQ(.gz) file; writes concatenated records and their offsets.  Returns the number of records.
 DB200H_API int64_t db200h_read_records(const char *path, char *bases, uint64_t cap, uint64_t *offs, uint64_t maxrec) {
     try {
-        uint64_t at = 0, nrec = 0;
-        bool overflow = false;
+        // the window form the batch driver uses (records land in the caller's buffer; -2 = window too small)
+        std::vector<uint64_t> ends;
+        if (db200h::parse_into_window(path, bases, cap, ends) == SIZE_MAX || ends.size() > maxrec) return -2;
         offs[0] = 0;
-        db200h::for_each_record(path, [&](const char *s, size_t l) {
-            if (at + l > cap || nrec + 1 > maxrec) { overflow = true; return; }
-            std::memcpy(bases + at, s, l); at += l; offs[++nrec] = at;
-        });
-        return overflow ? -2 : (int64_t)nrec;
+        for (size_t i = 0; i < ends.size(); ++i) offs[i + 1] = ends[i];
+        return (int64_t)ends.size();
     } catch (const std::exception &e) { std::fprintf(stderr, "%s\n", e.what()); return -1; }
+}
+// file_capacity(): the window the batch driver reserves for a file
+DB200H_API uint64_t db200h_file_capacity(const char *path) {
+    try { return db200h::file_window(path); } catch (const std::exception &e) { std::fprintf(stderr, "%s\n", e.what()); return UINT64_MAX; }
 }
 }

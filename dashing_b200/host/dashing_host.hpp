@@ -67,6 +67,11 @@ struct DistOptions : SketchOptions {
     std::string sizes_path, dist_path;       // empty -> stdout
 };
 // sketch_core<hll_t>, src/sketch_and_cmp.h:445-538: one .hll per input path
+// Parses a file's records straight into a caller window (what the batch driver does per file): returns the bytes used
+// (record ends relative to the window in `ends`) or SIZE_MAX when the window is too small.  file_window(): the window
+// the driver reserves — the file size, or the ISIZE trailer for gzip (RFC 1952; too small for multi-member files).
+size_t parse_into_window(const std::string &file, char *dst, size_t cap, std::vector<uint64_t> &ends);
+size_t file_window(const std::string &file);
 void sketch_core(const SketchOptions &o, std::vector<std::string> paths);
 // dist_sketch_and_cmp<hll_t> + dist_loop / partdist_loop, src/sketch_and_cmp.h:268-417, :785-880; src/dashing.h:660-712.
 // The last nq entries of inpaths are queries (rectangular mode).

@@ -85,6 +85,9 @@ DB200_API const char *db200_last_error(void);
 DB200_API int db200_version(void);
 /* Number of usable CUDA devices (0 when there is no driver/GPU; never fails). */
 DB200_API int db200_device_count(void);
+/* Optional: creates the CUDA context of `device` now (seconds on a multi-GPU node) instead of inside the first compute
+ * call, so a host can overlap it with file parsing from another thread. */
+DB200_API int db200_warmup(int device);
 /* Page-locked host memory, so host-pointer entry points can DMA straight from caller buffers. */
 DB200_API int db200_host_alloc(void **out, size_t bytes);
 DB200_API int db200_host_free(void *ptr);

@@ -25,6 +25,8 @@ def load():
     l.db200h_format_neighbors.argtypes = [C.c_char_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint32, C.c_int, C.c_char_p, C.c_uint64]
     l.db200h_read_records.restype = C.c_int64
     l.db200h_read_records.argtypes = [C.c_char_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
+    l.db200h_file_capacity.restype = C.c_uint64
+    l.db200h_file_capacity.argtypes = [C.c_char_p]
     return l
 
 

@@ -134,3 +134,38 @@ def test_neighbor_formats_byte_exact(host, cli):
         nb = np.array(rows, dtype=dt)
         assert hostlib.format_neighbors(host, names, 0, nb, 0) == want, run
     assert b"\t-1:-3.40282e+38\n" in cli["nn_tsv_ji_all_dist"].tobytes()
+
+
+def test_file_windows(host, cli, tmp_path):
+    """The batch driver parses every file into a window sized from the file (plain: its size; gzip: the ISIZE trailer).
+    The window must hold the file's sequence, and a multi-member gzip file (ISIZE covers the last member only) must be
+    reported as too small so the driver re-reads it through the growing-string path."""
+    import ctypes as C
+    import gzip
+    names = hostlib.materialise_inputs(cli, str(tmp_path))
+    for n in names:
+        path = str(tmp_path / n)
+        cap = host.db200h_file_capacity(path.encode())
+        recs = hostlib.read_records(host, path)
+        assert sum(len(r) for r in recs) <= cap, n
+        raw = open(path, "rb").read()
+        if raw[:2] == b"\x1f\x8b":
+            assert cap == len(gzip.decompress(raw))
+        else:
+            assert cap == len(raw)
+        # a window of the sequence length (+1: a CR is dropped only after it has been appended) works, a smaller one does not
+        need = sum(len(r) for r in recs)
+        bases = np.zeros(need + 1, dtype=np.uint8); offs = np.zeros(1000, dtype=np.uint64)
+        assert host.db200h_read_records(path.encode(), bases.ctypes.data, need + 1, offs.ctypes.data, 999) == len(recs)
+        if need:
+            assert host.db200h_read_records(path.encode(), bases.ctypes.data, need - 1, offs.ctypes.data, 999) == -2
+    # two gzip members back to back: zlib reads both, ISIZE describes the second only
+    a = b">r1\n" + b"ACGT" * 500 + b"\n"
+    b = b">r2\nGGCC\n"
+    mm = tmp_path / "multi.fa.gz"
+    mm.write_bytes(gzip.compress(a) + gzip.compress(b))
+    assert host.db200h_file_capacity(str(mm).encode()) == len(b)
+    recs = hostlib.read_records(host, str(mm))
+    assert [len(r) for r in recs] == [2000, 4]
+    small = np.zeros(len(b), dtype=np.uint8); offs = np.zeros(10, dtype=np.uint64)
+    assert host.db200h_read_records(str(mm).encode(), small.ctypes.data, len(b), offs.ctypes.data, 9) == -2
