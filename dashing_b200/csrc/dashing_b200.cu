@@ -498,10 +498,10 @@ static int plan_run(db200_dist_plan *pl, const db200_dist_params *prm, int rect,
         const int lhs_is_b = rect ? 1 : (prm->order == DB200_ORDER_COL_FIRST ? 1 : 0);
         if (wide) {
             DB200_CUDA(cudaFuncSetAttribute(dist_jmle_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 << 10));
-            dist_jmle_kernel<uint32_t><<<(unsigned)ntiles, DIST_THREADS, smem, stream>>>(pl->tmap16, pl->tmap, a, lhs_is_b);
+            dist_jmle_kernel<uint32_t><<<(unsigned)ntiles, JTHREADS, smem, stream>>>(pl->tmap16, pl->tmap, a, lhs_is_b);
         } else {
             DB200_CUDA(cudaFuncSetAttribute(dist_jmle_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 << 10));
-            dist_jmle_kernel<uint16_t><<<(unsigned)ntiles, DIST_THREADS, smem, stream>>>(pl->tmap16, pl->tmap, a, lhs_is_b);
+            dist_jmle_kernel<uint16_t><<<(unsigned)ntiles, JTHREADS, smem, stream>>>(pl->tmap16, pl->tmap, a, lhs_is_b);
         }
     }
     DB200_LAUNCHED();

@@ -633,9 +633,13 @@ constexpr int JT = 16;                                 // A-panel rows of the jo
 constexpr int JBOX_A = JT * 128, JBOX_B = DT * 128;
 constexpr int JSTAGE_BYTES = 2 * (JBOX_A + JBOX_B);    // A_k, A_{k+1}, B_k, B_{k+1}
 constexpr int JPAIRS = JT * DT;
+// One pair per consumer thread (16 consumer warps + the TMA producer warp): shared memory allows a single CTA per SM
+// here, so the warps have to come from the CTA itself (8 consumer warps left the schedulers half idle: ALU 68 %,
+// XU 64 %, issue 51 % — profiles/r01l_jmle_kernel_ncu.txt).
+constexpr int JCONSUMERS = JPAIRS, JTHREADS = JCONSUMERS + 32;
 
 template <typename GT>
-__global__ void __launch_bounds__(DIST_THREADS, 1) dist_jmle_kernel(const __grid_constant__ CUtensorMap tmapA,
+__global__ void __launch_bounds__(JTHREADS, 1) dist_jmle_kernel(const __grid_constant__ CUtensorMap tmapA,
                                                                     const __grid_constant__ CUtensorMap tmapB, const DistArgs a,
                                                                     const int lhs_is_b) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -659,13 +663,13 @@ __global__ void __launch_bounds__(DIST_THREADS, 1) dist_jmle_kernel(const __grid
     const int iters = (Td - 1 - lo) * nbox;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < S; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, DIST_CONSUMERS / 32); }
+        for (int s = 0; s < S; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, JCONSUMERS / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (warp == DIST_CONSUMERS / 32) {
+    if (warp == JCONSUMERS / 32) {
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmapA) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmapB) : "memory");
@@ -685,48 +689,44 @@ __global__ void __launch_bounds__(DIST_THREADS, 1) dist_jmle_kernel(const __grid
             }
         }
     } else {
-        const uint32_t ti = threadIdx.x >> 4, tj = threadIdx.x & 15;   // A row ti, B rows {tj, tj+16}
+        const uint32_t ti = threadIdx.x >> 5, tj = lane;               // pair (A row ti, B row tj)
         const uint32_t swA = (ti & 7) << 4, swB = (tj & 7) << 4;
-        uint32_t u0 = 0, u1 = 0, x0 = 0, x1 = 0, y0 = 0, y1 = 0;
-        // carry-save planes (weight 1, 2, 4) per (pair, family): half of every box is counted on the ALU pipe (see dist_kernel)
-        uint32_t ou0 = 0, ou1 = 0, ox0 = 0, ox1 = 0, oy0 = 0, oy1 = 0;
-        uint32_t tu0 = 0, tu1 = 0, tx0 = 0, tx1 = 0, ty0 = 0, ty1 = 0;
-        uint32_t fu0 = 0, fu1 = 0, fx0 = 0, fx1 = 0, fy0 = 0, fy1 = 0;
-        const uint32_t eight = 8u * (uint32_t)a.one;
+        uint32_t u0 = 0, x0 = 0, y0 = 0;
+        // carry-save planes (weight 1, 2, 4) per family: half of every box is counted on the ALU pipe (see dist_kernel)
+        uint32_t ou0 = 0, ox0 = 0, oy0 = 0, tu0 = 0, tx0 = 0, ty0 = 0, fu0 = 0, fx0 = 0, fy0 = 0;
+        const uint32_t one = (uint32_t)a.one, eight = 8u * one;
         int s = 0, wb = 0;
         size_t tl = 0;
         uint32_t ph = 0;
         for (int it = 0; it < iters; ++it) {
             mbar_wait(full0 + 8 * s, ph);
             const uint8_t *A0 = stage_mem + (size_t)s * JSTAGE_BYTES, *A1 = A0 + JBOX_A, *B0 = A0 + 2 * JBOX_A, *B1 = B0 + JBOX_B;
-#define DB200_POP4(p, q) (__popc(p.x | q.x) + __popc(p.y | q.y) + __popc(p.z | q.z) + __popc(p.w | q.w))
+#define DB200_POP4(acc, p, q)                                                    \
+    do {                                                                         \
+        acc = (uint32_t)__popc(p.x | q.x) * one + acc;                           \
+        acc = (uint32_t)__popc(p.y | q.y) * one + acc;                           \
+        acc = (uint32_t)__popc(p.z | q.z) * one + acc;                           \
+        acc = (uint32_t)__popc(p.w | q.w) * one + acc;                           \
+    } while (0)
 #pragma unroll
             for (uint32_t c = 0; c < 4; ++c) {
-                const uint32_t oa = ti * 128 + ((c << 4) ^ swA), ob0 = tj * 128 + ((c << 4) ^ swB), ob1 = ob0 + 16 * 128;
+                const uint32_t oa = ti * 128 + ((c << 4) ^ swA), ob = tj * 128 + ((c << 4) ^ swB);
                 const uint4 ak = *reinterpret_cast<const uint4 *>(A0 + oa), an = *reinterpret_cast<const uint4 *>(A1 + oa);
-                const uint4 bk0 = *reinterpret_cast<const uint4 *>(B0 + ob0), bn0 = *reinterpret_cast<const uint4 *>(B1 + ob0);
-                const uint4 bk1 = *reinterpret_cast<const uint4 *>(B0 + ob1), bn1 = *reinterpret_cast<const uint4 *>(B1 + ob1);
-                u0 += DB200_POP4(ak, bk0); x0 += DB200_POP4(ak, bn0); y0 += DB200_POP4(an, bk0);
-                u1 += DB200_POP4(ak, bk1); x1 += DB200_POP4(ak, bn1); y1 += DB200_POP4(an, bk1);
+                const uint4 bk = *reinterpret_cast<const uint4 *>(B0 + ob), bn = *reinterpret_cast<const uint4 *>(B1 + ob);
+                DB200_POP4(u0, ak, bk); DB200_POP4(x0, ak, bn); DB200_POP4(y0, an, bk);
             }
 #undef DB200_POP4
 #pragma unroll
             for (uint32_t c = 4; c < 8; c += 2) {
                 const uint32_t oa = ti * 128 + ((c << 4) ^ swA), oa2 = ti * 128 + (((c + 1) << 4) ^ swA);
-                const uint32_t ob0 = tj * 128 + ((c << 4) ^ swB), ob02 = tj * 128 + (((c + 1) << 4) ^ swB);
-                const uint32_t ob1 = ob0 + 16 * 128, ob12 = ob02 + 16 * 128;
+                const uint32_t ob = tj * 128 + ((c << 4) ^ swB), ob2 = tj * 128 + (((c + 1) << 4) ^ swB);
                 const uint4 ak = *reinterpret_cast<const uint4 *>(A0 + oa), ak2 = *reinterpret_cast<const uint4 *>(A0 + oa2);
                 const uint4 an = *reinterpret_cast<const uint4 *>(A1 + oa), an2 = *reinterpret_cast<const uint4 *>(A1 + oa2);
-                const uint4 bk0 = *reinterpret_cast<const uint4 *>(B0 + ob0), bk02 = *reinterpret_cast<const uint4 *>(B0 + ob02);
-                const uint4 bn0 = *reinterpret_cast<const uint4 *>(B1 + ob0), bn02 = *reinterpret_cast<const uint4 *>(B1 + ob02);
-                const uint4 bk1 = *reinterpret_cast<const uint4 *>(B0 + ob1), bk12 = *reinterpret_cast<const uint4 *>(B0 + ob12);
-                const uint4 bn1 = *reinterpret_cast<const uint4 *>(B1 + ob1), bn12 = *reinterpret_cast<const uint4 *>(B1 + ob12);
-                DB200_HS8(u0, ou0, tu0, fu0, ak, ak2, bk0, bk02);
-                DB200_HS8(x0, ox0, tx0, fx0, ak, ak2, bn0, bn02);
-                DB200_HS8(y0, oy0, ty0, fy0, an, an2, bk0, bk02);
-                DB200_HS8(u1, ou1, tu1, fu1, ak, ak2, bk1, bk12);
-                DB200_HS8(x1, ox1, tx1, fx1, ak, ak2, bn1, bn12);
-                DB200_HS8(y1, oy1, ty1, fy1, an, an2, bk1, bk12);
+                const uint4 bk = *reinterpret_cast<const uint4 *>(B0 + ob), bk2 = *reinterpret_cast<const uint4 *>(B0 + ob2);
+                const uint4 bn = *reinterpret_cast<const uint4 *>(B1 + ob), bn2 = *reinterpret_cast<const uint4 *>(B1 + ob2);
+                DB200_HS8(u0, ou0, tu0, fu0, ak, ak2, bk, bk2);
+                DB200_HS8(x0, ox0, tx0, fx0, ak, ak2, bn, bn2);
+                DB200_HS8(y0, oy0, ty0, fy0, an, an2, bk, bk2);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(empty0 + 8 * s);
@@ -734,14 +734,14 @@ __global__ void __launch_bounds__(DIST_THREADS, 1) dist_jmle_kernel(const __grid
             if (++wb == nbox) {
                 wb = 0;
                 GT *gu = G + tl * JPAIRS, *gx = G + ((size_t)Kcap + tl) * JPAIRS, *gy = G + ((size_t)2 * Kcap + tl) * JPAIRS;
-                const uint32_t p0 = ti * DT + tj, p1 = p0 + 16;
+                const uint32_t p0 = ti * DT + tj;
 #define DB200_FLUSH(acc, o, t, f) ((GT)((acc) + __popc(o) + 2 * __popc(t) + 4 * __popc(f)))
-                gu[p0] = DB200_FLUSH(u0, ou0, tu0, fu0); gu[p1] = DB200_FLUSH(u1, ou1, tu1, fu1);
-                gx[p0] = DB200_FLUSH(x0, ox0, tx0, fx0); gx[p1] = DB200_FLUSH(x1, ox1, tx1, fx1);
-                gy[p0] = DB200_FLUSH(y0, oy0, ty0, fy0); gy[p1] = DB200_FLUSH(y1, oy1, ty1, fy1);
+                gu[p0] = DB200_FLUSH(u0, ou0, tu0, fu0);
+                gx[p0] = DB200_FLUSH(x0, ox0, tx0, fx0);
+                gy[p0] = DB200_FLUSH(y0, oy0, ty0, fy0);
 #undef DB200_FLUSH
-                u0 = u1 = x0 = x1 = y0 = y1 = 0;
-                ou0 = ou1 = ox0 = ox1 = oy0 = oy1 = tu0 = tu1 = tx0 = tx1 = ty0 = ty1 = fu0 = fu1 = fx0 = fx1 = fy0 = fy1 = 0;
+                u0 = x0 = y0 = 0;
+                ou0 = ox0 = oy0 = tu0 = tx0 = ty0 = fu0 = fx0 = fy0 = 0;
                 ++tl;
             }
         }
@@ -754,7 +754,7 @@ __global__ void __launch_bounds__(DIST_THREADS, 1) dist_jmle_kernel(const __grid
     uint32_t *L = reinterpret_cast<uint32_t *>(stage_mem);             // [JT + DT][SPARSE_C]
     uint32_t *CN = L + (JT + DT) * SPARSE_C;                           // [JT + DT][ns + 1]: #{reg >= Td + kk}
     if (ns > 0) {
-        for (uint32_t row = warp; row < (uint32_t)(JT + DT); row += DIST_THREADS / 32) {
+        for (uint32_t row = warp; row < (uint32_t)(JT + DT); row += JTHREADS / 32) {
             const uint64_t sk = row < JT ? rowA0 + row : rowB0 + (row - JT);
             const uint32_t e0 = sk < a.n ? a.lists[sk * SPARSE_C + lane] : 0u, e1 = sk < a.n ? a.lists[sk * SPARSE_C + 32 + lane] : 0u;
             const bool k0 = (int)(e0 & 0xFFu) >= Td, k1 = (int)(e1 & 0xFFu) >= Td;
@@ -765,7 +765,7 @@ __global__ void __launch_bounds__(DIST_THREADS, 1) dist_jmle_kernel(const __grid
             if (k1) dst[n0 + __popc(b1 & lt)] = e1;
             for (uint32_t i2 = tot + lane; i2 < (uint32_t)SPARSE_C; i2 += 32) dst[i2] = 0u;
         }
-        for (uint32_t e = threadIdx.x; e < (uint32_t)((JT + DT) * (ns + 1)); e += DIST_THREADS) {
+        for (uint32_t e = threadIdx.x; e < (uint32_t)((JT + DT) * (ns + 1)); e += JTHREADS) {
             const uint32_t row = e / (ns + 1);
             const int k = Td + (int)(e % (ns + 1));
             const uint64_t sk = row < JT ? rowA0 + row : rowB0 + (row - JT);
@@ -774,7 +774,7 @@ __global__ void __launch_bounds__(DIST_THREADS, 1) dist_jmle_kernel(const __grid
     }
     __syncthreads();
 
-    for (uint32_t pair = threadIdx.x; pair < (uint32_t)JPAIRS; pair += DIST_THREADS) {
+    for (uint32_t pair = threadIdx.x; pair < (uint32_t)JPAIRS; pair += JTHREADS) {
         const uint32_t il = pair >> 5, jl = pair & 31;
         const uint64_t i = rowA0 + il, j = rowB0 + jl;
         uint64_t oidx;
