@@ -57,6 +57,8 @@ _SIGS = {
     "db200_packed_genomes_stats": (C.c_int, [vp, u64p, u64p, u64p]),
     "db200_sketch_packed_dev": (C.c_int, [vp, C.c_int, C.c_int, vp, vp]),
     "db200_cardinalities": (C.c_int, [C.c_int, u8p, C.c_uint64, C.c_int, C.c_int, f64p]),
+    "db200_union": (C.c_int, [C.c_int, u8p, C.c_uint64, C.c_int, u8p]),
+    "db200_compress": (C.c_int, [C.c_int, u8p, C.c_uint64, C.c_int, C.c_int, u8p]),
     "db200_dist_symmetric": (C.c_int, [C.c_int, u8p, C.c_uint64, C.POINTER(DistParams), f32p]),
     "db200_dist_symmetric_rows": (C.c_int, [C.c_int, u8p, C.c_uint64, C.POINTER(DistParams), C.c_uint64, C.c_uint64, f32p]),
     "db200_dist_rect": (C.c_int, [C.c_int, u8p, C.c_uint64, u8p, C.c_uint64, C.POINTER(DistParams), f32p]),

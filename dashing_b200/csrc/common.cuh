@@ -4,6 +4,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdarg>
+#include <cstdlib>
 #include <atomic>
 #include <string>
 
@@ -32,6 +33,26 @@ extern std::atomic<uint64_t> g_kernel_launches;
 
 #define DB200_LAUNCHED() (++::db200::g_kernel_launches)
 
+// Logical devices.  Normally logical == physical.  DB200_VIRTUAL_DEVICES=N (a test / debugging knob) exposes N logical
+// devices mapped round-robin onto the physical ones, so that the multi-device code paths (device = DB200_ALL_DEVICES)
+// can be exercised on a single-GPU box; every logical device has its own streams and buffers.
+inline int phys_device_count() {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+inline int logical_device_count() {
+    const int n = phys_device_count();
+    if (n == 0) return 0;
+    const char *e = std::getenv("DB200_VIRTUAL_DEVICES");
+    const int v = e ? std::atoi(e) : 0;
+    return v > 0 ? (v > 64 ? 64 : v) : n;
+}
+inline int phys_of(int logical) {
+    const int n = phys_device_count();
+    return n > 0 ? logical % n : 0;
+}
+
 inline int check_device(int device) {
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
@@ -41,11 +62,12 @@ inline int check_device(int device) {
         cudaGetLastError();
         return DB200_ENODEV;
     }
-    if (device < 0 || device >= n) {
-        set_error("device %d out of range [0,%d)", device, n);
+    const int nl = logical_device_count();
+    if (device < 0 || device >= nl) {
+        set_error("device %d out of range [0,%d)", device, nl);
         return DB200_EINVAL;
     }
-    DB200_CUDA(cudaSetDevice(device));
+    DB200_CUDA(cudaSetDevice(device % n));
     return DB200_OK;
 }
 

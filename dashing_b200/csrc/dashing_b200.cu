@@ -6,10 +6,13 @@
 #include "estimators.cuh"
 #include "sketch.cuh"
 #include "dist.cuh"
+#include "setops.cuh"
 
 #include <algorithm>
 #include <cstring>
 #include <mutex>
+#include <thread>
+#include <functional>
 #include <vector>
 #include <memory>
 
@@ -31,7 +34,7 @@ static int g_num_sms(int device) {
     static int cache[64] = {0};
     if (device < 64 && cache[device]) return cache[device];
     int v = 148;
-    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device);
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, phys_of(device));
     if (device < 64) cache[device] = v;
     return v;
 }
@@ -613,6 +616,39 @@ static HostCtx &host_ctx(int device) {
     return ctx[device & 63];
 }
 
+// device = DB200_ALL_DEVICES: one host thread per logical device, each driving the single-device entry point on its share
+// of the units (genomes, sketches, block rows, queries).  The host already holds every input, so no device-to-device
+// exchange is needed; the first failure (with its device number) becomes the caller's error.
+static int for_each_device(int ndev, const std::function<int(int)> &fn) {
+    if (ndev <= 0) return check_device(0);
+    std::vector<int> rc((size_t)ndev, DB200_OK);
+    std::vector<std::string> err((size_t)ndev);
+    std::vector<std::thread> th;
+    for (int d = 1; d < ndev; ++d)
+        th.emplace_back([&, d] { rc[d] = fn(d); if (rc[d] != DB200_OK) err[d] = t_err; });
+    rc[0] = fn(0);
+    if (rc[0] != DB200_OK) err[0] = t_err;
+    for (auto &t : th) t.join();
+    for (int d = 0; d < ndev; ++d)
+        if (rc[d] != DB200_OK) { set_error("device %d: %s", d, err[d].c_str()); return rc[d]; }
+    return DB200_OK;
+}
+
+// contiguous split of [0, n) into `parts` ranges of (nearly) equal weight; weight(i) = prefix weight of the first i units
+static std::vector<uint64_t> split_by_weight(uint64_t n, int parts, const std::function<uint64_t(uint64_t)> &prefix) {
+    std::vector<uint64_t> cut((size_t)parts + 1, n);
+    cut[0] = 0;
+    const uint64_t total = prefix(n);
+    uint64_t at = 0;
+    for (int d = 1; d < parts; ++d) {
+        const uint64_t target = total / (uint64_t)parts * (uint64_t)d + total % (uint64_t)parts * (uint64_t)d / (uint64_t)parts;
+        uint64_t lo = at, hi = n;           // first i with prefix(i) >= target
+        while (lo < hi) { const uint64_t mid = lo + (hi - lo) / 2; if (prefix(mid) >= target) hi = mid; else lo = mid + 1; }
+        cut[d] = at = lo;
+    }
+    return cut;
+}
+
 } // namespace db200
 
 using namespace db200;
@@ -627,12 +663,13 @@ int db200_version(void) { return DB200_VERSION; }
 uint64_t db200_kernel_launches(void) { return g_kernel_launches.load(); }
 
 int db200_device_count(void) {
-    int n = 0;
-    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
-    return n;
+    return logical_device_count();
 }
 
 int db200_warmup(int device) {
+    if (device == DB200_ALL_DEVICES) {
+        return for_each_device(logical_device_count(), [](int d) { return db200_warmup(d); });
+    }
     DB200_TRY(check_device(device));
     DB200_CUDA(cudaFree(nullptr));
     return DB200_OK;
@@ -666,7 +703,7 @@ int db200_pack_genomes(int device, const char *bases, const uint64_t *rec_offset
 }
 
 int db200_packed_genomes_free(db200_packed_genomes *g) {
-    if (g) { cudaSetDevice(g->device); delete g; }
+    if (g) { cudaSetDevice(phys_of(g->device)); delete g; }
     return DB200_OK;
 }
 
@@ -685,8 +722,14 @@ int db200_sketch_packed_dev(const db200_packed_genomes *g, int p, int canon, uin
     return sketch_packed_impl(g, p, canon, d_registers, (cudaStream_t)stream);
 }
 
+static int sketch_batch_all(int p, int k, int canon, const char *bases, const uint64_t *rec_offsets, uint64_t nrecords,
+                            const uint64_t *genome_rec_begin, uint64_t ngenomes, uint8_t *registers_out);
+
 int db200_sketch_batch(int device, int p, int k, int canon, const char *bases, const uint64_t *rec_offsets, uint64_t nrecords,
                        const uint64_t *genome_rec_begin, uint64_t ngenomes, uint8_t *registers_out) {
+    if (device == DB200_ALL_DEVICES && logical_device_count() > 1 && rec_offsets && genome_rec_begin && ngenomes > 1)
+        return sketch_batch_all(p, k, canon, bases, rec_offsets, nrecords, genome_rec_begin, ngenomes, registers_out);
+    if (device == DB200_ALL_DEVICES) device = 0;
     if (!registers_out && ngenomes) { set_error("db200_sketch_batch: null output"); return DB200_EINVAL; }
     if (!rec_offsets || !genome_rec_begin || (!bases && nrecords)) { set_error("db200_sketch_batch: null argument"); return DB200_EINVAL; }
     if (k < 1 || k > 32) { set_error("sketch: k=%d outside [1,32]", k); return DB200_EUNSUPPORTED; }
@@ -722,7 +765,7 @@ int db200_sketcher_create(int p, int k, int canon, int device, uint32_t nslots, 
     if (!out || nslots == 0) { set_error("db200_sketcher_create: bad arguments"); return DB200_EINVAL; }
     if (k < 1 || k > 32) { set_error("sketch: k=%d outside [1,32]", k); return DB200_EUNSUPPORTED; }
     if (p < 7 || p > 24) { set_error("sketch: p=%d outside the GPU path's range [7,24]", p); return DB200_EUNSUPPORTED; }
-    DB200_TRY(check_device(device));
+    DB200_TRY(check_device(device == DB200_ALL_DEVICES ? 0 : device));
     db200_sketcher *h = new db200_sketcher{p, k, canon, device, {}};
     h->slots.resize(nslots);
     *out = h;
@@ -743,7 +786,9 @@ int db200_sketcher_finish(db200_sketcher *h, uint32_t slot, uint8_t *registers_o
     if (!h || slot >= h->slots.size() || !registers_out) { set_error("db200_sketcher_finish: bad arguments"); return DB200_EINVAL; }
     auto &s = h->slots[slot];
     const uint64_t grb[2] = {0, s.offs.size() - 1};
-    const int rc = db200_sketch_batch(h->device, h->p, h->k, h->canon, s.bases.data(), s.offs.data(), s.offs.size() - 1, grb, 1, registers_out);
+    // all devices: slots are spread round-robin (one genome per call, so the call itself uses one device)
+    const int dev = h->device == DB200_ALL_DEVICES ? (int)(slot % (uint32_t)std::max(logical_device_count(), 1)) : h->device;
+    const int rc = db200_sketch_batch(dev, h->p, h->k, h->canon, s.bases.data(), s.offs.data(), s.offs.size() - 1, grb, 1, registers_out);
     s.bases.clear();
     s.offs.assign(1, 0);
     return rc;
@@ -756,6 +801,16 @@ int db200_cardinalities(int device, const uint8_t *regs, uint64_t n, int p, int 
     if ((!regs || !out) && n) { set_error("db200_cardinalities: null argument"); return DB200_EINVAL; }
     if (p < 7 || p > 24) { set_error("cardinalities: p=%d outside the GPU path's range [7,24]", p); return DB200_EUNSUPPORTED; }
     if (estim < 0 || estim > 2) { set_error("unknown estimation method %d", estim); return DB200_EINVAL; }
+    if (device == DB200_ALL_DEVICES) {
+        const int nd = (int)std::min<uint64_t>((uint64_t)std::max(logical_device_count(), 1), std::max<uint64_t>(n >> 8, 1));
+        if (nd > 1) {
+            return for_each_device(nd, [&](int d) {
+                const uint64_t a = n * (uint64_t)d / (uint64_t)nd, b = n * (uint64_t)(d + 1) / (uint64_t)nd;
+                return db200_cardinalities(d, regs + (a << p), b - a, p, estim, out + a);
+            });
+        }
+        device = 0;
+    }
     DB200_TRY(check_device(device));
     if (n == 0) return DB200_OK;
     HostCtx &hc = host_ctx(device);
@@ -772,6 +827,62 @@ int db200_cardinalities(int device, const uint8_t *regs, uint64_t n, int p, int 
     return DB200_OK;
 }
 
+// ---- set operations (union / fold) ----------------------------------------------------------
+int db200_union(int device, const uint8_t *regs, uint64_t n, int p, uint8_t *out) {
+    if (!out || (!regs && n)) { set_error("db200_union: null argument"); return DB200_EINVAL; }
+    if (p < 7 || p > 24) { set_error("union: p=%d outside the GPU path's range [7,24]", p); return DB200_EUNSUPPORTED; }
+    if (device == DB200_ALL_DEVICES) device = 0;      // one pass over n * 2^p bytes: PCIe-bound from host memory, one device is enough
+    DB200_TRY(check_device(device));
+    HostCtx &hc = host_ctx(device);
+    std::lock_guard<std::mutex> lk(hc.mu);
+    DB200_TRY(hc.init(device));
+    const uint64_t m = 1ull << p;
+    DB200_TRY(hc.out.reserve(m));
+    DB200_CUDA(cudaMemsetAsync(hc.out.ptr, 0, m, hc.stream));
+    // sketches stream through the register buffer in slabs (a union of 10^6 sketches need not fit in HBM at once)
+    const uint64_t slab = std::max<uint64_t>(1, std::min<uint64_t>(n, (uint64_t(1) << 30) >> p));
+    if (n) DB200_TRY(hc.regs.reserve(slab << p));
+    const uint32_t m16 = (uint32_t)(m / 16), gx = (m16 + 255) / 256;
+    for (uint64_t s0 = 0; s0 < n; s0 += slab) {
+        const uint64_t cnt = std::min(slab, n - s0);
+        DB200_CUDA(cudaMemcpyAsync(hc.regs.ptr, regs + (s0 << p), cnt << p, cudaMemcpyHostToDevice, hc.stream));
+        const uint64_t want_y = std::max<uint64_t>(1, (uint64_t)g_num_sms(device) * 8 / gx);
+        const uint64_t rows_per = std::max<uint64_t>(4, (cnt + want_y - 1) / want_y);
+        const unsigned gy = (unsigned)((cnt + rows_per - 1) / rows_per);
+        union_kernel<<<dim3(gx, gy), 256, 0, hc.stream>>>(hc.regs.as<uint4>(), cnt, m16, rows_per, hc.out.as<uint32_t>(),
+                                                          (gy > 1 || n > slab) ? 1 : 0);
+        DB200_LAUNCHED();
+    }
+    DB200_CUDA(cudaGetLastError());
+    DB200_CUDA(cudaMemcpyAsync(out, hc.out.ptr, m, cudaMemcpyDeviceToHost, hc.stream));
+    DB200_CUDA(cudaStreamSynchronize(hc.stream));
+    return DB200_OK;
+}
+
+int db200_compress(int device, const uint8_t *regs, uint64_t n, int p, int new_p, uint8_t *out) {
+    if ((!regs || !out) && n) { set_error("db200_compress: null argument"); return DB200_EINVAL; }
+    if (p < 7 || p > 24) { set_error("compress: p=%d outside the GPU path's range [7,24]", p); return DB200_EUNSUPPORTED; }
+    // hll.h:907-909: equal sizes copy, a larger target throws
+    if (new_p > p) { set_error("Can't compress to a larger size. Current: %d. Requested new size: %d", p, new_p); return DB200_EINVAL; }
+    if (new_p < 1) { set_error("compress: new p=%d must be positive", new_p); return DB200_EINVAL; }
+    if (device == DB200_ALL_DEVICES) device = 0;
+    DB200_TRY(check_device(device));
+    if (n == 0) return DB200_OK;
+    HostCtx &hc = host_ctx(device);
+    std::lock_guard<std::mutex> lk(hc.mu);
+    DB200_TRY(hc.init(device));
+    DB200_TRY(hc.regs.reserve(n << p));
+    DB200_TRY(hc.out.reserve(n << new_p));
+    DB200_CUDA(cudaMemcpyAsync(hc.regs.ptr, regs, n << p, cudaMemcpyHostToDevice, hc.stream));
+    const uint64_t total = n << new_p;
+    compress_kernel<<<(unsigned)((total + 255) / 256), 256, 0, hc.stream>>>(hc.regs.as<uint8_t>(), n, p, new_p, hc.out.as<uint8_t>());
+    DB200_LAUNCHED();
+    DB200_CUDA(cudaGetLastError());
+    DB200_CUDA(cudaMemcpyAsync(out, hc.out.ptr, total, cudaMemcpyDeviceToHost, hc.stream));
+    DB200_CUDA(cudaStreamSynchronize(hc.stream));
+    return DB200_OK;
+}
+
 // ---- dist plan ------------------------------------------------------------------------------
 int db200_dist_plan_create(int device, db200_dist_plan **out) {
     if (!out) { set_error("db200_dist_plan_create: null out"); return DB200_EINVAL; }
@@ -782,7 +893,7 @@ int db200_dist_plan_create(int device, db200_dist_plan **out) {
     return DB200_OK;
 }
 int db200_dist_plan_destroy(db200_dist_plan *pl) {
-    if (pl) { cudaSetDevice(pl->device); delete pl; }
+    if (pl) { cudaSetDevice(phys_of(pl->device)); delete pl; }
     return DB200_OK;
 }
 int db200_dist_plan_prepare_dev(db200_dist_plan *pl, const uint8_t *d_regs, uint64_t n, int p, int estim, void *stream) {
@@ -833,6 +944,9 @@ int db200_dist_plan_run_knn_dev(db200_dist_plan *pl, const db200_dist_params *pr
 int db200_dist_knn_symmetric(int device, const uint8_t *regs, uint64_t n, const db200_dist_params *prm, uint32_t nneighbors,
                              db200_neighbor *out) {
     if (!prm || ((!regs || !out) && n)) { set_error("db200_dist_knn_symmetric: null argument"); return DB200_EINVAL; }
+    // The retained sets depend on the ascending visiting order (ties at the cut), so per-device partial tables cannot be
+    // merged exactly: with DB200_ALL_DEVICES the symmetric table is computed on device 0 (the -Q/-F form shards by query).
+    if (device == DB200_ALL_DEVICES) device = 0;
     DB200_TRY(check_device(device));
     if (n == 0) return DB200_OK;
     if (prm->p < 7 || prm->p > 20) { set_error("dist: p=%d outside the GPU path's range [7,20]", prm->p); return DB200_EUNSUPPORTED; }
@@ -852,6 +966,17 @@ int db200_dist_knn_symmetric(int device, const uint8_t *regs, uint64_t n, const 
 int db200_dist_knn_rect(int device, const uint8_t *ref_regs, uint64_t nr, const uint8_t *qry_regs, uint64_t nq, const db200_dist_params *prm,
                         uint32_t nneighbors, db200_neighbor *out) {
     if (!prm || ((!ref_regs || !qry_regs || !out) && nr && nq)) { set_error("db200_dist_knn_rect: null argument"); return DB200_EINVAL; }
+    if (device == DB200_ALL_DEVICES) {
+        const int nd = (int)std::min<uint64_t>((uint64_t)std::max(logical_device_count(), 1), std::max<uint64_t>(nq / DT, 1));
+        if (nd > 1 && nr && prm->p >= 7 && prm->p <= 20) {
+            const uint64_t m = 1ull << prm->p;
+            return for_each_device(nd, [&](int d) {
+                const uint64_t a = nq * (uint64_t)d / (uint64_t)nd, b = nq * (uint64_t)(d + 1) / (uint64_t)nd;
+                return db200_dist_knn_rect(d, ref_regs, nr, qry_regs + a * m, b - a, prm, nneighbors, out + a * nneighbors);
+            });
+        }
+        device = 0;
+    }
     DB200_TRY(check_device(device));
     if (nr == 0 || nq == 0) return DB200_OK;
     if (prm->p < 7 || prm->p > 20) { set_error("dist: p=%d outside the GPU path's range [7,20]", prm->p); return DB200_EUNSUPPORTED; }
@@ -887,6 +1012,22 @@ int db200_dist_plan_last_run_info(const db200_dist_plan *pl, uint64_t *pairs, ui
 int db200_dist_symmetric_rows(int device, const uint8_t *regs, uint64_t n, const db200_dist_params *prm, uint64_t row_begin, uint64_t row_end,
                               float *out) {
     if (!prm || (!regs && n)) { set_error("db200_dist_symmetric_rows: null argument"); return DB200_EINVAL; }
+    if (device == DB200_ALL_DEVICES) {
+        // block rows balanced by pair count (row i holds n-1-i pairs); rows are contiguous in distmat order, so every
+        // device writes its own slice of `out`
+        const uint64_t r0 = std::min(row_begin, n), r1 = std::min(row_end, n);
+        auto tri = [n](uint64_t r) { return (r * (2 * n - r - 1)) / 2; };
+        const uint64_t npairs = r1 > r0 ? tri(r1) - tri(r0) : 0;
+        const int nd = (int)std::min<uint64_t>((uint64_t)std::max(logical_device_count(), 1), std::max<uint64_t>(npairs >> 16, 1));
+        if (nd > 1 && row_begin <= row_end) {
+            const std::vector<uint64_t> cut = split_by_weight(r1 - r0, nd, [&](uint64_t i) { return tri(r0 + i) - tri(r0); });
+            return for_each_device(nd, [&](int d) {
+                const uint64_t a = r0 + cut[d], b = r0 + cut[d + 1];
+                return db200_dist_symmetric_rows(d, regs, n, prm, a, b, out ? out + (tri(a) - tri(r0)) : nullptr);
+            });
+        }
+        device = 0;
+    }
     DB200_TRY(check_device(device));
     if (row_end > n) row_end = n;
     if (row_begin > row_end) { set_error("row_begin > row_end"); return DB200_EINVAL; }
@@ -934,6 +1075,17 @@ int db200_dist_symmetric(int device, const uint8_t *regs, uint64_t n, const db20
 int db200_dist_rect(int device, const uint8_t *ref_regs, uint64_t nr, const uint8_t *qry_regs, uint64_t nq, const db200_dist_params *prm,
                     float *out) {
     if (!prm || ((!ref_regs || !qry_regs || !out) && nr && nq)) { set_error("db200_dist_rect: null argument"); return DB200_EINVAL; }
+    if (device == DB200_ALL_DEVICES) {
+        const int nd = (int)std::min<uint64_t>((uint64_t)std::max(logical_device_count(), 1), std::max<uint64_t>(nq / DT, 1));
+        if (nd > 1 && nr && prm->p >= 7 && prm->p <= 20) {
+            const uint64_t m = 1ull << prm->p;
+            return for_each_device(nd, [&](int d) {
+                const uint64_t a = nq * (uint64_t)d / (uint64_t)nd, b = nq * (uint64_t)(d + 1) / (uint64_t)nd;
+                return db200_dist_rect(d, ref_regs, nr, qry_regs + a * m, b - a, prm, out + a * nr);
+            });
+        }
+        device = 0;
+    }
     DB200_TRY(check_device(device));
     if (nr == 0 || nq == 0) return DB200_OK;
     if (prm->p < 7 || prm->p > 20) { set_error("dist: p=%d outside the GPU path's range [7,20]", prm->p); return DB200_EUNSUPPORTED; }
@@ -954,3 +1106,21 @@ int db200_dist_rect(int device, const uint8_t *ref_regs, uint64_t nr, const uint
 }
 
 } // extern "C"
+
+// Genomes are independent units: contiguous ranges of genomes, balanced by their bases, one range per device.
+static int sketch_batch_all(int p, int k, int canon, const char *bases, const uint64_t *rec_offsets, uint64_t nrecords,
+                            const uint64_t *genome_rec_begin, uint64_t ngenomes, uint8_t *registers_out) {
+    (void)nrecords;
+    const int nd = (int)std::min<uint64_t>((uint64_t)logical_device_count(), ngenomes);
+    const uint64_t b0 = rec_offsets[genome_rec_begin[0]];
+    const std::vector<uint64_t> cut = split_by_weight(ngenomes, nd, [&](uint64_t g) { return rec_offsets[genome_rec_begin[g]] - b0 + g; });
+    return for_each_device(nd, [&](int d) {
+        const uint64_t g0 = cut[d], g1 = cut[d + 1];
+        if (g1 <= g0) return (int)DB200_OK;
+        const uint64_t r0 = genome_rec_begin[g0], r1 = genome_rec_begin[g1];
+        std::vector<uint64_t> grb(g1 - g0 + 1);
+        for (uint64_t g = g0; g <= g1; ++g) grb[g - g0] = genome_rec_begin[g] - r0;
+        return db200_sketch_batch(d, p, k, canon, bases, rec_offsets + r0, r1 - r0, grb.data(), g1 - g0,
+                                  registers_out ? registers_out + (g0 << p) : nullptr);
+    });
+}

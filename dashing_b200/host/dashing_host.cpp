@@ -79,6 +79,34 @@ HllFile read_hll(const std::string &path) {
     return h;
 }
 
+void write_hll_stream(gzFile fp, const uint8_t *regs, uint32_t p, int estim, int jestim, double value) {
+    const auto buf = hll_payload(regs, p, estim, jestim, value);
+    if (gzwrite(fp, buf.data(), (unsigned)buf.size()) != (int)buf.size()) throw Error("Error writing to file.");
+}
+
+// hll_t(gzFile) repeatedly (dist_by_seq, src/sketch_and_cmp.h:85-88): `count` sketches from one gzip stream
+std::vector<HllFile> read_hll_container(const std::string &path, size_t count) {
+    gzFile fp = gzopen(path.c_str(), "rb");
+    if (!fp) throw Error("Failed to open file at " + path);
+    std::vector<HllFile> out;
+    auto rd = [&](void *dst, size_t len) {
+        if ((size_t)gzread(fp, dst, (unsigned)len) != len) { gzclose(fp); throw Error("Error reading from file " + path); }
+    };
+    while (out.size() < count) {
+        HllFile h;
+        uint32_t bf[5];
+        rd(bf, 20);
+        h.is_calculated = bf[0]; h.estim = bf[1]; h.jestim = bf[2]; h.marker = bf[3]; h.p = bf[4];
+        rd(&h.value, 8);
+        if (h.p > 40) { gzclose(fp); throw Error("implausible sketch size in " + path); }
+        h.core.resize(size_t(1) << h.p);
+        rd(h.core.data(), h.core.size());
+        out.push_back(std::move(h));
+    }
+    gzclose(fp);
+    return out;
+}
+
 std::string make_fname(const char *path, size_t sketch_p, int /*wsz*/, int k, int /*csz*/, const std::string &spacing,
                        const std::string &suffix, const std::string &prefix) {
     std::string ret(prefix);
@@ -116,13 +144,12 @@ std::vector<std::string> split_paths(const std::string &s, char sep) {
 }
 
 std::vector<std::string> get_paths(const std::string &file) {
+    // get_lines (bonsai/include/bonsai/util.h:1176-1184): empty lines and lines starting with '#' are skipped; a file that
+    // cannot be opened yields no paths (the callers then stop with "No paths")
     std::ifstream is(file);
-    if (!is.good()) throw Error("Could not open file at " + file);
     std::vector<std::string> out;
-    for (std::string line; std::getline(is, line);) {
-        if (!line.empty() && line.back() == '\r') line.pop_back();
-        if (!line.empty()) out.push_back(line);
-    }
+    for (std::string line; std::getline(is, line);)
+        if (!line.empty() && line.front() != '#') out.push_back(line);
     return out;
 }
 
@@ -196,8 +223,9 @@ struct LineReader {
     }
 };
 
-// kseq_read's record loop (bonsai/klib/kseq.h:177-218) over one file; record boundaries (sink lengths) go to `ends`.
-void parse_records(const std::string &file, SeqSink &sink, std::vector<uint64_t> &ends) {
+// kseq_read's record loop (bonsai/klib/kseq.h:177-218) over one file; record boundaries (sink lengths) go to `ends`, and,
+// when asked for, the record names (header up to the first whitespace, kseq.h:190) to `names`.
+void parse_records(const std::string &file, SeqSink &sink, std::vector<uint64_t> &ends, std::vector<std::string> *names = nullptr) {
     gzFile fp = gzopen(file.c_str(), "rb");
     if (!fp) throw Error("Could not open file at " + file + ". Abort!");
     gzbuffer(fp, 1 << 18);
@@ -205,7 +233,15 @@ void parse_records(const std::string &file, SeqSink &sink, std::vector<uint64_t>
     int c;
     while ((c = lr.peek()) != -1 && !sink.overflow) {
         if (c != '>' && c != '@') { lr.line(nullptr); continue; }   // skip to the next header
-        lr.line(nullptr);                                          // name + comment
+        if (names) {
+            std::string hdr;
+            SeqSink hs;
+            hs.str = &hdr;
+            lr.line(&hs, 0);
+            size_t e = 1;
+            while (e < hdr.size() && !std::isspace((unsigned char)hdr[e])) ++e;
+            names->push_back(hdr.substr(1, e - 1));
+        } else lr.line(nullptr);                                   // name + comment
         const size_t rs = sink.len;
         while ((c = lr.peek()) != -1 && c != '>' && c != '+' && c != '@') lr.line(&sink, rs);
         if (c == '+') {                                            // FASTQ: skip the '+' line and the qualities
@@ -220,6 +256,17 @@ void parse_records(const std::string &file, SeqSink &sink, std::vector<uint64_t>
     gzclose(fp);
 }
 } // namespace
+
+void for_each_named_record(const std::string &file, const std::function<void(const std::string &, const char *, size_t)> &fn) {
+    std::string seq;
+    SeqSink sink;
+    sink.str = &seq;
+    std::vector<uint64_t> ends;
+    std::vector<std::string> names;
+    parse_records(file, sink, ends, &names);
+    uint64_t b = 0;
+    for (size_t i = 0; i < ends.size(); ++i) { fn(names[i], seq.data() + b, ends[i] - b); b = ends[i]; }
+}
 
 size_t parse_into_window(const std::string &file, char *dst, size_t cap, std::vector<uint64_t> &ends) {
     SeqSink sk;
@@ -487,12 +534,52 @@ void sketch_core(const SketchOptions &o, std::vector<std::string> paths) {
     if (!o.avoid_sorting) sort_paths_by_fsize(paths);
     std::vector<std::string> fnames(paths.size());
     std::vector<size_t> todo;
+    const size_t m = size_t(1) << o.p;
+    const bool container = !o.output_file.empty();
+    // container mode: sketchdest (src/sketch_and_cmp.h:458-463) and the header each entry will be written with
+    std::vector<uint8_t> all;
+    struct Hdr { int estim; double value; };
+    std::vector<Hdr> hdr(paths.size(), Hdr{o.estim, -1.});
+    if (container) {
+        // labels first (:470-478), then every sketch into one gzip stream (:527-535)
+        gzFile lf = gzopen((o.output_file + ".labels.gz").c_str(), "w");
+        if (!lf) throw Error("Failed to write sequence labels to file");
+        for (auto &pth : paths) { gzwrite(lf, pth.data(), (unsigned)pth.size()); gzputc(lf, '\n'); }
+        gzclose(lf);
+        all.assign(paths.size() * m, 0);
+    }
     for (size_t i = 0; i < paths.size(); ++i) {
         fnames[i] = make_fname(paths[i].c_str(), o.p, o.k, o.k, o.k, "", o.suffix, o.prefix);
-        if (o.skip_cached && isfile(fnames[i])) continue;           // src/sketch_and_cmp.h:492-495
+        if (o.skip_cached && isfile(fnames[i])) {                   // src/sketch_and_cmp.h:499-504
+            if (!container) continue;
+            // h.read(fname) with no `continue` (:500-503): the path's k-mers are then added ON TOP of the cached registers,
+            // and the value read() computed (hll.h:1078) is never invalidated (add() does not call not_ready()), so the entry
+            // is written as "calculated" with the cached sketch's estimate under the cached file's estimator
+            const HllFile h = read_hll(fnames[i]);
+            if (h.p != (uint32_t)o.p) throw Error("cached sketch " + fnames[i] + " has the wrong size");
+            std::memcpy(&all[i * m], h.core.data(), m);
+            hdr[i].estim = (int)h.estim;
+            if (h.value >= 0.) hdr[i].value = h.value;
+            else {
+                if (h.estim > 2) throw Error("cached sketch " + fnames[i] + " names an unknown estimation method");
+                check(db200_cardinalities(o.device, h.core.data(), 1, o.p, (int)h.estim, &hdr[i].value));
+            }
+        }
         todo.push_back(i);
     }
-    sketch_paths(o, paths, todo, [&](size_t i, const uint8_t *regs) { write_hll(fnames[i], regs, o.p, 2, 2, -1.); });
+    if (!container) {
+        sketch_paths(o, paths, todo, [&](size_t i, const uint8_t *regs) { write_hll(fnames[i], regs, o.p, o.estim, o.jestim, -1.); });
+        return;
+    }
+    sketch_paths(o, paths, todo, [&](size_t i, const uint8_t *regs) {
+        uint8_t *dst = &all[i * m];
+        for (size_t r = 0; r < m; ++r) dst[r] = std::max(dst[r], regs[r]);   // a plain copy unless a cached sketch was read first
+    });
+    gzFile fp = gzopen(o.output_file.c_str(), "w");
+    if (!fp) throw Error("Failed to write sketches to file");
+    // sketchdest[i] = h copies estim_ but not jestim_ (hll.h:947-956): the entry keeps the command line's joint estimator
+    for (size_t i = 0; i < paths.size(); ++i) write_hll_stream(fp, &all[i * m], o.p, hdr[i].estim, o.jestim, hdr[i].value);
+    gzclose(fp);
 }
 
 // TSV table of nndist_loop (src/sketch_and_cmp.h:741-781): "<path>(\t<index>:<%g value>)*"; the index goes through
@@ -520,44 +607,10 @@ void write_binary_neighbors(std::FILE *fp, uint32_t npaths, const Neighbor *nb, 
         throw Error("Failed to write neighbors to disk (binary)");
 }
 
-void dist_sketch_and_cmp(const DistOptions &o, std::vector<std::string> inpaths, size_t nq) {
+// dist_loop / partdist_loop / nndist_loop and their emitters (src/sketch_and_cmp.h:785-880, :712-783; src/dashing.h:660-712)
+// over n = inpaths.size() sketches held as rows of `regs`; the last nq are queries.
+void compare_and_emit(const DistOptions &o, const std::vector<std::string> &inpaths, const std::vector<uint8_t> &regs, size_t nq) {
     const size_t n = inpaths.size(), m = size_t(1) << o.p;
-    if (nq > n) throw Error("more queries than paths");
-    std::vector<uint8_t> regs(n * m);
-    // ---- phase A: load or sketch (src/sketch_and_cmp.h:314-360)
-    std::vector<size_t> todo;
-    std::vector<std::string> fnames(n);
-    for (size_t i = 0; i < n; ++i) {
-        if (o.presketched) {
-            HllFile h = read_hll(inpaths[i]);
-            if (h.p != (uint32_t)o.p) throw Error("sketch " + inpaths[i] + " has p=" + std::to_string(h.p) + ", expected " + std::to_string(o.p));
-            std::memcpy(&regs[i * m], h.core.data(), m);
-            continue;
-        }
-        fnames[i] = make_fname(inpaths[i].c_str(), o.p, o.k, o.k, o.k, "", o.suffix, o.prefix);
-        if (o.cache_sketches && isfile(fnames[i])) {
-            HllFile h = read_hll(fnames[i]);
-            if (h.p != (uint32_t)o.p) throw Error("cached sketch " + fnames[i] + " has the wrong size");
-            std::memcpy(&regs[i * m], h.core.data(), m);
-        } else todo.push_back(i);
-    }
-    sketch_paths(o, inpaths, todo, [&](size_t i, const uint8_t *r) {
-        std::memcpy(&regs[i * m], r, m);
-        if (o.cache_sketches) write_hll(fnames[i], r, o.p, 2, 2, -1.);
-    });
-    // ---- phase B: sizes (:372-385)
-    phase("sketches ready");
-    std::vector<double> card(n);
-    check(db200_cardinalities(o.device, regs.data(), n, o.p, o.estim, card.data()));
-    {
-        const std::string s = format_sizes(inpaths, card.data());
-        std::FILE *fp = o.sizes_path.empty() ? stdout : std::fopen(o.sizes_path.c_str(), "w");
-        if (!fp) throw Error("Could not open file at " + o.sizes_path + " for writing.");
-        std::fwrite(s.data(), 1, s.size(), fp);
-        if (fp != stdout) std::fclose(fp); else std::fflush(fp);
-    }
-    // ---- phase C: all pairs (:785-880, src/dashing.h:660-712)
-    phase("sizes written");
     std::FILE *pfp = o.dist_path.empty() ? stdout : std::fopen(o.dist_path.c_str(), "wb");
     if (!pfp) throw Error("Could not open file at " + o.dist_path + " for writing.");
     db200_dist_params prm{o.p, o.k, o.estim, o.jestim, o.result_type, DB200_ORDER_ROW_FIRST};
@@ -622,6 +675,63 @@ void dist_sketch_and_cmp(const DistOptions &o, std::vector<std::string> inpaths,
     phase("distances written");
 }
 
+// hll_t::read() computes the cardinality at once under the FILE's estimator (csum(), hll.h:1078) and the reference then
+// keeps that cached value for the sizes file and the per-sketch terms of every pair, whatever -E/-I/-m says.  This layer
+// always evaluates cardinalities under the command line's estimator; say so when the two differ.
+static void warn_estim(const HllFile &h, const std::string &path, int estim) {
+    if ((int)h.estim != estim)
+        std::fprintf(stderr, "[dashing_b200] note: %s was written under estimation method %u; cardinalities are evaluated under %d "
+                             "(the reference would keep the value cached under %u)\n", path.c_str(), h.estim, estim, h.estim);
+}
+
+void dist_sketch_and_cmp(const DistOptions &o_in, std::vector<std::string> inpaths, size_t nq) {
+    DistOptions o = o_in;
+    if (o.defer_hll) o.estim = o.jestim = DB200_ERTL_MLE;   // hllbase_t(p) inside make_hll(): ERTL_MLE for both (hll.h:765)
+    const size_t n = inpaths.size(), m = size_t(1) << o.p;
+    if (nq > n) throw Error("more queries than paths");
+    std::vector<uint8_t> regs(n * m);
+    // ---- phase A: load or sketch (src/sketch_and_cmp.h:314-360)
+    std::vector<size_t> todo;
+    std::vector<std::string> fnames(n);
+    for (size_t i = 0; i < n; ++i) {
+        if (o.presketched) {
+            HllFile h = read_hll(inpaths[i]);
+            if (h.p != (uint32_t)o.p) throw Error("sketch " + inpaths[i] + " has p=" + std::to_string(h.p) + ", expected " + std::to_string(o.p));
+            warn_estim(h, inpaths[i], o.estim);
+            std::memcpy(&regs[i * m], h.core.data(), m);
+            continue;
+        }
+        fnames[i] = make_fname(inpaths[i].c_str(), o.p, o.k, o.k, o.k, "", o.suffix, o.prefix);
+        if (o.cache_sketches && isfile(fnames[i])) {
+            HllFile h = read_hll(fnames[i]);
+            if (h.p != (uint32_t)o.p) throw Error("cached sketch " + fnames[i] + " has the wrong size");
+            warn_estim(h, fnames[i], o.estim);
+            std::memcpy(&regs[i * m], h.core.data(), m);
+        } else todo.push_back(i);
+    }
+    sketch_paths(o, inpaths, todo, [&](size_t i, const uint8_t *r) {
+        std::memcpy(&regs[i * m], r, m);
+        // sketches carry the command line's estimators (set_estim_and_jestim, src/sketch_and_cmp.h:285-288)
+        if (o.cache_sketches && !o.defer_hll) write_hll(fnames[i], r, o.p, o.estim, o.jestim, -1.);
+    });
+    // ---- phase B: sizes (:372-385)
+    phase("sketches ready");
+    std::vector<double> card(n);
+    check(db200_cardinalities(o.device, regs.data(), n, o.p, o.estim, card.data()));
+    {
+        const std::string s = format_sizes(inpaths, card.data());
+        std::FILE *fp = o.sizes_path.empty() ? stdout : std::fopen(o.sizes_path.c_str(), "w");
+        if (!fp) throw Error("Could not open file at " + o.sizes_path + " for writing.");
+        std::fwrite(s.data(), 1, s.size(), fp);
+        if (fp != stdout) std::fclose(fp); else std::fflush(fp);
+    }
+    if (o.defer_hll && o.cache_sketches)     // final_sketches[i].write(fpath) after make_hll()'s sum() (bbmh.h:1175-1184): value included
+        for (size_t i : todo) write_hll(fnames[i], &regs[i * m], o.p, 2, 2, card[i]);
+    // ---- phase C: all pairs
+    phase("sizes written");
+    compare_and_emit(o, inpaths, regs, nq);
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // CLI (hot subset of src/distmain.cpp:47-100 and src/dashing.cpp:307-337)
 // ---------------------------------------------------------------------------------------------------------------
@@ -630,40 +740,68 @@ void dist_sketch_and_cmp(const DistOptions &o, std::vector<std::string> inpaths,
                 "run the reference binary for it");
 }
 
+// Option tables: the reference declares most boolean long options as getopt FLAG entries (LO_FLAG, src/dashing.h:33) that
+// set a variable and return 0, and gives them a short letter that its switch often has no case for — so `--presketched`
+// works while `-H` is accepted and ignored, `-n` swallows an argument and does nothing, etc.  The tables below reproduce
+// that: long flags get private codes (>= 256), short letters do exactly what the reference's switch does with them.
+enum LongOnly {
+    L_AVOID_SORTING = 256, L_CACHE, L_BINARY, L_FULL_MASH, L_FULL_TSV, L_NO_CANON, L_PHYLIP, L_PRESKETCHED, L_SIZES, L_SCI, L_MASH,
+    L_CONT_INDEX, L_CONT_DIST, L_FULL_CONT_DIST, L_SYM_CONT_INDEX, L_SYM_CONT_DIST, L_SKIP_CACHED, L_DEFER_HLL, L_DEVICE,
+    L_COUNTMIN, L_BY_FNAME, L_ENTROPY, L_OTHER_SKETCH, L_OTHER_HASH, L_WJ, L_NN, L_IGNORED_ARG
+};
+
+static int parse_device(const char *arg) {
+    return (!std::strcmp(arg, "all") || !std::strcmp(arg, "-1")) ? DB200_ALL_DEVICES : std::atoi(arg);
+}
+
 int dist_main(int argc, char **argv) {
     DistOptions o;
     std::string paths_file;
     std::vector<std::string> querypaths;
-    int lo_result = -1, lo_fmt = -1, flag_sort = 0, flag_presk = 0, flag_cache = 0, flag_nocanon = 0;
-    static option longopts[] = {
-        {"avoid-sorting", no_argument, nullptr, 'n'}, {"cache-sketches", no_argument, nullptr, 'W'}, {"emit-binary", no_argument, nullptr, 'b'},
-        {"full-mash-dist", no_argument, nullptr, 'l'}, {"full-tsv", no_argument, nullptr, 'T'}, {"no-canon", no_argument, nullptr, 'C'},
-        {"phylip", no_argument, nullptr, 'U'}, {"presketched", no_argument, nullptr, 'H'}, {"sizes", no_argument, nullptr, 'Z'},
-        {"ertl-joint-mle", no_argument, nullptr, 'J'}, {"ertl-mle", no_argument, nullptr, 'm'}, {"improved", no_argument, nullptr, 'I'},
-        {"original", no_argument, nullptr, 'E'}, {"kmer-length", required_argument, nullptr, 'k'}, {"nthreads", required_argument, nullptr, 'p'},
-        {"out-dists", required_argument, nullptr, 'O'}, {"out-sizes", required_argument, nullptr, 'o'}, {"paths", required_argument, nullptr, 'F'},
-        {"prefix", required_argument, nullptr, 'P'}, {"query-paths", required_argument, nullptr, 'Q'}, {"sketch-size", required_argument, nullptr, 'S'},
-        {"suffix", required_argument, nullptr, 'x'}, {"mash-dist", no_argument, nullptr, 'M'},
-        {"containment-index", no_argument, nullptr, 131}, {"containment-dist", no_argument, nullptr, 132}, {"full-containment-dist", no_argument, nullptr, 133},
-        {"symmetric-containment-index", no_argument, nullptr, 137}, {"symmetric-containment-dist", no_argument, nullptr, 138},
-        {"spacing", required_argument, nullptr, 's'}, {"window-size", required_argument, nullptr, 'w'}, {"countmin", no_argument, nullptr, 'y'},
-        {"use-bb-minhash", no_argument, nullptr, '8'}, {"nearest-neighbors", required_argument, nullptr, 143}, {"device", required_argument, nullptr, 1001},
+    static option longopts[] = {   // DIST_LONG_OPTS, src/dashing.h:46-108
+        {"avoid-sorting", no_argument, nullptr, L_AVOID_SORTING}, {"by-entropy", no_argument, nullptr, L_ENTROPY},
+        {"cache-sketches", no_argument, nullptr, L_CACHE}, {"countmin", no_argument, nullptr, L_COUNTMIN},
+        {"emit-binary", no_argument, nullptr, L_BINARY}, {"full-mash-dist", no_argument, nullptr, L_FULL_MASH},
+        {"full-tsv", no_argument, nullptr, L_FULL_TSV}, {"no-canon", no_argument, nullptr, L_NO_CANON}, {"phylip", no_argument, nullptr, L_PHYLIP},
+        {"presketched", no_argument, nullptr, L_PRESKETCHED}, {"sizes", no_argument, nullptr, L_SIZES},
+        {"sketch-by-fname", no_argument, nullptr, L_BY_FNAME}, {"use-bb-minhash", no_argument, nullptr, L_OTHER_SKETCH},
+        {"use-scientific", no_argument, nullptr, L_SCI}, {"bbits", required_argument, nullptr, 'B'}, {"cm-sketch-size", required_argument, nullptr, 't'},
+        // LO_ARG: these four demand an argument in their LONG form (src/dashing.h:62-65, :71)
+        {"ertl-joint-mle", required_argument, nullptr, 'J'}, {"ertl-mle", required_argument, nullptr, 'm'}, {"improved", required_argument, nullptr, 'I'},
+        {"original", required_argument, nullptr, 'E'},
+        {"kmer-length", required_argument, nullptr, 'k'}, {"min-count", required_argument, nullptr, 'c'}, {"nhashes", required_argument, nullptr, 'q'},
+        {"nthreads", required_argument, nullptr, 'p'}, {"out-dists", required_argument, nullptr, 'O'}, {"out-sizes", required_argument, nullptr, 'o'},
+        {"paths", required_argument, nullptr, 'F'}, {"prefix", required_argument, nullptr, 'P'}, {"query-paths", required_argument, nullptr, 'Q'},
+        {"seed", required_argument, nullptr, 'R'}, {"sketch-size", required_argument, nullptr, 'S'}, {"spacing", required_argument, nullptr, 's'},
+        {"suffix", required_argument, nullptr, 'x'}, {"window-size", required_argument, nullptr, 'w'},
+        {"use-range-minhash", no_argument, nullptr, L_OTHER_SKETCH}, {"use-full-khash-sets", no_argument, nullptr, L_OTHER_SKETCH},
+        {"use-full-hash-sets", no_argument, nullptr, L_OTHER_SKETCH}, {"use-hash-sets", no_argument, nullptr, L_OTHER_SKETCH},
+        {"hash-sets", no_argument, nullptr, L_OTHER_SKETCH}, {"use-full-sets", no_argument, nullptr, L_OTHER_SKETCH},
+        {"use-bloom-filter", no_argument, nullptr, L_OTHER_SKETCH}, {"use-wide-hll", no_argument, nullptr, L_OTHER_SKETCH},
+        {"use-nthash", no_argument, nullptr, L_OTHER_HASH}, {"use-cyclic-hash", no_argument, nullptr, L_OTHER_HASH},
+        {"full-containment-dist", no_argument, nullptr, L_FULL_CONT_DIST}, {"containment-index", no_argument, nullptr, L_CONT_INDEX},
+        {"containment-dist", no_argument, nullptr, L_CONT_DIST}, {"mash-dist", no_argument, nullptr, L_MASH},
+        {"symmetric-containment-index", no_argument, nullptr, L_SYM_CONT_INDEX}, {"symmetric-containment-dist", no_argument, nullptr, L_SYM_CONT_DIST},
+        {"wj", no_argument, nullptr, L_WJ}, {"wj-exact", no_argument, nullptr, L_WJ}, {"wj-cm-sketch-size", required_argument, nullptr, L_WJ},
+        {"wj-cm-nhashes", required_argument, nullptr, L_WJ}, {"nearest-neighbors", required_argument, nullptr, L_NN},
+        {"defer-hll", no_argument, nullptr, L_DEFER_HLL}, {"nperbatch", required_argument, nullptr, L_IGNORED_ARG},
+        {"device", required_argument, nullptr, L_DEVICE},   // this engine's only addition: a GPU index, or "all"
         {nullptr, 0, nullptr, 0}};
-    (void)lo_result; (void)lo_fmt; (void)flag_sort; (void)flag_presk; (void)flag_cache; (void)flag_nocanon;
     optind = 1;
     int co;
-    while ((co = getopt_long(argc, argv, "nQ:P:x:F:p:o:s:w:O:S:k:8TlICbMEHJZUmWy", longopts, nullptr)) >= 0) {
+    // the reference's own short-option string (src/distmain.cpp:47)
+    while ((co = getopt_long(argc, argv, "n:Q:P:x:F:c:p:o:s:w:O:S:k:=:t:R:D:8TgazlICbMEeHJhZBNyUmqW?", longopts, nullptr)) >= 0) {
         switch (co) {
-            case 'n': o.avoid_sorting = true; break;
-            case 'W': o.cache_sketches = true; break;
-            case 'b': o.emit_fmt = BINARY; break;
-            case 'l': o.result_type = DB200_FULL_MASH_DIST; break;
-            case 'T': o.emit_fmt = FULL_TSV; break;
-            case 'C': o.canon = false; break;
-            case 'U': o.emit_fmt = UPPER_TRIANGULAR; break;
-            case 'H': o.presketched = true; break;
-            case 'Z': o.result_type = DB200_SIZES; break;
-            case 'M': o.result_type = DB200_MASH_DIST; break;
+            case L_AVOID_SORTING: o.avoid_sorting = true; break;
+            case 'W': case L_CACHE: o.cache_sketches = true; break;
+            case 'b': case L_BINARY: o.emit_fmt = BINARY; break;
+            case 'l': case L_FULL_MASH: o.result_type = DB200_FULL_MASH_DIST; break;
+            case 'T': case L_FULL_TSV: o.emit_fmt = FULL_TSV; break;
+            case 'C': case L_NO_CANON: o.canon = false; break;
+            case 'U': case L_PHYLIP: o.emit_fmt = UPPER_TRIANGULAR; break;
+            case L_PRESKETCHED: o.presketched = true; break;           // the short -H has no case in the reference's switch
+            case L_SIZES: o.result_type = DB200_SIZES; break;          // nor has -Z
+            case 'M': case L_MASH: o.result_type = DB200_MASH_DIST; break;
             case 'J': o.jestim = DB200_ERTL_JOINT_MLE; break;
             case 'm': o.jestim = o.estim = DB200_ERTL_MLE; break;
             case 'I': o.jestim = o.estim = DB200_ERTL_IMPROVED; break;
@@ -677,21 +815,27 @@ int dist_main(int argc, char **argv) {
             case 'Q': querypaths = get_paths(optarg); break;
             case 'P': o.prefix = optarg; break;
             case 'x': o.suffix = optarg; break;
-            case 131: o.result_type = DB200_CONTAINMENT_INDEX; break;
-            case 132: o.result_type = DB200_CONTAINMENT_DIST; break;
-            case 133: o.result_type = DB200_FULL_CONTAINMENT_DIST; break;
-            case 137: o.result_type = DB200_SYMMETRIC_CONTAINMENT_INDEX; break;
-            case 138: o.result_type = DB200_SYMMETRIC_CONTAINMENT_DIST; break;
-            case 1001: o.device = std::atoi(optarg); break;
-            case 's': unsupported("-s/--spacing");
-            case 'w': unsupported("-w/--window-size");
-            case 'y': unsupported("-y/--countmin");
-            case '8': unsupported("-8/--use-bb-minhash");
-            case 143:                                                           // src/distmain.cpp:89-93
+            case L_CONT_INDEX: o.result_type = DB200_CONTAINMENT_INDEX; break;
+            case L_CONT_DIST: o.result_type = DB200_CONTAINMENT_DIST; break;
+            case L_FULL_CONT_DIST: o.result_type = DB200_FULL_CONTAINMENT_DIST; break;
+            case L_SYM_CONT_INDEX: o.result_type = DB200_SYMMETRIC_CONTAINMENT_INDEX; break;
+            case L_SYM_CONT_DIST: o.result_type = DB200_SYMMETRIC_CONTAINMENT_DIST; break;
+            case L_DEFER_HLL: o.defer_hll = true; break;
+            case L_DEVICE: o.device = parse_device(optarg); break;
+            case 's': if (*optarg) unsupported("-s/--spacing"); break;
+            case 'w': if (std::atoi(optarg) > o.k) unsupported("-w/--window-size"); break;   // wsz <= k is "unwindowed" (src/distmain.cpp:168)
+            case L_COUNTMIN: unsupported("--countmin");
+            case L_BY_FNAME: unsupported("--sketch-by-fname");
+            case L_ENTROPY: case 'g': unsupported("-g/--by-entropy");
+            case L_OTHER_SKETCH: case '8': unsupported("a non-HLL sketch type");
+            case L_OTHER_HASH: unsupported("--use-nthash/--use-cyclic-hash");
+            case L_WJ: unsupported("--wj (weighted Jaccard)");
+            case L_NN:                                                            // src/distmain.cpp:89-93
                 if (std::atoi(optarg) <= 0) throw Error("--nearest-neighbors needs a positive count");
                 o.nneighbors = (unsigned)std::atoi(optarg);
                 break;
-            default: throw Error("unknown option; see the reference's `dashing dist` usage for the supported subset");
+            case 'h': case '?': throw Error("see the reference's `dashing dist` usage: this binary takes the same flags");
+            default: break;   // -n X, -c X, -q X, -t X, -R X, -D X, -B X, -e, -H, -Z, -N, -y, -a, -z, --nperbatch: accepted, no effect on the HLL path
         }
     }
     if (o.k > 32) throw Error("k must be <= 32 for non-rolling hashes.");     // src/distmain.cpp:101-102
@@ -709,34 +853,66 @@ int dist_main(int argc, char **argv) {
     return 0;
 }
 
+// SKETCH_LONG_OPTS (src/dashing.cpp:253-291) and the switch of sketch_main / sketch_by_seq_main (:307-337, :487-517).
+// Returns false for options the caller has to look at itself.
+static option sketch_longopts[] = {
+    {"countmin", no_argument, nullptr, L_COUNTMIN}, {"sketch-by-fname", no_argument, nullptr, L_BY_FNAME}, {"no-canon", no_argument, nullptr, L_NO_CANON},
+    {"skip-cached", no_argument, nullptr, L_SKIP_CACHED}, {"by-entropy", no_argument, nullptr, L_ENTROPY}, {"use-bb-minhash", no_argument, nullptr, L_OTHER_SKETCH},
+    {"bbits", required_argument, nullptr, 'B'}, {"paths", required_argument, nullptr, 'F'}, {"prefix", required_argument, nullptr, 'P'},
+    {"nhashes", required_argument, nullptr, 'H'}, {"original", required_argument, nullptr, 'E'}, {"improved", required_argument, nullptr, 'I'},
+    {"ertl-joint-mle", required_argument, nullptr, 'J'}, {"seed", required_argument, nullptr, 'R'}, {"sketch-size", required_argument, nullptr, 'S'},
+    {"kmer-length", required_argument, nullptr, 'k'}, {"min-count", required_argument, nullptr, 'n'}, {"nthreads", required_argument, nullptr, 'p'},
+    {"cm-sketch-size", required_argument, nullptr, 'q'}, {"spacing", required_argument, nullptr, 's'}, {"window-size", required_argument, nullptr, 'w'},
+    {"suffix", required_argument, nullptr, 'x'}, {"wj-cm-sketch-size", required_argument, nullptr, L_WJ}, {"wj-cm-nhashes", required_argument, nullptr, L_WJ},
+    {"use-range-minhash", no_argument, nullptr, L_OTHER_SKETCH}, {"use-full-khash-sets", no_argument, nullptr, L_OTHER_SKETCH},
+    {"use-bloom-filter", no_argument, nullptr, L_OTHER_SKETCH}, {"use-wide-hll", no_argument, nullptr, L_OTHER_SKETCH},
+    {"use-nthash", no_argument, nullptr, L_OTHER_HASH}, {"use-cyclic-hash", no_argument, nullptr, L_OTHER_HASH},
+    {"avoid-sorting", no_argument, nullptr, L_AVOID_SORTING}, {"wj", no_argument, nullptr, L_WJ}, {"wj-exact", no_argument, nullptr, L_WJ},
+    {"defer-hll", no_argument, nullptr, L_DEFER_HLL}, {"device", required_argument, nullptr, L_DEVICE},
+    {nullptr, 0, nullptr, 0}};
+
+static bool sketch_option(int co, SketchOptions &o, bool &defer_hll) {
+    switch (co) {
+        case L_AVOID_SORTING: o.avoid_sorting = true; return true;
+        case L_SKIP_CACHED: o.skip_cached = true; return true;         // the short -c / -C / -e / -f / -j have no case in the reference's switch
+        case L_NO_CANON: o.canon = false; return true;
+        case 'E': o.jestim = o.estim = DB200_ORIGINAL; return true;
+        case 'I': o.jestim = o.estim = DB200_ERTL_IMPROVED; return true;
+        case 'J': o.jestim = DB200_ERTL_JOINT_MLE; return true;
+        case 'k': o.k = std::atoi(optarg); return true;
+        case 'p': o.nthreads = std::atoi(optarg); return true;
+        case 'S': o.p = std::atoi(optarg); return true;
+        case 'P': o.prefix = optarg; return true;
+        case 'x': o.suffix = optarg; return true;
+        case L_DEVICE: o.device = parse_device(optarg); return true;
+        case L_DEFER_HLL: defer_hll = true; return true;
+        case 's': if (*optarg) unsupported("-s/--spacing"); return true;
+        case 'w': if (std::atoi(optarg) > o.k) unsupported("-w/--window-size"); return true;
+        case 'b': case L_COUNTMIN: unsupported("-b/--countmin");
+        case L_BY_FNAME: unsupported("--sketch-by-fname");
+        case L_ENTROPY: unsupported("--by-entropy");
+        case L_OTHER_SKETCH: case '8': unsupported("a non-HLL sketch type");
+        case L_OTHER_HASH: unsupported("--use-nthash/--use-cyclic-hash");
+        case L_WJ: unsupported("--wj (weighted Jaccard)");
+        case 'h': case '?': throw Error("see the reference's `dashing sketch` usage: this binary takes the same flags");
+        default: return false;
+    }
+}
+
 int sketch_main(int argc, char **argv) {
     SketchOptions o;
     std::string paths_file;
-    static option longopts[] = {
-        {"avoid-sorting", no_argument, nullptr, 'n'}, {"skip-cached", no_argument, nullptr, 'c'}, {"no-canon", no_argument, nullptr, 'C'},
-        {"kmer-length", required_argument, nullptr, 'k'}, {"nthreads", required_argument, nullptr, 'p'}, {"paths", required_argument, nullptr, 'F'},
-        {"prefix", required_argument, nullptr, 'P'}, {"sketch-size", required_argument, nullptr, 'S'}, {"suffix", required_argument, nullptr, 'x'},
-        {"spacing", required_argument, nullptr, 's'}, {"window-size", required_argument, nullptr, 'w'}, {"device", required_argument, nullptr, 1001},
-        {nullptr, 0, nullptr, 0}};
+    bool defer_hll = false;
     optind = 1;
     int co;
-    while ((co = getopt_long(argc, argv, "nP:F:p:x:s:S:k:w:cC", longopts, nullptr)) >= 0) {
-        switch (co) {
-            case 'n': o.avoid_sorting = true; break;
-            case 'c': o.skip_cached = true; break;
-            case 'C': o.canon = false; break;
-            case 'k': o.k = std::atoi(optarg); break;
-            case 'p': o.nthreads = std::atoi(optarg); break;
-            case 'S': o.p = std::atoi(optarg); break;
-            case 'F': paths_file = optarg; break;
-            case 'P': o.prefix = optarg; break;
-            case 'x': o.suffix = optarg; break;
-            case 1001: o.device = std::atoi(optarg); break;
-            case 's': unsupported("-s/--spacing");
-            case 'w': unsupported("-w/--window-size");
-            default: throw Error("unknown option; see the reference's `dashing sketch` usage for the supported subset");
-        }
+    while ((co = getopt_long(argc, argv, "n:P:F:o:p:x:R:s:S:k:w:H:q:B:8JbfjEIcCeh?", sketch_longopts, nullptr)) >= 0) {   // src/dashing.cpp:307
+        if (sketch_option(co, o, defer_hll)) continue;
+        if (co == 'F') paths_file = optarg;
+        else if (co == 'o') o.output_file = optarg;
+        // -n X (min count), -R X, -H X, -q X, -B X, -c, -C, -e, -f, -j: accepted, no effect on the HLL path
     }
+    // sketch_core<HyperLogLogHasher<>>::write is BBitMinHasher's: it emits a b-bit minhash under the .hll name (bbmh.h:962-969)
+    if (defer_hll) unsupported("--defer-hll (`sketch` then writes b-bit minhash files, not HLLs)");
     if (o.k > 32) throw Error("k must be <= 32 for non-rolling hashes.");
     o.nthreads = std::max(o.nthreads, 1);
     std::vector<std::string> inpaths = (!paths_file.empty() && isfile(paths_file)) ? get_paths(paths_file) : std::vector<std::string>(argv + optind, argv + argc);
@@ -745,14 +921,386 @@ int sketch_main(int argc, char **argv) {
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// union / hll / fold / view / card / sketch_by_seq / dist_by_seq
+// ---------------------------------------------------------------------------------------------------------------
+static void write_hll_mode(const std::string &path, const char *mode, const uint8_t *regs, uint32_t p, int estim, int jestim, double value) {
+    gzFile fp = gzopen(path.c_str(), mode);
+    if (!fp) throw Error("Could not open file at " + path);
+    write_hll_stream(fp, regs, p, estim, jestim, value);
+    if (gzclose(fp) != Z_OK) throw Error("Failed to close ofp");
+}
+
+// union_main + union_core<hll_t>, src/union.cpp:33-108
+int union_main(int argc, char **argv) {
+    int compression_level = 6, device = 0;
+    std::string opath = "/dev/stdout";
+    std::vector<std::string> paths;
+    static option longopts[] = {{"device", required_argument, nullptr, L_DEVICE}, {nullptr, 0, nullptr, 0}};
+    optind = 1;
+    for (int c; (c = getopt_long(argc, argv, "p:b:o:F:zZ:h?", longopts, nullptr)) >= 0;) {
+        switch (c) {
+            case 'h': case '?': throw Error("Usage: union [-o out.hll] [-Z level] [-F paths.txt] sketch1.hll <sketch2.hll>...");
+            case 'Z': compression_level = std::atoi(optarg); [[fallthrough]];    // the reference falls through here, so -Z N also names
+            case 'o': opath = optarg; break;                                     // the output file N unless a later -o overrides it
+            case 'F': paths = get_paths(optarg); break;
+            case 'b': unsupported("-b (the reference's getopt string gives it an argument and its switch then selects bloom filters)");
+            case L_DEVICE: device = parse_device(optarg); break;
+            default: break;                                                      // -p threads, -z: nothing to do here
+        }
+    }
+    for (int i = optind; i < argc; ++i) paths.push_back(argv[i]);
+    if (paths.empty()) throw Error("require >= 1 paths. See usage.");
+    // T(paths[i]) for every input, then += (element-wise max, hll.h:958-992) and sum() (perform_sum): the result keeps the FIRST
+    // sketch's estimators and carries its cardinality
+    std::vector<uint8_t> regs;
+    uint32_t p = 0, estim = 2, jestim = 2;
+    for (size_t i = 0; i < paths.size(); ++i) {
+        const HllFile h = read_hll(paths[i]);
+        if (i == 0) { p = h.p; estim = h.estim; jestim = h.jestim; regs.reserve(paths.size() << p); }
+        else if (h.p != p) throw Error("mismatched sketch sizes.");            // PREC_REQ, hll.h:959
+        regs.insert(regs.end(), h.core.begin(), h.core.end());
+    }
+    if (estim > 2) throw Error("sketch " + paths[0] + " names an unknown estimation method");
+    std::vector<uint8_t> out(size_t(1) << p);
+    check(db200_union(device, regs.data(), paths.size(), (int)p, out.data()));
+    double value = -1.;
+    check(db200_cardinalities(device, out.data(), 1, (int)p, (int)estim, &value));
+    char mode[8];
+    if (compression_level) std::snprintf(mode, sizeof mode, "wb%d", compression_level % 23);
+    else std::snprintf(mode, sizeof mode, "wT");
+    write_hll_mode(opath, mode, out.data(), p, (int)estim, (int)jestim, value);
+    return 0;
+}
+
+// hll_main -> estimate_cardinality -> make_hll -> fill_sketch, src/hllmain.cpp:4-40, src/dashing.h:618-657: every path folded into
+// ONE sketch of 2^S registers (default S = 24), its ERTL_MLE estimate truncated to u64
+int hll_main(int argc, char **argv) {
+    SketchOptions o;
+    o.p = 24;
+    int wsz = 0;
+    std::string spacing;
+    if (argc < 2) throw Error("Usage: hll <opts> <paths>\nFlags:\n-k:\tkmer length (Default: 31. Max: 32)\n-S:\tsketch size (default: 24)\n-p:\tnumber of threads.\n-C:\tdo not canonicalize");
+    static option longopts[] = {{"device", required_argument, nullptr, L_DEVICE}, {nullptr, 0, nullptr, 0}};
+    optind = 1;
+    for (int c; (c = getopt_long(argc, argv, "Cw:s:S:p:k:tfh?", longopts, nullptr)) >= 0;) {
+        switch (c) {
+            case 'C': o.canon = false; break;
+            case 'h': case '?': throw Error("Usage: hll <opts> <paths>");
+            case 'k': o.k = std::atoi(optarg); break;
+            case 'p': o.nthreads = std::atoi(optarg); break;
+            case 's': spacing = optarg; break;
+            case 'S': o.p = std::atoi(optarg); break;
+            case 'w': wsz = std::atoi(optarg); break;
+            case L_DEVICE: o.device = parse_device(optarg); break;
+            default: break;
+        }
+    }
+    if (!spacing.empty()) unsupported("-s (spacing)");
+    if (wsz > o.k) unsupported("-w (window size)");
+    if (o.k > 32) throw Error("k must be <= 32 for non-rolling hashes.");
+    if (o.nthreads < 1) o.nthreads = 16;                               // negative -> hardware_concurrency (src/dashing.h:622-625)
+    std::vector<std::string> inpaths(argv + optind, argv + argc);      // (-F is parsed nowhere in the reference's getopt string)
+    // one "genome" whose files are all the inputs: FNAME_SEP-joined paths are exactly that (src/substrs.h:7-26)
+    std::string joined;
+    for (auto &pth : inpaths) {
+        if (pth.find(' ') != std::string::npos) throw Error("hll: paths with spaces are not supported");
+        if (!joined.empty()) joined += ' ';
+        joined += pth;
+    }
+    std::vector<uint8_t> regs(size_t(1) << o.p, 0);
+    if (!inpaths.empty())
+        sketch_paths(o, std::vector<std::string>{joined}, std::vector<size_t>{0}, [&](size_t, const uint8_t *r) { std::memcpy(regs.data(), r, regs.size()); });
+    double est = 0.;
+    check(db200_cardinalities(o.device == DB200_ALL_DEVICES ? 0 : o.device, regs.data(), 1, o.p, DB200_ERTL_MLE, &est));
+    std::fprintf(stdout, "Estimated number of unique exact matches: %lf\n", (double)(uint64_t)est);
+    return 0;
+}
+
+// fold_main, src/dashing.cpp:575-595: hll_t(in).compress(destp).write(out)
+int fold_main(int argc, char **argv) {
+    std::string out = "/dev/stdout", in = "/dev/stdin";
+    int destp = -1, device = 0;
+    static option longopts[] = {{"device", required_argument, nullptr, L_DEVICE}, {nullptr, 0, nullptr, 0}};
+    optind = 1;
+    for (int c; (c = getopt_long(argc, argv, "p:o:h?", longopts, nullptr)) >= 0;) {
+        switch (c) {
+            case 'o': out = optarg; break;
+            case 'p': destp = std::atoi(optarg); break;
+            case L_DEVICE: device = parse_device(optarg); break;
+            default: throw Error("Usage: dashing fold <flags> [in1.hll]\n-o: Write to <path> instead of stdout\n-p: set destination p [must be smaller than the input sketch");
+        }
+    }
+    if (argc - optind == 1) in = argv[optind];
+    else if (argc - optind != 0) throw Error("Usage: dashing fold <flags> [in1.hll]");
+    const HllFile h = read_hll(in);
+    if (out == "-") out = "/dev/stdout";
+    if (destp <= 0) destp = (int)h.p - 1;
+    if ((uint32_t)destp == h.p) {
+        // compress() returns a copy here (hll.h:907), cached cardinality included (read() computed it, hll.h:1078)
+        double value = h.value;
+        if (value < 0.) { if (h.estim > 2) throw Error("unknown estimation method in " + in); check(db200_cardinalities(device, h.core.data(), 1, (int)h.p, (int)h.estim, &value)); }
+        write_hll(out, h.core.data(), h.p, (int)h.estim, (int)h.jestim, value);
+        return 0;
+    }
+    if ((uint32_t)destp > h.p)
+        throw Error("Can't compress to a larger size. Current: " + std::to_string(h.p) + ". Requested new size: " + std::to_string(destp));
+    std::vector<uint8_t> folded(size_t(1) << destp);
+    check(db200_compress(device, h.core.data(), 1, (int)h.p, destp, folded.data()));
+    write_hll(out, folded.data(), (uint32_t)destp, (int)h.estim, (int)h.jestim, -1.);   // a fresh hllbase_t(new_np, estim, jestim): not calculated
+    return 0;
+}
+
+// view_main, src/dashing.cpp:562-566: hll_t::printf (hll.h:888-893) of every file, back to back
+int view_main(int argc, char **argv) {
+    if (argc < 2) throw Error("Usage: dashing view f1.hll [f2.hll ...]. Only HLLs currently supported.");
+    for (int i = 1; i < argc; ++i) {
+        const HllFile h = read_hll(argv[i]);
+        std::string s = "[";
+        for (size_t r = 0; r + 1 < h.core.size(); ++r) { s += std::to_string((int)h.core[r]); s += ", "; }
+        s += std::to_string((int)h.core.back());
+        s += ']';
+        std::fwrite(s.data(), 1, s.size(), stdout);
+    }
+    std::fflush(stdout);
+    return 0;
+}
+
+// card_main + size_sketch_and_emit<hll_t>, src/cardmain.cpp, src/sketch_and_cmp.h:122-265: per-path cardinalities, as FLOATS
+int card_main(int argc, char **argv) {
+    DistOptions o;
+    std::string paths_file, out_path;
+    bool use_scientific = false;
+    if (argc == 1) throw Error("see the reference's `dashing dist` usage: `card` takes the same flags");
+    static option longopts[] = {
+        {"avoid-sorting", no_argument, nullptr, L_AVOID_SORTING}, {"cache-sketches", no_argument, nullptr, L_CACHE}, {"emit-binary", no_argument, nullptr, L_BINARY},
+        {"no-canon", no_argument, nullptr, L_NO_CANON}, {"use-scientific", no_argument, nullptr, L_SCI}, {"presketched", no_argument, nullptr, L_PRESKETCHED},
+        {"countmin", no_argument, nullptr, L_COUNTMIN}, {"sketch-by-fname", no_argument, nullptr, L_BY_FNAME}, {"use-bb-minhash", no_argument, nullptr, L_OTHER_SKETCH},
+        {"kmer-length", required_argument, nullptr, 'k'}, {"nthreads", required_argument, nullptr, 'p'}, {"out-sizes", required_argument, nullptr, 'o'},
+        {"paths", required_argument, nullptr, 'F'}, {"prefix", required_argument, nullptr, 'P'}, {"sketch-size", required_argument, nullptr, 'S'},
+        {"suffix", required_argument, nullptr, 'x'}, {"spacing", required_argument, nullptr, 's'}, {"window-size", required_argument, nullptr, 'w'},
+        {"original", required_argument, nullptr, 'E'}, {"improved", required_argument, nullptr, 'I'}, {"ertl-joint-mle", required_argument, nullptr, 'J'},
+        {"ertl-mle", required_argument, nullptr, 'm'}, {"defer-hll", no_argument, nullptr, L_DEFER_HLL}, {"device", required_argument, nullptr, L_DEVICE},
+        {nullptr, 0, nullptr, 0}};
+    optind = 1;
+    int co;
+    while ((co = getopt_long(argc, argv, "n:Q:P:x:F:c:p:o:s:w:O:S:k:=:t:R:D:8TgazlICbMEeHJhZBNyUmqW?", longopts, nullptr)) >= 0) {   // src/cardmain.cpp:27
+        switch (co) {
+            case L_AVOID_SORTING: o.avoid_sorting = true; break;
+            case 'W': case L_CACHE: o.cache_sketches = true; break;
+            case 'b': case L_BINARY: o.emit_fmt = BINARY; break;
+            case 'C': case L_NO_CANON: o.canon = false; break;
+            case 'e': case L_SCI: use_scientific = true; break;
+            case L_PRESKETCHED: o.presketched = true; break;
+            case 'J': o.jestim = DB200_ERTL_JOINT_MLE; break;
+            case 'm': o.jestim = o.estim = DB200_ERTL_MLE; break;
+            case 'I': o.jestim = o.estim = DB200_ERTL_IMPROVED; break;
+            case 'E': o.jestim = o.estim = DB200_ORIGINAL; break;
+            case 'k': o.k = std::atoi(optarg); break;
+            case 'p': o.nthreads = std::atoi(optarg); break;
+            case 'S': o.p = std::atoi(optarg); break;
+            case 'o': out_path = optarg; break;
+            case 'F': paths_file = optarg; break;
+            case 'P': o.prefix = optarg; break;
+            case 'x': o.suffix = optarg; break;
+            case L_DEVICE: o.device = parse_device(optarg); break;
+            case L_DEFER_HLL: o.defer_hll = true; break;
+            case 's': if (*optarg) unsupported("-s/--spacing"); break;
+            case 'w': if (std::atoi(optarg) > o.k) unsupported("-w/--window-size"); break;
+            case L_COUNTMIN: unsupported("--countmin");
+            case L_BY_FNAME: unsupported("--sketch-by-fname");
+            case L_OTHER_SKETCH: case '8': unsupported("a non-HLL sketch type");
+            case 'g': unsupported("-g/--by-entropy");
+            case 'h': case '?': throw Error("see the reference's `dashing dist` usage: `card` takes the same flags");
+            default: break;
+        }
+    }
+    if (o.k > 32) throw Error("k must be <= 32 for non-rolling hashes.");
+    if (o.nthreads < 1) o.nthreads = 1;
+    if (o.defer_hll) o.estim = o.jestim = DB200_ERTL_MLE;
+    std::vector<std::string> inpaths = paths_file.empty() ? std::vector<std::string>(argv + optind, argv + argc) : get_paths(paths_file);
+    if (inpaths.empty()) throw Error("No paths. See usage.");
+    if (!o.presketched && !o.avoid_sorting) sort_paths_by_fsize(inpaths);
+    // card_main hands (prefix, suffix) to a callee that takes (suffix, prefix) (src/cardmain.cpp:4-6 vs src/sketch_and_cmp.h:126)
+    std::swap(o.prefix, o.suffix);
+    const size_t n = inpaths.size(), m = size_t(1) << o.p;
+    std::vector<uint8_t> regs(n * m);
+    std::vector<size_t> todo;
+    std::vector<std::string> fnames(n);
+    for (size_t i = 0; i < n; ++i) {
+        if (o.presketched) {
+            const HllFile h = read_hll(inpaths[i]);
+            if (h.p != (uint32_t)o.p) throw Error("sketch " + inpaths[i] + " has p=" + std::to_string(h.p) + ", expected " + std::to_string(o.p));
+            warn_estim(h, inpaths[i], o.estim);
+            std::memcpy(&regs[i * m], h.core.data(), m);
+            continue;
+        }
+        fnames[i] = make_fname(inpaths[i].c_str(), o.p, o.k, o.k, o.k, "", o.suffix, o.prefix);
+        if (o.cache_sketches && isfile(fnames[i])) {
+            const HllFile h = read_hll(fnames[i]);
+            if (h.p != (uint32_t)o.p) throw Error("cached sketch " + fnames[i] + " has the wrong size");
+            warn_estim(h, fnames[i], o.estim);
+            std::memcpy(&regs[i * m], h.core.data(), m);
+        } else todo.push_back(i);
+    }
+    sketch_paths(o, inpaths, todo, [&](size_t i, const uint8_t *r) {
+        std::memcpy(&regs[i * m], r, m);
+        if (o.cache_sketches && !o.defer_hll) write_hll(fnames[i], r, o.p, o.estim, o.jestim, -1.);
+    });
+    std::vector<double> card(n);
+    check(db200_cardinalities(o.device, regs.data(), n, o.p, o.estim, card.data()));
+    if (o.defer_hll && o.cache_sketches) for (size_t i : todo) write_hll(fnames[i], &regs[i * m], o.p, 2, 2, card[i]);
+    std::FILE *fp = out_path.empty() ? stdout : std::fopen(out_path.c_str(), "w");
+    if (!fp) throw Error("Could not open file at " + out_path + " for writing.");
+    std::vector<float> fbuf(n);
+    for (size_t i = 0; i < n; ++i) fbuf[i] = (float)card[i];           // :231-236
+    if (o.emit_fmt == BINARY) {
+        if (std::fwrite(fbuf.data(), sizeof(float), n, fp) != n) throw Error("Failed to write cardinality estimates to file");
+    } else {
+        std::string s("#Path\tSize (est.)\n");
+        char buf[64];
+        for (size_t i = 0; i < n; ++i) {
+            s += inpaths[i];
+            const int l = std::snprintf(buf, sizeof buf, use_scientific ? "\t%0.12g\n" : "\t%0.8f\n", (double)fbuf[i]);   // :247-249
+            s.append(buf, l);
+        }
+        std::fwrite(s.data(), 1, s.size(), fp);
+    }
+    if (fp != stdout) std::fclose(fp); else std::fflush(fp);
+    return 0;
+}
+
+// sketch_by_seq_main + sketch_by_seq_core, src/dashing.cpp:470-556, src/sketch_and_cmp.h:540-602: one sketch per RECORD of one
+// sequence file, all into one gzip stream, record names into <out>.names
+int sketch_by_seq_main(int argc, char **argv) {
+    SketchOptions o;
+    std::string outpath = "/dev/stdout";
+    bool defer_hll = false;
+    optind = 1;
+    int co;
+    while ((co = getopt_long(argc, argv, "o:n:P:p:x:R:s:S:k:w:H:q:B:8JbfjEIcCeh?", sketch_longopts, nullptr)) >= 0) {   // src/dashing.cpp:487
+        if (sketch_option(co, o, defer_hll)) continue;
+        if (co == 'o') outpath = optarg;
+    }
+    if (o.k > 32) throw Error("k must be <= 32 for non-rolling hashes.");
+    if (argc != optind + 1) throw Error("Usage: sketch_by_seq <opts> [same as sketch] -o out_path sequence_file");
+    // src/dashing.cpp:541-544 tests the flag the wrong way round: WITHOUT --defer-hll it instantiates HyperLogLogHasher, whose
+    // inherited write(gzFile) emits b-bit minhash records (bbmh.h:962-969); only --defer-hll yields hll_t records
+    if (!defer_hll)
+        unsupported("sketch_by_seq without --defer-hll (the reference then writes b-bit minhash records, not HLLs; pass --defer-hll for HLL records)");
+    const std::string inpath = argv[optind];
+    // kseq_read: names + sequences
+    std::vector<std::string> names;
+    std::string bases;
+    std::vector<uint64_t> offs{0};
+    for_each_named_record(inpath, [&](const std::string &name, const char *sq, size_t l) {
+        names.push_back(name);
+        bases.append(sq, l);
+        offs.push_back(bases.size());
+    });
+    const std::string namepath = outpath == "/dev/stdout" ? std::string("stdout.names") : outpath + ".names";
+    std::FILE *nfp = std::fopen(namepath.c_str(), "w");
+    if (!nfp) throw Error("Failed to open file for writing at " + namepath);
+    std::fprintf(nfp, "#k=%d:Names for sequences sketched\n", o.k);
+    for (auto &nm : names) { std::fwrite(nm.data(), 1, nm.size(), nfp); std::fputc('\n', nfp); }
+    std::fclose(nfp);
+    const size_t n = names.size(), m = size_t(1) << o.p;
+    std::vector<uint8_t> regs(n * m);
+    if (n) {
+        std::vector<uint64_t> grb(n + 1);
+        for (size_t i = 0; i <= n; ++i) grb[i] = i;                   // every record is its own "genome"
+        if (bases.empty()) bases.push_back('N');
+        check(db200_sketch_batch(o.device, o.p, o.k, o.canon, bases.data(), offs.data(), n, grb.data(), n, regs.data()));
+    }
+    gzFile ofp = gzopen(outpath.c_str(), "wb");
+    if (!ofp) throw Error("Failed to open file for writing at " + outpath);
+    for (size_t i = 0; i < n; ++i) write_hll_stream(ofp, &regs[i * m], o.p, o.estim, o.jestim, -1.);
+    gzclose(ofp);
+    return 0;
+}
+
+// dist_by_seq_main + dist_by_seq<hll_t>, src/distbyseq.cpp:50-138, src/sketch_and_cmp.h:76-118: all pairs over the records of a
+// sketch_by_seq container, labelled by its .names file
+int dist_by_seq_main(int argc, char **argv) {
+    DistOptions o;
+    o.k = -1;
+    std::string namefile, otherpath, outpath = "/dev/stdout";
+    static option longopts[] = {
+        {"containment-index", no_argument, nullptr, L_CONT_INDEX}, {"containment-dist", no_argument, nullptr, L_CONT_DIST}, {"mash-dist", no_argument, nullptr, L_MASH},
+        {"symmetric-containment-index", no_argument, nullptr, L_SYM_CONT_INDEX}, {"symmetric-containment-dist", no_argument, nullptr, L_SYM_CONT_DIST},
+        {"sizes", no_argument, nullptr, L_SIZES}, {"device", required_argument, nullptr, L_DEVICE}, {nullptr, 0, nullptr, 0}};
+    optind = 1;
+    int c;
+    while ((c = getopt_long(argc, argv, "q:o:k:n:p:EIJMBbS8KCTrh?", longopts, nullptr)) >= 0) {   // src/distbyseq.cpp:71
+        switch (c) {
+            case 'B': case 'S': case '8': case 'K': case 'r': unsupported("a non-HLL sketch type");
+            case 'p': o.nthreads = std::atoi(optarg); break;
+            case 'o': outpath = optarg; break;
+            case 'E': o.jestim = o.estim = DB200_ORIGINAL; break;
+            case 'I': o.jestim = o.estim = DB200_ERTL_IMPROVED; break;
+            case 'J': o.jestim = DB200_ERTL_JOINT_MLE; break;
+            case 'k': o.k = std::atoi(optarg); break;
+            case 'n': namefile = optarg; break;
+            case 'q': otherpath = optarg; break;
+            case 'b': o.emit_fmt = BINARY; break;
+            case 'T': o.emit_fmt = FULL_TSV; break;
+            case L_MASH: o.result_type = DB200_MASH_DIST; break;   // --mash-dist is a long FLAG entry; the short -M is accepted but has no case in the reference's switch
+            case L_CONT_INDEX: o.result_type = DB200_CONTAINMENT_INDEX; break;
+            case L_CONT_DIST: o.result_type = DB200_CONTAINMENT_DIST; break;
+            case L_SYM_CONT_INDEX: o.result_type = DB200_SYMMETRIC_CONTAINMENT_INDEX; break;
+            case L_SYM_CONT_DIST: o.result_type = DB200_SYMMETRIC_CONTAINMENT_DIST; break;
+            case L_SIZES: o.result_type = DB200_SIZES; break;
+            case L_DEVICE: o.device = parse_device(optarg); break;
+            case 'h': case '?': throw Error("Usage: dist_by_seq <flags> -n [namefile] input_file");
+            default: break;                                              // -C: listed, no case
+        }
+    }
+    if (optind + 1 != argc || namefile.empty()) throw Error("Usage: dist_by_seq <flags> -n [namefile] input_file");
+    // -q reads the query sketches from the SAME stream, past its end (src/sketch_and_cmp.h:89-98): nothing to reproduce
+    if (!otherpath.empty()) unsupported("-q (the reference reads the extra sketches past the end of the input stream)");
+    const std::vector<std::string> labels = get_paths(namefile);
+    if (o.k <= 0) {                                                     // "#k=<k>:Names ..." (src/distbyseq.cpp:104-111)
+        std::ifstream reader(namefile);
+        std::string line;
+        std::getline(reader, line);
+        int tmp = line.size() > 3 ? std::atoi(line.c_str() + 3) : 0;
+        o.k = tmp > 0 ? tmp : 31;
+    }
+    const int rt = o.result_type;
+    if (rt == DB200_CONTAINMENT_INDEX || rt == DB200_CONTAINMENT_DIST || rt == DB200_FULL_CONTAINMENT_DIST)
+        throw Error("Can't perform asymmetric comparison without query paths");   // src/sketch_and_cmp.h:100-102
+    const std::vector<HllFile> hs = read_hll_container(argv[optind], labels.size());
+    if (hs.empty()) throw Error("no sketches to compare");
+    o.p = (int)hs[0].p;
+    const size_t m = size_t(1) << o.p;
+    std::vector<uint8_t> regs(hs.size() * m);
+    for (size_t i = 0; i < hs.size(); ++i) {
+        if (hs[i].p != hs[0].p) throw Error("mismatched sketch sizes.");
+        warn_estim(hs[i], labels[i], o.estim);
+        std::memcpy(&regs[i * m], hs[i].core.data(), m);
+    }
+    o.dist_path = outpath;
+    compare_and_emit(o, labels, regs, 0);
+    return 0;
+}
+
 int cli_main(int argc, char **argv) {
     phase("start");
     try {
-        if (argc < 2) throw Error("usage: dashing_b200 <sketch|dist|cmp> [options] (the hot subset of dashing's flags)");
+        if (argc < 2) throw Error("usage: dashing_b200 <sketch|dist|cmp|union|hll|fold|view|card|sketch_by_seq|dist_by_seq> [options] (dashing's own flags)");
         const std::string sub = argv[1];
+        // src/main.cpp:24-40
         if (sub == "sketch") return sketch_main(argc - 1, argv + 1);
-        if (sub == "dist" || sub == "cmp") return dist_main(argc - 1, argv + 1);
-        throw Error("subcommand '" + sub + "' is outside the B200 engine's scope (sketch, dist, cmp)");
+        if (sub == "dist" || sub == "cmp" || sub == "setdist") return dist_main(argc - 1, argv + 1);
+        if (sub == "union") return union_main(argc - 1, argv + 1);
+        if (sub == "hll") return hll_main(argc - 1, argv + 1);
+        if (sub == "fold") return fold_main(argc - 1, argv + 1);
+        if (sub == "view") return view_main(argc - 1, argv + 1);
+        if (sub == "card") return card_main(argc - 1, argv + 1);
+        if (sub == "sketch_by_seq" || sub == "sbs") return sketch_by_seq_main(argc - 1, argv + 1);
+        if (sub == "dist_by_seq" || sub == "cmp_by_seq") return dist_by_seq_main(argc - 1, argv + 1);
+        throw Error("subcommand '" + sub + "' is outside the B200 engine's scope (sketch, dist/cmp, union, hll, fold, view, card, "
+                    "sketch_by_seq, dist_by_seq; not panel, printmat, mkdist, flatten)");
     } catch (const std::exception &e) {
         std::fprintf(stderr, "%s\n", e.what());                   // UNRECOVERABLE_ERROR: message + exit(1)
         return 1;

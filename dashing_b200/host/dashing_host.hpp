@@ -28,6 +28,8 @@ struct HllFile {
 std::vector<uint8_t> hll_payload(const uint8_t *regs, uint32_t p, int estim, int jestim, double value);
 void write_hll(const std::string &path, const uint8_t *regs, uint32_t p, int estim = 2, int jestim = 2, double value = -1.);
 HllFile read_hll(const std::string &path);
+// several sketches in one gzip stream: what `sketch -o` and `sketch_by_seq` write and `dist_by_seq` reads
+std::vector<HllFile> read_hll_container(const std::string &path, size_t count);
 // make_fname<hll_t>, src/dashing.h:497-526
 std::string make_fname(const char *path, size_t sketch_p, int wsz, int k, int csz, const std::string &spacing,
                        const std::string &suffix = "", const std::string &prefix = "");
@@ -40,6 +42,8 @@ void sort_paths_by_fsize(std::vector<std::string> &paths);
 
 // ---- FASTA / FASTQ records with kseq semantics (bonsai/klib/kseq.h:177-218), gz transparent --------------------
 void for_each_record(const std::string &file, const std::function<void(const char *, size_t)> &fn);
+// ... with the record name (ks->name.s: the header up to the first whitespace), for sketch_by_seq
+void for_each_named_record(const std::string &file, const std::function<void(const std::string &, const char *, size_t)> &fn);
 
 // ---- emitters — src/sketch_and_cmp.h:16-35, :372-397, :838-878; src/dashing.h:675-705 -------------------------
 std::string format_sizes(const std::vector<std::string> &paths, const double *card);
@@ -55,14 +59,20 @@ void write_binary_matrix(std::FILE *fp, const float *packed, uint64_t n);   // '
 // ---- drivers ----------------------------------------------------------------------------------------------------
 struct SketchOptions {
     int k = 31, p = 10, nthreads = 1, device = 0;
+    int estim = 2, jestim = 2;              // -E/-I/-J: stored in the header of every .hll written (set_estim_and_jestim)
     bool canon = true, skip_cached = false, avoid_sorting = false;
     std::string prefix, suffix;
+    std::string output_file;                // sketch -o: all sketches into one gzip stream + <file>.labels.gz (src/sketch_and_cmp.h:466-536)
     size_t batch_bytes = size_t(1) << 30;   // ASCII handed to one db200_sketch_batch call
 };
 struct DistOptions : SketchOptions {
-    int estim = 2, jestim = 2, result_type = 1 /* JI */;
+    int result_type = 1 /* JI */;
     EmissionFormat emit_fmt = UT_TSV;
     bool presketched = false, cache_sketches = false;
+    // --defer-hll (dist_sketch_and_cmp<HyperLogLogHasher<>>, src/distmain.cpp:177): the per-bucket minima finalize to the
+    // same registers (bbmh.h:1175-1184), but the final hll_t objects keep the constructor's ERTL_MLE / ERTL_MLE whatever
+    // -E/-I/-J said, and cached sketches are written with their cardinality already computed
+    bool defer_hll = false;
     unsigned nneighbors = 0;                 // --nearest-neighbors (gargs.number_neighbors, src/dashing.h:255); 0 = all pairs
     std::string sizes_path, dist_path;       // empty -> stdout
 };
@@ -80,9 +90,19 @@ void dist_sketch_and_cmp(const DistOptions &o, std::vector<std::string> inpaths,
 struct Neighbor { float value; uint32_t index; };
 std::string format_neighbors(const std::vector<std::string> &names, size_t qoffset, const Neighbor *nb, size_t rows, unsigned nn);
 void write_binary_neighbors(std::FILE *fp, uint32_t npaths, const Neighbor *nb, size_t rows, unsigned nn);
+// dist_loop / partdist_loop / nndist_loop over in-memory register rows (last nq rows are queries)
+void compare_and_emit(const DistOptions &o, const std::vector<std::string> &names, const std::vector<uint8_t> &regs, size_t nq);
 // sketch_main / dist_main (src/dashing.cpp:294-409, src/distmain.cpp:28-204): the hot subset of the flags
 int sketch_main(int argc, char **argv);
 int dist_main(int argc, char **argv);
+// SURVEY.md §8(f)3 — the subcommands that reuse the same primitives:
+int union_main(int argc, char **argv);          // src/union.cpp:60-108 (HLL sketches)
+int hll_main(int argc, char **argv);            // src/hllmain.cpp:4-40
+int fold_main(int argc, char **argv);           // src/dashing.cpp:575-595
+int view_main(int argc, char **argv);           // src/dashing.cpp:562-566
+int card_main(int argc, char **argv);           // src/cardmain.cpp (size_sketch_and_emit<hll_t>, src/sketch_and_cmp.h:122-265)
+int sketch_by_seq_main(int argc, char **argv);  // src/dashing.cpp:470-556 (sketch_by_seq_core, src/sketch_and_cmp.h:540-602)
+int dist_by_seq_main(int argc, char **argv);    // src/distbyseq.cpp:50-138 (dist_by_seq, src/sketch_and_cmp.h:76-118)
 int cli_main(int argc, char **argv);
 
 } // namespace db200h

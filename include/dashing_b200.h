@@ -80,10 +80,22 @@ typedef struct db200_dist_params {
     int32_t order;       /* enum db200_order (symmetric mode only) */
 } db200_dist_params;
 
+/* S4 multi-GPU: every HOST-pointer compute entry point accepts device = DB200_ALL_DEVICES and then
+ * shards its units over all visible GPUs, one host thread per device, no change to callers: genomes (sketch_batch,
+ * sketcher slots), sketches (cardinalities), block rows of the packed triangle balanced by pair count
+ * (dist_symmetric[_rows]) and queries (dist_rect, dist_knn_rect).  The host already holds every input, so each device
+ * receives what it needs by H2D and writes its own slice of the output; there is no device-to-device exchange in this
+ * form (the multi-process form — one rank per GPU, NCCL all-gather of register shards — is dashing_b200/multigpu.py
+ * over the `_dev` entry points).  dist_knn_symmetric runs on device 0 (its tie rule is order dependent).
+ * Device-resident objects (packed stores, plans) belong to one device and take a real index. */
+#define DB200_ALL_DEVICES (-1)
+
 /* ------------------------------------------------------------------------------------------ */
 DB200_API const char *db200_last_error(void);
 DB200_API int db200_version(void);
-/* Number of usable CUDA devices (0 when there is no driver/GPU; never fails). */
+/* Number of usable CUDA devices (0 when there is no driver/GPU; never fails).  DB200_VIRTUAL_DEVICES=N in the
+ * environment exposes N logical devices mapped round-robin onto the physical ones (testing the multi-device paths on
+ * a single-GPU box). */
 DB200_API int db200_device_count(void);
 /* Optional: creates the CUDA context of `device` now (seconds on a multi-GPU node) instead of inside the first compute
  * call, so a host can overlap it with file parsing from another thread. */
@@ -130,6 +142,14 @@ DB200_API int db200_sketch_packed_dev(const db200_packed_genomes *g, int p, int 
 
 /* ---- S2: per-sketch cardinalities ---------------------------------------------------------- */
 DB200_API int db200_cardinalities(int device, const uint8_t *regs, uint64_t n, int p, int estim, double *out);
+
+/* ---- set operations: `dashing union` and `dashing fold` ---------------------------------------
+ * db200_union: element-wise maximum of n register arrays — hll_t::operator+= (hll.h:958-992) folded over the inputs
+ * as union_core does (src/union.cpp:33-58).  out: uint8_t[2^p].  n == 0 gives the empty sketch.
+ * db200_compress: hll_t::compress(new_p) (hll.h:903-924) applied to each of n sketches; out: uint8_t[n][2^new_p].
+ * new_p == p copies, new_p > p is the reference's "Can't compress to a larger size" error (DB200_EINVAL). */
+DB200_API int db200_union(int device, const uint8_t *regs, uint64_t n, int p, uint8_t *out);
+DB200_API int db200_compress(int device, const uint8_t *regs, uint64_t n, int p, int new_p, uint8_t *out);
 
 /* ---- S3: all-pairs ------------------------------------------------------------------------
  * Symmetric mode: out is the packed upper triangle in distmat order,

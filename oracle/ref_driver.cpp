@@ -24,6 +24,8 @@
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline/--impl reference
 // legs may load the resulting library.
 #include "sketch_and_cmp.h"   // pulls in dashing.h; gives access to the reference's own drivers
+#include "union.cpp"          // the reference's union_core<T> / union_main, compiled where it lies (src/union.cpp)
+#include "hllmain.cpp"        // the reference's hll_main (src/hllmain.cpp)
 #include <omp.h>
 #include <cstring>
 #include <vector>
@@ -32,6 +34,8 @@
 // process-global option block of the reference (declared extern in src/dashing.h:264, defined in src/dashing.cpp:8,
 // which is not linked here)
 namespace bns { GlobalArgs gargs; }
+// union_main's usage text lives in src/dashing.cpp (not linked here); it only runs on bad flags
+namespace bns { void union_usage(char *) { std::exit(1); } }
 
 using namespace bns;
 using namespace sketch;
@@ -338,6 +342,137 @@ int dref_cli_sketch(int npaths, const char **paths, int k, int p, int canon, int
         sketch_core<hll::hll_t>(p, nthreads, sp.c_, k, sp, inpaths, suffix, prefix, cms, hll::ERTL_MLE,
                                 (hll::JointEstimationMethod)hll::ERTL_MLE, kseqs, use_filter, "", flags, 1, BONSAI, "");
     } catch(const std::exception &e) { std::fprintf(stderr, "dref_cli_sketch: %s\n", e.what()); return 1; }
+    return 0;
+}
+
+// ---- union / fold / hll / sketch -o / sketch_by_seq / card ------------------------------------
+// hll_t::compress (hll.h:903-924)
+int dref_compress(const uint8_t *regs, int p, int new_p, uint8_t *out) {
+    try {
+        hll_t h = make_sketch(regs, p, 2, 2);
+        hll_t c = h.compress(new_p);
+        std::memcpy(out, c.data(), c.size());
+    } catch(const std::exception &e) { std::fprintf(stderr, "dref_compress: %s\n", e.what()); return 1; }
+    return 0;
+}
+
+// hll_t::operator+= folded over n in-memory sketches (hll.h:958-992)
+int dref_union(const uint8_t *regs, uint64_t n, int p, uint8_t *out) {
+    hll_t acc(p);
+    const size_t m = size_t(1) << p;
+    for(uint64_t i = 0; i < n; ++i) acc += make_sketch(regs + i * m, p, 2, 2);
+    std::memcpy(out, acc.data(), m);
+    return 0;
+}
+
+// `dashing union` / `dashing hll` / `dashing fold` / `dashing view`: the reference's own mains (union.cpp, hllmain.cpp)
+// or, for the two that live in src/dashing.cpp (not compiled here), their bodies (fold_main :575-595, view_main :562-566).
+int dref_union_main(int argc, char **argv) {
+    optind = 1;
+    try { return union_main(argc, argv); } catch(const std::exception &e) { std::fprintf(stderr, "dref_union_main: %s\n", e.what()); return 1; }
+}
+int dref_hll_main(int argc, char **argv) {
+    optind = 1;
+    try { return hll_main(argc, argv); } catch(const std::exception &e) { std::fprintf(stderr, "dref_hll_main: %s\n", e.what()); return 1; }
+}
+int dref_fold(const char *in, const char *out, int destp) {
+    try {
+        hll_t h{std::string(in)};
+        if(destp <= 0) destp = h.p() - 1;
+        h.compress(destp).write(out);
+    } catch(const std::exception &e) { std::fprintf(stderr, "dref_fold: %s\n", e.what()); return 1; }
+    return 0;
+}
+int dref_view(const char *in, const char *out) {
+    try {
+        std::FILE *fp = std::fopen(out, "w");
+        if(!fp) return 2;
+        hll_t(std::string(in)).printf(fp);
+        std::fclose(fp);
+    } catch(const std::exception &e) { std::fprintf(stderr, "dref_view: %s\n", e.what()); return 1; }
+    return 0;
+}
+
+// `dashing sketch -o FILE`: sketch_core<hll_t> with an output_file (src/sketch_and_cmp.h:466-536): one gzip stream of
+// all sketches + FILE.labels.gz
+int dref_cli_sketch_container(int npaths, const char **paths, int k, int p, int canon, int nthreads, const char *output_file) {
+    try {
+        std::vector<std::string> inpaths(paths, paths + npaths);
+        std::vector<CountingSketch> cms;
+        std::vector<bool> use_filter;
+        KSeqBufferHolder kseqs(nthreads);
+        omp_set_num_threads(nthreads);
+        Spacer sp(k, 0);
+        const int flags = (int(canon != 0) << 1);
+        sketch_core<hll::hll_t>(p, nthreads, sp.c_, k, sp, inpaths, "", "", cms, hll::ERTL_MLE,
+                                (hll::JointEstimationMethod)hll::ERTL_MLE, kseqs, use_filter, "", flags, 1, BONSAI, output_file);
+    } catch(const std::exception &e) { std::fprintf(stderr, "dref_cli_sketch_container: %s\n", e.what()); return 1; }
+    return 0;
+}
+
+// `dashing sketch_by_seq --defer-hll` == sketch_by_seq_core<hll_t> (src/dashing.cpp:542: the flag test is inverted there; the
+// default instantiates HyperLogLogHasher, whose inherited write() emits a b-bit minhash, not an HLL)
+int dref_cli_sketch_by_seq(const char *inpath, const char *outpath, int k, int p, int canon, int estim, int jestim) {
+    try {
+        Spacer sp(k, 0);
+        const int flags = (int(canon != 0) << 1);
+        sketch_by_seq_core<hll::hll_t>(p, 1, sp, inpath, outpath, nullptr, (hll::EstimationMethod)estim, (hll::JointEstimationMethod)jestim,
+                                       false, flags, 1, BONSAI);
+    } catch(const std::exception &e) { std::fprintf(stderr, "dref_cli_sketch_by_seq: %s\n", e.what()); return 1; }
+    return 0;
+}
+
+// `dashing dist_by_seq`: dist_by_seq<hll_t> (src/sketch_and_cmp.h:76-118)
+int dref_cli_dist_by_seq(const char *namefile, const char *datapath, const char *outpath, int k, int estim, int jestim, int rtype,
+                         int emit_fmt, int nthreads, int skip_header) {
+    try {
+        auto labels = get_paths(namefile);
+        if(skip_header && !labels.empty()) labels.erase(labels.begin());
+        std::FILE *ofp = std::fopen(outpath, "wb");
+        if(!ofp) return 2;
+        omp_set_num_threads(nthreads);
+        dist_by_seq<hll::hll_t>(labels, datapath, ofp, outpath, k, (hll::EstimationMethod)estim, (hll::JointEstimationMethod)jestim,
+                                (EmissionType)rtype, (EmissionFormat)emit_fmt, nthreads, "");
+        std::fclose(ofp);
+    } catch(const std::exception &e) { std::fprintf(stderr, "dref_cli_dist_by_seq: %s\n", e.what()); return 1; }
+    return 0;
+}
+
+// `dashing card`: size_sketch_and_emit<hll_t> (src/sketch_and_cmp.h:122-265) as card_main calls it (src/cardmain.cpp:4-6 —
+// note the call passes (prefix, suffix) where the callee expects (suffix, prefix))
+int dref_cli_card(int npaths, const char **paths, int k, int p, int canon, int estim, int jestim, int presketched, int emit_binary,
+                  int use_scientific, int nthreads, const char *outpath) {
+    try {
+        std::vector<std::string> inpaths(paths, paths + npaths);
+        std::vector<CountingSketch> cms;
+        KSeqBufferHolder kseqs(nthreads);
+        omp_set_num_threads(nthreads);
+        std::FILE *ofp = std::fopen(outpath, "w");
+        if(!ofp) return 2;
+        Spacer sp(k, 0);
+        size_sketch_and_emit<hll::hll_t>(inpaths, cms, kseqs, ofp, sp, p, 5, BONSAI, (hll::EstimationMethod)estim,
+                                         (hll::JointEstimationMethod)jestim, false, emit_binary != 0, use_scientific != 0, presketched != 0,
+                                         nthreads, "", "", canon != 0, "");
+    } catch(const std::exception &e) { std::fprintf(stderr, "dref_cli_card: %s\n", e.what()); return 1; }
+    return 0;
+}
+
+// dist --defer-hll (src/distmain.cpp:177): dist_sketch_and_cmp<HyperLogLogHasher<>>
+int dref_cli_dist_defer(int npaths, const char **paths, int nq, int k, int p, int canon, int estim, int jestim, int rtype, int emit_fmt,
+                        int nthreads, const char *sizes_path, const char *dist_path, int cache, const char *prefix, const char *suffix) {
+    try {
+        std::vector<std::string> inpaths(paths, paths + npaths);
+        std::vector<CountingSketch> cms;
+        KSeqBufferHolder kseqs(nthreads);
+        std::FILE *ofp = std::fopen(sizes_path, "w"), *pairofp = std::fopen(dist_path, "wb");
+        if(!ofp || !pairofp) return 2;
+        omp_set_num_threads(nthreads);
+        Spacer sp(k, 0);
+        dist_sketch_and_cmp<HyperLogLogHasher<>>(inpaths, cms, kseqs, ofp, pairofp, dist_path, sp, p, 5, (hll::EstimationMethod)estim,
+                                        (hll::JointEstimationMethod)jestim, cache != 0, (EmissionType)rtype, (EmissionFormat)emit_fmt,
+                                        false, nthreads, false, suffix, prefix, canon != 0, false, "", nq, BONSAI);
+        if(pairofp) std::fclose(pairofp);
+    } catch(const std::exception &e) { std::fprintf(stderr, "dref_cli_dist_defer: %s\n", e.what()); return 1; }
     return 0;
 }
 
