@@ -20,6 +20,7 @@ ORIGINAL, ERTL_IMPROVED, ERTL_MLE, ERTL_JOINT_MLE = 0, 1, 2, 3
 MASH_DIST, JI, SIZES, FULL_MASH_DIST, FULL_CONTAINMENT_DIST, CONTAINMENT_INDEX, CONTAINMENT_DIST, \
     SYMMETRIC_CONTAINMENT_INDEX, SYMMETRIC_CONTAINMENT_DIST = range(9)
 ORDER_ROW_FIRST, ORDER_COL_FIRST = 0, 1
+ALL_DEVICES = -1   # DB200_ALL_DEVICES: host-pointer entry points shard over every visible GPU
 
 
 class Db200Error(RuntimeError):
@@ -203,6 +204,22 @@ def cardinalities(regs, p, estim=ERTL_MLE, device=0) -> np.ndarray:
     regs = _np(regs, np.uint8).reshape(-1, 1 << p)
     out = np.zeros(regs.shape[0], dtype=np.float64)
     _check(lib.db200_cardinalities(device, regs.ctypes.data_as(u8p), regs.shape[0], p, estim, out.ctypes.data_as(f64p)))
+    return out
+
+
+def union(regs, p, device=0) -> np.ndarray:
+    """Element-wise maximum of the rows (hll_t::operator+= folded, src/union.cpp:33-58)."""
+    regs = _np(regs, np.uint8).reshape(-1, 1 << p)
+    out = np.zeros(1 << p, dtype=np.uint8)
+    _check(lib.db200_union(device, regs.ctypes.data_as(u8p), regs.shape[0], p, out.ctypes.data_as(u8p)))
+    return out
+
+
+def compress(regs, p, new_p, device=0) -> np.ndarray:
+    """hll_t::compress(new_p) (hll.h:903-924) of every row -> uint8[n][2^new_p]."""
+    regs = _np(regs, np.uint8).reshape(-1, 1 << p)
+    out = np.zeros((regs.shape[0], 1 << max(min(new_p, p), 0)), dtype=np.uint8)
+    _check(lib.db200_compress(device, regs.ctypes.data_as(u8p), regs.shape[0], p, new_p, out.ctypes.data_as(u8p)))
     return out
 
 

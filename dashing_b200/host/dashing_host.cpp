@@ -1382,6 +1382,22 @@ DB200H_API int64_t db200h_read_records(const char *path, char *bases, uint64_t c
         return (int64_t)ends.size();
     } catch (const std::exception &e) { std::fprintf(stderr, "%s\n", e.what()); return -1; }
 }
+// record names of a FASTA/FASTQ(.gz) file (what sketch_by_seq writes to <out>.names), newline-terminated.  Returns bytes needed.
+DB200H_API int64_t db200h_record_names(const char *path, char *out, uint64_t cap) {
+    try {
+        std::string s;
+        db200h::for_each_named_record(path, [&](const std::string &nm, const char *, size_t) { s += nm; s += '\n'; });
+        if (s.size() <= cap) std::memcpy(out, s.data(), s.size());
+        return (int64_t)s.size();
+    } catch (const std::exception &e) { std::fprintf(stderr, "%s\n", e.what()); return -1; }
+}
+// get_paths(): newline-terminated entries.  Returns bytes needed.
+DB200H_API int64_t db200h_get_paths(const char *file, char *out, uint64_t cap) {
+    std::string s;
+    for (auto &p : db200h::get_paths(file)) { s += p; s += '\n'; }
+    if (s.size() <= cap) std::memcpy(out, s.data(), s.size());
+    return (int64_t)s.size();
+}
 // file_capacity(): the window the batch driver reserves for a file
 DB200H_API uint64_t db200h_file_capacity(const char *path) {
     try { return db200h::file_window(path); } catch (const std::exception &e) { std::fprintf(stderr, "%s\n", e.what()); return UINT64_MAX; }

@@ -150,6 +150,7 @@ def main():
     np.savez_compressed(os.path.join(OUT, "hll_payload.npz"), **h)
     make_cli_golden(R)
     make_knn_golden(R)
+    make_subcmd_golden(R)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 
@@ -260,8 +261,137 @@ def make_cli_golden(R):
     np.savez_compressed(os.path.join(OUT, "cli.npz"), **out)
 
 
+def _capture_stdout(fn):
+    """Runs fn() with file descriptor 1 redirected to a temporary file (the reference prints with C stdio)."""
+    sys.stdout.flush()
+    with tempfile.TemporaryFile() as tf:
+        saved = os.dup(1)
+        os.dup2(tf.fileno(), 1)
+        try:
+            fn()
+        finally:
+            import ctypes
+            ctypes.CDLL(None).fflush(None)
+            os.dup2(saved, 1)
+            os.close(saved)
+        tf.seek(0)
+        return tf.read()
+
+
+REAL_BINARY = "/tmp/oracle/dashing/dashing"   # `make dashing` of the unmodified reference, when someone built it (SURVEY.md §8(c))
+
+
+def _real(*args, cwd="."):
+    """Runs the real reference binary, if present, for cross-checking the driver-made fixtures."""
+    import subprocess
+    if not os.path.exists(REAL_BINARY):
+        return None
+    return subprocess.run([REAL_BINARY, *args], cwd=cwd, capture_output=True, timeout=600)
+
+
+def make_subcmd_golden(R):
+    """SURVEY.md §8(f)3 subcommands — union, hll, fold, view, sketch -o, sketch_by_seq, dist_by_seq, card, dist --defer-hll —
+    through the reference's own mains / templates (oracle/ref_driver.cpp), cross-checked against the real binary when built."""
+    files = cli_inputs()
+    names = ["a.fa", "b.fa", "d.fa", "f.fa"]
+    out = {"names": np.array(names)}
+    rd = lambda f: np.frombuffer(open(f, "rb").read(), dtype=np.uint8)
+    gz = lambda f: np.frombuffer(gzip.open(f, "rb").read(), dtype=np.uint8)
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as td:
+        os.chdir(td)
+        try:
+            for n in names:
+                write_fasta(n, **files[n])
+                out["file_" + n] = rd(n)
+            os.makedirs("sk", exist_ok=True)
+            R.cli_sketch(names, k=21, p=12, prefix="sk")
+            hp = [R.make_fname(n, 12, 21, 21, 21, "", "", "sk") for n in names]
+            out["hllnames"] = np.array(hp)
+            for n, h in zip(names, hp):
+                out["hll_" + n] = gz(h)
+            # union
+            R.union_main("-o", "u3.hll", hp[0], hp[1], hp[2])
+            out["union3"] = gz("u3.hll")
+            R.union_main("-o", "u1.hll", hp[3])
+            out["union1"] = gz("u1.hll")
+            open("plist.txt", "w").write("\n".join(hp) + "\n")
+            R.union_main("-p", "3", "-o", "u4.hll", "-F", "plist.txt")
+            out["union4_F"] = gz("u4.hll")
+            # hll
+            out["hll_stdout"] = np.frombuffer(_capture_stdout(lambda: R.hll_main("-k", "21", "-S", "14", "-p", "2", *names)), dtype=np.uint8)
+            out["hll_stdout_nocanon_p1"] = np.frombuffer(_capture_stdout(lambda: R.hll_main("-k", "17", "-S", "12", "-p", "1", "-C", names[0], names[3])), dtype=np.uint8)
+            # fold / view
+            R.fold(hp[0], "f8.hll", 8)
+            out["fold_a_8"] = gz("f8.hll")
+            R.fold(hp[1], "f11.hll", -1)
+            out["fold_b_default"] = gz("f11.hll")
+            R.fold(hp[0], "f12.hll", 12)
+            out["fold_a_same"] = gz("f12.hll")
+            R.fold("u3.hll", "fu.hll", 10)
+            out["fold_union3_10"] = gz("fu.hll")
+            R.view("f8.hll", "view.txt")
+            out["view_f8"] = rd("view.txt")
+            # sketch -o (one gzip stream of all sketches + labels)
+            R.cli_sketch_container(names, "cont.bin", k=21, p=12)
+            out["container"] = gz("cont.bin")
+            out["container_labels"] = gz("cont.bin.labels.gz")
+            # sketch_by_seq --defer-hll (hll_t records), dist_by_seq on its output
+            R.cli_sketch_by_seq("f.fa", "sbs.bin", k=21, p=10)
+            out["sbs"] = gz("sbs.bin")
+            out["sbs_names"] = rd("sbs.bin.names")
+            multi = [g[i:i + 4000].tobytes() for g in synth.genomes(99, 3, 16000, group=3) for i in range(0, 16000, 4000)]
+            write_fasta("multi.fa", multi, width=90)
+            out["file_multi.fa"] = rd("multi.fa")
+            R.cli_sketch_by_seq("multi.fa", "m.bin", k=15, p=10, estim=0, jestim=0)
+            out["sbs_multi"] = gz("m.bin")
+            out["sbs_multi_names"] = rd("m.bin.names")
+            dbs = {"dbs_tsv_ji": dict(), "dbs_bin_mash": dict(rtype=0, emit_fmt=1), "dbs_full_jmle": dict(emit_fmt=3, jestim=3),
+                   "dbs_tsv_sizes_k": dict(rtype=2, k=15)}
+            out["dbs_runs"] = np.array(list(dbs))
+            for rn, kw in dbs.items():
+                kk = kw.pop("k", 15)
+                R.cli_dist_by_seq("m.bin.names", "m.bin", "dbs.out", k=kk, **kw)
+                out[rn] = rd("dbs.out")
+                out[rn + "_kw"] = np.array(json.dumps(dict(kw, k=kk)))
+            # card
+            R.cli_card(names, "card.txt", k=21, p=12)
+            out["card_txt"] = rd("card.txt")
+            R.cli_card(names, "card_e.txt", k=21, p=12, use_scientific=True, estim=1, jestim=1)
+            out["card_sci_improved"] = rd("card_e.txt")
+            R.cli_card(names, "card.bin", k=21, p=12, emit_binary=True)
+            out["card_bin"] = rd("card.bin")
+            # dist --defer-hll -W: -E and -J are ignored, cached sketches carry their value
+            os.makedirs("dk", exist_ok=True)
+            R.cli_dist_defer(names, "ds.txt", "dd.txt", k=21, p=12, estim=0, jestim=3, rtype=0, cache=True, prefix="dk")
+            out["defer_sizes"] = rd("ds.txt")
+            out["defer_dist"] = rd("dd.txt")
+            for n in names:
+                out["defer_hll_" + n] = gz(R.make_fname(n, 12, 21, 21, 21, "", "", "dk"))
+            # ---- cross-check with the real binary where it was built
+            if os.path.exists(REAL_BINARY):
+                chk = lambda a, b, what: (_ for _ in ()).throw(AssertionError(what)) if bytes(a) != bytes(b) else None
+                _real("union", "-o", "ru3.hll", hp[0], hp[1], hp[2]); chk(gz("ru3.hll"), out["union3"], "union3 vs real binary")
+                r = _real("hll", "-k", "21", "-S", "14", "-p", "2", *names); chk(r.stdout, out["hll_stdout"], "hll vs real binary")
+                _real("fold", "-p", "8", "-o", "rf8.hll", hp[0]); chk(gz("rf8.hll"), out["fold_a_8"], "fold vs real binary")
+                r = _real("view", "f8.hll"); chk(r.stdout, out["view_f8"], "view vs real binary")
+                _real("sketch", "-k21", "-S12", "-p8", "--avoid-sorting", "-o", "rcont.bin", *names); chk(gz("rcont.bin"), out["container"], "sketch -o vs real binary")
+                _real("sketch_by_seq", "-k15", "-S10", "-E", "--defer-hll", "-o", "rm.bin", "multi.fa"); chk(gz("rm.bin"), out["sbs_multi"], "sketch_by_seq vs real binary")
+                chk(rd("rm.bin.names"), out["sbs_multi_names"], "sketch_by_seq names vs real binary")
+                _real("dist_by_seq", "-n", "m.bin.names", "-o", "rdbs.out", "m.bin"); chk(rd("rdbs.out"), out["dbs_tsv_ji"], "dist_by_seq vs real binary")
+                _real("card", "-k21", "-S12", "--avoid-sorting", "-o", "rcard.txt", *names); chk(rd("rcard.txt"), out["card_txt"], "card vs real binary")
+                _real("dist", "-k21", "-S12", "-E", "-J", "-M", "--defer-hll", "--avoid-sorting", "-o", "rds.txt", "-O", "rdd.txt", *names)
+                chk(rd("rds.txt"), out["defer_sizes"], "defer sizes vs real binary"); chk(rd("rdd.txt"), out["defer_dist"], "defer dist vs real binary")
+                print("subcmd fixtures agree with the real binary")
+        finally:
+            os.chdir(cwd)
+    np.savez_compressed(os.path.join(OUT, "subcmd.npz"), **out)
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "knn":       # only the nearest-neighbour fixtures (knn.npz + cli.npz)
+    if len(sys.argv) > 1 and sys.argv[1] == "subcmd":
+        make_subcmd_golden(O.ref())
+    elif len(sys.argv) > 1 and sys.argv[1] == "knn":       # only the nearest-neighbour fixtures (knn.npz + cli.npz)
         make_cli_golden(O.ref())
         make_knn_golden(O.ref())
     else:

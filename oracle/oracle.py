@@ -145,6 +145,20 @@ class Port(_Common):
         l.orc_knn.argtypes = [u8p, C.c_uint64] + [C.c_int] * 5 + [C.c_uint64, C.c_uint32, C.c_void_p]
         l.orc_hll_payload.restype = C.c_uint64
         l.orc_hll_payload.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_double, u8p, C.c_uint64]
+        l.orc_union.argtypes = [u8p, C.c_uint64, C.c_int, u8p]
+        l.orc_compress.argtypes = [u8p, C.c_int, C.c_int, u8p]
+
+    def union(self, regs2d, p):
+        regs2d = np.ascontiguousarray(regs2d, dtype=np.uint8).reshape(-1, 1 << p)
+        out = np.zeros(1 << p, dtype=np.uint8)
+        self.l.orc_union(_ptr(regs2d, u8p), regs2d.shape[0], p, _ptr(out, u8p))
+        return out
+
+    def compress(self, regs, p, new_p):
+        out = np.zeros(1 << min(new_p, p), dtype=np.uint8)
+        if self.l.orc_compress(_ptr(np.ascontiguousarray(regs, dtype=np.uint8), u8p), p, new_p, _ptr(out, u8p)):
+            raise ValueError("Can't compress to a larger size")
+        return out
 
     def wang(self, x):
         return int(self.l.orc_wang(C.c_uint64(x & 0xFFFFFFFFFFFFFFFF)))
@@ -273,6 +287,85 @@ class Ref(_Common):
                                     C.POINTER(C.c_int), f64p]
         l.dref_make_fname.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_char_p, C.c_char_p,
                                       C.c_char_p, C.c_uint64]
+
+        l.dref_compress.argtypes = [u8p, C.c_int, C.c_int, u8p]
+        l.dref_union.argtypes = [u8p, C.c_uint64, C.c_int, u8p]
+        l.dref_union_main.argtypes = [C.c_int, C.POINTER(C.c_char_p)]
+        l.dref_hll_main.argtypes = [C.c_int, C.POINTER(C.c_char_p)]
+        l.dref_fold.argtypes = [C.c_char_p, C.c_char_p, C.c_int]
+        l.dref_view.argtypes = [C.c_char_p, C.c_char_p]
+        l.dref_cli_sketch_container.argtypes = [C.c_int, C.POINTER(C.c_char_p)] + [C.c_int] * 4 + [C.c_char_p]
+        l.dref_cli_sketch_by_seq.argtypes = [C.c_char_p, C.c_char_p] + [C.c_int] * 5
+        l.dref_cli_dist_by_seq.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p] + [C.c_int] * 6
+        l.dref_cli_card.argtypes = [C.c_int, C.POINTER(C.c_char_p)] + [C.c_int] * 9 + [C.c_char_p]
+        l.dref_cli_dist_defer.argtypes = [C.c_int, C.POINTER(C.c_char_p)] + [C.c_int] * 9 + [C.c_char_p, C.c_char_p, C.c_int, C.c_char_p, C.c_char_p]
+
+    # ---- SURVEY.md §8(f)3 -------------------------------------------------------------------------------------------
+    def union(self, regs2d, p):
+        regs2d = np.ascontiguousarray(regs2d, dtype=np.uint8).reshape(-1, 1 << p)
+        out = np.zeros(1 << p, dtype=np.uint8)
+        self.l.dref_union(_ptr(regs2d, u8p), regs2d.shape[0], p, _ptr(out, u8p))
+        return out
+
+    def compress(self, regs, p, new_p):
+        out = np.zeros(1 << min(new_p, p), dtype=np.uint8)
+        if self.l.dref_compress(_ptr(np.ascontiguousarray(regs, dtype=np.uint8), u8p), p, new_p, _ptr(out, u8p)):
+            raise ValueError("Can't compress to a larger size")
+        return out
+
+    @staticmethod
+    def _argv(args):
+        return (C.c_char_p * (len(args) + 1))(*[os.fsencode(a) for a in args], None)
+
+    def union_main(self, *args):
+        """The reference's own `dashing union` main (src/union.cpp:60-108)."""
+        a = ["union", *args]
+        if self.l.dref_union_main(len(a), self._argv(a)):
+            raise RuntimeError("dref_union_main failed")
+
+    def hll_main(self, *args):
+        """The reference's own `dashing hll` main (src/hllmain.cpp); prints to this process's stdout."""
+        a = ["hll", *args]
+        if self.l.dref_hll_main(len(a), self._argv(a)):
+            raise RuntimeError("dref_hll_main failed")
+
+    def fold(self, inp, out, destp=-1):
+        if self.l.dref_fold(os.fsencode(inp), os.fsencode(out), destp):
+            raise RuntimeError("dref_fold failed")
+
+    def view(self, inp, out):
+        if self.l.dref_view(os.fsencode(inp), os.fsencode(out)):
+            raise RuntimeError("dref_view failed")
+
+    def cli_sketch_container(self, paths, output_file, k=31, p=10, canon=True, nthreads=None):
+        """`dashing sketch -o`; the reference indexes its worker sketches by path index here, so nthreads >= len(paths)."""
+        arr = (C.c_char_p * len(paths))(*[os.fsencode(p_) for p_ in paths])
+        if self.l.dref_cli_sketch_container(len(paths), arr, k, p, int(canon), nthreads or len(paths), os.fsencode(output_file)):
+            raise RuntimeError("dref_cli_sketch_container failed")
+
+    def cli_sketch_by_seq(self, inpath, outpath, k=31, p=10, canon=True, estim=2, jestim=2):
+        if self.l.dref_cli_sketch_by_seq(os.fsencode(inpath), os.fsencode(outpath), k, p, int(canon), estim, jestim):
+            raise RuntimeError("dref_cli_sketch_by_seq failed")
+
+    def cli_dist_by_seq(self, namefile, datapath, outpath, k=31, estim=2, jestim=2, rtype=1, emit_fmt=0, nthreads=1):
+        if self.l.dref_cli_dist_by_seq(os.fsencode(namefile), os.fsencode(datapath), os.fsencode(outpath), k, estim, jestim, rtype,
+                                       emit_fmt, nthreads, 0):
+            raise RuntimeError("dref_cli_dist_by_seq failed")
+
+    def cli_card(self, paths, outpath, k=31, p=10, canon=True, estim=2, jestim=2, presketched=False, emit_binary=False,
+                 use_scientific=False, nthreads=1):
+        arr = (C.c_char_p * len(paths))(*[os.fsencode(p_) for p_ in paths])
+        if self.l.dref_cli_card(len(paths), arr, k, p, int(canon), estim, jestim, int(presketched), int(emit_binary),
+                                int(use_scientific), nthreads, os.fsencode(outpath)):
+            raise RuntimeError("dref_cli_card failed")
+
+    def cli_dist_defer(self, paths, sizes_path, dist_path, nq=0, k=31, p=10, canon=True, estim=2, jestim=2, rtype=1, emit_fmt=0,
+                       nthreads=1, cache=False, prefix="", suffix=""):
+        """`dashing dist --defer-hll` (dist_sketch_and_cmp<HyperLogLogHasher<>>)."""
+        arr = (C.c_char_p * len(paths))(*[os.fsencode(p_) for p_ in paths])
+        if self.l.dref_cli_dist_defer(len(paths), arr, nq, k, p, int(canon), estim, jestim, rtype, emit_fmt, nthreads,
+                                      os.fsencode(sizes_path), os.fsencode(dist_path), int(cache), prefix.encode(), suffix.encode()):
+            raise RuntimeError("dref_cli_dist_defer failed")
 
     def simd_tier(self):
         return int(self.l.dref_simd_tier())

@@ -467,3 +467,41 @@ ORC_API uint64_t orc_hll_payload(const uint8_t *regs, int p, int estim, int jest
     memcpy(out + 28, regs, m);
     return nb;
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * (f)3. union — hll_t::operator+= (bonsai/hll/include/sketch/hll.h:958-992) folded over n sketches as
+ * union_core does (src/union.cpp:33-58): element-wise byte maximum.  out: 2^p bytes.
+ * ------------------------------------------------------------------------------------------- */
+ORC_API void orc_union(const uint8_t *regs, uint64_t n, int p, uint8_t *out) {
+    const uint64_t m = 1ull << p;
+    memset(out, 0, m);
+    for (uint64_t s = 0; s < n; ++s)
+        for (uint64_t i = 0; i < m; ++i)
+            if (regs[s * m + i] > out[i]) out[i] = regs[s * m + i];
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * (f)3. fold — hll_t::compress(new_np) (hll.h:903-924).  ratio = 2^(p - new_p) old registers per new one; j = offset of
+ * the first non-zero old register of the group; none -> 0, j == 0 -> min(q'+1, old + diff), else min(q'+1, clz64(j) + 1)
+ * with q' = 64 - new_p.  (clz is the 64-bit overload, integral.h: j is a size_t.)  Returns 1 for new_p > p (the
+ * reference throws "Can't compress to a larger size"), 0 otherwise; new_p == p copies.
+ * ------------------------------------------------------------------------------------------- */
+ORC_API int orc_compress(const uint8_t *regs, int p, int new_p, uint8_t *out) {
+    if (new_p > p) return 1;
+    if (new_p == p) { memcpy(out, regs, (size_t)1 << p); return 0; }
+    const unsigned diff = (unsigned)(p - new_p);
+    const uint64_t ratio = 1ull << diff, new_size = 1ull << new_p;
+    const unsigned cap = (unsigned)(64 - new_p) + 1u;
+    uint64_t b = 0;
+    for (uint64_t i = 0; i < new_size; ++i, b += ratio) {
+        uint64_t j = 0;
+        while (j < ratio && regs[j + b] == 0) ++j;
+        unsigned v = 0;
+        if (j != ratio) {
+            const unsigned cand = j ? (unsigned)__builtin_clzll(j) + 1u : (unsigned)regs[b] + diff;
+            v = cand < cap ? cand : cap;
+        }
+        out[i] = (uint8_t)v;
+    }
+    return 0;
+}

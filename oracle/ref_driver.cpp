@@ -433,7 +433,9 @@ int dref_cli_dist_by_seq(const char *namefile, const char *datapath, const char 
         omp_set_num_threads(nthreads);
         dist_by_seq<hll::hll_t>(labels, datapath, ofp, outpath, k, (hll::EstimationMethod)estim, (hll::JointEstimationMethod)jestim,
                                 (EmissionType)rtype, (EmissionFormat)emit_fmt, nthreads, "");
-        std::fclose(ofp);
+        // dist_loop's BINARY branch closes the stream itself (src/sketch_and_cmp.h:845); dist_by_seq_main closes it again
+        // (src/distbyseq.cpp:136) — a double fclose this driver does not repeat
+        if(emit_fmt != BINARY) std::fclose(ofp);
     } catch(const std::exception &e) { std::fprintf(stderr, "dref_cli_dist_by_seq: %s\n", e.what()); return 1; }
     return 0;
 }

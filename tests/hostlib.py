@@ -25,6 +25,10 @@ def load():
     l.db200h_format_neighbors.argtypes = [C.c_char_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint32, C.c_int, C.c_char_p, C.c_uint64]
     l.db200h_read_records.restype = C.c_int64
     l.db200h_read_records.argtypes = [C.c_char_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
+    l.db200h_record_names.restype = C.c_int64
+    l.db200h_record_names.argtypes = [C.c_char_p, C.c_char_p, C.c_uint64]
+    l.db200h_get_paths.restype = C.c_int64
+    l.db200h_get_paths.argtypes = [C.c_char_p, C.c_char_p, C.c_uint64]
     l.db200h_file_capacity.restype = C.c_uint64
     l.db200h_file_capacity.argtypes = [C.c_char_p]
     return l
@@ -79,6 +83,20 @@ def read_records(l, path, cap=1 << 22):
     n = l.db200h_read_records(os.fsencode(path), bases.ctypes.data, cap, offs.ctypes.data, offs.size - 1)
     assert n >= 0, n
     return [bases[int(offs[i]):int(offs[i + 1])].tobytes() for i in range(n)]
+
+
+def record_names(l, path):
+    buf = C.create_string_buffer(1 << 20)
+    n = l.db200h_record_names(os.fsencode(path), buf, 1 << 20)
+    assert 0 <= n <= (1 << 20), n
+    return buf.raw[:n]
+
+
+def get_paths(l, path):
+    buf = C.create_string_buffer(1 << 20)
+    n = l.db200h_get_paths(os.fsencode(path), buf, 1 << 20)
+    assert 0 <= n <= (1 << 20), n
+    return buf.raw[:n].decode().split("\n")[:-1]
 
 
 def materialise_inputs(cli_npz, directory):

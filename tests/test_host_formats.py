@@ -169,3 +169,22 @@ def test_file_windows(host, cli, tmp_path):
     assert [len(r) for r in recs] == [2000, 4]
     small = np.zeros(len(b), dtype=np.uint8); offs = np.zeros(10, dtype=np.uint64)
     assert host.db200h_read_records(str(mm).encode(), small.ctypes.data, len(b), offs.ctypes.data, 9) == -2
+
+
+def test_record_names_and_path_lists(host, golden_dir, tmp_path):
+    """sketch_by_seq's .names content (kseq's name = header up to the first whitespace) and get_lines' rules (bonsai util.h:1176-1184:
+    empty lines and '#' lines are skipped, a missing file gives no paths), against the reference-written names file."""
+    sub = np.load(os.path.join(golden_dir, "subcmd.npz"))
+    for fn, key in (("multi.fa", "sbs_multi_names"), ("f.fa", "sbs_names")):
+        (tmp_path / fn).write_bytes(sub["file_" + fn].tobytes())
+        want = sub[key].tobytes()
+        assert want.startswith(b"#k=")
+        assert hostlib.record_names(host, str(tmp_path / fn)) == want.split(b"\n", 1)[1]
+        # and dist_by_seq reads that names file as its labels: the '#k=..' header line is not a label
+        (tmp_path / (fn + ".names")).write_bytes(want)
+        assert hostlib.get_paths(host, str(tmp_path / (fn + ".names"))) == want.decode().split("\n")[1:-1]
+    (tmp_path / "fq.fq").write_bytes(b"@r1 comment here\nACGT\n+\nIIII\n@r2\tx\nGGCC\n+r2\nIIII\n")
+    assert hostlib.record_names(host, str(tmp_path / "fq.fq")) == b"r1\nr2\n"
+    (tmp_path / "list.txt").write_text("a.fa\n\n#skipped\nb c.fa\n")
+    assert hostlib.get_paths(host, str(tmp_path / "list.txt")) == ["a.fa", "b c.fa"]
+    assert hostlib.get_paths(host, str(tmp_path / "missing.txt")) == []
