@@ -63,6 +63,7 @@ _SIGS = {
     "db200_dist_symmetric": (C.c_int, [C.c_int, u8p, C.c_uint64, C.POINTER(DistParams), f32p]),
     "db200_dist_symmetric_rows": (C.c_int, [C.c_int, u8p, C.c_uint64, C.POINTER(DistParams), C.c_uint64, C.c_uint64, f32p]),
     "db200_dist_rect": (C.c_int, [C.c_int, u8p, C.c_uint64, u8p, C.c_uint64, C.POINTER(DistParams), f32p]),
+    "db200_dist_use_cardinalities": (C.c_int, [f64p, C.c_uint64]),
     "db200_dist_plan_create": (C.c_int, [C.c_int, C.POINTER(vp)]),
     "db200_dist_plan_destroy": (C.c_int, [vp]),
     "db200_dist_plan_prepare_dev": (C.c_int, [vp, vp, C.c_uint64, C.c_int, C.c_int, vp]),
@@ -221,6 +222,16 @@ def compress(regs, p, new_p, device=0) -> np.ndarray:
     out = np.zeros((regs.shape[0], 1 << max(min(new_p, p), 0)), dtype=np.uint8)
     _check(lib.db200_compress(device, regs.ctypes.data_as(u8p), regs.shape[0], p, new_p, out.ctypes.data_as(u8p)))
     return out
+
+
+def use_cardinalities(card):
+    """Cached per-sketch cardinalities for this thread's next dist_* / knn_* call (db200_dist_use_cardinalities)."""
+    if card is None:
+        _check(lib.db200_dist_use_cardinalities(None, 0))
+        return None
+    card = _np(card, np.float64)
+    _check(lib.db200_dist_use_cardinalities(card.ctypes.data_as(f64p), card.size))
+    return card      # keep alive until the call
 
 
 def dist_symmetric(regs, p, k=31, estim=ERTL_MLE, jestim=ERTL_MLE, result_type=JI, order=ORDER_ROW_FIRST, device=0,

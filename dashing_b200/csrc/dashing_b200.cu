@@ -591,6 +591,15 @@ static int plan_knn(db200_dist_plan *pl, const db200_dist_params *prm, uint64_t 
     return DB200_OK;
 }
 
+// Caller-supplied per-sketch cardinalities replace the ones card_kernel evaluated (the reference's hll_t objects carry a cached
+// value_: sketches loaded from files keep what read() computed under the FILE's estimator, hll.h:1078).  Rows [0, n1) and
+// [qbase, qbase + n2) of the plan.  Pageable sources are staged by the runtime before cudaMemcpyAsync returns.
+static int plan_override_cards(db200_dist_plan *pl, const double *c1, uint64_t n1, const double *c2, uint64_t n2, cudaStream_t stream) {
+    if (c1 && n1) DB200_CUDA(cudaMemcpyAsync(pl->card.as<double>(), c1, n1 * 8, cudaMemcpyHostToDevice, stream));
+    if (c2 && n2) DB200_CUDA(cudaMemcpyAsync(pl->card.as<double>() + pl->qbase, c2, n2 * 8, cudaMemcpyHostToDevice, stream));
+    return DB200_OK;
+}
+
 // Default per-device resources for the host-pointer entry points.
 struct HostCtx {
     std::mutex mu;
@@ -941,8 +950,8 @@ int db200_dist_plan_run_knn_dev(db200_dist_plan *pl, const db200_dist_params *pr
     }
     return plan_knn(pl, prm, nr, nq, nneighbors, reinterpret_cast<Neighbor *>(d_out), (cudaStream_t)stream);
 }
-int db200_dist_knn_symmetric(int device, const uint8_t *regs, uint64_t n, const db200_dist_params *prm, uint32_t nneighbors,
-                             db200_neighbor *out) {
+static int knn_symmetric_impl(int device, const uint8_t *regs, uint64_t n, const db200_dist_params *prm, uint32_t nneighbors,
+                              db200_neighbor *out, const double *card) {
     if (!prm || ((!regs || !out) && n)) { set_error("db200_dist_knn_symmetric: null argument"); return DB200_EINVAL; }
     // The retained sets depend on the ascending visiting order (ties at the cut), so per-device partial tables cannot be
     // merged exactly: with DB200_ALL_DEVICES the symmetric table is computed on device 0 (the -Q/-F form shards by query).
@@ -958,13 +967,14 @@ int db200_dist_knn_symmetric(int device, const uint8_t *regs, uint64_t n, const 
     DB200_TRY(hc.nbrs.reserve(n * nneighbors * sizeof(db200_neighbor)));
     DB200_CUDA(cudaMemcpyAsync(hc.regs.ptr, regs, n * m, cudaMemcpyHostToDevice, hc.stream));
     DB200_TRY(plan_prepare(hc.plan.get(), hc.regs.as<uint8_t>(), n, n, 0, 0, prm->p, prm->estim, hc.stream));
+    DB200_TRY(plan_override_cards(hc.plan.get(), card, n, nullptr, 0, hc.stream));
     DB200_TRY(plan_knn(hc.plan.get(), prm, 0, 0, nneighbors, hc.nbrs.as<Neighbor>(), hc.stream));
     DB200_CUDA(cudaMemcpyAsync(out, hc.nbrs.ptr, n * nneighbors * sizeof(db200_neighbor), cudaMemcpyDeviceToHost, hc.stream));
     DB200_CUDA(cudaStreamSynchronize(hc.stream));
     return DB200_OK;
 }
-int db200_dist_knn_rect(int device, const uint8_t *ref_regs, uint64_t nr, const uint8_t *qry_regs, uint64_t nq, const db200_dist_params *prm,
-                        uint32_t nneighbors, db200_neighbor *out) {
+static int knn_rect_impl(int device, const uint8_t *ref_regs, uint64_t nr, const uint8_t *qry_regs, uint64_t nq, const db200_dist_params *prm,
+                         uint32_t nneighbors, db200_neighbor *out, const double *card_ref, const double *card_qry) {
     if (!prm || ((!ref_regs || !qry_regs || !out) && nr && nq)) { set_error("db200_dist_knn_rect: null argument"); return DB200_EINVAL; }
     if (device == DB200_ALL_DEVICES) {
         const int nd = (int)std::min<uint64_t>((uint64_t)std::max(logical_device_count(), 1), std::max<uint64_t>(nq / DT, 1));
@@ -972,7 +982,8 @@ int db200_dist_knn_rect(int device, const uint8_t *ref_regs, uint64_t nr, const 
             const uint64_t m = 1ull << prm->p;
             return for_each_device(nd, [&](int d) {
                 const uint64_t a = nq * (uint64_t)d / (uint64_t)nd, b = nq * (uint64_t)(d + 1) / (uint64_t)nd;
-                return db200_dist_knn_rect(d, ref_regs, nr, qry_regs + a * m, b - a, prm, nneighbors, out + a * nneighbors);
+                return knn_rect_impl(d, ref_regs, nr, qry_regs + a * m, b - a, prm, nneighbors, out + a * nneighbors, card_ref,
+                                     card_qry ? card_qry + a : nullptr);
             });
         }
         device = 0;
@@ -990,6 +1001,7 @@ int db200_dist_knn_rect(int device, const uint8_t *ref_regs, uint64_t nr, const 
     DB200_CUDA(cudaMemcpyAsync(hc.regs.ptr, ref_regs, nr * m, cudaMemcpyHostToDevice, hc.stream));
     DB200_CUDA(cudaMemcpyAsync(hc.regs.as<uint8_t>() + qbase * m, qry_regs, nq * m, cudaMemcpyHostToDevice, hc.stream));
     DB200_TRY(plan_prepare(hc.plan.get(), hc.regs.as<uint8_t>(), nrows, nr, qbase, nq, prm->p, prm->estim, hc.stream));
+    DB200_TRY(plan_override_cards(hc.plan.get(), card_ref, nr, card_qry, nq, hc.stream));
     DB200_TRY(plan_knn(hc.plan.get(), prm, nr, nq, nneighbors, hc.nbrs.as<Neighbor>(), hc.stream));
     DB200_CUDA(cudaMemcpyAsync(out, hc.nbrs.ptr, nq * nneighbors * sizeof(db200_neighbor), cudaMemcpyDeviceToHost, hc.stream));
     DB200_CUDA(cudaStreamSynchronize(hc.stream));
@@ -1009,8 +1021,8 @@ int db200_dist_plan_last_run_info(const db200_dist_plan *pl, uint64_t *pairs, ui
 }
 
 // ---- host-pointer all-pairs -----------------------------------------------------------------
-int db200_dist_symmetric_rows(int device, const uint8_t *regs, uint64_t n, const db200_dist_params *prm, uint64_t row_begin, uint64_t row_end,
-                              float *out) {
+static int symmetric_rows_impl(int device, const uint8_t *regs, uint64_t n, const db200_dist_params *prm, uint64_t row_begin, uint64_t row_end,
+                               float *out, const double *card) {
     if (!prm || (!regs && n)) { set_error("db200_dist_symmetric_rows: null argument"); return DB200_EINVAL; }
     if (device == DB200_ALL_DEVICES) {
         // block rows balanced by pair count (row i holds n-1-i pairs); rows are contiguous in distmat order, so every
@@ -1023,7 +1035,7 @@ int db200_dist_symmetric_rows(int device, const uint8_t *regs, uint64_t n, const
             const std::vector<uint64_t> cut = split_by_weight(r1 - r0, nd, [&](uint64_t i) { return tri(r0 + i) - tri(r0); });
             return for_each_device(nd, [&](int d) {
                 const uint64_t a = r0 + cut[d], b = r0 + cut[d + 1];
-                return db200_dist_symmetric_rows(d, regs, n, prm, a, b, out ? out + (tri(a) - tri(r0)) : nullptr);
+                return symmetric_rows_impl(d, regs, n, prm, a, b, out ? out + (tri(a) - tri(r0)) : nullptr, card);
             });
         }
         device = 0;
@@ -1044,6 +1056,7 @@ int db200_dist_symmetric_rows(int device, const uint8_t *regs, uint64_t n, const
     DB200_TRY(hc.out.reserve(std::max<uint64_t>(npairs, 1) * 4));
     DB200_CUDA(cudaMemcpyAsync(hc.regs.ptr, regs, n * m, cudaMemcpyHostToDevice, hc.stream));
     DB200_TRY(plan_prepare(hc.plan.get(), hc.regs.as<uint8_t>(), n, n, 0, 0, prm->p, prm->estim, hc.stream));
+    DB200_TRY(plan_override_cards(hc.plan.get(), card, n, nullptr, 0, hc.stream));
     // Row blocks (equal pair counts, up to NSLOT of them): block b's device->host copy runs on the copy stream while block
     // b+1 computes, so only the last block's transfer is exposed.
     const int nblk = npairs >= (uint64_t(4) << 20) ? db200_dist_plan::NSLOT : 1;
@@ -1068,12 +1081,8 @@ int db200_dist_symmetric_rows(int device, const uint8_t *regs, uint64_t n, const
     return DB200_OK;
 }
 
-int db200_dist_symmetric(int device, const uint8_t *regs, uint64_t n, const db200_dist_params *prm, float *out) {
-    return db200_dist_symmetric_rows(device, regs, n, prm, 0, n, out);
-}
-
-int db200_dist_rect(int device, const uint8_t *ref_regs, uint64_t nr, const uint8_t *qry_regs, uint64_t nq, const db200_dist_params *prm,
-                    float *out) {
+static int rect_impl(int device, const uint8_t *ref_regs, uint64_t nr, const uint8_t *qry_regs, uint64_t nq, const db200_dist_params *prm,
+                     float *out, const double *card_ref, const double *card_qry) {
     if (!prm || ((!ref_regs || !qry_regs || !out) && nr && nq)) { set_error("db200_dist_rect: null argument"); return DB200_EINVAL; }
     if (device == DB200_ALL_DEVICES) {
         const int nd = (int)std::min<uint64_t>((uint64_t)std::max(logical_device_count(), 1), std::max<uint64_t>(nq / DT, 1));
@@ -1081,7 +1090,7 @@ int db200_dist_rect(int device, const uint8_t *ref_regs, uint64_t nr, const uint
             const uint64_t m = 1ull << prm->p;
             return for_each_device(nd, [&](int d) {
                 const uint64_t a = nq * (uint64_t)d / (uint64_t)nd, b = nq * (uint64_t)(d + 1) / (uint64_t)nd;
-                return db200_dist_rect(d, ref_regs, nr, qry_regs + a * m, b - a, prm, out + a * nr);
+                return rect_impl(d, ref_regs, nr, qry_regs + a * m, b - a, prm, out + a * nr, card_ref, card_qry ? card_qry + a : nullptr);
             });
         }
         device = 0;
@@ -1099,10 +1108,55 @@ int db200_dist_rect(int device, const uint8_t *ref_regs, uint64_t nr, const uint
     DB200_CUDA(cudaMemcpyAsync(hc.regs.ptr, ref_regs, nr * m, cudaMemcpyHostToDevice, hc.stream));
     DB200_CUDA(cudaMemcpyAsync(hc.regs.as<uint8_t>() + qbase * m, qry_regs, nq * m, cudaMemcpyHostToDevice, hc.stream));
     DB200_TRY(plan_prepare(hc.plan.get(), hc.regs.as<uint8_t>(), nrows, nr, qbase, nq, prm->p, prm->estim, hc.stream));
+    DB200_TRY(plan_override_cards(hc.plan.get(), card_ref, nr, card_qry, nq, hc.stream));
     DB200_TRY(plan_run(hc.plan.get(), prm, 1, 0, 0, nr, nq, hc.out.as<float>(), hc.stream));
     DB200_CUDA(cudaMemcpyAsync(out, hc.out.ptr, nr * nq * 4, cudaMemcpyDeviceToHost, hc.stream));
     DB200_CUDA(cudaStreamSynchronize(hc.stream));
     return DB200_OK;
+}
+
+} // extern "C"
+
+// ---- public all-pairs entry points: they consume the calling thread's pending cardinality override ----------------------
+namespace db200 {
+struct CardOverride { const double *ptr = nullptr; uint64_t n = 0; };
+static thread_local CardOverride t_cards;
+static CardOverride take_cards() { const CardOverride c = t_cards; t_cards = CardOverride{}; return c; }
+} // namespace db200
+
+extern "C" {
+
+int db200_dist_use_cardinalities(const double *card, uint64_t n) {
+    t_cards.ptr = card; t_cards.n = card ? n : 0;
+    return DB200_OK;
+}
+
+int db200_dist_symmetric_rows(int device, const uint8_t *regs, uint64_t n, const db200_dist_params *prm, uint64_t row_begin, uint64_t row_end,
+                              float *out) {
+    const CardOverride c = take_cards();
+    if (c.ptr && c.n != n) { set_error("cardinality override holds %llu values for %llu sketches", (unsigned long long)c.n, (unsigned long long)n); return DB200_EINVAL; }
+    return symmetric_rows_impl(device, regs, n, prm, row_begin, row_end, out, c.ptr);
+}
+int db200_dist_symmetric(int device, const uint8_t *regs, uint64_t n, const db200_dist_params *prm, float *out) {
+    return db200_dist_symmetric_rows(device, regs, n, prm, 0, n, out);
+}
+int db200_dist_rect(int device, const uint8_t *ref_regs, uint64_t nr, const uint8_t *qry_regs, uint64_t nq, const db200_dist_params *prm,
+                    float *out) {
+    const CardOverride c = take_cards();
+    if (c.ptr && c.n != nr + nq) { set_error("cardinality override holds %llu values for %llu + %llu sketches", (unsigned long long)c.n, (unsigned long long)nr, (unsigned long long)nq); return DB200_EINVAL; }
+    return rect_impl(device, ref_regs, nr, qry_regs, nq, prm, out, c.ptr, c.ptr ? c.ptr + nr : nullptr);
+}
+int db200_dist_knn_symmetric(int device, const uint8_t *regs, uint64_t n, const db200_dist_params *prm, uint32_t nneighbors,
+                             db200_neighbor *out) {
+    const CardOverride c = take_cards();
+    if (c.ptr && c.n != n) { set_error("cardinality override holds %llu values for %llu sketches", (unsigned long long)c.n, (unsigned long long)n); return DB200_EINVAL; }
+    return knn_symmetric_impl(device, regs, n, prm, nneighbors, out, c.ptr);
+}
+int db200_dist_knn_rect(int device, const uint8_t *ref_regs, uint64_t nr, const uint8_t *qry_regs, uint64_t nq, const db200_dist_params *prm,
+                        uint32_t nneighbors, db200_neighbor *out) {
+    const CardOverride c = take_cards();
+    if (c.ptr && c.n != nr + nq) { set_error("cardinality override holds %llu values for %llu + %llu sketches", (unsigned long long)c.n, (unsigned long long)nr, (unsigned long long)nq); return DB200_EINVAL; }
+    return knn_rect_impl(device, ref_regs, nr, qry_regs, nq, prm, nneighbors, out, c.ptr, c.ptr ? c.ptr + nr : nullptr);
 }
 
 } // extern "C"

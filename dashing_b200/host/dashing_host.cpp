@@ -609,8 +609,11 @@ void write_binary_neighbors(std::FILE *fp, uint32_t npaths, const Neighbor *nb, 
 
 // dist_loop / partdist_loop / nndist_loop and their emitters (src/sketch_and_cmp.h:785-880, :712-783; src/dashing.h:660-712)
 // over n = inpaths.size() sketches held as rows of `regs`; the last nq are queries.
-void compare_and_emit(const DistOptions &o, const std::vector<std::string> &inpaths, const std::vector<uint8_t> &regs, size_t nq) {
+void compare_and_emit(const DistOptions &o, const std::vector<std::string> &inpaths, const std::vector<uint8_t> &regs, size_t nq,
+                      const double *cached_card) {
     const size_t n = inpaths.size(), m = size_t(1) << o.p;
+    // cached value_ of loaded sketches: handed to the library before every all-pairs call (each call consumes it)
+    auto use_cards = [&] { if (cached_card) check(db200_dist_use_cardinalities(cached_card, n)); };
     std::FILE *pfp = o.dist_path.empty() ? stdout : std::fopen(o.dist_path.c_str(), "wb");
     if (!pfp) throw Error("Could not open file at " + o.dist_path + " for writing.");
     db200_dist_params prm{o.p, o.k, o.estim, o.jestim, o.result_type, DB200_ORDER_ROW_FIRST};
@@ -627,6 +630,7 @@ void compare_and_emit(const DistOptions &o, const std::vector<std::string> &inpa
         std::vector<Neighbor> nb(rows * nn);
         static_assert(sizeof(Neighbor) == sizeof(db200_neighbor), "neighbour layout");
         prm.order = DB200_ORDER_COL_FIRST;                                     // func(sketches[j], h1), :670
+        use_cards();
         if (nq) check(db200_dist_knn_rect(o.device, regs.data(), n - nq, regs.data() + (n - nq) * m, nq, &prm, nn, reinterpret_cast<db200_neighbor *>(nb.data())));
         else check(db200_dist_knn_symmetric(o.device, regs.data(), n, &prm, nn, reinterpret_cast<db200_neighbor *>(nb.data())));
         // The reference's emitters loop over ALL paths even in the -Q/-F mode, where only nq rows exist (an out-of-bounds
@@ -637,6 +641,7 @@ void compare_and_emit(const DistOptions &o, const std::vector<std::string> &inpa
         if (nq >= n) throw Error("Wrong number of query/references.");
         const size_t nr = n - nq;
         std::vector<float> out(nr * nq);
+        use_cards();
         check(db200_dist_rect(o.device, regs.data(), nr, regs.data() + nr * m, nq, &prm, out.data()));
         if (o.emit_fmt == UPPER_TRIANGULAR) std::fprintf(pfp, "%zu\n", n);     // :394-397 runs before dist_loop even in this mode
         for (size_t q = 0; q < nq; ++q) {
@@ -652,7 +657,7 @@ void compare_and_emit(const DistOptions &o, const std::vector<std::string> &inpa
         // operand order: TSV / PHYLIP rows come from perform_core_op (cmp(s[j], s[i])), binary and the upper half of FULL_TSV
         // from cmp(s[i], s[j]); only the joint MLE can tell the difference
         prm.order = (o.emit_fmt == UT_TSV || o.emit_fmt == UPPER_TRIANGULAR) ? DB200_ORDER_COL_FIRST : DB200_ORDER_ROW_FIRST;
-        if (n >= 2) check(db200_dist_symmetric(o.device, regs.data(), n, &prm, out.data()));
+        if (n >= 2) { use_cards(); check(db200_dist_symmetric(o.device, regs.data(), n, &prm, out.data())); }
         if (o.emit_fmt == BINARY) {
             write_binary_matrix(pfp, out.data(), n);
             if (!o.dist_path.empty()) {                                      // src/distmain.cpp:191-200
@@ -665,6 +670,7 @@ void compare_and_emit(const DistOptions &o, const std::vector<std::string> &inpa
             if (o.emit_fmt == FULL_TSV && joint && n >= 2) {
                 lower.resize(np);
                 prm.order = DB200_ORDER_COL_FIRST;
+                use_cards();
                 check(db200_dist_symmetric(o.device, regs.data(), n, &prm, lower.data()));
             }
             const std::string s = format_symmetric(inpaths, out.data(), o.emit_fmt, lower.empty() ? nullptr : lower.data());
@@ -675,13 +681,27 @@ void compare_and_emit(const DistOptions &o, const std::vector<std::string> &inpa
     phase("distances written");
 }
 
-// hll_t::read() computes the cardinality at once under the FILE's estimator (csum(), hll.h:1078) and the reference then
-// keeps that cached value for the sizes file and the per-sketch terms of every pair, whatever -E/-I/-m says.  This layer
-// always evaluates cardinalities under the command line's estimator; say so when the two differ.
-static void warn_estim(const HllFile &h, const std::string &path, int estim) {
-    if ((int)h.estim != estim)
-        std::fprintf(stderr, "[dashing_b200] note: %s was written under estimation method %u; cardinalities are evaluated under %d "
-                             "(the reference would keep the value cached under %u)\n", path.c_str(), h.estim, estim, h.estim);
+// hll_t::read() computes the cardinality at once under the FILE's estimator (csum(), hll.h:1078) unless the file already
+// stores one, and the reference keeps that cached value_ for the sizes file and for the per-sketch terms of every pair,
+// whatever -E/-I/-m says on the command line (set_estim_and_jestim only changes what LATER evaluations use).
+struct Cached { bool loaded = false; uint32_t estim = 2; double value = -1.; };
+static Cached cached_of(const HllFile &h) { return Cached{true, h.estim, h.value >= 0. ? h.value : -1.}; }   // is_calculated() is value_ >= 0 (hll.h:1038)
+
+// card[] arrives evaluated under `estim` for every sketch; entries of loaded sketches are replaced by their cached value.
+// Returns whether any sketch was loaded (the pair loop then needs db200_dist_use_cardinalities).
+static bool apply_cached(int device, int p, int estim, const std::vector<uint8_t> &regs, const std::vector<Cached> &info, std::vector<double> &card) {
+    bool any = false;
+    const size_t m = size_t(1) << p;
+    for (size_t i = 0; i < info.size(); ++i) {
+        if (!info[i].loaded) continue;
+        any = true;
+        if (info[i].value >= 0.) card[i] = info[i].value;
+        else if ((int)info[i].estim != estim) {
+            if (info[i].estim > 2) throw Error("a loaded sketch names an unknown estimation method");
+            check(db200_cardinalities(device == DB200_ALL_DEVICES ? 0 : device, &regs[i * m], 1, p, (int)info[i].estim, &card[i]));
+        }
+    }
+    return any;
 }
 
 void dist_sketch_and_cmp(const DistOptions &o_in, std::vector<std::string> inpaths, size_t nq) {
@@ -693,11 +713,12 @@ void dist_sketch_and_cmp(const DistOptions &o_in, std::vector<std::string> inpat
     // ---- phase A: load or sketch (src/sketch_and_cmp.h:314-360)
     std::vector<size_t> todo;
     std::vector<std::string> fnames(n);
+    std::vector<Cached> info(n);
     for (size_t i = 0; i < n; ++i) {
         if (o.presketched) {
             HllFile h = read_hll(inpaths[i]);
             if (h.p != (uint32_t)o.p) throw Error("sketch " + inpaths[i] + " has p=" + std::to_string(h.p) + ", expected " + std::to_string(o.p));
-            warn_estim(h, inpaths[i], o.estim);
+            info[i] = cached_of(h);
             std::memcpy(&regs[i * m], h.core.data(), m);
             continue;
         }
@@ -705,7 +726,7 @@ void dist_sketch_and_cmp(const DistOptions &o_in, std::vector<std::string> inpat
         if (o.cache_sketches && isfile(fnames[i])) {
             HllFile h = read_hll(fnames[i]);
             if (h.p != (uint32_t)o.p) throw Error("cached sketch " + fnames[i] + " has the wrong size");
-            warn_estim(h, fnames[i], o.estim);
+            info[i] = cached_of(h);
             std::memcpy(&regs[i * m], h.core.data(), m);
         } else todo.push_back(i);
     }
@@ -718,6 +739,7 @@ void dist_sketch_and_cmp(const DistOptions &o_in, std::vector<std::string> inpat
     phase("sketches ready");
     std::vector<double> card(n);
     check(db200_cardinalities(o.device, regs.data(), n, o.p, o.estim, card.data()));
+    const bool any_cached = apply_cached(o.device, o.p, o.estim, regs, info, card);
     {
         const std::string s = format_sizes(inpaths, card.data());
         std::FILE *fp = o.sizes_path.empty() ? stdout : std::fopen(o.sizes_path.c_str(), "w");
@@ -729,7 +751,7 @@ void dist_sketch_and_cmp(const DistOptions &o_in, std::vector<std::string> inpat
         for (size_t i : todo) write_hll(fnames[i], &regs[i * m], o.p, 2, 2, card[i]);
     // ---- phase C: all pairs
     phase("sizes written");
-    compare_and_emit(o, inpaths, regs, nq);
+    compare_and_emit(o, inpaths, regs, nq, any_cached ? card.data() : nullptr);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1127,11 +1149,12 @@ int card_main(int argc, char **argv) {
     std::vector<uint8_t> regs(n * m);
     std::vector<size_t> todo;
     std::vector<std::string> fnames(n);
+    std::vector<Cached> info(n);
     for (size_t i = 0; i < n; ++i) {
         if (o.presketched) {
             const HllFile h = read_hll(inpaths[i]);
             if (h.p != (uint32_t)o.p) throw Error("sketch " + inpaths[i] + " has p=" + std::to_string(h.p) + ", expected " + std::to_string(o.p));
-            warn_estim(h, inpaths[i], o.estim);
+            info[i] = cached_of(h);
             std::memcpy(&regs[i * m], h.core.data(), m);
             continue;
         }
@@ -1139,7 +1162,7 @@ int card_main(int argc, char **argv) {
         if (o.cache_sketches && isfile(fnames[i])) {
             const HllFile h = read_hll(fnames[i]);
             if (h.p != (uint32_t)o.p) throw Error("cached sketch " + fnames[i] + " has the wrong size");
-            warn_estim(h, fnames[i], o.estim);
+            info[i] = cached_of(h);
             std::memcpy(&regs[i * m], h.core.data(), m);
         } else todo.push_back(i);
     }
@@ -1149,6 +1172,7 @@ int card_main(int argc, char **argv) {
     });
     std::vector<double> card(n);
     check(db200_cardinalities(o.device, regs.data(), n, o.p, o.estim, card.data()));
+    apply_cached(o.device, o.p, o.estim, regs, info, card);
     if (o.defer_hll && o.cache_sketches) for (size_t i : todo) write_hll(fnames[i], &regs[i * m], o.p, 2, 2, card[i]);
     std::FILE *fp = out_path.empty() ? stdout : std::fopen(out_path.c_str(), "w");
     if (!fp) throw Error("Could not open file at " + out_path + " for writing.");
@@ -1274,13 +1298,18 @@ int dist_by_seq_main(int argc, char **argv) {
     o.p = (int)hs[0].p;
     const size_t m = size_t(1) << o.p;
     std::vector<uint8_t> regs(hs.size() * m);
+    std::vector<Cached> info(hs.size());
     for (size_t i = 0; i < hs.size(); ++i) {
         if (hs[i].p != hs[0].p) throw Error("mismatched sketch sizes.");
-        warn_estim(hs[i], labels[i], o.estim);
+        info[i] = cached_of(hs[i]);
         std::memcpy(&regs[i * m], hs[i].core.data(), m);
     }
+    // every sketch came from a file: its cardinality is what read() cached under the FILE's estimator (hll.h:1078)
+    std::vector<double> card(hs.size());
+    check(db200_cardinalities(o.device, regs.data(), hs.size(), o.p, o.estim, card.data()));
+    apply_cached(o.device, o.p, o.estim, regs, info, card);
     o.dist_path = outpath;
-    compare_and_emit(o, labels, regs, 0);
+    compare_and_emit(o, labels, regs, 0, card.data());
     return 0;
 }
 

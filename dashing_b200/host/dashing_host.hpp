@@ -91,7 +91,9 @@ struct Neighbor { float value; uint32_t index; };
 std::string format_neighbors(const std::vector<std::string> &names, size_t qoffset, const Neighbor *nb, size_t rows, unsigned nn);
 void write_binary_neighbors(std::FILE *fp, uint32_t npaths, const Neighbor *nb, size_t rows, unsigned nn);
 // dist_loop / partdist_loop / nndist_loop over in-memory register rows (last nq rows are queries)
-void compare_and_emit(const DistOptions &o, const std::vector<std::string> &names, const std::vector<uint8_t> &regs, size_t nq);
+// cached_card: per-sketch cardinalities that sketches loaded from files carry (hll_t::value_), or nullptr
+void compare_and_emit(const DistOptions &o, const std::vector<std::string> &names, const std::vector<uint8_t> &regs, size_t nq,
+                      const double *cached_card = nullptr);
 // sketch_main / dist_main (src/dashing.cpp:294-409, src/distmain.cpp:28-204): the hot subset of the flags
 int sketch_main(int argc, char **argv);
 int dist_main(int argc, char **argv);

@@ -164,6 +164,15 @@ DB200_API int db200_dist_symmetric_rows(int device, const uint8_t *regs, uint64_
 DB200_API int db200_dist_rect(int device, const uint8_t *ref_regs, uint64_t nr, const uint8_t *qry_regs, uint64_t nq,
                     const db200_dist_params *prm, float *out);
 
+/* Cached cardinalities.  The reference's hll_t carries a cached estimate (value_): a sketch loaded from a file keeps what
+ * hll_t::read() computed under the FILE's estimation method (csum(), hll.h:1078) — or the value stored in the file — and the
+ * pair loop uses that for the per-sketch terms (creport(), hll.h:780-783) even when the command line names another estimator.
+ * A host that loaded such sketches passes their cached values here; they then replace the per-sketch cardinalities the
+ * library would evaluate from the registers, for the calling thread's NEXT db200_dist_symmetric[_rows] / db200_dist_rect /
+ * db200_dist_knn_* call only (n values in sketch order; rect / knn_rect: the nr references, then the nq queries).
+ * NULL clears a pending override. */
+DB200_API int db200_dist_use_cardinalities(const double *card, uint64_t n);
+
 /* Device-resident form.  A plan owns the derived HBM structures (threshold bit-planes,
  * per-sketch cardinalities and value ranges); prepare() builds them from a device register
  * matrix, run_*() enqueue the all-pairs kernel.  `stream` is a cudaStream_t. */

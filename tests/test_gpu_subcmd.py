@@ -99,6 +99,38 @@ def test_compress_golden_and_errors(gpu, sub):
     assert e.value.code == gpu.EINVAL and "Can't compress to a larger size" in str(e.value)
 
 
+def test_cached_cardinality_override(gpu):
+    """db200_dist_use_cardinalities: the per-sketch terms of the next all-pairs call come from the caller (the reference's
+    cached hll_t::value_), the union term still from the registers; consumed by exactly one call."""
+    p = 12
+    regs = synth.registers(77, 40, p, card=1e5, group=8)
+    card = gpu.cardinalities(regs, p)
+    base = gpu.dist_symmetric(regs, p, result_type=gpu.JI)
+    keep = gpu.use_cardinalities(card)
+    same = gpu.dist_symmetric(regs, p, result_type=gpu.JI)
+    assert np.array_equal(same.view(np.uint32), base.view(np.uint32))
+    scaled = card * np.linspace(0.9, 1.1, card.size)
+    keep = gpu.use_cardinalities(scaled)
+    got = gpu.dist_symmetric(regs, p, result_type=gpu.JI).astype(np.float64)
+    again = gpu.dist_symmetric(regs, p, result_type=gpu.JI)               # the override is gone
+    assert np.array_equal(again.view(np.uint32), base.view(np.uint32))
+    iu = np.triu_indices(card.size, 1)
+    union = gpu.dist_symmetric(regs, p, result_type=gpu.SIZES).astype(np.float64)   # I = cA + cB - U  ->  U
+    U = card[iu[0]] + card[iu[1]] - union
+    pos = union > 1e-3 * card.max()
+    want = np.maximum(0.0, (scaled[iu[0]] + scaled[iu[1]] - U) / U)
+    assert_close(got[pos], want[pos], rtol=2e-5, what="JI under overridden cardinalities")
+    # rect: references then queries; wrong length is an error
+    keep = gpu.use_cardinalities(scaled)
+    r = gpu.dist_rect(regs[:25], regs[25:], p, result_type=gpu.JI).astype(np.float64)
+    full = np.zeros((card.size, card.size)); full[iu] = got; full = full + full.T
+    assert_close(r, full[25:, :25], rtol=1e-6, what="rect under overridden cardinalities")
+    keep = gpu.use_cardinalities(scaled[:-1])
+    with pytest.raises(gpu.Db200Error):
+        gpu.dist_symmetric(regs, p)
+    del keep
+
+
 # ---- multi-device form of the host-pointer entry points ---------------------------------------------------------------
 def test_all_devices_matches_single_device(gpu, monkeypatch):
     """device = DB200_ALL_DEVICES: genomes / sketches / block rows / queries sharded over every logical device.  On a
