@@ -53,6 +53,7 @@ _SIGS = {
     "db200_sketcher_finish": (C.c_int, [vp, C.c_uint32, u8p]),
     "db200_sketcher_destroy": (C.c_int, [vp]),
     "db200_sketch_batch": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, vp, u64p, C.c_uint64, u64p, C.c_uint64, u8p]),
+    "db200_sketch_fasta_batch": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, vp, u64p, u64p, C.c_uint64, u64p, C.c_uint64, u8p, u8p]),
     "db200_pack_genomes": (C.c_int, [C.c_int, vp, u64p, C.c_uint64, u64p, C.c_uint64, C.c_int, C.POINTER(vp)]),
     "db200_packed_genomes_free": (C.c_int, [vp]),
     "db200_packed_genomes_stats": (C.c_int, [vp, u64p, u64p, u64p]),
@@ -140,6 +141,38 @@ def sketch_batch(bases, rec_offsets, genome_rec_begin, k, p, canon=True, device=
     _check(lib.db200_sketch_batch(device, p, k, int(canon), bases.ctypes.data_as(vp), offs.ctypes.data_as(u64p), offs.size - 1,
                                   grb.ctypes.data_as(u64p), ng, out.ctypes.data_as(u8p)))
     return out
+
+
+FASTA_ALIGN = 8192
+
+
+def fasta_layout(genome_files):
+    """genome_files: list of genomes, each a list of raw file contents (bytes).
+    -> (text uint8[], file_off uint64[nf], file_len uint64[nf], genome_file_begin uint64[ng+1]) with every file on a
+    DB200_FASTA_ALIGN boundary (gaps are filled with junk on purpose: the library must ignore them)."""
+    offs, lens, gfb, parts, at = [], [], [0], [], 0
+    for files in genome_files:
+        for raw in files:
+            offs.append(at)
+            lens.append(len(raw))
+            pad = (-len(raw)) % FASTA_ALIGN or (FASTA_ALIGN if len(raw) == 0 else 0)
+            junk = (b">junk\nACGTTGCA\r\n@q\n+\n" * (pad // 16 + 1))[:pad]
+            parts.append(bytes(raw) + junk)
+            at += len(raw) + pad
+        gfb.append(len(offs))
+    text = np.frombuffer(b"".join(parts) + b"\0" * 64, dtype=np.uint8).copy()
+    return text, np.asarray(offs, np.uint64), np.asarray(lens, np.uint64), np.asarray(gfb, np.uint64)
+
+
+def sketch_fasta(genome_files, k, p, canon=True, device=0):
+    """Raw FASTA text -> (registers uint8[ng][2^p], file_status uint8[nf]) through db200_sketch_fasta_batch."""
+    text, offs, lens, gfb = fasta_layout(genome_files)
+    ng = gfb.size - 1
+    out = np.zeros((ng, 1 << p), dtype=np.uint8)
+    status = np.zeros(max(offs.size, 1), dtype=np.uint8)
+    _check(lib.db200_sketch_fasta_batch(device, p, k, int(canon), text.ctypes.data_as(vp), offs.ctypes.data_as(u64p), lens.ctypes.data_as(u64p),
+                                        offs.size, gfb.ctypes.data_as(u64p), ng, out.ctypes.data_as(u8p), status.ctypes.data_as(u8p)))
+    return out, status[:offs.size]
 
 
 def sketch_genomes(genomes, k, p, canon=True, device=0) -> np.ndarray:

@@ -7,6 +7,7 @@
 #include "sketch.cuh"
 #include "dist.cuh"
 #include "setops.cuh"
+#include "fasta.cuh"
 
 #include <algorithm>
 #include <cstring>
@@ -606,6 +607,7 @@ struct HostCtx {
     cudaStream_t stream = nullptr, cstream = nullptr;
     cudaEvent_t blk_done[db200_dist_plan::NSLOT] = {nullptr, nullptr, nullptr, nullptr};
     DevBuf regs, out, cards, nbrs;
+    DevBuf fa_text, fa_sums, fa_state, fa_pos, fa_tab, fa_gend, fa_carry, fa_flags;   // device-side FASTA parsing (fasta.cuh)
     Uploader up;
     std::unique_ptr<db200_dist_plan> plan;
     std::unique_ptr<db200_packed_genomes> store;   // reused by db200_sketch_batch
@@ -1160,6 +1162,223 @@ int db200_dist_knn_rect(int device, const uint8_t *ref_regs, uint64_t nr, const 
 }
 
 } // extern "C"
+
+// ---- device-side FASTA parsing -----------------------------------------------------------------------------------
+// Raw file text goes up in 64 MiB chunks; each chunk is summarised, chained and emitted (fasta.cuh) while the next one is in
+// flight, and every genome group is sketched as soon as its last chunk has been emitted.  Genome g's bases land in a window
+// of the position space sized by the raw length of its files (an upper bound); the work items laid over the window are
+// clipped on the device to what the parse produced.
+static int sketch_fasta_one(int device, int p, int k, int canon, const char *text, const uint64_t *file_off, const uint64_t *file_len,
+                            uint64_t nfiles, const uint64_t *genome_file_begin, uint64_t ngenomes, uint8_t *registers_out,
+                            uint8_t *file_status_out) {
+    DB200_TRY(check_device(device));
+    HostCtx &hc = host_ctx(device);
+    std::lock_guard<std::mutex> lk(hc.mu);
+    DB200_TRY(hc.init(device));
+    DB200_TRY(hc.up.init());
+    Uploader &up = hc.up;
+    cudaStream_t stream = hc.stream;
+    db200_packed_genomes *pg = hc.store.get();
+    const uint64_t B = FA_BLOCK;
+    const uint64_t text_end = nfiles ? file_off[nfiles - 1] + file_len[nfiles - 1] : 0;
+    const uint64_t nblk_text = (text_end + B - 1) / B;
+    // ---- tables: first block / length / window start / genome of every file; window of every genome
+    std::vector<uint64_t> fblk(nfiles), gpos0(nfiles, ~0ull), gbase(ngenomes + 1, 0);
+    std::vector<uint32_t> fgen(nfiles);
+    uint64_t posn = 0;
+    for (uint64_t g = 0; g < ngenomes; ++g) {
+        gbase[g] = posn;
+        uint64_t raw = 0;
+        for (uint64_t f = genome_file_begin[g]; f < genome_file_begin[g + 1]; ++f) {
+            fblk[f] = file_off[f] / B;
+            fgen[f] = (uint32_t)g;
+            if (f == genome_file_begin[g]) gpos0[f] = posn;
+            raw += file_len[f];
+        }
+        posn = (posn + raw + 63 + 64) & ~63ull;     // at least one all-invalid block between genomes
+    }
+    gbase[ngenomes] = posn;
+    pg->device = device; pg->k = k; pg->nbases = posn; pg->ngenomes = ngenomes; pg->kmers = 0;
+    pg->nblk = posn / 64 + 1;
+    DB200_TRY(pg->bases2.reserve(pg->nblk * 16));
+    DB200_TRY(pg->nb.reserve(pg->nblk * 8));
+    DB200_TRY(pg->st.reserve(pg->nblk * 8));
+    DB200_TRY(pg->counter.reserve(64));
+    DB200_CUDA(cudaMemsetAsync(pg->bases2.ptr, 0, pg->nblk * 16, stream));
+    DB200_CUDA(cudaMemsetAsync(pg->nb.ptr, 0, pg->nblk * 8, stream));
+    DB200_CUDA(cudaMemsetAsync(pg->st.ptr, 0, pg->nblk * 8, stream));
+    DB200_CUDA(cudaMemsetAsync(pg->counter.ptr, 0, 64, stream));
+    const uint64_t bytes = ngenomes << p;
+    DB200_TRY(hc.regs.reserve(std::max<uint64_t>(bytes, 16)));
+    DB200_CUDA(cudaMemsetAsync(hc.regs.ptr, 0, std::max<uint64_t>(bytes, 16), stream));
+    DB200_TRY(hc.fa_text.reserve(std::max<uint64_t>(nblk_text, 1) * B + 64));
+    DB200_TRY(hc.fa_sums.reserve(std::max<uint64_t>(nblk_text, 1) * 8));
+    DB200_TRY(hc.fa_state.reserve(std::max<uint64_t>(nblk_text, 1)));
+    DB200_TRY(hc.fa_pos.reserve(std::max<uint64_t>(nblk_text, 1) * 8));
+    DB200_TRY(hc.fa_gend.reserve((ngenomes + 1) * 8));
+    DB200_TRY(hc.fa_carry.reserve(32));
+    DB200_TRY(hc.fa_flags.reserve(std::max<uint64_t>(nfiles, 1) * 4));
+    const uint64_t tab_bytes = nfiles * (8 + 8 + 8 + 4);
+    DB200_TRY(hc.fa_tab.reserve(std::max<uint64_t>(tab_bytes, 16)));
+    uint64_t *d_fblk = hc.fa_tab.as<uint64_t>(), *d_flen = d_fblk + nfiles, *d_gpos0 = d_flen + nfiles;
+    uint32_t *d_fgen = reinterpret_cast<uint32_t *>(d_gpos0 + nfiles);
+    if (nfiles) {
+        DB200_CUDA(cudaMemcpyAsync(d_fblk, fblk.data(), nfiles * 8, cudaMemcpyHostToDevice, stream));
+        DB200_CUDA(cudaMemcpyAsync(d_flen, file_len, nfiles * 8, cudaMemcpyHostToDevice, stream));
+        DB200_CUDA(cudaMemcpyAsync(d_gpos0, gpos0.data(), nfiles * 8, cudaMemcpyHostToDevice, stream));
+        DB200_CUDA(cudaMemcpyAsync(d_fgen, fgen.data(), nfiles * 4, cudaMemcpyHostToDevice, stream));
+    }
+    // genome_end starts at each window's begin (a genome without sequence bytes clips all its items away)
+    DB200_CUDA(cudaMemcpyAsync(hc.fa_gend.ptr, gbase.data(), (ngenomes + 1) * 8, cudaMemcpyHostToDevice, stream));
+    DB200_CUDA(cudaMemsetAsync(hc.fa_carry.ptr, 0, 32, stream));
+    DB200_CUDA(cudaMemsetAsync(hc.fa_flags.ptr, 0, std::max<uint64_t>(nfiles, 1) * 4, stream));
+    // ---- work items over the windows, in up to NGROUP genome groups of similar raw size (as in pack_genomes_impl)
+    std::vector<SketchItem> items;
+    pg->group_item_begin.assign(1, 0u);
+    pg->group_end.clear();                       // here: text offset after which the group is complete
+    {
+        const uint64_t target_items = (uint64_t)g_num_sms(device) * 16;
+        uint64_t chunk = posn / std::max<uint64_t>(target_items, 1);
+        chunk = std::min<uint64_t>(std::max<uint64_t>(chunk, 1ull << 16), 1ull << 20);
+        uint64_t g0 = 0;
+        for (int grp = 0; grp < Uploader::NGROUP && g0 < ngenomes; ++grp) {
+            uint64_t g1 = ngenomes;
+            if (grp + 1 < Uploader::NGROUP) {
+                const uint64_t want = posn * (uint64_t)(grp + 1) / (uint64_t)Uploader::NGROUP;
+                g1 = g0 + 1;
+                while (g1 < ngenomes && gbase[g1] < want) ++g1;
+            }
+            std::vector<std::pair<uint32_t, SketchItem>> tmp;
+            for (uint64_t g = g0; g < g1; ++g) {
+                const uint64_t gs = gbase[g], ge = gbase[g + 1] - 64;     // window without the separating block
+                if (ge <= gs) continue;
+                const uint64_t nch = (ge - gs + chunk - 1) / chunk;
+                const uint64_t step = (((ge - gs + nch - 1) / nch) + 63) & ~63ull;
+                uint32_t ci = 0;
+                for (uint64_t st = gs; st < ge; st += step, ++ci) tmp.push_back({ci, SketchItem{st, std::min(ge, st + step), (uint32_t)g, 0}});
+            }
+            std::stable_sort(tmp.begin(), tmp.end(), [](const auto &a, const auto &b) { return a.first < b.first; });
+            for (auto &t : tmp) items.push_back(t.second);
+            pg->group_item_begin.push_back((uint32_t)items.size());
+            // the group is complete once the last byte of its last file is on the device and emitted
+            const uint64_t lf = genome_file_begin[g1] - 1;
+            pg->group_end.push_back(genome_file_begin[g1] > genome_file_begin[g0] ? file_off[lf] + file_len[lf] : 0);
+            g0 = g1;
+        }
+    }
+    pg->nitems = (uint32_t)items.size();
+    if (!items.empty()) {
+        DB200_TRY(pg->items.reserve(items.size() * sizeof(SketchItem)));
+        DB200_CUDA(cudaMemcpyAsync(pg->items.ptr, items.data(), items.size() * sizeof(SketchItem), cudaMemcpyHostToDevice, stream));
+    }
+    // ---- chunks
+    uint64_t CH = 64ull << 20;                   // a multiple of FA_BLOCK
+    if (const char *cenv = std::getenv("DB200_FASTA_CHUNK")) {   // testing knob: chunk boundaries every few blocks
+        const uint64_t v = std::strtoull(cenv, nullptr, 10) / B * B;
+        if (v) CH = v;
+    }
+    const uint64_t nchunks = (text_end + CH - 1) / CH;
+    DB200_CUDA(cudaEventRecord(up.packed[0], stream));
+    DB200_CUDA(cudaStreamWaitEvent(up.cs, up.packed[0], 0));
+    uint8_t *d_text = hc.fa_text.as<uint8_t>();
+    size_t next_group = 0;
+    for (uint64_t c = 0; c < nchunks; ++c) {
+        const int b = (int)(c & 1);
+        const uint64_t off = c * CH, len = std::min<uint64_t>(CH, text_end - off);
+        DB200_CUDA(cudaMemcpyAsync(d_text + off, text + off, len, cudaMemcpyDefault, up.cs));
+        DB200_CUDA(cudaEventRecord(up.copied[b], up.cs));
+        DB200_CUDA(cudaStreamWaitEvent(stream, up.copied[b], 0));
+        const uint64_t blk0 = off / B, nb = (len + B - 1) / B;
+        const uint32_t next_byte = off + len < text_end ? (uint32_t)(uint8_t)text[off + len] : (uint32_t)'\n';
+        fa_summary_kernel<<<(unsigned)nb, FA_THREADS, 0, stream>>>(d_text, blk0, d_fblk, d_flen, (uint32_t)nfiles, off + len, next_byte, hc.fa_sums.as<FaSum>());
+        DB200_LAUNCHED();
+        fa_chain_kernel<<<1, 256, 0, stream>>>(hc.fa_sums.as<FaSum>(), blk0, nb, d_fblk, d_gpos0, d_fgen, (uint32_t)nfiles, hc.fa_carry.as<uint64_t>(),
+                                               hc.fa_state.as<uint8_t>(), hc.fa_pos.as<uint64_t>(), hc.fa_gend.as<uint64_t>());
+        DB200_LAUNCHED();
+        fa_emit_kernel<<<(unsigned)nb, FA_THREADS, 0, stream>>>(d_text, blk0, d_fblk, d_flen, (uint32_t)nfiles, off + len, next_byte, hc.fa_state.as<uint8_t>(),
+                                                                hc.fa_pos.as<uint64_t>(), pg->bases2.as<uint32_t>(), pg->nb.as<uint32_t>(),
+                                                                pg->st.as<uint32_t>(), hc.fa_flags.as<uint32_t>());
+        DB200_LAUNCHED();
+        while (next_group < pg->group_end.size() && pg->group_end[next_group] <= off + len) {
+            const uint32_t ib = pg->group_item_begin[next_group], ie = pg->group_item_begin[next_group + 1];
+            if (ie > ib) {
+                fa_clip_items_kernel<<<(ie - ib + 255) / 256, 256, 0, stream>>>(pg->items.as<SketchItem>() + ib, ie - ib, hc.fa_gend.as<uint64_t>());
+                DB200_LAUNCHED();
+                DB200_CUDA(cudaEventRecord(up.group_packed[next_group], stream));
+                DB200_CUDA(cudaStreamWaitEvent(up.ss, up.group_packed[next_group], 0));
+                DB200_TRY(sketch_launch(pg, p, canon, hc.regs.as<uint8_t>(), up.ss, ib, ie - ib, (int)next_group));
+            }
+            ++next_group;
+        }
+    }
+    // groups made of empty files only (no chunk ever reached them)
+    while (next_group < pg->group_end.size()) {
+        const uint32_t ib = pg->group_item_begin[next_group], ie = pg->group_item_begin[next_group + 1];
+        if (ie > ib) {
+            fa_clip_items_kernel<<<(ie - ib + 255) / 256, 256, 0, stream>>>(pg->items.as<SketchItem>() + ib, ie - ib, hc.fa_gend.as<uint64_t>());
+            DB200_LAUNCHED();
+            DB200_CUDA(cudaEventRecord(up.group_packed[next_group], stream));
+            DB200_CUDA(cudaStreamWaitEvent(up.ss, up.group_packed[next_group], 0));
+            DB200_TRY(sketch_launch(pg, p, canon, hc.regs.as<uint8_t>(), up.ss, ib, ie - ib, (int)next_group));
+        }
+        ++next_group;
+    }
+    DB200_CUDA(cudaGetLastError());
+    {
+        const cudaError_t es = cudaStreamSynchronize(up.ss);
+        if (es != cudaSuccess) { set_error("sketch (device-parsed FASTA): %s", cudaGetErrorString(es)); return DB200_ECUDA; }
+    }
+    std::vector<uint32_t> flags(nfiles, 0);
+    if (nfiles) DB200_CUDA(cudaMemcpyAsync(flags.data(), hc.fa_flags.ptr, nfiles * 4, cudaMemcpyDeviceToHost, stream));
+    if (bytes) DB200_CUDA(cudaMemcpyAsync(registers_out, hc.regs.ptr, bytes, cudaMemcpyDeviceToHost, stream));
+    const cudaError_t e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) { set_error("sketch (device-parsed FASTA): %s", cudaGetErrorString(e)); return DB200_ECUDA; }
+    if (file_status_out) for (uint64_t f = 0; f < nfiles; ++f) file_status_out[f] = (uint8_t)(flags[f] & 1u);
+    return DB200_OK;
+}
+
+extern "C" int db200_sketch_fasta_batch(int device, int p, int k, int canon, const char *text, const uint64_t *file_off, const uint64_t *file_len,
+                                        uint64_t nfiles, const uint64_t *genome_file_begin, uint64_t ngenomes, uint8_t *registers_out,
+                                        uint8_t *file_status_out) {
+    if (!registers_out && ngenomes) { set_error("db200_sketch_fasta_batch: null output"); return DB200_EINVAL; }
+    if (!genome_file_begin || ((!file_off || !file_len || !text) && nfiles)) { set_error("db200_sketch_fasta_batch: null argument"); return DB200_EINVAL; }
+    if (k < 1 || k > 32) { set_error("sketch: k=%d outside [1,32]", k); return DB200_EUNSUPPORTED; }
+    if (p < 7 || p > 24) { set_error("sketch: p=%d outside the GPU path's range [7,24]", p); return DB200_EUNSUPPORTED; }
+    if (ngenomes >= (1ull << 32) || nfiles >= (1ull << 32)) { set_error("too many genomes / files"); return DB200_EINVAL; }
+    if (genome_file_begin[0] != 0 || genome_file_begin[ngenomes] != nfiles) { set_error("db200_sketch_fasta_batch: genome_file_begin must run from 0 to nfiles"); return DB200_EINVAL; }
+    for (uint64_t g = 0; g < ngenomes; ++g)
+        if (genome_file_begin[g] > genome_file_begin[g + 1]) { set_error("db200_sketch_fasta_batch: genome_file_begin must ascend"); return DB200_EINVAL; }
+    for (uint64_t f = 0; f < nfiles; ++f) {
+        if (file_off[f] % FA_BLOCK) { set_error("db200_sketch_fasta_batch: file %llu does not start on a multiple of %d bytes", (unsigned long long)f, FA_BLOCK); return DB200_EINVAL; }
+        if (f + 1 < nfiles && (file_off[f + 1] <= file_off[f] || file_off[f] + file_len[f] > file_off[f + 1])) {
+            set_error("db200_sketch_fasta_batch: files must ascend, one block at least apart, without overlap (file %llu)", (unsigned long long)f);
+            return DB200_EINVAL;
+        }
+    }
+    if (device == DB200_ALL_DEVICES && logical_device_count() > 1 && ngenomes > 1) {
+        const int nd = (int)std::min<uint64_t>((uint64_t)logical_device_count(), ngenomes);
+        std::vector<uint64_t> raw(ngenomes + 1, 0);
+        for (uint64_t g = 0; g < ngenomes; ++g) {
+            raw[g + 1] = raw[g] + 1;
+            for (uint64_t f = genome_file_begin[g]; f < genome_file_begin[g + 1]; ++f) raw[g + 1] += file_len[f];
+        }
+        const std::vector<uint64_t> cut = split_by_weight(ngenomes, nd, [&](uint64_t g) { return raw[g]; });
+        return for_each_device(nd, [&](int d) {
+            const uint64_t g0 = cut[d], g1 = cut[d + 1];
+            if (g1 <= g0) return (int)DB200_OK;
+            const uint64_t f0 = genome_file_begin[g0], f1 = genome_file_begin[g1];
+            // the device's share as a batch of its own: offsets relative to its first file's block
+            const uint64_t base = f1 > f0 ? file_off[f0] : 0;
+            std::vector<uint64_t> fo(f1 - f0), gfb(g1 - g0 + 1);
+            for (uint64_t f = f0; f < f1; ++f) fo[f - f0] = file_off[f] - base;
+            for (uint64_t g = g0; g <= g1; ++g) gfb[g - g0] = genome_file_begin[g] - f0;
+            return sketch_fasta_one(d, p, k, canon, text + base, fo.data(), file_len + f0, f1 - f0, gfb.data(), g1 - g0,
+                                    registers_out + (g0 << p), file_status_out ? file_status_out + f0 : nullptr);
+        });
+    }
+    return sketch_fasta_one(device == DB200_ALL_DEVICES ? 0 : device, p, k, canon, text, file_off, file_len, nfiles, genome_file_begin, ngenomes,
+                            registers_out, file_status_out);
+}
 
 // Genomes are independent units: contiguous ranges of genomes, balanced by their bases, one range per device.
 static int sketch_batch_all(int p, int k, int canon, const char *bases, const uint64_t *rec_offsets, uint64_t nrecords,

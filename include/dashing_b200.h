@@ -126,6 +126,20 @@ DB200_API int db200_sketch_batch(int device, int p, int k, int canon,
                        const char *bases, const uint64_t *rec_offsets, uint64_t nrecords,
                        const uint64_t *genome_rec_begin, uint64_t ngenomes, uint8_t *registers_out);
 
+/* Device-side FASTA parsing — the step BEFORE S1 moved onto the GPU as well.  Instead of kseq records the
+ * host hands over RAW file text (what read() or gz inflate produced: header lines, newlines, CR and all); the library
+ * applies kseq_read's record rules per byte on the device (bonsai/klib/kseq.h:177-218; dashing_b200/csrc/fasta.cuh), packs
+ * and sketches.  File f is text[file_off[f] .. file_off[f] + file_len[f]); file_off must be multiples of
+ * DB200_FASTA_ALIGN, ascending, at least one block apart and non-overlapping (what lies between files is ignored); genome g
+ * is the files [genome_file_begin[g], genome_file_begin[g+1]) folded into one sketch (FNAME_SEP paths, src/substrs.h:7-26).
+ * file_status_out (optional, one byte per file): 0 = parsed; 1 = the file shows FASTQ record syntax ('@' headers, '+'
+ * lines) which this path does not cover — the registers of ITS GENOME are then unspecified and the host must sketch that
+ * genome through the record interface (db200_sketch_batch) instead. */
+#define DB200_FASTA_ALIGN 8192
+DB200_API int db200_sketch_fasta_batch(int device, int p, int k, int canon, const char *text, const uint64_t *file_off,
+                                       const uint64_t *file_len, uint64_t nfiles, const uint64_t *genome_file_begin, uint64_t ngenomes,
+                                       uint8_t *registers_out, uint8_t *file_status_out);
+
 /* Device-resident form used by bench.py (`value`) and the multi-GPU driver.  The packed genome
  * store is the HBM-resident input format of the sketch kernel: 2-bit bases (64 per 16-byte word),
  * a validity bit-plane and a record-start bit-plane (DESIGN.md "Data layout"). */
