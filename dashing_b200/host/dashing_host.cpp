@@ -408,26 +408,73 @@ size_t file_capacity(const std::string &f) {
 struct Batch {
     std::vector<size_t> which;          // genome -> index into the caller's path list
     std::vector<FileSlot> slots;
-    std::vector<uint64_t> rec_offs, grb;
-    std::vector<uint8_t> regs;
+    std::vector<uint64_t> file_off, file_len, gfb;
+    std::vector<uint8_t> regs, status;
     std::vector<size_t> redo;           // batch genomes to be re-read through load_genome
     size_t bytes = 0;
 };
 
-// Sketch a list of paths through db200_sketch_batch.  Files are parsed in parallel straight into one reusable arena per
-// batch (no per-genome strings, no concatenation pass; the unused tail of a window becomes a record of 'N's, which holds
-// no k-mer), and the GPU call + register hand-off of batch b run on a helper thread while batch b+1 is being parsed.
+// The raw bytes of a file (inflated if it is gzip) straight into a caller window; SIZE_MAX when the window is too small.
+size_t slurp_into_window(const std::string &file, char *dst, size_t cap) {
+    std::FILE *fp = std::fopen(file.c_str(), "rb");
+    if (!fp) throw Error("Could not open file at " + file + ". Abort!");
+    unsigned char magic[2] = {0, 0};
+    const bool gz = std::fread(magic, 1, 2, fp) == 2 && magic[0] == 0x1f && magic[1] == 0x8b;
+    size_t used = 0;
+    if (!gz) {
+        std::rewind(fp);
+        for (;;) {
+            const size_t n = std::fread(dst + used, 1, cap - used, fp);
+            used += n;
+            if (n == 0 || used == cap) break;
+        }
+        const bool more = used == cap && std::fgetc(fp) != EOF;     // the file grew since it was measured
+        std::fclose(fp);
+        return more ? SIZE_MAX : used;
+    }
+    std::fclose(fp);
+    gzFile g = gzopen(file.c_str(), "rb");
+    if (!g) throw Error("Could not open file at " + file + ". Abort!");
+    gzbuffer(g, 1 << 18);
+    for (;;) {
+        if (used == cap) {
+            char extra;
+            const int n = gzread(g, &extra, 1);                      // multi-member gzip: ISIZE covers the last member only
+            gzclose(g);
+            return n > 0 ? SIZE_MAX : used;
+        }
+        const int n = gzread(g, dst + used, (unsigned)std::min<size_t>(cap - used, 1u << 30));
+        if (n < 0) { gzclose(g); throw Error("Error reading from file " + file); }
+        if (n == 0) break;
+        used += (size_t)n;
+    }
+    gzclose(g);
+    return used;
+}
+
+// Sketch a list of paths.  The host only moves bytes: every file's raw text (inflated if gzip) is read in parallel straight
+// into its window of one reusable arena per batch, and db200_sketch_fasta_batch parses, packs and sketches it on the GPU
+// (kseq's record rules run there: dashing_b200/csrc/fasta.cuh).  The GPU call + register hand-off of batch b run on a helper
+// thread while batch b+1 is being read.  Genomes holding a FASTQ file (by its first byte, or flagged by the device), or a
+// file that outgrew its window, take the kseq-compatible host reader + db200_sketch_batch instead.
 void sketch_paths(const SketchOptions &o, const std::vector<std::string> &paths, const std::vector<size_t> &which,
                   const std::function<void(size_t, const uint8_t *)> &sink) {
     if (which.empty()) return;
     const size_t m = size_t(1) << o.p;
     const int nt = std::max(1, o.nthreads);
-    // CUDA initialisation (seconds on a multi-GPU node) overlaps the parsing of the first batch
+    const size_t AL = DB200_FASTA_ALIGN;
+    // CUDA initialisation (seconds on a multi-GPU node) overlaps the reading of the first batch
     std::future<std::string> warm = std::async(std::launch::async, [&o] {   // (the error text is thread-local: carry it over)
         return db200_warmup(o.device) == DB200_OK ? std::string() : std::string(db200_last_error());
     });
-    std::unique_ptr<char[]> arena[2];
-    size_t arena_cap[2] = {0, 0};
+    // Two arenas (one being read into, one being sketched).  DB200_PINNED_ARENA=1 page-locks them (db200_host_alloc) so the
+    // upload DMAs straight from them; that costs the page-locking time up front and needs the CUDA context first.
+    static const bool pinned = std::getenv("DB200_PINNED_ARENA") != nullptr && std::atoi(std::getenv("DB200_PINNED_ARENA")) != 0;
+    struct Arena {
+        char *ptr = nullptr; size_t cap = 0; bool pinned = false;
+        void release() { if (ptr) { if (pinned) db200_host_free(ptr); else delete[] ptr; } ptr = nullptr; cap = 0; }
+        ~Arena() { release(); }
+    } arena[2];
     std::future<void> inflight;
     int cur = 0;
     size_t at = 0;
@@ -436,61 +483,70 @@ void sketch_paths(const SketchOptions &o, const std::vector<std::string> &paths,
         while (at < which.size()) {
             phase("batch begin");
             auto bt = std::make_shared<Batch>();
-            // ---- batch layout from file sizes
+            // ---- batch layout from file sizes: every file on its own DB200_FASTA_ALIGN boundary
+            bt->gfb.assign(1, 0);
             while (at < which.size() && (bt->which.empty() || bt->bytes < o.batch_bytes)) {
                 for (auto &f : split_paths(paths[which[at]])) {
                     FileSlot sl;
                     sl.genome = bt->which.size(); sl.path = f; sl.cap = file_capacity(f); sl.off = bt->bytes;
-                    bt->bytes += (sl.cap + 63) & ~size_t(63);
+                    bt->bytes += std::max(AL, (sl.cap + AL - 1) / AL * AL);
                     bt->slots.push_back(std::move(sl));
                 }
                 bt->which.push_back(which[at++]);
+                bt->gfb.push_back(bt->slots.size());
             }
-            if (arena_cap[cur] < bt->bytes + 64) { arena[cur].reset(new char[bt->bytes + 64]); arena_cap[cur] = bt->bytes + 64; }
-            char *base = arena[cur].get();
-            // ---- parse (kseq + gz inflate are the host's job, as in the reference)
+            if (arena[cur].cap < bt->bytes + 64) {
+                arena[cur].release();
+                // (later batches are never larger than batch_bytes + one genome: size the arena for that once)
+                const size_t want = std::max(bt->bytes + 64, at < which.size() ? o.batch_bytes + (o.batch_bytes >> 2) : size_t(0));
+                if (pinned) {
+                    if (warm.valid()) { const std::string werr = warm.get(); if (!werr.empty()) throw Error(werr); }
+                    void *pp = nullptr;
+                    check(db200_host_alloc(&pp, want));
+                    arena[cur].ptr = static_cast<char *>(pp); arena[cur].pinned = true;
+                } else arena[cur].ptr = new char[want];
+                arena[cur].cap = want;
+            }
+            char *base = arena[cur].ptr;
+            // ---- read (file IO and gz inflate stay the host's job, as in the reference; nothing is parsed here)
             std::string err;
 #pragma omp parallel for schedule(dynamic) num_threads(nt)
             for (size_t i = 0; i < bt->slots.size(); ++i) {
                 FileSlot &sl = bt->slots[i];
-                const size_t window = (i + 1 < bt->slots.size() ? bt->slots[i + 1].off : bt->bytes) - sl.off;
                 try {
-                    const size_t used = parse_into_window(sl.path, base + sl.off, sl.cap, sl.ends);
-                    if (used == SIZE_MAX) { sl.redo = true; sl.ends.clear(); sl.used = 0; }
-                    else sl.used = used;
+                    const size_t used = slurp_into_window(sl.path, base + sl.off, sl.cap);
+                    if (used == SIZE_MAX) { sl.redo = true; sl.used = 0; }
+                    else {
+                        sl.used = used;
+                        size_t j = 0;
+                        while (j < used && (base[sl.off + j] == '\n' || base[sl.off + j] == '\r')) ++j;
+                        if (j < used && base[sl.off + j] == '@') { sl.redo = true; sl.used = 0; }   // FASTQ: the record interface
+                    }
                 } catch (const std::exception &e) {
 #pragma omp critical
                     err = e.what();
                 }
-                std::memset(base + sl.off + sl.used, 'N', window - sl.used);
             }
             if (!err.empty()) throw Error(err);
-            phase("files parsed");
-            // ---- record table: the records of each file, then one filler record up to the next window
-            bt->rec_offs.assign(1, 0);
-            bt->grb.assign(1, 0);
-            std::vector<char> redo_genome(bt->which.size(), 0);
-            for (size_t i = 0; i < bt->slots.size(); ++i) {
-                const FileSlot &sl = bt->slots[i];
-                if (i && sl.genome != bt->slots[i - 1].genome)
-                    for (size_t g = bt->slots[i - 1].genome; g < sl.genome; ++g) bt->grb.push_back(bt->rec_offs.size() - 1);
-                for (uint64_t e : sl.ends) bt->rec_offs.push_back(sl.off + e);
-                const uint64_t wend = i + 1 < bt->slots.size() ? bt->slots[i + 1].off : bt->bytes;
-                if (wend > bt->rec_offs.back()) bt->rec_offs.push_back(wend);
-                if (sl.redo) redo_genome[sl.genome] = 1;
-            }
-            while (bt->grb.size() < bt->which.size() + 1) bt->grb.push_back(bt->rec_offs.size() - 1);
-            for (size_t g = 0; g < redo_genome.size(); ++g) if (redo_genome[g]) bt->redo.push_back(g);
+            phase("files read");
+            bt->file_off.resize(bt->slots.size());
+            bt->file_len.resize(bt->slots.size());
+            for (size_t i = 0; i < bt->slots.size(); ++i) { bt->file_off[i] = bt->slots[i].off; bt->file_len[i] = bt->slots[i].used; }
+            bt->status.assign(bt->slots.size(), 0);
             bt->regs.resize(bt->which.size() * m);
             // ---- previous batch must be through before its arena's twin is reused two batches later; hand this one over
             finish(inflight);
             if (warm.valid()) { const std::string werr = warm.get(); if (!werr.empty()) throw Error(werr); }
             phase("previous batch done");
             inflight = std::async(std::launch::async, [bt, base, m, nt, &o, &paths, &sink] {
-                check(db200_sketch_batch(o.device, o.p, o.k, o.canon, base, bt->rec_offs.data(), bt->rec_offs.size() - 1, bt->grb.data(),
-                                         bt->which.size(), bt->regs.data()));
+                check(db200_sketch_fasta_batch(o.device, o.p, o.k, o.canon, base, bt->file_off.data(), bt->file_len.data(), bt->slots.size(),
+                                               bt->gfb.data(), bt->which.size(), bt->regs.data(), bt->status.data()));
+                std::vector<char> redo_genome(bt->which.size(), 0);
+                for (size_t i = 0; i < bt->slots.size(); ++i)
+                    if (bt->slots[i].redo || bt->status[i]) redo_genome[bt->slots[i].genome] = 1;
+                for (size_t g = 0; g < redo_genome.size(); ++g) if (redo_genome[g]) bt->redo.push_back(g);
                 if (!bt->redo.empty()) {
-                    // windows that were too small: the old route (private strings, one more call)
+                    // FASTQ, multi-member gzip, ...: the kseq-compatible host reader and the record interface
                     std::string all;
                     std::vector<uint64_t> ro{0}, gb{0};
                     for (size_t g : bt->redo) {
@@ -500,6 +556,7 @@ void sketch_paths(const SketchOptions &o, const std::vector<std::string> &paths,
                         for (size_t r = 1; r < gn.offs.size(); ++r) ro.push_back(b0 + gn.offs[r]);
                         gb.push_back(ro.size() - 1);
                     }
+                    if (all.empty()) all.push_back('N');
                     std::vector<uint8_t> rr(bt->redo.size() * m);
                     check(db200_sketch_batch(o.device, o.p, o.k, o.canon, all.data(), ro.data(), ro.size() - 1, gb.data(), bt->redo.size(), rr.data()));
                     for (size_t j = 0; j < bt->redo.size(); ++j) std::memcpy(&bt->regs[bt->redo[j] * m], &rr[j * m], m);
