@@ -13,6 +13,7 @@
 #include <cstring>
 #include <mutex>
 #include <thread>
+#include <condition_variable>
 #include <functional>
 #include <vector>
 #include <memory>
@@ -55,6 +56,129 @@ struct db200_packed_genomes {
 };
 
 namespace db200 {
+// Host -> device copies from PAGEABLE memory.  cudaMemcpyAsync would stage them through the driver's own bounce buffer with one
+// thread (~10 GB/s measured on the B200 boxes, against ~55 GB/s for page-locked sources); page-locking the caller's buffer
+// costs ~0.5 s per GB.  Instead the library keeps a small ring of page-locked buffers per device and fills it with several
+// host threads, so the DMA engine sees page-locked sources at memory-copy speed.  Page-locked sources are passed through.
+class CopyPool {
+public:
+    explicit CopyPool(unsigned n) : nworkers_(n) {
+        for (unsigned i = 0; i < n; ++i) th_.emplace_back([this, i] { run(i); });
+    }
+    ~CopyPool() {
+        { std::lock_guard<std::mutex> lk(mu_); stop_ = true; ++gen_; }
+        cv_.notify_all();
+        for (auto &t : th_) t.join();
+    }
+    // dst[0, n) = src[0, n), split over the workers and the calling thread
+    void copy(char *dst, const char *src, size_t n) {
+        if (n < (size_t(1) << 20) || nworkers_ == 0) { std::memcpy(dst, src, n); return; }
+        const size_t parts = nworkers_ + 1, each = ((n + parts - 1) / parts + 4095) & ~size_t(4095);
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            dst_ = dst; src_ = src; n_ = n; each_ = each; pending_ = nworkers_; ++gen_;
+        }
+        cv_.notify_all();
+        const size_t off = each * nworkers_;
+        if (off < n) std::memcpy(dst + off, src + off, n - off);
+        std::unique_lock<std::mutex> lk(mu_);
+        done_.wait(lk, [this] { return pending_ == 0; });
+    }
+private:
+    void run(unsigned i) {
+        uint64_t seen = 0;
+        for (;;) {
+            std::unique_lock<std::mutex> lk(mu_);
+            cv_.wait(lk, [&] { return gen_ != seen; });
+            seen = gen_;
+            if (stop_) return;
+            char *d = dst_; const char *s = src_; const size_t n = n_, each = each_;
+            lk.unlock();
+            const size_t off = each * i;
+            if (off < n) std::memcpy(d + off, s + off, std::min(each, n - off));
+            lk.lock();
+            if (--pending_ == 0) done_.notify_one();
+        }
+    }
+    unsigned nworkers_;
+    std::vector<std::thread> th_;
+    std::mutex mu_;
+    std::condition_variable cv_, done_;
+    char *dst_ = nullptr; const char *src_ = nullptr;
+    size_t n_ = 0, each_ = 0;
+    unsigned pending_ = 0;
+    uint64_t gen_ = 0;
+    bool stop_ = false;
+};
+
+struct HostStager {
+    static constexpr int NSLOT = 4;
+    static constexpr size_t SLOT = size_t(16) << 20;
+    char *slot[NSLOT] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t freed[NSLOT] = {nullptr, nullptr, nullptr, nullptr};
+    bool used[NSLOT] = {false, false, false, false};
+    unsigned next = 0;
+    std::unique_ptr<CopyPool> pool;
+    int init() {
+        if (slot[0]) return DB200_OK;
+        for (int i = 0; i < NSLOT; ++i) {
+            DB200_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&slot[i]), SLOT, cudaHostAllocDefault));
+            DB200_CUDA(cudaEventCreateWithFlags(&freed[i], cudaEventDisableTiming));
+        }
+        const char *e = std::getenv("DB200_COPY_THREADS");
+        int n = e ? std::atoi(e) : 8;
+        n = std::max(1, std::min(n, 64));
+        pool.reset(new CopyPool((unsigned)n - 1));
+        return DB200_OK;
+    }
+    static bool page_locked(const void *p) {
+        cudaPointerAttributes a;
+        const bool ok = cudaPointerGetAttributes(&a, p) == cudaSuccess && (a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged || a.type == cudaMemoryTypeDevice);
+        cudaGetLastError();
+        return ok;
+    }
+    // Device -> host into possibly pageable memory, ordered after the work already queued on `cs`.  Page-locked destinations get
+    // one asynchronous copy; pageable ones are filled from the bounce buffers by the copy threads while the next piece is in
+    // flight (the call then returns with the data in place).
+    int download(char *dst, const void *src, size_t n, cudaStream_t cs) {
+        if (n == 0) return DB200_OK;
+        if (page_locked(dst)) { DB200_CUDA(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, cs)); return DB200_OK; }
+        DB200_TRY(init());
+        size_t poff = 0, plen = 0;
+        unsigned ps = 0;
+        bool have = false;
+        for (size_t off = 0; off < n; off += SLOT) {
+            const size_t len = std::min(SLOT, n - off);
+            const unsigned sl = next++ % NSLOT;
+            if (used[sl]) DB200_CUDA(cudaEventSynchronize(freed[sl]));
+            DB200_CUDA(cudaMemcpyAsync(slot[sl], static_cast<const char *>(src) + off, len, cudaMemcpyDeviceToHost, cs));
+            DB200_CUDA(cudaEventRecord(freed[sl], cs));
+            used[sl] = true;
+            if (have) { DB200_CUDA(cudaEventSynchronize(freed[ps])); pool->copy(dst + poff, slot[ps], plen); }
+            poff = off; plen = len; ps = sl; have = true;
+        }
+        if (have) { DB200_CUDA(cudaEventSynchronize(freed[ps])); pool->copy(dst + poff, slot[ps], plen); }
+        return DB200_OK;
+    }
+    // Enqueues dst[0, n) = src[0, n) on stream `cs`.  Returns once every byte of `src` has been read or handed to the DMA
+    // engine from a page-locked source (the caller may not reuse page-locked sources before the stream has drained).
+    int upload(void *dst, const char *src, size_t n, cudaStream_t cs) {
+        if (n == 0) return DB200_OK;
+        if (page_locked(src)) { DB200_CUDA(cudaMemcpyAsync(dst, src, n, cudaMemcpyDefault, cs)); return DB200_OK; }
+        DB200_TRY(init());
+        for (size_t off = 0; off < n; off += SLOT) {
+            const size_t len = std::min(SLOT, n - off);
+            const unsigned s = next++ % NSLOT;
+            if (used[s]) DB200_CUDA(cudaEventSynchronize(freed[s]));
+            pool->copy(slot[s], src + off, len);
+            DB200_CUDA(cudaMemcpyAsync(static_cast<char *>(dst) + off, slot[s], len, cudaMemcpyHostToDevice, cs));
+            DB200_CUDA(cudaEventRecord(freed[s], cs));
+            used[s] = true;
+        }
+        return DB200_OK;
+    }
+};
+
 // ASCII upload pipeline state (two device staging buffers, a copy stream and events), kept across calls:
 // cudaMalloc/cudaFree of multi-GB buffers costs more than the transfers they serve.
 struct Uploader {
@@ -62,6 +186,7 @@ struct Uploader {
     cudaStream_t cs = nullptr;
     cudaEvent_t copied[2] = {nullptr, nullptr}, packed[2] = {nullptr, nullptr};
     static constexpr int NGROUP = 4;
+    HostStager stager;                         // pageable sources go through page-locked bounce buffers filled by several threads
     cudaStream_t ss = nullptr;                 // sketch stream: group g is sketched while later groups are still uploading
     cudaEvent_t group_packed[NGROUP] = {nullptr, nullptr, nullptr, nullptr};
     int init() {
@@ -194,7 +319,7 @@ static int pack_genomes_impl(int device, const char *bases, const uint64_t *rec_
             src = reinterpret_cast<const uint8_t *>(bases) + base0 + off;
         } else {
             if (c >= 2) DB200_CUDA(cudaStreamWaitEvent(up.cs, up.packed[b], 0));  // staging buffer free again
-            DB200_CUDA(cudaMemcpyAsync(up.stage[b].ptr, bases + base0 + off, len, cudaMemcpyDefault, up.cs));
+            DB200_TRY(up.stager.upload(up.stage[b].ptr, bases + base0 + off, len, up.cs));
             DB200_CUDA(cudaEventRecord(up.copied[b], up.cs));
             DB200_CUDA(cudaStreamWaitEvent(stream, up.copied[b], 0));
             src = up.stage[b].as<uint8_t>();
@@ -829,7 +954,7 @@ int db200_cardinalities(int device, const uint8_t *regs, uint64_t n, int p, int 
     DB200_TRY(hc.init(device));
     DB200_TRY(hc.regs.reserve(n << p));
     DB200_TRY(hc.cards.reserve(n * 8));
-    DB200_CUDA(cudaMemcpyAsync(hc.regs.ptr, regs, n << p, cudaMemcpyHostToDevice, hc.stream));
+    DB200_TRY(hc.up.stager.upload(hc.regs.ptr, reinterpret_cast<const char *>(regs), n << p, hc.stream));
     cardinality_kernel<<<(unsigned)n, 128, 0, hc.stream>>>(hc.regs.as<uint32_t>(), p, estim, hc.cards.as<double>());
     DB200_LAUNCHED();
     DB200_CUDA(cudaGetLastError());
@@ -884,7 +1009,7 @@ int db200_compress(int device, const uint8_t *regs, uint64_t n, int p, int new_p
     DB200_TRY(hc.init(device));
     DB200_TRY(hc.regs.reserve(n << p));
     DB200_TRY(hc.out.reserve(n << new_p));
-    DB200_CUDA(cudaMemcpyAsync(hc.regs.ptr, regs, n << p, cudaMemcpyHostToDevice, hc.stream));
+    DB200_TRY(hc.up.stager.upload(hc.regs.ptr, reinterpret_cast<const char *>(regs), n << p, hc.stream));
     const uint64_t total = n << new_p;
     compress_kernel<<<(unsigned)((total + 255) / 256), 256, 0, hc.stream>>>(hc.regs.as<uint8_t>(), n, p, new_p, hc.out.as<uint8_t>());
     DB200_LAUNCHED();
@@ -967,7 +1092,7 @@ static int knn_symmetric_impl(int device, const uint8_t *regs, uint64_t n, const
     const uint64_t m = 1ull << prm->p;
     DB200_TRY(hc.regs.reserve(n * m));
     DB200_TRY(hc.nbrs.reserve(n * nneighbors * sizeof(db200_neighbor)));
-    DB200_CUDA(cudaMemcpyAsync(hc.regs.ptr, regs, n * m, cudaMemcpyHostToDevice, hc.stream));
+    DB200_TRY(hc.up.stager.upload(hc.regs.ptr, reinterpret_cast<const char *>(regs), n * m, hc.stream));
     DB200_TRY(plan_prepare(hc.plan.get(), hc.regs.as<uint8_t>(), n, n, 0, 0, prm->p, prm->estim, hc.stream));
     DB200_TRY(plan_override_cards(hc.plan.get(), card, n, nullptr, 0, hc.stream));
     DB200_TRY(plan_knn(hc.plan.get(), prm, 0, 0, nneighbors, hc.nbrs.as<Neighbor>(), hc.stream));
@@ -1000,8 +1125,8 @@ static int knn_rect_impl(int device, const uint8_t *ref_regs, uint64_t nr, const
     const uint64_t qbase = (nr + DT - 1) / DT * DT, nrows = qbase + nq;
     DB200_TRY(hc.regs.reserve(nrows * m));
     DB200_TRY(hc.nbrs.reserve(nq * nneighbors * sizeof(db200_neighbor)));
-    DB200_CUDA(cudaMemcpyAsync(hc.regs.ptr, ref_regs, nr * m, cudaMemcpyHostToDevice, hc.stream));
-    DB200_CUDA(cudaMemcpyAsync(hc.regs.as<uint8_t>() + qbase * m, qry_regs, nq * m, cudaMemcpyHostToDevice, hc.stream));
+    DB200_TRY(hc.up.stager.upload(hc.regs.ptr, reinterpret_cast<const char *>(ref_regs), nr * m, hc.stream));
+    DB200_TRY(hc.up.stager.upload(hc.regs.as<uint8_t>() + qbase * m, reinterpret_cast<const char *>(qry_regs), nq * m, hc.stream));
     DB200_TRY(plan_prepare(hc.plan.get(), hc.regs.as<uint8_t>(), nrows, nr, qbase, nq, prm->p, prm->estim, hc.stream));
     DB200_TRY(plan_override_cards(hc.plan.get(), card_ref, nr, card_qry, nq, hc.stream));
     DB200_TRY(plan_knn(hc.plan.get(), prm, nr, nq, nneighbors, hc.nbrs.as<Neighbor>(), hc.stream));
@@ -1056,13 +1181,13 @@ static int symmetric_rows_impl(int device, const uint8_t *regs, uint64_t n, cons
     if (prm->p < 7 || prm->p > 20) { set_error("dist: p=%d outside the GPU path's range [7,20]", prm->p); return DB200_EUNSUPPORTED; }
     DB200_TRY(hc.regs.reserve(n * m));
     DB200_TRY(hc.out.reserve(std::max<uint64_t>(npairs, 1) * 4));
-    DB200_CUDA(cudaMemcpyAsync(hc.regs.ptr, regs, n * m, cudaMemcpyHostToDevice, hc.stream));
+    DB200_TRY(hc.up.stager.upload(hc.regs.ptr, reinterpret_cast<const char *>(regs), n * m, hc.stream));
     DB200_TRY(plan_prepare(hc.plan.get(), hc.regs.as<uint8_t>(), n, n, 0, 0, prm->p, prm->estim, hc.stream));
     DB200_TRY(plan_override_cards(hc.plan.get(), card, n, nullptr, 0, hc.stream));
     // Row blocks (equal pair counts, up to NSLOT of them): block b's device->host copy runs on the copy stream while block
     // b+1 computes, so only the last block's transfer is exposed.
     const int nblk = npairs >= (uint64_t(4) << 20) ? db200_dist_plan::NSLOT : 1;
-    uint64_t rb = row_begin;
+    uint64_t rb = row_begin, boff[db200_dist_plan::NSLOT] = {0}, bcnt[db200_dist_plan::NSLOT] = {0};
     for (int b = 0; b < nblk; ++b) {
         uint64_t re = row_end;
         if (b + 1 < nblk) {
@@ -1071,12 +1196,16 @@ static int symmetric_rows_impl(int device, const uint8_t *regs, uint64_t n, cons
             while (re < row_end && tri(re) < target) ++re;       // block boundaries are whole rows
         }
         if (re == rb) continue;
-        const uint64_t off = tri(rb) - tri(row_begin), cnt = tri(re) - tri(rb);
-        DB200_TRY(plan_run(hc.plan.get(), prm, 0, rb, re, 0, 0, hc.out.as<float>() + off, hc.stream, b));
+        boff[b] = tri(rb) - tri(row_begin); bcnt[b] = tri(re) - tri(rb);
+        DB200_TRY(plan_run(hc.plan.get(), prm, 0, rb, re, 0, 0, hc.out.as<float>() + boff[b], hc.stream, b));
         DB200_CUDA(cudaEventRecord(hc.blk_done[b], hc.stream));
-        DB200_CUDA(cudaStreamWaitEvent(hc.cstream, hc.blk_done[b], 0));
-        if (cnt) DB200_CUDA(cudaMemcpyAsync(out + off, hc.out.as<float>() + off, cnt * 4, cudaMemcpyDeviceToHost, hc.cstream));
         rb = re;
+    }
+    // every block's kernel is queued by now, so a copy that blocks this thread (pageable `out`) still overlaps the kernels behind it
+    for (int b = 0; b < nblk; ++b) {
+        if (!bcnt[b]) continue;
+        DB200_CUDA(cudaStreamWaitEvent(hc.cstream, hc.blk_done[b], 0));
+        DB200_TRY(hc.up.stager.download(reinterpret_cast<char *>(out + boff[b]), hc.out.as<float>() + boff[b], bcnt[b] * 4, hc.cstream));
     }
     DB200_CUDA(cudaStreamSynchronize(hc.stream));
     DB200_CUDA(cudaStreamSynchronize(hc.cstream));
@@ -1107,12 +1236,12 @@ static int rect_impl(int device, const uint8_t *ref_regs, uint64_t nr, const uin
     const uint64_t qbase = (nr + DT - 1) / DT * DT, nrows = qbase + nq;
     DB200_TRY(hc.regs.reserve(nrows * m));
     DB200_TRY(hc.out.reserve(nr * nq * 4));
-    DB200_CUDA(cudaMemcpyAsync(hc.regs.ptr, ref_regs, nr * m, cudaMemcpyHostToDevice, hc.stream));
-    DB200_CUDA(cudaMemcpyAsync(hc.regs.as<uint8_t>() + qbase * m, qry_regs, nq * m, cudaMemcpyHostToDevice, hc.stream));
+    DB200_TRY(hc.up.stager.upload(hc.regs.ptr, reinterpret_cast<const char *>(ref_regs), nr * m, hc.stream));
+    DB200_TRY(hc.up.stager.upload(hc.regs.as<uint8_t>() + qbase * m, reinterpret_cast<const char *>(qry_regs), nq * m, hc.stream));
     DB200_TRY(plan_prepare(hc.plan.get(), hc.regs.as<uint8_t>(), nrows, nr, qbase, nq, prm->p, prm->estim, hc.stream));
     DB200_TRY(plan_override_cards(hc.plan.get(), card_ref, nr, card_qry, nq, hc.stream));
     DB200_TRY(plan_run(hc.plan.get(), prm, 1, 0, 0, nr, nq, hc.out.as<float>(), hc.stream));
-    DB200_CUDA(cudaMemcpyAsync(out, hc.out.ptr, nr * nq * 4, cudaMemcpyDeviceToHost, hc.stream));
+    DB200_TRY(hc.up.stager.download(reinterpret_cast<char *>(out), hc.out.ptr, nr * nq * 4, hc.stream));
     DB200_CUDA(cudaStreamSynchronize(hc.stream));
     return DB200_OK;
 }
@@ -1285,14 +1414,14 @@ static int sketch_fasta_one(int device, int p, int k, int canon, const char *tex
     for (uint64_t c = 0; c < nchunks; ++c) {
         const int b = (int)(c & 1);
         const uint64_t off = c * CH, len = std::min<uint64_t>(CH, text_end - off);
-        DB200_CUDA(cudaMemcpyAsync(d_text + off, text + off, len, cudaMemcpyDefault, up.cs));
+        DB200_TRY(up.stager.upload(d_text + off, text + off, len, up.cs));
         DB200_CUDA(cudaEventRecord(up.copied[b], up.cs));
         DB200_CUDA(cudaStreamWaitEvent(stream, up.copied[b], 0));
         const uint64_t blk0 = off / B, nb = (len + B - 1) / B;
         const uint32_t next_byte = off + len < text_end ? (uint32_t)(uint8_t)text[off + len] : (uint32_t)'\n';
         fa_summary_kernel<<<(unsigned)nb, FA_THREADS, 0, stream>>>(d_text, blk0, d_fblk, d_flen, (uint32_t)nfiles, off + len, next_byte, hc.fa_sums.as<FaSum>());
         DB200_LAUNCHED();
-        fa_chain_kernel<<<1, 256, 0, stream>>>(hc.fa_sums.as<FaSum>(), blk0, nb, d_fblk, d_gpos0, d_fgen, (uint32_t)nfiles, hc.fa_carry.as<uint64_t>(),
+        fa_chain_kernel<<<1, 32, 0, stream>>>(hc.fa_sums.as<FaSum>(), blk0, nb, d_fblk, d_gpos0, d_fgen, (uint32_t)nfiles, hc.fa_carry.as<uint64_t>(),
                                                hc.fa_state.as<uint8_t>(), hc.fa_pos.as<uint64_t>(), hc.fa_gend.as<uint64_t>());
         DB200_LAUNCHED();
         fa_emit_kernel<<<(unsigned)nb, FA_THREADS, 0, stream>>>(d_text, blk0, d_fblk, d_flen, (uint32_t)nfiles, off + len, next_byte, hc.fa_state.as<uint8_t>(),

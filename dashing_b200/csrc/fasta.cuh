@@ -158,53 +158,120 @@ __global__ void __launch_bounds__(FA_THREADS) fa_summary_kernel(const uint8_t *_
     if (threadIdx.x == 0) sums[blk] = s_warp[FA_THREADS / 32];
 }
 
-// Pass 2: chain the blocks of one chunk.  carry[0] = state, carry[1] = next output position, carry[2] = index of the next
-// file start to come, carry[3] = current genome.  A file start resets the state to SKIP; the first file of a genome also
-// moves the output position to that genome's window (gpos0[f] != ~0).  genome_end[g] = one past the last sequence byte
-// written for genome g so far (final once a later genome has started or the text has ended).
-constexpr int FA_CHAIN_TILE = 2048;
-__global__ void __launch_bounds__(256) fa_chain_kernel(const FaSum *__restrict__ sums, uint64_t blk0, uint64_t nblk, const uint64_t *__restrict__ fblk,
+// Pass 2: chain the blocks of one chunk.  carry[0] = state, carry[1] = next output position after the previous chunk.  A file
+// start resets the state to SKIP; the first file of a genome also moves the output position to that genome's window
+// (gpos0[f] != ~0).  genome_end[g] = one past the last sequence byte written for genome g so far (final once a later genome has
+// started or the text has ended).
+// One warp.  Lane l owns 64 consecutive blocks of a 2048-block tile: it first folds them into one map of the incoming
+// (state, position) — speculating over the four possible incoming states —, the 32 maps are scanned with shuffles, and the lane
+// then walks its blocks again with the now known incoming state and position.  File starts reset the state; a genome's first
+// file makes the position absolute (its window), which the map records as (has_abs, abs).
+constexpr int FA_CHAIN_PER_LANE = 64, FA_CHAIN_TILE = 32 * FA_CHAIN_PER_LANE;
+struct FaChainMap {
+    uint32_t tf;        // 2 bits per incoming state
+    uint32_t c[4];      // sequence bytes per incoming state (since the last genome start if has_abs)
+    uint32_t has_abs;
+    uint64_t abs;       // window start of the last genome started inside the run
+};
+__device__ __forceinline__ FaChainMap fa_chain_compose(const FaChainMap &a, const FaChainMap &b) {   // a first, then b
+    FaChainMap r;
+    r.tf = 0;
+#pragma unroll
+    for (uint32_t s = 0; s < 4; ++s) {
+        const uint32_t t = (a.tf >> (2 * s)) & 3u;
+        r.tf |= ((b.tf >> (2 * t)) & 3u) << (2 * s);
+        r.c[s] = (b.has_abs ? 0u : a.c[s]) + b.c[t];
+    }
+    r.has_abs = a.has_abs | b.has_abs;
+    r.abs = b.has_abs ? b.abs : a.abs;
+    return r;
+}
+__device__ __forceinline__ FaChainMap fa_chain_shfl_up(const FaChainMap &m, int d) {
+    FaChainMap r;
+    r.tf = __shfl_up_sync(0xFFFFFFFFu, m.tf, d);
+#pragma unroll
+    for (int s = 0; s < 4; ++s) r.c[s] = __shfl_up_sync(0xFFFFFFFFu, m.c[s], d);
+    r.has_abs = __shfl_up_sync(0xFFFFFFFFu, m.has_abs, d);
+    r.abs = __shfl_up_sync(0xFFFFFFFFu, m.abs, d);
+    return r;
+}
+
+__global__ void __launch_bounds__(32) fa_chain_kernel(const FaSum *__restrict__ sums, uint64_t blk0, uint64_t nblk, const uint64_t *__restrict__ fblk,
                                 const uint64_t *__restrict__ gpos0, const uint32_t *__restrict__ fgenome, uint32_t nfiles,
                                 uint64_t *__restrict__ carry, uint8_t *__restrict__ in_state, uint64_t *__restrict__ in_pos,
                                 uint64_t *__restrict__ genome_end) {
-    __shared__ FaSum s_sum[FA_CHAIN_TILE];
-    __shared__ uint64_t s_pos[FA_CHAIN_TILE];
-    __shared__ uint8_t s_state[FA_CHAIN_TILE];
-    // the chain itself is sequential (one thread); the other threads stage its inputs and outputs through shared memory
-    uint32_t state = 0, nf = 0, g = 0;
-    uint64_t pos = 0, next_fblk = ~0ull;
-    if (threadIdx.x == 0) {
-        state = (uint32_t)carry[0]; pos = carry[1]; nf = (uint32_t)carry[2]; g = (uint32_t)carry[3];
-        next_fblk = nf < nfiles ? fblk[nf] : ~0ull;
-    }
+    const uint32_t lane = threadIdx.x;
+    uint32_t state = (uint32_t)carry[0];      // carried from tile to tile (identical in every lane)
+    uint64_t pos = carry[1];
     for (uint64_t t0 = 0; t0 < nblk; t0 += FA_CHAIN_TILE) {
-        const uint32_t tn = (uint32_t)min((uint64_t)FA_CHAIN_TILE, nblk - t0);
-        for (uint32_t i = threadIdx.x; i < tn; i += blockDim.x) s_sum[i] = sums[blk0 + t0 + i];
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            for (uint32_t i = 0; i < tn; ++i) {
-                const uint64_t b = blk0 + t0 + i;
-                while (b == next_fblk) {
-                    state = FS_SKIP;
-                    if (gpos0[nf] != ~0ull) { genome_end[g] = pos; pos = gpos0[nf]; g = fgenome[nf]; }
-                    ++nf;
-                    next_fblk = nf < nfiles ? fblk[nf] : ~0ull;
-                }
-                s_state[i] = (uint8_t)state;
-                s_pos[i] = pos;
-                const FaSum s = s_sum[i];
-                pos += fa_cnt(s, state);
-                state = fa_tf(s, state);
-            }
+        const uint64_t b_lo = min(blk0 + t0 + (uint64_t)lane * FA_CHAIN_PER_LANE, blk0 + nblk);
+        const uint64_t b_hi = min(b_lo + FA_CHAIN_PER_LANE, blk0 + nblk);
+        // first file starting at or after b_lo
+        uint32_t nf0;
+        {
+            uint32_t lo = 0, hi = nfiles;
+            while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(fblk + mid) < b_lo) lo = mid + 1; else hi = mid; }
+            nf0 = lo;
         }
-        __syncthreads();
-        for (uint32_t i = threadIdx.x; i < tn; i += blockDim.x) { in_state[blk0 + t0 + i] = s_state[i]; in_pos[blk0 + t0 + i] = s_pos[i]; }
-        __syncthreads();
+        // ---- pass 1: the lane's map
+        FaChainMap m;
+        m.tf = 0xE4u; m.c[0] = m.c[1] = m.c[2] = m.c[3] = 0; m.has_abs = 0; m.abs = 0;
+        {
+            uint32_t st[4] = {0, 1, 2, 3};
+            uint32_t nf = nf0;
+            uint64_t next_fblk = nf < nfiles ? __ldg(fblk + nf) : ~0ull;
+            for (uint64_t b = b_lo; b < b_hi; ++b) {
+                while (b == next_fblk) {
+                    st[0] = st[1] = st[2] = st[3] = FS_SKIP;
+                    const uint64_t gp = __ldg(gpos0 + nf);
+                    if (gp != ~0ull) { m.has_abs = 1; m.abs = gp; m.c[0] = m.c[1] = m.c[2] = m.c[3] = 0; }
+                    ++nf;
+                    next_fblk = nf < nfiles ? __ldg(fblk + nf) : ~0ull;
+                }
+                const FaSum sm = __ldg(sums + b);
+#pragma unroll
+                for (int s = 0; s < 4; ++s) { m.c[s] += fa_cnt(sm, st[s]); st[s] = fa_tf(sm, st[s]); }
+            }
+            m.tf = st[0] | (st[1] << 2) | (st[2] << 4) | (st[3] << 6);
+        }
+        // ---- inclusive scan over the lanes, then this lane's incoming (state, position)
+        FaChainMap inc = m;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const FaChainMap o = fa_chain_shfl_up(inc, d);
+            if (lane >= (uint32_t)d) inc = fa_chain_compose(o, inc);
+        }
+        FaChainMap exc = fa_chain_shfl_up(inc, 1);
+        if (lane == 0) { exc.tf = 0xE4u; exc.c[0] = exc.c[1] = exc.c[2] = exc.c[3] = 0; exc.has_abs = 0; exc.abs = 0; }
+        uint32_t my_state = (exc.tf >> (2 * state)) & 3u;
+        uint64_t my_pos = (exc.has_abs ? exc.abs : pos) + exc.c[state];
+        // ---- pass 2: walk the blocks with the real state
+        {
+            uint32_t nf = nf0;
+            uint32_t g = nf0 ? __ldg(fgenome + nf0 - 1) : 0u;
+            uint64_t next_fblk = nf < nfiles ? __ldg(fblk + nf) : ~0ull;
+            for (uint64_t b = b_lo; b < b_hi; ++b) {
+                while (b == next_fblk) {
+                    my_state = FS_SKIP;
+                    const uint64_t gp = __ldg(gpos0 + nf);
+                    if (gp != ~0ull) { atomicMax(reinterpret_cast<unsigned long long *>(genome_end + g), (unsigned long long)my_pos); my_pos = gp; g = __ldg(fgenome + nf); }
+                    ++nf;
+                    next_fblk = nf < nfiles ? __ldg(fblk + nf) : ~0ull;
+                }
+                in_state[b] = (uint8_t)my_state;
+                in_pos[b] = my_pos;
+                const FaSum sm = __ldg(sums + b);
+                my_pos += fa_cnt(sm, my_state);
+                my_state = fa_tf(sm, my_state);
+            }
+            // the genome current at the end of this lane's run has reached my_pos (positions only grow inside a genome: max)
+            if (b_hi > b_lo) atomicMax(reinterpret_cast<unsigned long long *>(genome_end + g), (unsigned long long)my_pos);
+        }
+        // tile carry = state / position after the last lane
+        state = __shfl_sync(0xFFFFFFFFu, my_state, 31);
+        pos = __shfl_sync(0xFFFFFFFFu, my_pos, 31);
     }
-    if (threadIdx.x == 0) {
-        genome_end[g] = pos;
-        carry[0] = state; carry[1] = pos; carry[2] = nf; carry[3] = g;
-    }
+    if (lane == 0) { carry[0] = state; carry[1] = pos; }
 }
 
 // Work items were laid out over each genome's WINDOW (an upper bound: the raw size of its files); cut them back to the
