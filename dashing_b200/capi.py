@@ -35,6 +35,7 @@ class DistParams(C.Structure):
 
 
 u8p, u64p, f32p, f64p, vp = C.POINTER(C.c_uint8), C.POINTER(C.c_uint64), C.POINTER(C.c_float), C.POINTER(C.c_double), C.c_void_p
+ROWS_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint64, C.c_uint64, f32p, C.c_uint64)
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(f"{LIB_PATH} is not built — run `python -c 'import __graft_entry__ as g; g.build()'` "
@@ -63,6 +64,7 @@ _SIGS = {
     "db200_compress": (C.c_int, [C.c_int, u8p, C.c_uint64, C.c_int, C.c_int, u8p]),
     "db200_dist_symmetric": (C.c_int, [C.c_int, u8p, C.c_uint64, C.POINTER(DistParams), f32p]),
     "db200_dist_symmetric_rows": (C.c_int, [C.c_int, u8p, C.c_uint64, C.POINTER(DistParams), C.c_uint64, C.c_uint64, f32p]),
+    "db200_dist_symmetric_stream": (C.c_int, [C.c_int, u8p, C.c_uint64, C.POINTER(DistParams), C.c_uint64, C.c_uint64, C.c_uint64, ROWS_CB, vp]),
     "db200_dist_rect": (C.c_int, [C.c_int, u8p, C.c_uint64, u8p, C.c_uint64, C.POINTER(DistParams), f32p]),
     "db200_dist_use_cardinalities": (C.c_int, [f64p, C.c_uint64]),
     "db200_dist_plan_create": (C.c_int, [C.c_int, C.POINTER(vp)]),
@@ -279,6 +281,30 @@ def dist_symmetric(regs, p, k=31, estim=ERTL_MLE, jestim=ERTL_MLE, result_type=J
     prm = dist_params(p, k, estim, jestim, result_type, order)
     _check(lib.db200_dist_symmetric_rows(device, regs.ctypes.data_as(u8p), n, C.byref(prm), row_begin, re_, out.ctypes.data_as(f32p)))
     return out
+
+
+def dist_symmetric_stream(regs, p, on_rows, k=31, estim=ERTL_MLE, jestim=ERTL_MLE, result_type=JI, order=ORDER_ROW_FIRST, device=0,
+                          row_begin=0, row_end=None, block_pairs=0):
+    """Row-block streaming: on_rows(row_begin, row_end, values float32[]) per block (values are copied for the caller);
+    a non-zero / raising callback aborts the call."""
+    regs = _np(regs, np.uint8).reshape(-1, 1 << p)
+    n = regs.shape[0]
+    err = []
+
+    def tramp(_ud, rb, re_, vals, nv):
+        try:
+            r = on_rows(int(rb), int(re_), np.ctypeslib.as_array(vals, shape=(int(nv),)).copy() if nv else np.zeros(0, np.float32))
+            return int(r or 0)
+        except BaseException as e:   # noqa: BLE001 - must not propagate through the C frame
+            err.append(e)
+            return 1
+    cb = ROWS_CB(tramp)
+    prm = dist_params(p, k, estim, jestim, result_type, order)
+    rc = lib.db200_dist_symmetric_stream(device, regs.ctypes.data_as(u8p), n, C.byref(prm), row_begin, n if row_end is None else row_end,
+                                         block_pairs, cb, None)
+    if err:
+        raise err[0]
+    _check(rc)
 
 
 def dist_rect(refs, qrys, p, k=31, estim=ERTL_MLE, jestim=ERTL_MLE, result_type=JI, device=0) -> np.ndarray:

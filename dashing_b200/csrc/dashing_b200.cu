@@ -732,6 +732,10 @@ struct HostCtx {
     cudaStream_t stream = nullptr, cstream = nullptr;
     cudaEvent_t blk_done[db200_dist_plan::NSLOT] = {nullptr, nullptr, nullptr, nullptr};
     DevBuf regs, out, cards, nbrs;
+    static constexpr int NSTREAM = 3;          // row-block streaming: blocks in flight (kernel / copy / callback)
+    char *stream_host[NSTREAM] = {nullptr, nullptr, nullptr};
+    size_t stream_cap = 0;
+    cudaEvent_t stream_copied[NSTREAM] = {nullptr, nullptr, nullptr};
     DevBuf fa_text, fa_sums, fa_state, fa_pos, fa_tab, fa_gend, fa_carry, fa_flags;   // device-side FASTA parsing (fasta.cuh)
     Uploader up;
     std::unique_ptr<db200_dist_plan> plan;
@@ -1248,6 +1252,85 @@ static int rect_impl(int device, const uint8_t *ref_regs, uint64_t nr, const uin
 
 } // extern "C"
 
+// Row-block streaming form of the symmetric all-pairs call: the packed triangle never exists in full on either side.  Blocks of
+// whole rows (about `block_pairs` values each) go kernel -> device buffer -> page-locked host buffer -> callback, three blocks
+// in flight, so the host's writer runs while the next blocks are being computed and copied.
+static int symmetric_stream_impl(int device, const uint8_t *regs, uint64_t n, const db200_dist_params *prm, uint64_t row_begin, uint64_t row_end,
+                                 uint64_t block_pairs, db200_rows_cb cb, void *ud, const double *card) {
+    if (!prm || !cb || (!regs && n)) { set_error("db200_dist_symmetric_stream: null argument"); return DB200_EINVAL; }
+    if (row_end > n) row_end = n;
+    if (row_begin > row_end) { set_error("row_begin > row_end"); return DB200_EINVAL; }
+    auto tri = [n](uint64_t r) { return (r * (2 * n - r - 1)) / 2; };
+    if (device == DB200_ALL_DEVICES) {
+        const uint64_t npairs = tri(row_end) - tri(row_begin);
+        const int nd = (int)std::min<uint64_t>((uint64_t)std::max(logical_device_count(), 1), std::max<uint64_t>(npairs >> 16, 1));
+        if (nd > 1) {
+            const uint64_t r0 = row_begin;
+            const std::vector<uint64_t> cut = split_by_weight(row_end - r0, nd, [&](uint64_t i) { return tri(r0 + i) - tri(r0); });
+            return for_each_device(nd, [&](int d) {
+                return symmetric_stream_impl(d, regs, n, prm, r0 + cut[d], r0 + cut[d + 1], block_pairs, cb, ud, card);
+            });
+        }
+        device = 0;
+    }
+    DB200_TRY(check_device(device));
+    if (n < 2 || row_begin == row_end) return DB200_OK;
+    if (prm->p < 7 || prm->p > 20) { set_error("dist: p=%d outside the GPU path's range [7,20]", prm->p); return DB200_EUNSUPPORTED; }
+    HostCtx &hc = host_ctx(device);
+    std::lock_guard<std::mutex> lk(hc.mu);
+    DB200_TRY(hc.init(device));
+    const uint64_t m = 1ull << prm->p;
+    if (block_pairs == 0) block_pairs = uint64_t(8) << 20;
+    block_pairs = std::max<uint64_t>(block_pairs, n);                  // at least one whole row
+    constexpr int NS = HostCtx::NSTREAM;
+    // a block may overshoot the target by one row
+    const uint64_t slot_vals = block_pairs + n;
+    if (hc.stream_cap < slot_vals * 4) {
+        for (int i = 0; i < NS; ++i) {
+            if (hc.stream_host[i]) { cudaFreeHost(hc.stream_host[i]); hc.stream_host[i] = nullptr; }
+            DB200_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&hc.stream_host[i]), slot_vals * 4, cudaHostAllocDefault));
+            if (!hc.stream_copied[i]) DB200_CUDA(cudaEventCreateWithFlags(&hc.stream_copied[i], cudaEventDisableTiming));
+        }
+        hc.stream_cap = slot_vals * 4;
+    }
+    DB200_TRY(hc.regs.reserve(n * m));
+    DB200_TRY(hc.out.reserve(slot_vals * 4 * NS));
+    DB200_TRY(hc.up.stager.upload(hc.regs.ptr, reinterpret_cast<const char *>(regs), n * m, hc.stream));
+    DB200_TRY(plan_prepare(hc.plan.get(), hc.regs.as<uint8_t>(), n, n, 0, 0, prm->p, prm->estim, hc.stream));
+    DB200_TRY(plan_override_cards(hc.plan.get(), card, n, nullptr, 0, hc.stream));
+    struct Blk { uint64_t rb, re, cnt; };
+    Blk ring[NS];
+    uint64_t issued = 0, delivered = 0;
+    auto deliver = [&]() -> int {
+        const Blk &b = ring[delivered % NS];
+        DB200_CUDA(cudaEventSynchronize(hc.stream_copied[delivered % NS]));
+        const int rc = cb(ud, b.rb, b.re, reinterpret_cast<const float *>(hc.stream_host[delivered % NS]), b.cnt);
+        ++delivered;
+        if (rc != 0) { set_error("db200_dist_symmetric_stream: the callback returned %d for rows [%llu,%llu)", rc, (unsigned long long)b.rb, (unsigned long long)b.re); return DB200_EINVAL; }
+        return DB200_OK;
+    };
+    for (uint64_t rb = row_begin; rb < row_end;) {
+        uint64_t re = rb + 1;
+        while (re < row_end && tri(re) - tri(rb) < block_pairs) ++re;
+        const uint64_t cnt = tri(re) - tri(rb);
+        if (issued - delivered == NS) DB200_TRY(deliver());            // the slot about to be reused must have been handed over
+        const int sl = (int)(issued % NS);
+        float *d_out = hc.out.as<float>() + (uint64_t)sl * slot_vals;
+        DB200_TRY(plan_run(hc.plan.get(), prm, 0, rb, re, 0, 0, d_out, hc.stream, (int)(issued % db200_dist_plan::NSLOT)));
+        DB200_CUDA(cudaEventRecord(hc.blk_done[issued % db200_dist_plan::NSLOT], hc.stream));
+        DB200_CUDA(cudaStreamWaitEvent(hc.cstream, hc.blk_done[issued % db200_dist_plan::NSLOT], 0));
+        if (cnt) DB200_CUDA(cudaMemcpyAsync(hc.stream_host[sl], d_out, cnt * 4, cudaMemcpyDeviceToHost, hc.cstream));
+        DB200_CUDA(cudaEventRecord(hc.stream_copied[sl], hc.cstream));
+        ring[sl] = Blk{rb, re, cnt};
+        ++issued;
+        rb = re;
+    }
+    while (delivered < issued) DB200_TRY(deliver());
+    DB200_CUDA(cudaStreamSynchronize(hc.stream));
+    DB200_CUDA(cudaStreamSynchronize(hc.cstream));
+    return DB200_OK;
+}
+
 // ---- public all-pairs entry points: they consume the calling thread's pending cardinality override ----------------------
 namespace db200 {
 struct CardOverride { const double *ptr = nullptr; uint64_t n = 0; };
@@ -1270,6 +1353,12 @@ int db200_dist_symmetric_rows(int device, const uint8_t *regs, uint64_t n, const
 }
 int db200_dist_symmetric(int device, const uint8_t *regs, uint64_t n, const db200_dist_params *prm, float *out) {
     return db200_dist_symmetric_rows(device, regs, n, prm, 0, n, out);
+}
+int db200_dist_symmetric_stream(int device, const uint8_t *regs, uint64_t n, const db200_dist_params *prm, uint64_t row_begin, uint64_t row_end,
+                                uint64_t block_pairs, db200_rows_cb cb, void *user) {
+    const CardOverride c = take_cards();
+    if (c.ptr && c.n != n) { set_error("cardinality override holds %llu values for %llu sketches", (unsigned long long)c.n, (unsigned long long)n); return DB200_EINVAL; }
+    return symmetric_stream_impl(device, regs, n, prm, row_begin, row_end, block_pairs, cb, user, c.ptr);
 }
 int db200_dist_rect(int device, const uint8_t *ref_regs, uint64_t nr, const uint8_t *qry_regs, uint64_t nq, const db200_dist_params *prm,
                     float *out) {

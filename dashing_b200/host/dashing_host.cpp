@@ -12,6 +12,7 @@
 #include <memory>
 #include <getopt.h>
 #include <sys/stat.h>
+#include <unistd.h>
 #include <zlib.h>
 #ifdef _OPENMP
 #include <omp.h>
@@ -710,28 +711,79 @@ void compare_and_emit(const DistOptions &o, const std::vector<std::string> &inpa
         if (rt == DB200_CONTAINMENT_INDEX || rt == DB200_CONTAINMENT_DIST || rt == DB200_FULL_CONTAINMENT_DIST)
             throw Error("Can't perform symmetric distance comparisons with a symmetric method. Provide the same list of filenames to both -Q and -F.");
         const size_t np = n * (n - 1) / 2;
-        std::vector<float> out(std::max<size_t>(np, 1)), lower;
         // operand order: TSV / PHYLIP rows come from perform_core_op (cmp(s[j], s[i])), binary and the upper half of FULL_TSV
         // from cmp(s[i], s[j]); only the joint MLE can tell the difference
         prm.order = (o.emit_fmt == UT_TSV || o.emit_fmt == UPPER_TRIANGULAR) ? DB200_ORDER_COL_FIRST : DB200_ORDER_ROW_FIRST;
-        if (n >= 2) { use_cards(); check(db200_dist_symmetric(o.device, regs.data(), n, &prm, out.data())); }
-        if (o.emit_fmt == BINARY) {
-            write_binary_matrix(pfp, out.data(), n);
-            if (!o.dist_path.empty()) {                                      // src/distmain.cpp:191-200
-                std::FILE *lf = std::fopen((o.dist_path + ".labels").c_str(), "wb");
-                if (!lf) throw Error("Could not open file at '" + o.dist_path + ".labels' for writing");
-                for (auto &p : inpaths) { std::fwrite(p.data(), p.size(), 1, lf); std::fputc('\n', lf); }
-                std::fclose(lf);
+        auto write_labels = [&] {
+            if (o.dist_path.empty()) return;                                 // src/distmain.cpp:191-200
+            std::FILE *lf = std::fopen((o.dist_path + ".labels").c_str(), "wb");
+            if (!lf) throw Error("Could not open file at '" + o.dist_path + ".labels' for writing");
+            for (auto &p : inpaths) { std::fwrite(p.data(), p.size(), 1, lf); std::fputc('\n', lf); }
+            std::fclose(lf);
+        };
+        // Streaming forms (db200_dist_symmetric_stream): row blocks are written as they arrive, so the n(n-1)/2 floats are never
+        // held in memory — the binary matrix into a regular file at its distmat offset (any number of devices), the
+        // triangular text formats in row order (one device).
+        const bool one_device = o.device != DB200_ALL_DEVICES || db200_device_count() < 2;
+        struct StreamCtx {
+            const std::vector<std::string> *names; size_t n; EmissionFormat fmt; std::FILE *fp; int fd; int nthreads; std::string err;
+        } sc{&inpaths, n, o.emit_fmt, pfp, -1, std::max(1, o.nthreads), {}};
+        if (o.emit_fmt == BINARY && !o.dist_path.empty() && n >= 2) {
+            const uint64_t n64 = n;
+            std::fputc('\0', pfp);                                           // distmat magic for float + u64 n (distmat.h:188-208)
+            if (std::fwrite(&n64, sizeof n64, 1, pfp) != 1) throw Error("Failure");
+            std::fflush(pfp);
+            sc.fd = fileno(pfp);
+            if (::ftruncate(sc.fd, (off_t)(9 + np * sizeof(float))) != 0) throw Error("Error writing to binary file");
+            use_cards();
+            const int rc = db200_dist_symmetric_stream(o.device, regs.data(), n, &prm, 0, n, 0,
+                [](void *ud, uint64_t rb, uint64_t, const float *vals, uint64_t nv) -> int {
+                    StreamCtx *c = static_cast<StreamCtx *>(ud);
+                    const uint64_t nn = c->n, off = 9 + 4 * ((rb * (2 * nn - rb - 1)) / 2);
+                    const char *src = reinterpret_cast<const char *>(vals);
+                    for (uint64_t done = 0; done < nv * 4;) {
+                        const ssize_t w = ::pwrite(c->fd, src + done, nv * 4 - done, (off_t)(off + done));
+                        if (w <= 0) return 1;
+                        done += (uint64_t)w;
+                    }
+                    return 0;
+                }, &sc);
+            if (rc != DB200_OK) throw Error(std::string("Error writing to binary file: ") + db200_last_error());
+            write_labels();
+        } else if ((o.emit_fmt == UT_TSV || o.emit_fmt == UPPER_TRIANGULAR) && one_device && n >= 2) {
+            {
+                const std::string h = o.emit_fmt == UT_TSV ? format_ut_tsv_header(inpaths) : std::to_string(n) + "\n";   // :388-397
+                std::fwrite(h.data(), 1, h.size(), pfp);
             }
+            use_cards();
+            const int rc = db200_dist_symmetric_stream(o.device, regs.data(), n, &prm, 0, n, 0,
+                [](void *ud, uint64_t rb, uint64_t re, const float *vals, uint64_t) -> int {
+                    StreamCtx *c = static_cast<StreamCtx *>(ud);
+                    const uint64_t nn = c->n;
+                    auto tri = [nn](uint64_t r) { return (r * (2 * nn - r - 1)) / 2; };
+                    std::vector<std::string> rows(re - rb);
+#pragma omp parallel for schedule(dynamic, 4) num_threads(c->nthreads)
+                    for (uint64_t i = rb; i < re; ++i) append_ut_row(rows[i - rb], (*c->names)[i], vals + (tri(i) - tri(rb)), nn, i, c->fmt);
+                    for (auto &r : rows) if (std::fwrite(r.data(), 1, r.size(), c->fp) != r.size()) return 1;
+                    return 0;
+                }, &sc);
+            if (rc != DB200_OK) throw Error(std::string("Error writing distances: ") + db200_last_error());
         } else {
-            if (o.emit_fmt == FULL_TSV && joint && n >= 2) {
-                lower.resize(np);
-                prm.order = DB200_ORDER_COL_FIRST;
-                use_cards();
-                check(db200_dist_symmetric(o.device, regs.data(), n, &prm, lower.data()));
+            std::vector<float> out(std::max<size_t>(np, 1)), lower;
+            if (n >= 2) { use_cards(); check(db200_dist_symmetric(o.device, regs.data(), n, &prm, out.data())); }
+            if (o.emit_fmt == BINARY) {
+                write_binary_matrix(pfp, out.data(), n);
+                write_labels();
+            } else {
+                if (o.emit_fmt == FULL_TSV && joint && n >= 2) {
+                    lower.resize(np);
+                    prm.order = DB200_ORDER_COL_FIRST;
+                    use_cards();
+                    check(db200_dist_symmetric(o.device, regs.data(), n, &prm, lower.data()));
+                }
+                const std::string s = format_symmetric(inpaths, out.data(), o.emit_fmt, lower.empty() ? nullptr : lower.data());
+                std::fwrite(s.data(), 1, s.size(), pfp);
             }
-            const std::string s = format_symmetric(inpaths, out.data(), o.emit_fmt, lower.empty() ? nullptr : lower.data());
-            std::fwrite(s.data(), 1, s.size(), pfp);
         }
     }
     if (pfp != stdout) std::fclose(pfp); else std::fflush(pfp);

@@ -178,6 +178,18 @@ DB200_API int db200_dist_symmetric_rows(int device, const uint8_t *regs, uint64_
 DB200_API int db200_dist_rect(int device, const uint8_t *ref_regs, uint64_t nr, const uint8_t *qry_regs, uint64_t nq,
                     const db200_dist_params *prm, float *out);
 
+/* Row-block streaming form ("optional row-block callback lets the host keep its async TSV / PHYLIP / binary
+ * writers unchanged").  Rows [row_begin, row_end) of the symmetric matrix are computed in blocks of whole rows holding about
+ * `block_pairs` values (0 = 8 Mi) and handed to `cb` in ascending row order: values[0 .. nvalues) are rows [rb, re) in distmat
+ * order (row i contributes its n-1-i pairs), valid only during the call.  The kernel and the device->host copy of the next
+ * blocks run while the callback works, and no buffer of n(n-1)/2 floats exists on either side (100,000 sketches: 20 GB).
+ * A non-zero return from the callback aborts the call.  With DB200_ALL_DEVICES every device streams a contiguous row range
+ * from its own host thread: the callback is then entered concurrently (in row order per device, not globally) and must be
+ * thread-safe — e.g. pwrite() into the distmat file at offset 9 + 4 * idx(rb, rb + 1). */
+typedef int (*db200_rows_cb)(void *user, uint64_t row_begin, uint64_t row_end, const float *values, uint64_t nvalues);
+DB200_API int db200_dist_symmetric_stream(int device, const uint8_t *regs, uint64_t n, const db200_dist_params *prm,
+                                          uint64_t row_begin, uint64_t row_end, uint64_t block_pairs, db200_rows_cb cb, void *user);
+
 /* Cached cardinalities.  The reference's hll_t carries a cached estimate (value_): a sketch loaded from a file keeps what
  * hll_t::read() computed under the FILE's estimation method (csum(), hll.h:1078) — or the value stored in the file — and the
  * pair loop uses that for the per-sketch terms (creport(), hll.h:780-783) even when the command line names another estimator.
