@@ -140,3 +140,30 @@ def test_cli_multi_member_gzip_takes_the_reread_path(gpu, cli, tmp_path):
     assert got[28:] == cli["hll_a.fa"].tobytes()[28:]
     for n in ("b.fa", "d.fa"):
         assert gzip.open(tmp_path / str(cli["hllname_" + n]), "rb").read() == cli["hll_" + n].tobytes()
+
+
+def test_cli_device_all(gpu, cli, tmp_path):
+    """--device all: sketching, sizes and the streamed binary / text matrices sharded over every (logical) device give the files
+    the single-device run gives (on a one-GPU box DB200_VIRTUAL_DEVICES makes three logical devices out of it)."""
+    names = hostlib.materialise_inputs(cli, str(tmp_path))
+    env = dict(os.environ)
+    if gpu.device_count() < 2:
+        env["DB200_VIRTUAL_DEVICES"] = "3"
+    for run, flags in (("bin_mash", ["-b", "-M"]), ("tsv_ji", [])):
+        r = subprocess.run([hostlib.CLI, "dist", "-k31", "-S10", "-p2", "--avoid-sorting", "--device", "all", "-o", "sizes.txt", "-O", "dist.out", *flags, *names],
+                           cwd=tmp_path, capture_output=True, text=True, timeout=300, env=env)
+        assert r.returncode == 0, r.stderr
+        assert (tmp_path / "sizes.txt").read_bytes() == cli[run + "_sizes"].tobytes()
+        got, want = (tmp_path / "dist.out").read_bytes(), cli[run + "_dist"].tobytes()
+        if run == "bin_mash":
+            assert got[:9] == want[:9] and len(got) == len(want)
+            assert_close(np.frombuffer(got[9:], np.float32), np.frombuffer(want[9:], np.float32), what=run)
+            assert (tmp_path / "dist.out.labels").read_bytes() == cli[run + "_labels"].tobytes()
+        else:
+            hostlib.assert_text_matches(got, want, what=run)
+    os.makedirs(tmp_path / "sk")
+    r = subprocess.run([hostlib.CLI, "sketch", "-k31", "-S10", "-p2", "-P", "sk", "--avoid-sorting", "--device", "all", *names],
+                       cwd=tmp_path, capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0, r.stderr
+    for n in names:
+        assert gzip.open(tmp_path / str(cli["hllname_" + n]), "rb").read() == cli["hll_" + n].tobytes()
