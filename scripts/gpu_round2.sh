@@ -1,12 +1,30 @@
 #!/bin/bash
+# Round-end GPU pass: tests, smoke, bench (+ reference arm), ncu launch list, full captures of the kernels added this round,
+# compute-sanitizer on the new paths.  Outputs under gpurun_out/.
 set -u
 mkdir -p gpurun_out
-echo "=== cgroup / cpu"; cat /sys/fs/cgroup/cpu.max 2>/dev/null; nproc; python -c "import os; print('affinity', len(os.sched_getaffinity(0)))"; lscpu | grep -E "Socket|Core|Thread|NUMA node\(s\)"
+echo "=== nvidia-smi"; nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit --format=csv
 echo "=== pytest -m gpu"
-timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -15
-echo "=== ncu full: dist_kernel"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:^dist_kernel -s 1 -c 1 -f -o gpurun_out/prof_dist2 \
-    python bench.py --workload dist --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_dist2.log 2>&1
-tail -2 gpurun_out/ncu_dist2.log | cut -c1-200
-echo "=== omp threads test"
-for t in 16 32 64 128; do OMP_NUM_THREADS=$t timeout 300 python bench.py --impl reference --steps 1 --warmup 0 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print($t, d['value'], d['cpu_baseline']['sample'][:60])"; done
+timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -6
+echo "=== smoke"
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
+echo "=== bench"
+timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -4 gpurun_out/bench.err; cut -c1-400 gpurun_out/bench.json
+echo "=== bench reference"
+timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2>> gpurun_out/bench.err; cat gpurun_out/bench_ref.json
+echo "=== ncu launch list"
+KREGEX='regex:dist_kernel|dist_jmle_kernel|sketch_kernel|planes_kernel|card_kernel|range_kernel|pack_kernel|mark_starts_kernel|cardinality_kernel|fa_|union_kernel|compress_kernel|knn_'
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KREGEX" -c 1200 --csv --log-file gpurun_out/launches.csv \
+    python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
+tail -2 gpurun_out/ncu_bench.log | cut -c1-200; wc -l gpurun_out/launches.csv
+echo "=== ncu full: fasta kernels + union"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:fa_emit_kernel -s 3 -c 1 -f -o gpurun_out/prof_fa_emit python scripts/setops_run.py fasta > gpurun_out/ncu_fa.log 2>&1; tail -1 gpurun_out/ncu_fa.log | cut -c1-200
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:fa_summary_kernel -s 3 -c 1 -f -o gpurun_out/prof_fa_summary python scripts/setops_run.py fasta > gpurun_out/ncu_fa2.log 2>&1; tail -1 gpurun_out/ncu_fa2.log | cut -c1-200
+N=8000 timeout 600 ncu --set full --clock-control none --import-source on -k regex:union_kernel -s 1 -c 1 -f -o gpurun_out/prof_union python scripts/setops_run.py union > gpurun_out/ncu_union.log 2>&1; tail -2 gpurun_out/ncu_union.log | cut -c1-200
+echo "=== setops / fasta timings"
+N=8000 timeout 300 python scripts/setops_run.py all 2>&1 | tail -4
+echo "=== compute-sanitizer memcheck (small cases)"
+NG=2 N=128 timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python scripts/setops_run.py all > gpurun_out/sanitizer_memcheck.log 2>&1; echo "rc=$?"; tail -4 gpurun_out/sanitizer_memcheck.log
+echo "=== compute-sanitizer racecheck (fasta)"
+NG=1 timeout 900 compute-sanitizer --tool racecheck --error-exitcode 9 python scripts/setops_run.py fasta > gpurun_out/sanitizer_racecheck.log 2>&1; echo "rc=$?"; tail -4 gpurun_out/sanitizer_racecheck.log
+ls -la gpurun_out
