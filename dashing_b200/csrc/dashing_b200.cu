@@ -985,7 +985,7 @@ int db200_union(int device, const uint8_t *regs, uint64_t n, int p, uint8_t *out
     const uint32_t m16 = (uint32_t)(m / 16), gx = (m16 + 255) / 256;
     for (uint64_t s0 = 0; s0 < n; s0 += slab) {
         const uint64_t cnt = std::min(slab, n - s0);
-        DB200_CUDA(cudaMemcpyAsync(hc.regs.ptr, regs + (s0 << p), cnt << p, cudaMemcpyHostToDevice, hc.stream));
+        DB200_TRY(hc.up.stager.upload(hc.regs.ptr, reinterpret_cast<const char *>(regs) + (s0 << p), cnt << p, hc.stream));
         const uint64_t want_y = std::max<uint64_t>(1, (uint64_t)g_num_sms(device) * 8 / gx);
         const uint64_t rows_per = std::max<uint64_t>(4, (cnt + want_y - 1) / want_y);
         const unsigned gy = (unsigned)((cnt + rows_per - 1) / rows_per);

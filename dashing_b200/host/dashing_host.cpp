@@ -813,6 +813,37 @@ static bool apply_cached(int device, int p, int estim, const std::vector<uint8_t
     return any;
 }
 
+// Phase A of dist_sketch_and_cmp / size_sketch_and_emit (src/sketch_and_cmp.h:314-360, :155-183): sketches that exist as files
+// (--presketched, or -W with the file present) are read — in parallel, as the reference's OpenMP loop does — and the rest are
+// listed in `todo` for sketch_paths.
+static void load_existing(const DistOptions &o, const std::vector<std::string> &inpaths, std::vector<uint8_t> &regs, std::vector<Cached> &info,
+                          std::vector<std::string> &fnames, std::vector<size_t> &todo) {
+    const size_t n = inpaths.size(), m = size_t(1) << o.p;
+    std::vector<char> need(n, 0);
+    std::string err;
+#pragma omp parallel for schedule(dynamic, 16) num_threads(std::max(1, o.nthreads))
+    for (size_t i = 0; i < n; ++i) {
+        try {
+            std::string from;
+            if (o.presketched) from = inpaths[i];
+            else {
+                fnames[i] = make_fname(inpaths[i].c_str(), o.p, o.k, o.k, o.k, "", o.suffix, o.prefix);
+                if (o.cache_sketches && isfile(fnames[i])) from = fnames[i];
+            }
+            if (from.empty()) { need[i] = 1; continue; }
+            const HllFile h = read_hll(from);
+            if (h.p != (uint32_t)o.p) throw Error("sketch " + from + " has p=" + std::to_string(h.p) + ", expected " + std::to_string(o.p));
+            info[i] = cached_of(h);
+            std::memcpy(&regs[i * m], h.core.data(), m);
+        } catch (const std::exception &e) {
+#pragma omp critical
+            err = e.what();
+        }
+    }
+    if (!err.empty()) throw Error(err);
+    for (size_t i = 0; i < n; ++i) if (need[i]) todo.push_back(i);
+}
+
 void dist_sketch_and_cmp(const DistOptions &o_in, std::vector<std::string> inpaths, size_t nq) {
     DistOptions o = o_in;
     if (o.defer_hll) o.estim = o.jestim = DB200_ERTL_MLE;   // hllbase_t(p) inside make_hll(): ERTL_MLE for both (hll.h:765)
@@ -823,22 +854,7 @@ void dist_sketch_and_cmp(const DistOptions &o_in, std::vector<std::string> inpat
     std::vector<size_t> todo;
     std::vector<std::string> fnames(n);
     std::vector<Cached> info(n);
-    for (size_t i = 0; i < n; ++i) {
-        if (o.presketched) {
-            HllFile h = read_hll(inpaths[i]);
-            if (h.p != (uint32_t)o.p) throw Error("sketch " + inpaths[i] + " has p=" + std::to_string(h.p) + ", expected " + std::to_string(o.p));
-            info[i] = cached_of(h);
-            std::memcpy(&regs[i * m], h.core.data(), m);
-            continue;
-        }
-        fnames[i] = make_fname(inpaths[i].c_str(), o.p, o.k, o.k, o.k, "", o.suffix, o.prefix);
-        if (o.cache_sketches && isfile(fnames[i])) {
-            HllFile h = read_hll(fnames[i]);
-            if (h.p != (uint32_t)o.p) throw Error("cached sketch " + fnames[i] + " has the wrong size");
-            info[i] = cached_of(h);
-            std::memcpy(&regs[i * m], h.core.data(), m);
-        } else todo.push_back(i);
-    }
+    load_existing(o, inpaths, regs, info, fnames, todo);
     sketch_paths(o, inpaths, todo, [&](size_t i, const uint8_t *r) {
         std::memcpy(&regs[i * m], r, m);
         // sketches carry the command line's estimators (set_estim_and_jestim, src/sketch_and_cmp.h:285-288)
@@ -1259,22 +1275,7 @@ int card_main(int argc, char **argv) {
     std::vector<size_t> todo;
     std::vector<std::string> fnames(n);
     std::vector<Cached> info(n);
-    for (size_t i = 0; i < n; ++i) {
-        if (o.presketched) {
-            const HllFile h = read_hll(inpaths[i]);
-            if (h.p != (uint32_t)o.p) throw Error("sketch " + inpaths[i] + " has p=" + std::to_string(h.p) + ", expected " + std::to_string(o.p));
-            info[i] = cached_of(h);
-            std::memcpy(&regs[i * m], h.core.data(), m);
-            continue;
-        }
-        fnames[i] = make_fname(inpaths[i].c_str(), o.p, o.k, o.k, o.k, "", o.suffix, o.prefix);
-        if (o.cache_sketches && isfile(fnames[i])) {
-            const HllFile h = read_hll(fnames[i]);
-            if (h.p != (uint32_t)o.p) throw Error("cached sketch " + fnames[i] + " has the wrong size");
-            info[i] = cached_of(h);
-            std::memcpy(&regs[i * m], h.core.data(), m);
-        } else todo.push_back(i);
-    }
+    load_existing(o, inpaths, regs, info, fnames, todo);
     sketch_paths(o, inpaths, todo, [&](size_t i, const uint8_t *r) {
         std::memcpy(&regs[i * m], r, m);
         if (o.cache_sketches && !o.defer_hll) write_hll(fnames[i], r, o.p, o.estim, o.jestim, -1.);
