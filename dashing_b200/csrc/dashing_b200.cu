@@ -736,7 +736,7 @@ struct HostCtx {
     char *stream_host[NSTREAM] = {nullptr, nullptr, nullptr};
     size_t stream_cap = 0;
     cudaEvent_t stream_copied[NSTREAM] = {nullptr, nullptr, nullptr};
-    DevBuf fa_text, fa_sums, fa_state, fa_pos, fa_tab, fa_gend, fa_carry, fa_flags;   // device-side FASTA parsing (fasta.cuh)
+    DevBuf fa_text, fa_sums, fa_wsum, fa_state, fa_pos, fa_tab, fa_gend, fa_carry, fa_flags;   // device-side FASTA parsing (fasta.cuh)
     Uploader up;
     std::unique_ptr<db200_dist_plan> plan;
     std::unique_ptr<db200_packed_genomes> store;   // reused by db200_sketch_batch
@@ -1431,6 +1431,7 @@ static int sketch_fasta_one(int device, int p, int k, int canon, const char *tex
     DB200_CUDA(cudaMemsetAsync(hc.regs.ptr, 0, std::max<uint64_t>(bytes, 16), stream));
     DB200_TRY(hc.fa_text.reserve(std::max<uint64_t>(nblk_text, 1) * B + 64));
     DB200_TRY(hc.fa_sums.reserve(std::max<uint64_t>(nblk_text, 1) * 8));
+    DB200_TRY(hc.fa_wsum.reserve(((64ull << 20) / B) * (FA_THREADS / 32) * 8));      // per-warp maps of the chunk in flight
     DB200_TRY(hc.fa_state.reserve(std::max<uint64_t>(nblk_text, 1)));
     DB200_TRY(hc.fa_pos.reserve(std::max<uint64_t>(nblk_text, 1) * 8));
     DB200_TRY(hc.fa_gend.reserve((ngenomes + 1) * 8));
@@ -1493,7 +1494,7 @@ static int sketch_fasta_one(int device, int p, int k, int canon, const char *tex
     uint64_t CH = 64ull << 20;                   // a multiple of FA_BLOCK
     if (const char *cenv = std::getenv("DB200_FASTA_CHUNK")) {   // testing knob: chunk boundaries every few blocks
         const uint64_t v = std::strtoull(cenv, nullptr, 10) / B * B;
-        if (v) CH = v;
+        if (v) CH = std::min(v, CH);
     }
     const uint64_t nchunks = (text_end + CH - 1) / CH;
     DB200_CUDA(cudaEventRecord(up.packed[0], stream));
@@ -1508,13 +1509,13 @@ static int sketch_fasta_one(int device, int p, int k, int canon, const char *tex
         DB200_CUDA(cudaStreamWaitEvent(stream, up.copied[b], 0));
         const uint64_t blk0 = off / B, nb = (len + B - 1) / B;
         const uint32_t next_byte = off + len < text_end ? (uint32_t)(uint8_t)text[off + len] : (uint32_t)'\n';
-        fa_summary_kernel<<<(unsigned)nb, FA_THREADS, 0, stream>>>(d_text, blk0, d_fblk, d_flen, (uint32_t)nfiles, off + len, next_byte, hc.fa_sums.as<FaSum>());
+        fa_summary_kernel<<<(unsigned)nb, FA_THREADS, 0, stream>>>(d_text, blk0, d_fblk, d_flen, (uint32_t)nfiles, off + len, next_byte, hc.fa_sums.as<FaSum>(), hc.fa_wsum.as<FaSum>());
         DB200_LAUNCHED();
         fa_chain_kernel<<<1, 32, 0, stream>>>(hc.fa_sums.as<FaSum>(), blk0, nb, d_fblk, d_gpos0, d_fgen, (uint32_t)nfiles, hc.fa_carry.as<uint64_t>(),
                                                hc.fa_state.as<uint8_t>(), hc.fa_pos.as<uint64_t>(), hc.fa_gend.as<uint64_t>());
         DB200_LAUNCHED();
         fa_emit_kernel<<<(unsigned)nb, FA_THREADS, 0, stream>>>(d_text, blk0, d_fblk, d_flen, (uint32_t)nfiles, off + len, next_byte, hc.fa_state.as<uint8_t>(),
-                                                                hc.fa_pos.as<uint64_t>(), pg->bases2.as<uint32_t>(), pg->nb.as<uint32_t>(),
+                                                                hc.fa_pos.as<uint64_t>(), hc.fa_sums.as<FaSum>(), hc.fa_wsum.as<FaSum>(), pg->bases2.as<uint32_t>(), pg->nb.as<uint32_t>(),
                                                                 pg->st.as<uint32_t>(), hc.fa_flags.as<uint32_t>());
         DB200_LAUNCHED();
         while (next_group < pg->group_end.size() && pg->group_end[next_group] <= off + len) {

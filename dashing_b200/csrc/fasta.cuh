@@ -20,13 +20,13 @@
 #pragma once
 #include "common.cuh"
 #include "sketch.cuh"
+#include "fasta_logic.h"
 
 namespace db200 {
 
 constexpr int FA_THREADS = 512;                 // threads per CTA
 constexpr int FA_BPT = 16;                      // bytes per thread: one 16-byte load
 constexpr int FA_BLOCK = FA_THREADS * FA_BPT;   // 8 KiB of text per CTA; files start on multiples of this
-enum : uint32_t { FS_SKIP = 0, FS_HDR = 1, FS_SEQN = 2, FS_SEQ = 3 };
 
 // Transfer summary of a run of bytes: bits [2s, 2s+2) = state after the run when entered in state s;
 // bits [8 + 14 s, 8 + 14 (s+1)) = sequence bytes the run yields when entered in state s (<= 8192 per block).
@@ -44,93 +44,68 @@ __device__ __forceinline__ FaSum fa_compose(FaSum a, FaSum b) {   // a first, th
     return r;
 }
 
-// One byte.  `ls`: the byte is a line start; `drop`: it is '\n', or a '\r' directly before a '\n'.
-// Returns whether the byte is a sequence byte; `first` = it is the first one of its record.
-__device__ __forceinline__ bool fa_step(uint32_t &state, uint32_t c, bool ls, bool drop, bool &first) {
-    if (ls) {
-        if (c == '>') state = FS_HDR;
-        else if (state == FS_HDR) state = FS_SEQN;
-    }
-    const bool kept = state >= FS_SEQN && !drop;
-    first = kept && state == FS_SEQN;
-    if (kept) state = FS_SEQ;
-    return kept;
+// ---------------------------------------------------------------------------------------------
+// Byte classes of a lane's 16 bytes as 16-bit masks (SIMD within the four 32-bit words of one 16-byte load).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t fa_eq_nibble(uint32_t w, uint32_t pat4) {
+    const uint32_t x = w ^ pat4;
+    const uint32_t t = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);   // 0x80 in every byte of w equal to the pattern byte
+    return ((t >> 7) * 0x01020408u) >> 24;                                      // -> one bit per byte, bits 0..3
+}
+__device__ __forceinline__ uint32_t fa_eq16(const uint4 &v, uint32_t c) {
+    const uint32_t pat = c * 0x01010101u;
+    return fa_eq_nibble(v.x, pat) | (fa_eq_nibble(v.y, pat) << 4) | (fa_eq_nibble(v.z, pat) << 8) | (fa_eq_nibble(v.w, pat) << 12);
 }
 
-struct FaBytes {
-    uint32_t c[FA_BPT];
-    uint32_t ls, drop;     // bit i: byte i is a line start / is dropped
+struct FaCls {
+    uint4 raw;
+    uint32_t nl, cr, gt;       // byte-class masks; bytes past the file's end count as '\n'
+    uint32_t prev_nl, next_nl;
 };
 
-// Loads the 16 bytes of this thread, the byte before (line start of byte 0) and the byte after (CR before LF).
-// [file_start, file_end): the file this block belongs to — bytes of the block past the file's end (the gap up to the next
-// file's block-aligned start) read as '\n', whatever the caller left there.  `chunk_end` / `next_byte`: the first byte not
-// yet resident on the device and its value (the host reads it from its own copy of the text).
-__device__ __forceinline__ void fa_load(const uint8_t *__restrict__ text, uint64_t i0, uint64_t file_start, uint64_t file_end, uint64_t chunk_end,
-                                        uint32_t next_byte, FaBytes &fb) {
-    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(text + i0));
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-    for (int i = 0; i < FA_BPT; ++i) fb.c[i] = (i0 + i < file_end) ? ((w[i >> 2] >> (8 * (i & 3))) & 0xFFu) : (uint32_t)'\n';
-    const uint32_t prev = (i0 > file_start && i0 - 1 < file_end) ? (uint32_t)__ldg(text + i0 - 1) : (uint32_t)'\n';
-    const uint64_t in = i0 + FA_BPT;
-    const uint32_t next = in >= file_end ? (uint32_t)'\n' : (in < chunk_end ? (uint32_t)__ldg(text + in) : next_byte);
-    uint32_t ls = 0, drop = 0;
-#pragma unroll
-    for (int i = 0; i < FA_BPT; ++i) {
-        const uint32_t p = i ? fb.c[i - 1] : prev, n = i + 1 < FA_BPT ? fb.c[i + 1] : next;
-        ls |= (uint32_t)(p == '\n') << i;
-        drop |= (uint32_t)(fb.c[i] == '\n' || (fb.c[i] == '\r' && n == '\n')) << i;
+// Loads the lane's 16 bytes and classifies them.  [file_start, file_end): the file this block belongs to — bytes of the block
+// past the file's end (the gap up to the next file's block-aligned start) read as '\n', whatever the caller left there.
+// `chunk_end` / `next_byte`: the first byte not yet resident on the device and its value (the host reads it from its own
+// copy of the text).  The byte before / after a lane comes from the neighbouring lane; only the warp's edge lanes load it.
+__device__ __forceinline__ void fa_classify(const uint8_t *__restrict__ text, uint64_t i0, uint64_t file_start, uint64_t file_end, uint64_t chunk_end,
+                                            uint32_t next_byte, FaCls &c) {
+    const uint32_t lane = threadIdx.x & 31;
+    c.raw = __ldg(reinterpret_cast<const uint4 *>(text + i0));
+    const uint32_t nvalid = file_end > i0 ? (uint32_t)min((uint64_t)FA_BPT, file_end - i0) : 0u;
+    const uint32_t vm = fa_below(nvalid);
+    c.nl = (fa_eq16(c.raw, '\n') & vm) | (~vm & 0xFFFFu);
+    c.cr = fa_eq16(c.raw, '\r') & vm;
+    c.gt = fa_eq16(c.raw, '>') & vm;
+    uint32_t pn = __shfl_up_sync(0xFFFFFFFFu, c.nl >> 15, 1);
+    uint32_t nn = __shfl_down_sync(0xFFFFFFFFu, c.nl & 1u, 1);
+    if (lane == 0) pn = (i0 > file_start && i0 - 1 < file_end) ? (uint32_t)(__ldg(text + i0 - 1) == '\n') : 1u;
+    if (lane == 31) {
+        const uint64_t in = i0 + FA_BPT;
+        nn = in >= file_end ? 1u : (uint32_t)((in < chunk_end ? (uint32_t)__ldg(text + in) : next_byte) == '\n');
     }
-    fb.ls = ls; fb.drop = drop;
+    c.prev_nl = pn; c.next_nl = nn;
 }
 
-__device__ __forceinline__ FaSum fa_thread_summary(const FaBytes &fb) {
-    FaSum r = 0;
-#pragma unroll
-    for (uint32_t s = 0; s < 4; ++s) {
-        uint32_t st = s, cnt = 0;
-#pragma unroll
-        for (int i = 0; i < FA_BPT; ++i) {
-            bool first;
-            cnt += fa_step(st, fb.c[i], (fb.ls >> i) & 1u, (fb.drop >> i) & 1u, first);
-        }
-        r |= (FaSum)st << (2 * s);
-        r |= (FaSum)cnt << (8 + 14 * s);
-    }
-    return r;
+struct FaWarp { uint32_t b_hs, b_ls, b_kab, b_kb; };
+__device__ __forceinline__ FaWarp fa_ballots(const FaLane &L) {
+    FaWarp w;
+    w.b_hs = __ballot_sync(0xFFFFFFFFu, L.hs != 0);
+    w.b_ls = __ballot_sync(0xFFFFFFFFu, L.ls != 0);
+    w.b_kab = __ballot_sync(0xFFFFFFFFu, (L.kA | L.kB) != 0);
+    w.b_kb = __ballot_sync(0xFFFFFFFFu, L.kB != 0);
+    return w;
 }
-
-// Scan of the per-thread summaries over the CTA (thread order = byte order).  Returns this thread's EXCLUSIVE prefix (the map
-// of all bytes before its own); s_warp[FA_THREADS / 32] afterwards holds the whole block's map.
-__device__ __forceinline__ FaSum fa_block_scan(FaSum mine, FaSum *s_warp /* [FA_THREADS / 32 + 1] */) {
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    constexpr FaSum IDENT = 0xE4ull;   // tf: s -> s, counts 0
-    constexpr uint32_t NW = FA_THREADS / 32;
-    FaSum inc = mine;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const FaSum o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
-        if (lane >= (uint32_t)d) inc = fa_compose(o, inc);
-    }
-    if (lane == 31) s_warp[warp] = inc;
-    __syncthreads();
-    if (warp == 0) {                   // exclusive scan of the NW warp totals; the grand total goes to s_warp[NW]
-        FaSum w = lane < NW ? s_warp[lane] : IDENT;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const FaSum o = __shfl_up_sync(0xFFFFFFFFu, w, d);
-            if (lane >= (uint32_t)d) w = fa_compose(o, w);
-        }
-        const FaSum e = __shfl_up_sync(0xFFFFFFFFu, w, 1);
-        __syncwarp();
-        if (lane < NW) s_warp[lane] = lane ? e : IDENT;
-        if (lane == NW - 1) s_warp[NW] = w;
-    }
-    __syncthreads();
-    FaSum exc = __shfl_up_sync(0xFFFFFFFFu, inc, 1);
-    if (lane == 0) exc = IDENT;
-    return fa_compose(s_warp[warp], exc);
+// Incoming state of this lane when the warp is entered in state S (fasta_logic.h), det_out fetched from the lane that holds
+// the nearest header start below.
+__device__ __forceinline__ uint32_t fa_my_state(uint32_t S, const FaLane &L, const FaWarp &w) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t ph = w.b_hs & fa_below(lane);
+    const uint32_t det_h = __shfl_sync(0xFFFFFFFFu, L.det_out, ph ? FA_MSB(ph) : 0);
+    return fa_lane_state(S, lane, w.b_hs, w.b_ls, w.b_kab, w.b_kb, det_h);
+}
+__device__ __forceinline__ uint32_t fa_warp_out(uint32_t S, const FaLane &L, const FaWarp &w) {
+    const uint32_t det_h = __shfl_sync(0xFFFFFFFFu, L.det_out, w.b_hs ? FA_MSB(w.b_hs) : 0);
+    return fa_lane_state(S, 32u, w.b_hs, w.b_ls, w.b_kab, w.b_kb, det_h);
 }
 
 // A block's file: files start on block boundaries, `fblk` holds their first block (ascending).
@@ -140,22 +115,46 @@ __device__ __forceinline__ uint32_t fa_file_of_block(const uint64_t *__restrict_
     return lo;
 }
 
-// Pass 1: one summary per block.
+// Pass 1: one summary per block (sums[blk]) and one per warp (wsum[(blk - blk0) * 16 + warp], for pass 3).
+// A warp resolves its lanes' states with four ballots (fasta_logic.h), once per possible incoming state of the warp
+// (SEQN and SEQ differ in the outgoing state only), and adds the lanes' sequence-byte counts with redux.
 __global__ void __launch_bounds__(FA_THREADS) fa_summary_kernel(const uint8_t *__restrict__ text, uint64_t blk0, const uint64_t *__restrict__ fblk,
-                                                               const uint64_t *__restrict__ flen, uint32_t nfiles, uint64_t chunk_end, uint32_t next_byte, FaSum *__restrict__ sums) {
-    __shared__ FaSum s_warp[FA_THREADS / 32 + 1];
+                                                               const uint64_t *__restrict__ flen, uint32_t nfiles, uint64_t chunk_end, uint32_t next_byte,
+                                                               FaSum *__restrict__ sums, FaSum *__restrict__ wsum) {
+    constexpr uint32_t NW = FA_THREADS / 32;
+    __shared__ FaSum s_warp[NW];
     __shared__ uint64_t s_fstart, s_fend;
     const uint64_t blk = blk0 + blockIdx.x;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) {
         const uint32_t f = fa_file_of_block(fblk, nfiles, blk);
         s_fstart = __ldg(fblk + f) * (uint64_t)FA_BLOCK;
         s_fend = s_fstart + __ldg(flen + f);
     }
     __syncthreads();
-    FaBytes fb;
-    fa_load(text, blk * FA_BLOCK + (uint64_t)threadIdx.x * FA_BPT, s_fstart, s_fend, chunk_end, next_byte, fb);
-    fa_block_scan(fa_thread_summary(fb), s_warp);
-    if (threadIdx.x == 0) sums[blk] = s_warp[FA_THREADS / 32];
+    FaCls c;
+    fa_classify(text, blk * FA_BLOCK + (uint64_t)threadIdx.x * FA_BPT, s_fstart, s_fend, chunk_end, next_byte, c);
+    const FaLane L = fa_lane(c.nl, c.cr, c.gt, c.prev_nl, c.next_nl);
+    const FaWarp w = fa_ballots(L);
+    uint32_t cnt[3];
+    const uint32_t Sin[3] = {FS_SKIP, FS_HDR, FS_SEQ};
+#pragma unroll
+    for (int i = 0; i < 3; ++i) cnt[i] = __reduce_add_sync(0xFFFFFFFFu, FA_POPC(fa_keep(L, fa_my_state(Sin[i], L, w))));
+    const uint32_t o_skip = fa_warp_out(FS_SKIP, L, w), o_hdr = fa_warp_out(FS_HDR, L, w), o_seqn = fa_warp_out(FS_SEQN, L, w),
+                   o_seq = fa_warp_out(FS_SEQ, L, w);
+    const FaSum mine = (FaSum)(o_skip | (o_hdr << 2) | (o_seqn << 4) | (o_seq << 6)) | ((FaSum)cnt[0] << 8) | ((FaSum)cnt[1] << 22) |
+                       ((FaSum)cnt[2] << 36) | ((FaSum)cnt[2] << 50);
+    if (lane == 0) { s_warp[warp] = mine; wsum[(uint64_t)blockIdx.x * NW + warp] = mine; }
+    __syncthreads();
+    if (warp == 0) {                   // the block's map: the warps' maps composed in order
+        FaSum v = lane < NW ? s_warp[lane] : (FaSum)0xE4ull;
+#pragma unroll
+        for (int d = 1; d < (int)NW; d <<= 1) {
+            const FaSum o = __shfl_up_sync(0xFFFFFFFFu, v, d);
+            if (lane >= (uint32_t)d) v = fa_compose(o, v);
+        }
+        if (lane == NW - 1) sums[blk] = v;
+    }
 }
 
 // Pass 2: chain the blocks of one chunk.  carry[0] = state, carry[1] = next output position after the previous chunk.  A file
@@ -286,18 +285,24 @@ __global__ void fa_clip_items_kernel(SketchItem *__restrict__ items, uint32_t n,
 // Pass 3: emit 2-bit codes + validity + record-start planes.  The block's sequence bytes land on the contiguous positions
 // [P, P + n): they are assembled in shared memory relative to P & ~63 and flushed with plain stores for words the block
 // owns entirely and atomicOr for the (at most two) words per plane it shares with its neighbours; the planes start zeroed.
+// A warp finds its incoming state and offset by walking the maps of the warps before it (pass 1 left them in wsum), its
+// lanes' states with the ballots again, and the lanes' offsets with a shuffle scan of their sequence-byte counts.  Codes
+// and validity come from the SIMD-in-word packer of sketch.cuh and are squeezed by the lane's keep mask (fa_compress: one
+// step per run of dropped bytes — none for most lanes, one where a line ends).
 // flags[f] |= 1 when file f shows FASTQ record syntax ('@' header, or a '+' / '@' line inside a record).
 __global__ void __launch_bounds__(FA_THREADS) fa_emit_kernel(const uint8_t *__restrict__ text, uint64_t blk0, const uint64_t *__restrict__ fblk,
                                                             const uint64_t *__restrict__ flen, uint32_t nfiles, uint64_t chunk_end, uint32_t next_byte,
                                                             const uint8_t *__restrict__ in_state, const uint64_t *__restrict__ in_pos,
+                                                            const FaSum *__restrict__ sums, const FaSum *__restrict__ wsum,
                                                             uint32_t *__restrict__ codes, uint32_t *__restrict__ valid32, uint32_t *__restrict__ start32,
                                                             uint32_t *__restrict__ flags) {
     constexpr int CW = (FA_BLOCK + 64) / 16 + 1, PW = (FA_BLOCK + 64) / 32 + 1;
-    __shared__ FaSum s_warp[FA_THREADS / 32 + 1];
+    constexpr uint32_t NW = FA_THREADS / 32;
     __shared__ uint32_t s_codes[CW], s_valid[PW], s_start[PW];
     __shared__ uint64_t s_fstart, s_fend;
     __shared__ uint32_t s_file;
     const uint64_t blk = blk0 + blockIdx.x;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) {
         s_file = fa_file_of_block(fblk, nfiles, blk);
         s_fstart = __ldg(fblk + s_file) * (uint64_t)FA_BLOCK;
@@ -306,61 +311,83 @@ __global__ void __launch_bounds__(FA_THREADS) fa_emit_kernel(const uint8_t *__re
     for (int i = threadIdx.x; i < CW; i += FA_THREADS) s_codes[i] = 0;
     for (int i = threadIdx.x; i < PW; i += FA_THREADS) { s_valid[i] = 0; s_start[i] = 0; }
     __syncthreads();
-    FaBytes fb;
-    fa_load(text, blk * FA_BLOCK + (uint64_t)threadIdx.x * FA_BPT, s_fstart, s_fend, chunk_end, next_byte, fb);
-    const FaSum pre = fa_block_scan(fa_thread_summary(fb), s_warp);
-    const FaSum total = s_warp[FA_THREADS / 32];
+    FaCls c;
+    fa_classify(text, blk * FA_BLOCK + (uint64_t)threadIdx.x * FA_BPT, s_fstart, s_fend, chunk_end, next_byte, c);
+    const FaLane L = fa_lane(c.nl, c.cr, c.gt, c.prev_nl, c.next_nl);
+    const FaWarp w = fa_ballots(L);
     const uint32_t sin = in_state[blk];
     const uint64_t P = in_pos[blk], base0 = P & ~63ull;
-    const uint32_t nseq = fa_cnt(total, sin);
-    uint32_t state = fa_tf(pre, sin);
-    const uint32_t li0 = (uint32_t)(P - base0) + fa_cnt(pre, sin);     // local index of this thread's first sequence byte
-    uint64_t code = 0;
-    uint32_t vbits = 0, sbits = 0, n = 0;
-    bool fastq = false;
-#pragma unroll
-    for (int i = 0; i < FA_BPT; ++i) {
-        const uint32_t c = fb.c[i];
-        const bool ls = (fb.ls >> i) & 1u;
-        // FASTQ syntax: '@' opening a record, or a '+' / '@' line inside one (kseq.h:183, :196)
-        fastq |= ls && ((c == '@') || (c == '+' && state >= FS_SEQN));
-        bool first;
-        if (fa_step(state, c, ls, (fb.drop >> i) & 1u, first)) {
-            const uint32_t up = c & 0xDFu;
-            const uint32_t ok = (up == 'A') | (up == 'C') | (up == 'G') | (up == 'T');
-            code |= (uint64_t)(((c >> 1) ^ (c >> 2)) & 3u) << (2 * n);     // A0 C1 G2 T3 (anything for invalid bytes)
-            vbits |= ok << n;
-            sbits |= (uint32_t)first << n;
-            ++n;
-        }
+    const uint32_t nseq = fa_cnt(__ldg(sums + blk), sin);
+    // this warp's incoming state and offset: the maps of the warps before it, applied in order
+    uint32_t wst = sin, woff = 0;
+    for (uint32_t v = 0; v < warp; ++v) {
+        const FaSum m = __ldg(wsum + (uint64_t)blockIdx.x * NW + v);
+        woff += fa_cnt(m, wst);
+        wst = fa_tf(m, wst);
     }
-    if (fastq) atomicOr(&flags[s_file], 1u);
+    const uint32_t st = fa_my_state(wst, L, w);
+    const uint32_t K = fa_keep(L, st);
+    const uint32_t n = FA_POPC(K);
+    // FASTQ syntax is looked for only where a line starts in the lane
+    bool fq = false;
+    if (L.ls) {
+        const uint32_t vm = fa_below(s_fend > blk * FA_BLOCK + (uint64_t)threadIdx.x * FA_BPT
+                                         ? (uint32_t)min((uint64_t)FA_BPT, s_fend - (blk * FA_BLOCK + (uint64_t)threadIdx.x * FA_BPT)) : 0u);
+        fq = fa_fastq(L, st, fa_eq16(c.raw, '@') & vm, fa_eq16(c.raw, '+') & vm);
+    }
+    if (__any_sync(0xFFFFFFFFu, fq) && lane == 0) atomicOr(&flags[s_file], 1u);
+    // exclusive scan of the lanes' counts
+    uint32_t inc = n;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+        if (lane >= (uint32_t)d) inc += o;
+    }
     if (n) {
+        const uint32_t li0 = (uint32_t)(P - base0) + woff + (inc - n);     // local index of this lane's first sequence byte
+        uint32_t code = 0, vbits = 0;
+        {
+            const uint32_t ww[4] = {c.raw.x, c.raw.y, c.raw.z, c.raw.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                uint32_t c8, v4;
+                pack4(ww[i], c8, v4);
+                code |= c8 << (8 * i);
+                vbits |= v4 << (4 * i);
+            }
+        }
+        uint32_t sbits = fa_starts(L, st, K);
+        if (K != 0xFFFFu) {
+            code = fa_compress(code, K, 2u);
+            vbits = fa_compress(vbits & K, K, 1u);
+            if (sbits) sbits = fa_compress(sbits, K, 1u);
+        }
+        if (n < 16u) { code &= fa_below(2u * n); vbits &= fa_below(n); }
         // codes: 2 bits per base, 16 bases per word; up to 32 bits of payload straddle at most 2 words
         const uint32_t cw = li0 >> 4, cs = 2 * (li0 & 15u);
-        const uint64_t lo = code << cs;
+        const uint64_t lo = (uint64_t)code << cs;
         atomicOr(&s_codes[cw], (uint32_t)lo);
         if ((uint32_t)(lo >> 32)) atomicOr(&s_codes[cw + 1], (uint32_t)(lo >> 32));
         const uint32_t pw = li0 >> 5, ps = li0 & 31u;
-        const uint64_t v = (uint64_t)vbits << ps, s = (uint64_t)sbits << ps;
+        const uint64_t v = (uint64_t)vbits << ps, sb = (uint64_t)sbits << ps;
         if ((uint32_t)v) atomicOr(&s_valid[pw], (uint32_t)v);
         if ((uint32_t)(v >> 32)) atomicOr(&s_valid[pw + 1], (uint32_t)(v >> 32));
-        if ((uint32_t)s) atomicOr(&s_start[pw], (uint32_t)s);
-        if ((uint32_t)(s >> 32)) atomicOr(&s_start[pw + 1], (uint32_t)(s >> 32));
+        if ((uint32_t)sb) atomicOr(&s_start[pw], (uint32_t)sb);
+        if ((uint32_t)(sb >> 32)) atomicOr(&s_start[pw + 1], (uint32_t)(sb >> 32));
     }
     __syncthreads();
     if (nseq == 0) return;
     const uint32_t lo_b = (uint32_t)(P - base0), hi_b = lo_b + nseq;            // local range of owned bases
     uint32_t *gc = codes + (base0 >> 4), *gv = valid32 + (base0 >> 5), *gs = start32 + (base0 >> 5);
-    for (uint32_t w = threadIdx.x; w * 16 < hi_b; w += FA_THREADS) {
-        const uint32_t x = s_codes[w];
-        if (w * 16 >= lo_b && (w + 1) * 16 <= hi_b) gc[w] = x;
-        else if (x) atomicOr(gc + w, x);
+    for (uint32_t x = threadIdx.x; x * 16 < hi_b; x += FA_THREADS) {
+        const uint32_t y = s_codes[x];
+        if (x * 16 >= lo_b && (x + 1) * 16 <= hi_b) gc[x] = y;
+        else if (y) atomicOr(gc + x, y);
     }
-    for (uint32_t w = threadIdx.x; w * 32 < hi_b; w += FA_THREADS) {
-        const uint32_t x = s_valid[w], y = s_start[w];
-        if (w * 32 >= lo_b && (w + 1) * 32 <= hi_b) { gv[w] = x; if (y) gs[w] = y; }
-        else { if (x) atomicOr(gv + w, x); if (y) atomicOr(gs + w, y); }
+    for (uint32_t x = threadIdx.x; x * 32 < hi_b; x += FA_THREADS) {
+        const uint32_t y = s_valid[x], z = s_start[x];
+        if (x * 32 >= lo_b && (x + 1) * 32 <= hi_b) { gv[x] = y; if (z) gs[x] = z; }
+        else { if (y) atomicOr(gv + x, y); if (z) atomicOr(gs + x, z); }
     }
 }
 
