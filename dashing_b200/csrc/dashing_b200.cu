@@ -1511,7 +1511,7 @@ static int sketch_fasta_one(int device, int p, int k, int canon, const char *tex
         const uint32_t next_byte = off + len < text_end ? (uint32_t)(uint8_t)text[off + len] : (uint32_t)'\n';
         fa_summary_kernel<<<(unsigned)nb, FA_THREADS, 0, stream>>>(d_text, blk0, d_fblk, d_flen, (uint32_t)nfiles, off + len, next_byte, hc.fa_sums.as<FaSum>(), hc.fa_wsum.as<FaSum>());
         DB200_LAUNCHED();
-        fa_chain_kernel<<<1, 32, 0, stream>>>(hc.fa_sums.as<FaSum>(), blk0, nb, d_fblk, d_gpos0, d_fgen, (uint32_t)nfiles, hc.fa_carry.as<uint64_t>(),
+        fa_chain_kernel<<<1, FA_CHAIN_THREADS, 0, stream>>>(hc.fa_sums.as<FaSum>(), blk0, nb, d_fblk, d_gpos0, d_fgen, (uint32_t)nfiles, hc.fa_carry.as<uint64_t>(),
                                                hc.fa_state.as<uint8_t>(), hc.fa_pos.as<uint64_t>(), hc.fa_gend.as<uint64_t>());
         DB200_LAUNCHED();
         fa_emit_kernel<<<(unsigned)nb, FA_THREADS, 0, stream>>>(d_text, blk0, d_fblk, d_flen, (uint32_t)nfiles, off + len, next_byte, hc.fa_state.as<uint8_t>(),

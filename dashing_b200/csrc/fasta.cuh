@@ -161,11 +161,12 @@ __global__ void __launch_bounds__(FA_THREADS) fa_summary_kernel(const uint8_t *_
 // start resets the state to SKIP; the first file of a genome also moves the output position to that genome's window
 // (gpos0[f] != ~0).  genome_end[g] = one past the last sequence byte written for genome g so far (final once a later genome has
 // started or the text has ended).
-// One warp.  Lane l owns 64 consecutive blocks of a 2048-block tile: it first folds them into one map of the incoming
-// (state, position) — speculating over the four possible incoming states —, the 32 maps are scanned with shuffles, and the lane
-// then walks its blocks again with the now known incoming state and position.  File starts reset the state; a genome's first
-// file makes the position absolute (its window), which the map records as (has_abs, abs).
-constexpr int FA_CHAIN_PER_LANE = 64, FA_CHAIN_TILE = 32 * FA_CHAIN_PER_LANE;
+// One CTA of 1024 threads per chunk.  Thread t owns the consecutive blocks [t * per, (t + 1) * per) (per <= 8 for a 64 MiB chunk):
+// it first folds them into one map of the incoming (state, position) — speculating over the four possible incoming states —,
+// the maps are scanned (shuffles inside a warp, the 32 warp totals by warp 0), and the thread then walks its blocks again
+// with the now known incoming state and position.  File starts reset the state; a genome's first file makes the position
+// absolute (its window), which the map records as (has_abs, abs).
+constexpr int FA_CHAIN_THREADS = 1024;
 struct FaChainMap {
     uint32_t tf;        // 2 bits per incoming state
     uint32_t c[4];      // sequence bytes per incoming state (since the last genome start if has_abs)
@@ -195,82 +196,103 @@ __device__ __forceinline__ FaChainMap fa_chain_shfl_up(const FaChainMap &m, int 
     return r;
 }
 
-__global__ void __launch_bounds__(32) fa_chain_kernel(const FaSum *__restrict__ sums, uint64_t blk0, uint64_t nblk, const uint64_t *__restrict__ fblk,
+__device__ __forceinline__ FaChainMap fa_chain_identity() {
+    FaChainMap m;
+    m.tf = 0xE4u; m.c[0] = m.c[1] = m.c[2] = m.c[3] = 0; m.has_abs = 0; m.abs = 0;
+    return m;
+}
+
+__global__ void __launch_bounds__(FA_CHAIN_THREADS) fa_chain_kernel(const FaSum *__restrict__ sums, uint64_t blk0, uint64_t nblk, const uint64_t *__restrict__ fblk,
                                 const uint64_t *__restrict__ gpos0, const uint32_t *__restrict__ fgenome, uint32_t nfiles,
                                 uint64_t *__restrict__ carry, uint8_t *__restrict__ in_state, uint64_t *__restrict__ in_pos,
                                 uint64_t *__restrict__ genome_end) {
-    const uint32_t lane = threadIdx.x;
-    uint32_t state = (uint32_t)carry[0];      // carried from tile to tile (identical in every lane)
-    uint64_t pos = carry[1];
-    for (uint64_t t0 = 0; t0 < nblk; t0 += FA_CHAIN_TILE) {
-        const uint64_t b_lo = min(blk0 + t0 + (uint64_t)lane * FA_CHAIN_PER_LANE, blk0 + nblk);
-        const uint64_t b_hi = min(b_lo + FA_CHAIN_PER_LANE, blk0 + nblk);
-        // first file starting at or after b_lo
-        uint32_t nf0;
-        {
-            uint32_t lo = 0, hi = nfiles;
-            while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(fblk + mid) < b_lo) lo = mid + 1; else hi = mid; }
-            nf0 = lo;
-        }
-        // ---- pass 1: the lane's map
-        FaChainMap m;
-        m.tf = 0xE4u; m.c[0] = m.c[1] = m.c[2] = m.c[3] = 0; m.has_abs = 0; m.abs = 0;
-        {
-            uint32_t st[4] = {0, 1, 2, 3};
-            uint32_t nf = nf0;
-            uint64_t next_fblk = nf < nfiles ? __ldg(fblk + nf) : ~0ull;
-            for (uint64_t b = b_lo; b < b_hi; ++b) {
-                while (b == next_fblk) {
-                    st[0] = st[1] = st[2] = st[3] = FS_SKIP;
-                    const uint64_t gp = __ldg(gpos0 + nf);
-                    if (gp != ~0ull) { m.has_abs = 1; m.abs = gp; m.c[0] = m.c[1] = m.c[2] = m.c[3] = 0; }
-                    ++nf;
-                    next_fblk = nf < nfiles ? __ldg(fblk + nf) : ~0ull;
-                }
-                const FaSum sm = __ldg(sums + b);
-#pragma unroll
-                for (int s = 0; s < 4; ++s) { m.c[s] += fa_cnt(sm, st[s]); st[s] = fa_tf(sm, st[s]); }
+    __shared__ FaChainMap s_wmap[FA_CHAIN_THREADS / 32];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t state0 = (uint32_t)carry[0];      // state / position after the previous chunk
+    const uint64_t pos0 = carry[1];
+    const uint64_t per = (nblk + FA_CHAIN_THREADS - 1) / FA_CHAIN_THREADS;
+    const uint64_t b_lo = min(blk0 + (uint64_t)threadIdx.x * per, blk0 + nblk);
+    const uint64_t b_hi = min(b_lo + per, blk0 + nblk);
+    // first file starting at or after b_lo
+    uint32_t nf0;
+    {
+        uint32_t lo = 0, hi = nfiles;
+        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(fblk + mid) < b_lo) lo = mid + 1; else hi = mid; }
+        nf0 = lo;
+    }
+    // ---- pass 1: the thread's map
+    FaChainMap m = fa_chain_identity();
+    {
+        uint32_t st[4] = {0, 1, 2, 3};
+        uint32_t nf = nf0;
+        uint64_t next_fblk = nf < nfiles ? __ldg(fblk + nf) : ~0ull;
+        for (uint64_t b = b_lo; b < b_hi; ++b) {
+            while (b == next_fblk) {
+                st[0] = st[1] = st[2] = st[3] = FS_SKIP;
+                const uint64_t gp = __ldg(gpos0 + nf);
+                if (gp != ~0ull) { m.has_abs = 1; m.abs = gp; m.c[0] = m.c[1] = m.c[2] = m.c[3] = 0; }
+                ++nf;
+                next_fblk = nf < nfiles ? __ldg(fblk + nf) : ~0ull;
             }
-            m.tf = st[0] | (st[1] << 2) | (st[2] << 4) | (st[3] << 6);
+            const FaSum sm = __ldg(sums + b);
+#pragma unroll
+            for (int s = 0; s < 4; ++s) { m.c[s] += fa_cnt(sm, st[s]); st[s] = fa_tf(sm, st[s]); }
         }
-        // ---- inclusive scan over the lanes, then this lane's incoming (state, position)
-        FaChainMap inc = m;
+        m.tf = st[0] | (st[1] << 2) | (st[2] << 4) | (st[3] << 6);
+    }
+    // ---- scan: inside the warp, then the warp totals
+    FaChainMap inc = m;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const FaChainMap o = fa_chain_shfl_up(inc, d);
+        if (lane >= (uint32_t)d) inc = fa_chain_compose(o, inc);
+    }
+    FaChainMap exc = fa_chain_shfl_up(inc, 1);
+    if (lane == 0) exc = fa_chain_identity();
+    if (lane == 31) s_wmap[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        FaChainMap w = s_wmap[lane];
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            const FaChainMap o = fa_chain_shfl_up(inc, d);
-            if (lane >= (uint32_t)d) inc = fa_chain_compose(o, inc);
+            const FaChainMap o = fa_chain_shfl_up(w, d);
+            if (lane >= (uint32_t)d) w = fa_chain_compose(o, w);
         }
-        FaChainMap exc = fa_chain_shfl_up(inc, 1);
-        if (lane == 0) { exc.tf = 0xE4u; exc.c[0] = exc.c[1] = exc.c[2] = exc.c[3] = 0; exc.has_abs = 0; exc.abs = 0; }
-        uint32_t my_state = (exc.tf >> (2 * state)) & 3u;
-        uint64_t my_pos = (exc.has_abs ? exc.abs : pos) + exc.c[state];
-        // ---- pass 2: walk the blocks with the real state
-        {
-            uint32_t nf = nf0;
-            uint32_t g = nf0 ? __ldg(fgenome + nf0 - 1) : 0u;
-            uint64_t next_fblk = nf < nfiles ? __ldg(fblk + nf) : ~0ull;
-            for (uint64_t b = b_lo; b < b_hi; ++b) {
-                while (b == next_fblk) {
-                    my_state = FS_SKIP;
-                    const uint64_t gp = __ldg(gpos0 + nf);
-                    if (gp != ~0ull) { atomicMax(reinterpret_cast<unsigned long long *>(genome_end + g), (unsigned long long)my_pos); my_pos = gp; g = __ldg(fgenome + nf); }
-                    ++nf;
-                    next_fblk = nf < nfiles ? __ldg(fblk + nf) : ~0ull;
-                }
-                in_state[b] = (uint8_t)my_state;
-                in_pos[b] = my_pos;
-                const FaSum sm = __ldg(sums + b);
-                my_pos += fa_cnt(sm, my_state);
-                my_state = fa_tf(sm, my_state);
-            }
-            // the genome current at the end of this lane's run has reached my_pos (positions only grow inside a genome: max)
-            if (b_hi > b_lo) atomicMax(reinterpret_cast<unsigned long long *>(genome_end + g), (unsigned long long)my_pos);
+        FaChainMap we = fa_chain_shfl_up(w, 1);
+        if (lane == 0) we = fa_chain_identity();
+        __syncwarp();
+        s_wmap[lane] = we;                           // exclusive prefix of the warps
+        if (lane == 31) {                            // chunk carry = everything composed, applied to the incoming carry
+            carry[0] = (w.tf >> (2 * state0)) & 3u;
+            carry[1] = (w.has_abs ? w.abs : pos0) + w.c[state0];
         }
-        // tile carry = state / position after the last lane
-        state = __shfl_sync(0xFFFFFFFFu, my_state, 31);
-        pos = __shfl_sync(0xFFFFFFFFu, my_pos, 31);
     }
-    if (lane == 0) { carry[0] = state; carry[1] = pos; }
+    __syncthreads();
+    const FaChainMap pre = fa_chain_compose(s_wmap[warp], exc);
+    uint32_t my_state = (pre.tf >> (2 * state0)) & 3u;
+    uint64_t my_pos = (pre.has_abs ? pre.abs : pos0) + pre.c[state0];
+    // ---- pass 2: walk the blocks with the real state
+    if (b_hi > b_lo) {
+        uint32_t nf = nf0;
+        uint32_t g = nf0 ? __ldg(fgenome + nf0 - 1) : 0u;
+        uint64_t next_fblk = nf < nfiles ? __ldg(fblk + nf) : ~0ull;
+        for (uint64_t b = b_lo; b < b_hi; ++b) {
+            while (b == next_fblk) {
+                my_state = FS_SKIP;
+                const uint64_t gp = __ldg(gpos0 + nf);
+                if (gp != ~0ull) { atomicMax(reinterpret_cast<unsigned long long *>(genome_end + g), (unsigned long long)my_pos); my_pos = gp; g = __ldg(fgenome + nf); }
+                ++nf;
+                next_fblk = nf < nfiles ? __ldg(fblk + nf) : ~0ull;
+            }
+            in_state[b] = (uint8_t)my_state;
+            in_pos[b] = my_pos;
+            const FaSum sm = __ldg(sums + b);
+            my_pos += fa_cnt(sm, my_state);
+            my_state = fa_tf(sm, my_state);
+        }
+        // the genome current at the end of this thread's run has reached my_pos (positions only grow inside a genome: max)
+        atomicMax(reinterpret_cast<unsigned long long *>(genome_end + g), (unsigned long long)my_pos);
+    }
 }
 
 // Work items were laid out over each genome's WINDOW (an upper bound: the raw size of its files); cut them back to the
