@@ -71,3 +71,30 @@ def test_stream_all_devices(gpu, monkeypatch):
     got, seen = collect(gpu, regs, p, k=21, result_type=gpu.MASH_DIST, device=gpu.ALL_DEVICES, block_pairs=9000)
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
     assert sorted(seen)[0][0] == 0 and sorted(seen)[-1][1] == 700 and sum(b - a for a, b in seen) == 700
+
+
+def test_rows_beyond_2_pow_32_pairs(gpu, checker):
+    """BASELINE.json's C4 size: 100,000 sketches = 4.99995e9 pairs, so distmat offsets pass 2^32.  Rows deep in the triangle
+    (first pair index 4.99e9) through the one-shot and the streaming row-range calls, against the rectangular call on the
+    same sketches and the checker on samples."""
+    p, n = 7, 100_000
+    regs = synth.registers(31, n, p, card=4e3, group=32)
+    rb, re_ = 95_000, 95_160
+    tri = lambda r: r * (2 * n - r - 1) // 2
+    assert tri(rb) > 2 ** 32
+    rows = gpu.dist_symmetric(regs, p, k=21, result_type=gpu.MASH_DIST, row_begin=rb, row_end=re_)
+    assert rows.size == tri(re_) - tri(rb)
+    got = np.full(rows.size, np.nan, np.float32)
+
+    def on_rows(b0, b1, vals):
+        got[tri(b0) - tri(rb): tri(b1) - tri(rb)] = vals
+    gpu.dist_symmetric_stream(regs, p, on_rows, k=21, result_type=gpu.MASH_DIST, row_begin=rb, row_end=re_, block_pairs=100_000)
+    assert np.array_equal(got.view(np.uint32), rows.view(np.uint32))
+    # row i of the triangle = (i, j > i): the rectangular call with queries = those rows, references = everything after rb
+    rect = gpu.dist_rect(regs[rb:], regs[rb:re_], p, k=21, result_type=gpu.MASH_DIST)     # [q][j - rb]
+    for i in (rb, rb + 77, re_ - 1):
+        seg = rows[tri(i) - tri(rb): tri(i + 1) - tri(rb)]
+        assert np.array_equal(seg.view(np.uint32), rect[i - rb, i - rb + 1:].view(np.uint32)), i
+    from parity import assert_close
+    for i, j in ((rb, rb + 1), (rb + 100, n - 1), (re_ - 1, 99_000)):
+        assert_close(rows[tri(i) - tri(rb) + j - i - 1], checker.pair(regs[i], regs[j], p, rtype=0, k=21), what=f"pair {i},{j}")
