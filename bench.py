@@ -463,6 +463,8 @@ def run_gpu(args):
         # second end-to-end form: RAW FASTA text (headers + 80-column lines) parsed on the device (db200_sketch_fasta_batch) —
         # what the CLI feeds the library with; informational, the e2e key above stays the record interface
         try:
+            if world > 1:
+                raise RuntimeError("single-GPU runs only (a second 5 GB page-locked buffer per rank)")
             W = 80
             assert L % W == 0
             hdr_len = 16
