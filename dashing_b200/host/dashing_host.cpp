@@ -1100,14 +1100,29 @@ int union_main(int argc, char **argv) {
     if (paths.empty()) throw Error("require >= 1 paths. See usage.");
     // T(paths[i]) for every input, then += (element-wise max, hll.h:958-992) and sum() (perform_sum): the result keeps the FIRST
     // sketch's estimators and carries its cardinality
-    std::vector<uint8_t> regs;
-    uint32_t p = 0, estim = 2, jestim = 2;
-    for (size_t i = 0; i < paths.size(); ++i) {
-        const HllFile h = read_hll(paths[i]);
-        if (i == 0) { p = h.p; estim = h.estim; jestim = h.jestim; regs.reserve(paths.size() << p); }
-        else if (h.p != p) throw Error("mismatched sketch sizes.");            // PREC_REQ, hll.h:959
-        regs.insert(regs.end(), h.core.begin(), h.core.end());
+    int nthreads = 1;
+    {   // -p: re-scan the flags for it (the loop above ignores it, as far as the reference's union is concerned it only threads the reads)
+        optind = 1;
+        for (int c; (c = getopt_long(argc, argv, "p:b:o:F:zZ:h?", longopts, nullptr)) >= 0;) if (c == 'p') nthreads = std::max(1, std::atoi(optarg));
     }
+    const HllFile first = read_hll(paths[0]);
+    const uint32_t p = first.p, estim = first.estim, jestim = first.jestim;
+    const size_t m = size_t(1) << p;
+    std::vector<uint8_t> regs(paths.size() * m);
+    std::memcpy(regs.data(), first.core.data(), m);
+    std::string err;
+#pragma omp parallel for schedule(dynamic, 16) num_threads(nthreads)
+    for (size_t i = 1; i < paths.size(); ++i) {
+        try {
+            const HllFile h = read_hll(paths[i]);
+            if (h.p != p) throw Error("mismatched sketch sizes.");            // PREC_REQ, hll.h:959
+            std::memcpy(&regs[i * m], h.core.data(), m);
+        } catch (const std::exception &e) {
+#pragma omp critical
+            err = e.what();
+        }
+    }
+    if (!err.empty()) throw Error(err);
     if (estim > 2) throw Error("sketch " + paths[0] + " names an unknown estimation method");
     std::vector<uint8_t> out(size_t(1) << p);
     check(db200_union(device, regs.data(), paths.size(), (int)p, out.data()));
