@@ -259,7 +259,7 @@ def run_reference(args):
             "config": {"workload": workload, "estimator": "ERTL_MLE", "result": "JI", "reference": desc},
             "cpu_baseline": {"value": value, "unit": unit, "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit_result(line)
     return 0
 
 
@@ -554,14 +554,30 @@ def run_gpu(args):
                 line[other] = {k: o[k] for k in ("metric", "value", "unit", "ms_per_step", "config", "roofline", "e2e", "gpu_launches", "clocks") if k in o}
                 if "cpu_baseline" in o:
                     line[other]["cpu_baseline"] = o["cpu_baseline"]
-        print(json.dumps(line), flush=True)
+        emit_result(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
 
 
+_RESULT_OUT = None
+
+
+def emit_result(line: dict):
+    """The ONE JSON line of the contract goes to the process's original stdout."""
+    out = _RESULT_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    # Libraries write to file descriptor 1 behind Python's back (NCCL prints "NCCL version ..." there when the environment
+    # sets NCCL_DEBUG=VERSION): keep the real stdout for the result line only and point fd 1 at stderr for everything else.
+    global _RESULT_OUT
+    sys.stdout.flush()
+    _RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
