@@ -849,6 +849,8 @@ void dist_sketch_and_cmp(const DistOptions &o_in, std::vector<std::string> inpat
     if (o.defer_hll) o.estim = o.jestim = DB200_ERTL_MLE;   // hllbase_t(p) inside make_hll(): ERTL_MLE for both (hll.h:765)
     const size_t n = inpaths.size(), m = size_t(1) << o.p;
     if (nq > n) throw Error("more queries than paths");
+    // the CUDA context (0.6 s and more) comes up while the sketch files are being read
+    std::future<int> warm = std::async(std::launch::async, [dev = o.device] { return db200_warmup(dev); });
     std::vector<uint8_t> regs(n * m);
     // ---- phase A: load or sketch (src/sketch_and_cmp.h:314-360)
     std::vector<size_t> todo;
@@ -862,6 +864,7 @@ void dist_sketch_and_cmp(const DistOptions &o_in, std::vector<std::string> inpat
     });
     // ---- phase B: sizes (:372-385)
     phase("sketches ready");
+    warm.wait();
     std::vector<double> card(n);
     check(db200_cardinalities(o.device, regs.data(), n, o.p, o.estim, card.data()));
     const bool any_cached = apply_cached(o.device, o.p, o.estim, regs, info, card);
