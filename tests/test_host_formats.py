@@ -188,3 +188,16 @@ def test_record_names_and_path_lists(host, golden_dir, tmp_path):
     (tmp_path / "list.txt").write_text("a.fa\n\n#skipped\nb c.fa\n")
     assert hostlib.get_paths(host, str(tmp_path / "list.txt")) == ["a.fa", "b c.fa"]
     assert hostlib.get_paths(host, str(tmp_path / "missing.txt")) == []
+
+
+def test_text_numbers_are_printf_g6(host):
+    """The emitters format with std::to_chars(general, 6); the reference with "%.6g" / "%g" / "%0.6g".  Same characters, including
+    the exponent switch points, zeros, infinities and NaNs."""
+    rng = np.random.default_rng(5)
+    vals = np.concatenate([
+        rng.random(4000).astype(np.float32), (rng.random(2000) * 10.0 ** rng.integers(-12, 12, 2000)).astype(np.float32),
+        np.array([0.0, -0.0, 1.0, 0.5, 1e-5, 9.99999e-5, 1e-4, 999999.0, 999999.5, 1e6, 123456.7, np.inf, -np.inf, np.nan, 3.4028235e38, 1.4e-45],
+                 dtype=np.float32)])
+    got = hostlib.format_rect_row(host, "q", vals).decode().rstrip("\n").split("\t")[1:]
+    want = ["%g" % float(v) for v in vals]
+    assert got == want
