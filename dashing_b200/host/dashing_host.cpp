@@ -1087,7 +1087,7 @@ static void write_hll_mode(const std::string &path, const char *mode, const uint
 
 // union_main + union_core<hll_t>, src/union.cpp:33-108
 int union_main(int argc, char **argv) {
-    int compression_level = 6, device = 0;
+    int compression_level = 6, device = 0, nthreads = 1;
     std::string opath = "/dev/stdout";
     std::vector<std::string> paths;
     static option longopts[] = {{"device", required_argument, nullptr, L_DEVICE}, {nullptr, 0, nullptr, 0}};
@@ -1100,18 +1100,14 @@ int union_main(int argc, char **argv) {
             case 'F': paths = get_paths(optarg); break;
             case 'b': unsupported("-b (the reference's getopt string gives it an argument and its switch then selects bloom filters)");
             case L_DEVICE: device = parse_device(optarg); break;
-            default: break;                                                      // -p threads, -z: nothing to do here
+            case 'p': nthreads = std::max(1, std::atoi(optarg)); break;          // threads the reading of the inputs, as there
+            default: break;                                                      // -z: nothing to do here
         }
     }
     for (int i = optind; i < argc; ++i) paths.push_back(argv[i]);
     if (paths.empty()) throw Error("require >= 1 paths. See usage.");
     // T(paths[i]) for every input, then += (element-wise max, hll.h:958-992) and sum() (perform_sum): the result keeps the FIRST
     // sketch's estimators and carries its cardinality
-    int nthreads = 1;
-    {   // -p: re-scan the flags for it (the loop above ignores it, as far as the reference's union is concerned it only threads the reads)
-        optind = 1;
-        for (int c; (c = getopt_long(argc, argv, "p:b:o:F:zZ:h?", longopts, nullptr)) >= 0;) if (c == 'p') nthreads = std::max(1, std::atoi(optarg));
-    }
     const HllFile first = read_hll(paths[0]);
     const uint32_t p = first.p, estim = first.estim, jestim = first.jestim;
     const size_t m = size_t(1) << p;
