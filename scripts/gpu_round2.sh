@@ -17,14 +17,12 @@ KREGEX='regex:dist_kernel|dist_jmle_kernel|sketch_kernel|planes_kernel|card_kern
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KREGEX" -c 1200 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
 tail -2 gpurun_out/ncu_bench.log | cut -c1-200; wc -l gpurun_out/launches.csv
+echo "=== ncu full: dist_kernel, sketch_kernel"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:^dist_kernel -s 1 -c 1 -f -o gpurun_out/prof_dist \
+    python bench.py --workload dist --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_dist.log 2>&1; tail -1 gpurun_out/ncu_dist.log | cut -c1-200
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:sketch_kernel -s 1 -c 1 -f -o gpurun_out/prof_sketch \
+    python bench.py --workload sketch --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_sketch.log 2>&1; tail -1 gpurun_out/ncu_sketch.log | cut -c1-200
 echo "=== ncu full: fasta kernels + union"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:fa_emit_kernel -s 3 -c 1 -f -o gpurun_out/prof_fa_emit python scripts/setops_run.py fasta > gpurun_out/ncu_fa.log 2>&1; tail -1 gpurun_out/ncu_fa.log | cut -c1-200
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:fa_summary_kernel -s 3 -c 1 -f -o gpurun_out/prof_fa_summary python scripts/setops_run.py fasta > gpurun_out/ncu_fa2.log 2>&1; tail -1 gpurun_out/ncu_fa2.log | cut -c1-200
-N=8000 timeout 600 ncu --set full --clock-control none --import-source on -k regex:union_kernel -s 1 -c 1 -f -o gpurun_out/prof_union python scripts/setops_run.py union > gpurun_out/ncu_union.log 2>&1; tail -2 gpurun_out/ncu_union.log | cut -c1-200
-echo "=== setops / fasta timings"
-N=8000 timeout 300 python scripts/setops_run.py all 2>&1 | tail -4
-echo "=== compute-sanitizer memcheck (small cases)"
-NG=2 N=128 timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python scripts/setops_run.py all > gpurun_out/sanitizer_memcheck.log 2>&1; echo "rc=$?"; tail -4 gpurun_out/sanitizer_memcheck.log
-echo "=== compute-sanitizer racecheck (fasta)"
-NG=1 timeout 900 compute-sanitizer --tool racecheck --error-exitcode 9 python scripts/setops_run.py fasta > gpurun_out/sanitizer_racecheck.log 2>&1; echo "rc=$?"; tail -4 gpurun_out/sanitizer_racecheck.log
 ls -la gpurun_out
