@@ -185,10 +185,10 @@ struct Uploader {
     DevBuf stage[2];
     cudaStream_t cs = nullptr;
     cudaEvent_t copied[2] = {nullptr, nullptr}, packed[2] = {nullptr, nullptr};
-    static constexpr int NGROUP = 4;
+    static constexpr int NGROUP = 8;           // only the LAST group's sketch is exposed after the upload: keep it short
     HostStager stager;                         // pageable sources go through page-locked bounce buffers filled by several threads
     cudaStream_t ss = nullptr;                 // sketch stream: group g is sketched while later groups are still uploading
-    cudaEvent_t group_packed[NGROUP] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t group_packed[NGROUP] = {};
     int init() {
         if (cs) return DB200_OK;
         DB200_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
