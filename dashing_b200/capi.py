@@ -75,6 +75,7 @@ _SIGS = {
     "db200_dist_knn_symmetric": (C.c_int, [C.c_int, u8p, C.c_uint64, C.POINTER(DistParams), C.c_uint32, vp]),
     "db200_dist_knn_rect": (C.c_int, [C.c_int, u8p, C.c_uint64, u8p, C.c_uint64, C.POINTER(DistParams), C.c_uint32, vp]),
     "db200_dist_plan_run_knn_dev": (C.c_int, [vp, C.POINTER(DistParams), C.c_uint64, C.c_uint64, C.c_uint32, vp, vp]),
+    "db200_dist_plan_run_knn_rows_dev": (C.c_int, [vp, C.POINTER(DistParams), C.c_uint64, C.c_uint64, C.c_uint32, vp, vp]),
     "db200_dist_plan_cardinalities_dev": (C.c_int, [vp, C.POINTER(vp)]),
     "db200_kernel_launches": (C.c_uint64, []),
     "db200_dist_plan_last_run_info": (C.c_int, [vp, u64p, u64p, C.POINTER(C.c_int)]),
@@ -360,6 +361,9 @@ class DistPlan:
 
     def run_knn_dev(self, prm: DistParams, nr: int, nq: int, nneighbors: int, d_out: int, stream: int = 0):
         _check(lib.db200_dist_plan_run_knn_dev(self.h, C.byref(prm), nr, nq, nneighbors, vp(d_out), vp(stream)))
+
+    def run_knn_rows_dev(self, prm: DistParams, row_begin: int, row_end: int, nneighbors: int, d_out: int, stream: int = 0):
+        _check(lib.db200_dist_plan_run_knn_rows_dev(self.h, C.byref(prm), row_begin, row_end, nneighbors, vp(d_out), vp(stream)))
 
     def cardinalities_dev(self) -> int:
         ptr = vp()

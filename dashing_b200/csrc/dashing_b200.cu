@@ -656,7 +656,7 @@ static bool is_similarity(int rtype) {
 // k nearest neighbours: the all-pairs values of one row block at a time go to plan scratch, a second kernel folds them
 // into the per-sketch retained sets, a third sorts and decodes.  nq == 0: symmetric.
 static int plan_knn(db200_dist_plan *pl, const db200_dist_params *prm, uint64_t nr, uint64_t nq, uint32_t nn, Neighbor *d_out,
-                    cudaStream_t stream) {
+                    cudaStream_t stream, uint64_t sym_row_begin = 0, uint64_t sym_row_end = ~0ull) {
     if (!pl->ready) { set_error("dist plan not prepared"); return DB200_EINVAL; }
     if (nn < 1 || nn > 1024) { set_error("nearest neighbours: nneighbors=%u outside the GPU path's range [1,1024]", nn); return DB200_EUNSUPPORTED; }
     if (prm->result_type < 0 || prm->result_type > 8) { set_error("dist: unknown result type %d", prm->result_type); return DB200_EINVAL; }
@@ -675,10 +675,13 @@ static int plan_knn(db200_dist_plan *pl, const db200_dist_params *prm, uint64_t 
     uint64_t total_pairs = 0, total_tiles = 0;
     if (!rect) {
         auto tri = [n](uint64_t r) { return (r * (2 * n - r - 1)) / 2; };
-        for (uint64_t rb = 0; rb + 1 < n;) {
+        // (a row range: the partial table of the pairs (i, j > i) with i in the range — what one rank of the multi-process
+        // driver contributes; the full table is the range [0, n))
+        const uint64_t r_end = std::min(n, sym_row_end);
+        for (uint64_t rb = std::min(sym_row_begin, r_end); rb + 1 < n && rb < r_end;) {
             // as many whole panels of rows as fit the budget (at least one)
-            uint64_t re = std::min(n, (rb / DT + 1) * DT);
-            while (re < n && tri(std::min(n, re + DT)) - tri(rb) <= budget) re = std::min(n, re + DT);
+            uint64_t re = std::min(r_end, (rb / DT + 1) * DT);
+            while (re < r_end && tri(std::min(r_end, re + DT)) - tri(rb) <= budget) re = std::min(r_end, re + DT);
             const uint64_t npairs = tri(re) - tri(rb);
             if (npairs) {
                 DB200_TRY(pl->knn_vals.reserve(npairs * 4));
@@ -1365,6 +1368,14 @@ int db200_dist_rect(int device, const uint8_t *ref_regs, uint64_t nr, const uint
     const CardOverride c = take_cards();
     if (c.ptr && c.n != nr + nq) { set_error("cardinality override holds %llu values for %llu + %llu sketches", (unsigned long long)c.n, (unsigned long long)nr, (unsigned long long)nq); return DB200_EINVAL; }
     return rect_impl(device, ref_regs, nr, qry_regs, nq, prm, out, c.ptr, c.ptr ? c.ptr + nr : nullptr);
+}
+int db200_dist_plan_run_knn_rows_dev(db200_dist_plan *pl, const db200_dist_params *prm, uint64_t row_begin, uint64_t row_end, uint32_t nneighbors,
+                                     db200_neighbor *d_out, void *stream) {
+    if (!pl || !prm || !d_out) { set_error("db200_dist_plan_run_knn_rows_dev: null argument"); return DB200_EINVAL; }
+    if (row_begin > row_end) { set_error("row_begin > row_end"); return DB200_EINVAL; }
+    DB200_TRY(check_device(pl->device));
+    std::lock_guard<std::mutex> lk(pl->mu);
+    return plan_knn(pl, prm, 0, 0, nneighbors, reinterpret_cast<Neighbor *>(d_out), (cudaStream_t)stream, row_begin, row_end);
 }
 int db200_dist_knn_symmetric(int device, const uint8_t *regs, uint64_t n, const db200_dist_params *prm, uint32_t nneighbors,
                              db200_neighbor *out) {

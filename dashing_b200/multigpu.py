@@ -108,3 +108,48 @@ def dist_symmetric_sharded(local_regs, counts: Sequence[int], dist, compute_rows
     outs = [torch.zeros(smax, dtype=torch.float32) for _ in range(world)]
     dist.all_gather(outs, buf)  # host-side concatenation (gloo in tests)
     return (rb, re_), torch.cat([o[:s] for o, s in zip(outs, sizes)])
+
+
+# ---- nearest neighbours across ranks (multi-process form) ---------------------------------------------
+NEIGHBOR_DTYPE = np.dtype([("value", np.float32), ("index", np.uint32)])   # validx_t, src/sketch_and_cmp.h:605
+DIST_MEASURES = (0, 3, 4, 6, 8)   # MASH_DIST, FULL_MASH_DIST, FULL_CONTAINMENT_DIST, CONTAINMENT_DIST, SYMMETRIC_CONTAINMENT_DIST
+
+
+def merge_neighbor_tables(tables: np.ndarray) -> np.ndarray:
+    """tables: [world][n][nn] partial nearest-neighbour tables over DISJOINT row ranges of the triangle (structured
+    (value, index) entries, unused slots filled with (FLT_MAX, 0xFFFFFFFF)).  -> [n][nn], per row the nn smallest
+    (value, index) keys of the union, ascending.
+
+    Exact for the distance measures only: there the reference's heap (perform_nns, src/sketch_and_cmp.h:642-697: visit in
+    ascending index, replace the worst when STRICTLY better) ends with precisely the nn smallest (value, index) pairs, a
+    property of the multiset that survives any split of the sources.  For similarity measures the retained set depends on
+    the visiting order and no merge of partial tables reproduces it."""
+    tables = np.asarray(tables)
+    world, n, nn = tables.shape
+    cat = np.ascontiguousarray(np.transpose(tables, (1, 0, 2))).reshape(n, world * nn)
+    # -0.0 and +0.0 are the same value for the reference's comparisons: the index decides between them
+    order = np.lexsort((cat["index"], cat["value"] + np.float32(0.0)), axis=-1)[:, :nn]
+    return np.take_along_axis(cat, order, axis=-1)
+
+
+def knn_symmetric_sharded(local_regs, counts: Sequence[int], dist, compute_partial: Callable, result_type: int, nneighbors: int):
+    """All-gather of the register shards, one partial table per rank over its block rows, all-gather of the tables, merge.
+    compute_partial(full_regs, n, row_begin, row_end, nneighbors) -> structured array [n][nneighbors] (production:
+    DistPlan.run_knn_rows_dev).  Distance measures only (see merge_neighbor_tables)."""
+    import torch
+
+    if result_type not in DIST_MEASURES:
+        raise ValueError("nearest-neighbour tables of similarity measures do not merge across ranks: compute them on one GPU")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    full = allgather_registers(local_regs, counts, dist)
+    n = int(sum(counts))
+    rb, re_ = row_partition(n, world)[rank]
+    part = np.ascontiguousarray(compute_partial(full, n, rb, re_, nneighbors))
+    assert part.dtype == NEIGHBOR_DTYPE and part.shape == (n, nneighbors)
+    mine = torch.from_numpy(part.view(np.uint8).reshape(-1).copy())
+    if getattr(local_regs, "is_cuda", False):      # NCCL moves device tensors; gloo (CPU tests) host tensors
+        mine = mine.to(local_regs.device)
+    outs = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(outs, mine)          # n * nn * 8 bytes per rank
+    tables = np.stack([o.cpu().numpy().view(NEIGHBOR_DTYPE).reshape(n, nneighbors) for o in outs])
+    return merge_neighbor_tables(tables)

@@ -234,6 +234,13 @@ DB200_API int db200_dist_knn_rect(int device, const uint8_t *ref_regs, uint64_t 
 DB200_API int db200_dist_plan_run_knn_dev(db200_dist_plan *pl, const db200_dist_params *prm, uint64_t nr, uint64_t nq, uint32_t nneighbors,
                                 db200_neighbor *d_out, void *stream);
 
+/* Partial symmetric table: only the pairs (i, j > i) with i in [row_begin, row_end) are visited (ascending i, as always).  For the
+ * DISTANCE measures the retained set is the nneighbors smallest (value, index) keys, so the tables of disjoint row ranges merge
+ * exactly (per row: the nneighbors smallest keys of their union) — what dashing_b200/multigpu.py does across ranks.  For the
+ * similarity measures the reference's retained set depends on the visiting order and partial tables do not merge. */
+DB200_API int db200_dist_plan_run_knn_rows_dev(db200_dist_plan *pl, const db200_dist_params *prm, uint64_t row_begin, uint64_t row_end,
+                                               uint32_t nneighbors, db200_neighbor *d_out, void *stream);
+
 /* Device pointer to the plan's per-sketch cardinalities (double[n]) — valid until the next prepare/destroy. */
 DB200_API int db200_dist_plan_cardinalities_dev(db200_dist_plan *pl, const double **d_card);
 /* Launch accounting for bench.py: kernels launched by this library since process start. */

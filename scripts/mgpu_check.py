@@ -48,6 +48,24 @@ def main():
         want = capi.dist_symmetric(regs, p, k=k, result_type=capi.MASH_DIST, device=lr)
         ok = bool(np.array_equal(full, want))
         print(f"MGPU_CHECK world={world} pairs={want.size} equal={ok}", flush=True)
+    # nearest neighbours, distance measure: per-rank partial tables over the rank's block rows, all-gathered and merged
+    nn = 5
+    regs_all = capi.sketch_genomes(genomes, k, p, device=lr)
+    prm_nn = capi.dist_params(p, k, result_type=capi.MASH_DIST, order=capi.ORDER_COL_FIRST)
+
+    def compute_partial(full, n, rb, re_, k_nn):
+        d_out = torch.zeros(n * k_nn * 8, dtype=torch.uint8, device=dev)
+        plan.prepare_dev(full.data_ptr(), n, p, capi.ERTL_MLE, stream)
+        plan.run_knn_rows_dev(prm_nn, rb, re_, k_nn, d_out.data_ptr(), stream)
+        torch.cuda.synchronize()
+        return d_out.cpu().numpy().view(capi.NEIGHBOR_DTYPE).reshape(n, k_nn)
+
+    merged = multigpu.knn_symmetric_sharded(local, counts, dist, compute_partial, capi.MASH_DIST, nn)
+    if rank == 0:
+        want_nn = capi.knn_symmetric(regs_all, p, nn, k=k, result_type=capi.MASH_DIST, device=lr)
+        ok_nn = bool(np.array_equal(merged["index"], want_nn["index"]) and np.array_equal(merged["value"], want_nn["value"]))
+        print(f"MGPU_CHECK knn world={world} equal={ok_nn}", flush=True)
+        ok = ok and ok_nn
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)

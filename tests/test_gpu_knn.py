@@ -121,3 +121,32 @@ def test_knn_large(gpu):
         others = np.array([j for j in range(n) if j != r])
         want = _replay(row[others], others, nn, sim=True)
         assert [(float(v), int(i)) for v, i in sim[r]] == [(float(v), int(i)) for v, i in want], r
+
+
+def test_knn_partial_tables_merge_for_distance_measures(gpu):
+    """db200_dist_plan_run_knn_rows_dev: partial tables over disjoint block rows (what each rank of the multi-process driver
+    computes) merged by multigpu.merge_neighbor_tables equal the one-GPU table bit for bit — for a distance measure, with long
+    runs of exactly-1 Mash distances (unrelated groups) at the cut.  The plan API takes device memory: torch is the plumbing."""
+    import torch
+    from dashing_b200 import multigpu
+    p, nn = 10, 7
+    regs = synth.registers(21, 300, p, card=2e4, group=8)
+    n = regs.shape[0]
+    dev = torch.device("cuda", 0)
+    d_regs = torch.from_numpy(regs).to(dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    plan = gpu.DistPlan(0)
+    plan.prepare_dev(d_regs.data_ptr(), n, p, gpu.ERTL_MLE, stream)
+    for rtype, jestim in ((gpu.MASH_DIST, gpu.ERTL_MLE), (gpu.FULL_MASH_DIST, gpu.ERTL_JOINT_MLE)):
+        prm = gpu.dist_params(p, 21, gpu.ERTL_MLE, jestim, rtype, gpu.ORDER_COL_FIRST)
+        want = gpu.knn_symmetric(regs, p, nn, k=21, jestim=jestim, result_type=rtype)
+        for world in (2, 3, 7):
+            tables = []
+            for rb, re_ in multigpu.row_partition(n, world):
+                d_out = torch.zeros(n * nn * 8, dtype=torch.uint8, device=dev)
+                plan.run_knn_rows_dev(prm, rb, re_, nn, d_out.data_ptr(), stream)
+                torch.cuda.synchronize()
+                tables.append(d_out.cpu().numpy().view(gpu.NEIGHBOR_DTYPE).reshape(n, nn))
+            got = multigpu.merge_neighbor_tables(np.stack(tables))
+            assert np.array_equal(got["index"], want["index"]) and np.array_equal(got["value"].view(np.uint32), want["value"].view(np.uint32)), (rtype, world)
+    plan.close()

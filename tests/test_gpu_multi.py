@@ -18,4 +18,4 @@ def test_sharded_pipeline_matches_single_gpu(gpu):
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
                         "--master-port", "29617", os.path.join(ROOT, "scripts", "mgpu_check.py")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    assert "equal=True" in r.stdout
+    assert "equal=True" in r.stdout and "knn world=2 equal=True" in r.stdout, r.stdout[-2000:]

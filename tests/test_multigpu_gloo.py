@@ -82,3 +82,79 @@ def test_sharded_all_pairs_gloo_world2(n):
     assert all(r[0] for r in res), "all-gathered register matrix differs from the source"
     assert all(r[1] for r in res), "concatenated block-rows differ from the single-process matrix"
     assert sorted(r[2] for r in res) == multigpu.row_partition(n, world)
+
+
+def _partial_knn(full_dist, n, rb, re_, nn):
+    """Reference semantics restricted to the pairs (i, j > i) with i in [rb, re): what one rank contributes."""
+    out = np.zeros((n, nn), dtype=multigpu.NEIGHBOR_DTYPE)
+    out["value"], out["index"] = np.float32(3.4028234663852886e38), np.uint32(0xFFFFFFFF)
+    cand = [[] for _ in range(n)]
+    for i in range(rb, re_):
+        for j in range(i + 1, n):
+            v = full_dist[i, j]
+            cand[i].append((v, j)); cand[j].append((v, i))
+    for r in range(n):
+        best = sorted(cand[r])[:nn]
+        for s, (v, j) in enumerate(best):
+            out[r, s] = (v, j)
+    return out
+
+
+def test_merge_neighbor_tables_equals_the_sequential_heap(port):
+    """Distance measures: per-rank partial tables over disjoint block rows, merged, equal the reference's one-thread heap on the
+    whole set — including long runs of equal values (unrelated sketches: Mash distance exactly 1)."""
+    p, nn = 10, 6
+    regs = synth.registers(21, 48, p, card=2e4, group=8)
+    n = regs.shape[0]
+    want = port.knn(regs, p, nn, k=21, rtype=0)
+    packed = port.dist_rows(regs, p, k=21, rtype=0, order=1)
+    full = np.zeros((n, n), dtype=np.float32)
+    iu = np.triu_indices(n, 1)
+    full[iu] = packed
+    for world in (2, 3, 5):
+        parts = multigpu.row_partition(n, world)
+        tables = np.stack([_partial_knn(full, n, rb, re_, nn) for rb, re_ in parts])
+        got = multigpu.merge_neighbor_tables(tables)
+        # (the matrix path rounds ksinv = 1/k to float, nndist_loop keeps it in double: values agree to the last bits only)
+        assert np.array_equal(got["index"], want["index"]) and np.allclose(got["value"], want["value"], rtol=1e-6, atol=0), world
+    with pytest.raises(ValueError):
+        multigpu.knn_symmetric_sharded(None, [n], None, None, result_type=1, nneighbors=nn)
+
+
+def _knn_worker(rank, world, port_no, n, p, nn, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port_no))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import oracle as O
+        chk = O.port()
+        regs = synth.registers(33, n, p, card=2e4, group=8)
+        counts = multigpu.shard_counts(n, world)
+        start = sum(counts[:rank])
+        local = torch.from_numpy(regs[start:start + counts[rank]].copy())
+
+        def compute_partial(full, nt, rb, re_, k_nn):
+            packed = chk.dist_rows(full.numpy(), p, k=21, rtype=0, order=1)
+            fd = np.zeros((nt, nt), dtype=np.float32)
+            fd[np.triu_indices(nt, 1)] = packed
+            return _partial_knn(fd, nt, rb, re_, k_nn)
+
+        got = multigpu.knn_symmetric_sharded(local, counts, dist, compute_partial, result_type=0, nneighbors=nn)
+        want = chk.knn(regs, p, nn, k=21, rtype=0)
+        q.put(bool(np.array_equal(got["index"], want["index"]) and np.allclose(got["value"], want["value"], rtol=1e-6, atol=0)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_knn_gloo_world2():
+    world, n, p, nn = 2, 40, 10, 5
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port_no = _free_port()
+    procs = [ctx.Process(target=_knn_worker, args=(r, world, port_no, n, p, nn, q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    assert all(res), "merged per-rank neighbour tables differ from the single-process table"
