@@ -458,9 +458,9 @@ def run_gpu(args):
                 "bytes_per_kmer": alg_bytes / max(kmers_rank, 1), "kernel_ms": ms,
                 "note": "2-bit bases + validity + record-start planes + register write-back (SURVEY.md §8(d) + the start plane); "
                         "0.5 B per k-mer cannot be HBM bound: the binding unit is the ALU pipe",
-                "int_bound": {"sass_instr_per_kmer": 49, "alu_pipe_instr_per_kmer": 26, "fma_pipe_instr_per_kmer": 18,
-                              "alu_ceiling_kmers_per_s": 148 * 64 / 26 * 1.965e9 * 1.0,
-                              "frac_of_alu_ceiling": value / world / (148 * 64 / 26 * 1.965e9),
+                "int_bound": {"sass_instr_per_kmer": 48, "alu_pipe_instr_per_kmer": 25, "fma_pipe_instr_per_kmer": 18,
+                              "alu_ceiling_kmers_per_s": 148 * 64 / 25 * 1.965e9 * 1.0,
+                              "frac_of_alu_ceiling": value / world / (148 * 64 / 25 * 1.965e9),
                               "source": "cuobjdump -sass of sketch_kernel<0,1,true>, one unrolled base step (DESIGN.md §3)"}}
         clocks = sampler.window(t_wall0, t_wall1) if sampler else None
         # e2e: host ASCII (pinned) -> db200_sketch_batch -> host registers

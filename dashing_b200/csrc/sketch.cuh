@@ -237,10 +237,18 @@ __global__ void __launch_bounds__(SK_THREADS) sketch_kernel(const uint4 *__restr
         uint32_t *g32 = reinterpret_cast<uint32_t *>(greg);
         // seed the staged registers from HBM
         if (MODE == 0) {
+            // staged in the EXPONENT domain: a slot holds (biased exponent << 20) of the smallest double(T) seen for its register
+            // (rho = 1087 - biased exponent, so a smaller word is a larger rho); 0xFFFFFFFF = empty.
             uint4 *s4 = reinterpret_cast<uint4 *>(sregs);
             for (uint32_t w = threadIdx.x; w < m / 4; w += SK_THREADS) {
                 const uint32_t v = g32[w];
-                s4[w] = make_uint4(v & 0xFFu, (v >> 8) & 0xFFu, (v >> 16) & 0xFFu, v >> 24);
+                uint32_t e[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const uint32_t r = (v >> (8 * i)) & 0xFFu;
+                    e[i] = r ? ((1087u - r) << 20) : 0xFFFFFFFFu;
+                }
+                s4[w] = make_uint4(e[0], e[1], e[2], e[3]);
             }
         } else if (MODE == 1) {
             for (uint32_t w = threadIdx.x; w < m / 4; w += SK_THREADS) reinterpret_cast<uint32_t *>(sregs)[w] = g32[w];
@@ -304,10 +312,11 @@ __global__ void __launch_bounds__(SK_THREADS) sketch_kernel(const uint4 *__restr
                             const uint32_t addr = sbase + idx * 4u;
                             uint32_t cur;
                             asm volatile("ld.shared.u32 %0, [%1];" : "=r"(cur) : "r"(addr));
-                            // cur < rho  <=>  exponent < 1087 - cur  <=>  ehi < (1087 - cur) << 20   (one IMAD, one compare)
-                            if (emit && ehi < cur * kc.neg_2p20 + kc.c1087_2p20)
-                                asm volatile("{\n\t.reg .u32 t;\n\tshr.u32 t, %1, 20;\n\tsub.u32 t, 1087, t;\n\t"   // rho, only on the rare path
-                                             "red.shared.max.u32 [%0], t;\n\t}" ::"r"(addr), "r"(ehi) : "memory");
+                            // exponent domain: slots hold (biased exponent << 20) of the best T so far, so `ehi < cur` is exactly
+                            // "strictly larger rho" (equal exponents: ehi >= cur because of its mantissa bits) — one compare, and
+                            // on the rare path one mask + RED.MIN; no rho arithmetic per k-mer
+                            if (emit && ehi < cur)
+                                asm volatile("red.shared.min.u32 [%0], %1;" ::"r"(addr), "r"(ehi & 0xFFF00000u) : "memory");
                         } else {
                             const uint32_t rho = 1087u - (ehi >> 20);
                             const bool upd = emit && r8[idx] < rho;
@@ -325,7 +334,11 @@ __global__ void __launch_bounds__(SK_THREADS) sketch_kernel(const uint4 *__restr
             const uint4 *s4 = reinterpret_cast<const uint4 *>(sregs);
             for (uint32_t w = threadIdx.x; w < m / 4; w += SK_THREADS) {
                 const uint4 v = s4[w];
-                merge_word(g32 + w, v.x | (v.y << 8) | (v.z << 16) | (v.w << 24));
+                const uint32_t e[4] = {v.x, v.y, v.z, v.w};
+                uint32_t packed = 0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) packed |= (e[i] == 0xFFFFFFFFu ? 0u : 1087u - (e[i] >> 20)) << (8 * i);   // back to rho
+                merge_word(g32 + w, packed);
             }
         } else if (MODE == 1) {
             const uint32_t *s32 = reinterpret_cast<const uint32_t *>(sregs);
