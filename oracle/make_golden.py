@@ -156,7 +156,8 @@ def main():
 
 
 def write_fasta(path, records, width=70, gz=False, crlf=False, fastq=False):
-    op = gzip.open if gz else open
+    # (mtime=0: the gzip header then holds no timestamp, so regenerating the fixtures is byte-reproducible)
+    op = (lambda p_, m: gzip.GzipFile(p_, m, mtime=0)) if gz else open
     nl = b"\r\n" if crlf else b"\n"
     with op(path, "wb") as f:
         for i, r in enumerate(records):
