@@ -591,6 +591,7 @@ void sketch_paths(const SketchOptions &o, const std::vector<std::string> &paths,
 } // namespace
 
 size_t file_window(const std::string &f) { return file_capacity(f); }
+size_t slurp_file(const std::string &f, char *dst, size_t cap) { return slurp_into_window(f, dst, cap); }
 
 void sketch_core(const SketchOptions &o, std::vector<std::string> paths) {
     if (!o.avoid_sorting) sort_paths_by_fsize(paths);
@@ -1554,6 +1555,13 @@ DB200H_API int64_t db200h_get_paths(const char *file, char *out, uint64_t cap) {
     for (auto &p : db200h::get_paths(file)) { s += p; s += '\n'; }
     if (s.size() <= cap) std::memcpy(out, s.data(), s.size());
     return (int64_t)s.size();
+}
+// the raw bytes of a file (inflated if gzip) into the caller's window, as the batch driver reads them; -2 = window too small
+DB200H_API int64_t db200h_slurp(const char *path, char *dst, uint64_t cap) {
+    try {
+        const size_t n = db200h::slurp_file(path, dst, cap);
+        return n == SIZE_MAX ? -2 : (int64_t)n;
+    } catch (const std::exception &e) { std::fprintf(stderr, "%s\n", e.what()); return -1; }
 }
 // file_capacity(): the window the batch driver reserves for a file
 DB200H_API uint64_t db200h_file_capacity(const char *path) {

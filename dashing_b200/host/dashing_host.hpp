@@ -82,6 +82,9 @@ struct DistOptions : SketchOptions {
 // the driver reserves — the file size, or the ISIZE trailer for gzip (RFC 1952; too small for multi-member files).
 size_t parse_into_window(const std::string &file, char *dst, size_t cap, std::vector<uint64_t> &ends);
 size_t file_window(const std::string &file);
+// The raw bytes of a file (inflated if it is gzip) into a caller window — all the CLI does with sequence files before handing
+// them to db200_sketch_fasta_batch; SIZE_MAX when the window is too small (a multi-member gzip: its trailer sizes the last member).
+size_t slurp_file(const std::string &file, char *dst, size_t cap);
 void sketch_core(const SketchOptions &o, std::vector<std::string> paths);
 // dist_sketch_and_cmp<hll_t> + dist_loop / partdist_loop, src/sketch_and_cmp.h:268-417, :785-880; src/dashing.h:660-712.
 // The last nq entries of inpaths are queries (rectangular mode).

@@ -29,6 +29,8 @@ def load():
     l.db200h_record_names.argtypes = [C.c_char_p, C.c_char_p, C.c_uint64]
     l.db200h_get_paths.restype = C.c_int64
     l.db200h_get_paths.argtypes = [C.c_char_p, C.c_char_p, C.c_uint64]
+    l.db200h_slurp.restype = C.c_int64
+    l.db200h_slurp.argtypes = [C.c_char_p, C.c_void_p, C.c_uint64]
     l.db200h_file_capacity.restype = C.c_uint64
     l.db200h_file_capacity.argtypes = [C.c_char_p]
     return l

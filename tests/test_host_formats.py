@@ -201,3 +201,25 @@ def test_text_numbers_are_printf_g6(host):
     got = hostlib.format_rect_row(host, "q", vals).decode().rstrip("\n").split("\t")[1:]
     want = ["%g" % float(v) for v in vals]
     assert got == want
+
+
+def test_raw_file_windows(host, tmp_path):
+    """What the CLI does with a sequence file: size a window (file size, or the gzip ISIZE trailer) and read the raw bytes into
+    it — inflating gzip, overflowing on multi-member gzip (whose trailer covers the last member only), nothing parsed."""
+    raw = b">h1 x\r\nACGT\r\n\n>h2\nGGCC" * 1000
+    (tmp_path / "p.fa").write_bytes(raw)
+    (tmp_path / "g.fa.gz").write_bytes(gzip.compress(raw))
+    (tmp_path / "mm.fa.gz").write_bytes(gzip.compress(raw[:9000]) + gzip.compress(raw[9000:]))
+    (tmp_path / "e.fa").write_bytes(b"")
+    for name, want in (("p.fa", raw), ("g.fa.gz", raw), ("e.fa", b"")):
+        cap = host.db200h_file_capacity(str(tmp_path / name).encode())
+        assert cap == len(want), name
+        buf = np.zeros(cap + 16, dtype=np.uint8)
+        n = host.db200h_slurp(str(tmp_path / name).encode(), buf.ctypes.data, cap)
+        assert n == len(want) and buf[:n].tobytes() == want, name
+    cap = host.db200h_file_capacity(str(tmp_path / "mm.fa.gz").encode())
+    assert cap == len(raw) - 9000                      # ISIZE of the LAST member
+    buf = np.zeros(len(raw) + 16, dtype=np.uint8)
+    assert host.db200h_slurp(str(tmp_path / "mm.fa.gz").encode(), buf.ctypes.data, cap) == -2     # -> the re-read path
+    assert host.db200h_slurp(str(tmp_path / "mm.fa.gz").encode(), buf.ctypes.data, len(raw)) == len(raw) and buf[:len(raw)].tobytes() == raw
+    assert host.db200h_slurp(str(tmp_path / "missing.fa").encode(), buf.ctypes.data, 10) == -1
