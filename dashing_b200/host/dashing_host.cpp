@@ -227,31 +227,56 @@ struct LineReader {
 
 // kseq_read's record loop (bonsai/klib/kseq.h:177-218) over one file; record boundaries (sink lengths) go to `ends`, and,
 // when asked for, the record names (header up to the first whitespace, kseq.h:190) to `names`.
+//   * Without a pending header (start of the file, and after every FASTQ record: last_char == 0) kseq scans CHARACTERS, not
+//     lines, for the next '>' or '@' (:183) — a '>' in the middle of a junk line opens a record.
+//   * Sequence lines are read until a line STARTS with '>', '@' (the next header: consumed and remembered, :199) or '+' (:193).
+//   * A header character with nothing behind it (end of file) yields no record (:188).
 void parse_records(const std::string &file, SeqSink &sink, std::vector<uint64_t> &ends, std::vector<std::string> *names = nullptr) {
     gzFile fp = gzopen(file.c_str(), "rb");
     if (!fp) throw Error("Could not open file at " + file + ". Abort!");
     gzbuffer(fp, 1 << 18);
     LineReader lr(fp);
+    bool pending = false;                  // kseq's last_char != 0: the header character has been consumed already
     int c;
-    while ((c = lr.peek()) != -1 && !sink.overflow) {
-        if (c != '>' && c != '@') { lr.line(nullptr); continue; }   // skip to the next header
+    while (!sink.overflow) {
+        if (!pending) {
+            while ((c = lr.peek()) != -1 && c != '>' && c != '@') ++lr.pos;
+            if (c == -1) break;
+            ++lr.pos;                      // the header character
+        }
+        if (lr.peek() == -1) break;        // ks_getuntil(name) < 0: "normal exit: EOF"
         if (names) {
             std::string hdr;
             SeqSink hs;
             hs.str = &hdr;
             lr.line(&hs, 0);
-            size_t e = 1;
+            size_t e = 0;
             while (e < hdr.size() && !std::isspace((unsigned char)hdr[e])) ++e;
-            names->push_back(hdr.substr(1, e - 1));
-        } else lr.line(nullptr);                                   // name + comment
+            names->push_back(hdr.substr(0, e));
+        } else lr.line(nullptr);           // name + comment
         const size_t rs = sink.len;
-        while ((c = lr.peek()) != -1 && c != '>' && c != '+' && c != '@') lr.line(&sink, rs);
-        if (c == '+') {                                            // FASTQ: skip the '+' line and the qualities
+        while ((c = lr.peek()) != -1 && c != '>' && c != '+' && c != '@') {
+            if (c == '\n') { ++lr.pos; continue; }    // "skip empty lines" (:195): no ks_getuntil2, so no CR is stripped here
+            lr.line(&sink, rs);
+        }
+        pending = c == '>' || c == '@';
+        if (c != -1) ++lr.pos;             // the character that ended the record is consumed either way
+        if (c == '+') {                    // FASTQ: skip the rest of the '+' line, then quality lines until they cover the sequence
             lr.line(nullptr);
-            std::string qual;                                       // qual.l < seq.l, kseq.h:210
+            std::string qual;               // while (getuntil2(qual) >= 0 && qual.l < seq.l), kseq.h:210
             SeqSink qs;
             qs.str = &qual;
-            while (qs.len < sink.len - rs && lr.peek() != -1) lr.line(&qs, 0);
+            do {
+                if (lr.peek() == -1) break;
+                lr.line(&qs, 0);
+            } while (qs.len < sink.len - rs);
+            pending = false;
+            if (qs.len != sink.len - rs) {  // "truncated quality string": kseq_read returns -2 (:214) and the callers' loops
+                sink.len = rs;              // (`while(kseq_read(ks) >= 0)`, encoder.h) stop — the record is never seen
+                if (sink.str) sink.str->resize(rs);
+                if (names) names->pop_back();
+                break;
+            }
         }
         ends.push_back(sink.len);
     }
