@@ -9,8 +9,9 @@
 //     (ks_getuntil2 strips one trailing CR, kseq.h:140-141) — including blanks, digits, '>' in mid-line, ...: they are
 //     invalid bases, exactly what the reference's k-mer loop sees (encoder.h:252-253);
 //   * bytes before the first header of a file belong to no record (kseq.h:181-186);
-//   * a sequence line that starts with '+' or '@' switches kseq to FASTQ parsing (kseq.h:196-216): such files are not
-//     handled here — the file is flagged and the host sketches it through the record interface instead.
+//   * a sequence line that starts with '+' or '@' switches kseq to FASTQ parsing (kseq.h:196-216), and before a file's first
+//     header kseq scans characters rather than lines for '>' / '@' (kseq.h:183): files showing either are not handled here —
+//     the file is flagged and the host sketches it through the record interface instead.
 // Windows never span records (encoder.h:444): the first sequence byte of every record is marked in the record-start plane.
 //
 // States: SKIP (before a file's first header) / HDR (inside a header line) / SEQN (after a header, no sequence byte yet)
@@ -311,7 +312,8 @@ __global__ void fa_clip_items_kernel(SketchItem *__restrict__ items, uint32_t n,
 // lanes' states with the ballots again, and the lanes' offsets with a shuffle scan of their sequence-byte counts.  Codes
 // and validity come from the SIMD-in-word packer of sketch.cuh and are squeezed by the lane's keep mask (fa_compress: one
 // step per run of dropped bytes — none for most lanes, one where a line ends).
-// flags[f] |= 1 when file f shows FASTQ record syntax ('@' header, or a '+' / '@' line inside a record).
+// flags[f] |= 1 when file f shows FASTQ record syntax ('@' header, or a '+' / '@' line inside a record) or holds a '>' / '@' in the
+// junk before its first header line (kseq would open a record there): the host re-sketches it through the record interface.
 __global__ void __launch_bounds__(FA_THREADS) fa_emit_kernel(const uint8_t *__restrict__ text, uint64_t blk0, const uint64_t *__restrict__ fblk,
                                                             const uint64_t *__restrict__ flen, uint32_t nfiles, uint64_t chunk_end, uint32_t next_byte,
                                                             const uint8_t *__restrict__ in_state, const uint64_t *__restrict__ in_pos,
@@ -350,12 +352,13 @@ __global__ void __launch_bounds__(FA_THREADS) fa_emit_kernel(const uint8_t *__re
     const uint32_t st = fa_my_state(wst, L, w);
     const uint32_t K = fa_keep(L, st);
     const uint32_t n = FA_POPC(K);
-    // FASTQ syntax is looked for only where a line starts in the lane
+    // what the parser does not cover (FASTQ syntax; '>' / '@' in the junk before a file's first header) can only show where a
+    // line starts in the lane or while the file is still being skipped
     bool fq = false;
-    if (L.ls) {
+    if (L.ls || st == FS_SKIP) {
         const uint32_t vm = fa_below(s_fend > blk * FA_BLOCK + (uint64_t)threadIdx.x * FA_BPT
                                          ? (uint32_t)min((uint64_t)FA_BPT, s_fend - (blk * FA_BLOCK + (uint64_t)threadIdx.x * FA_BPT)) : 0u);
-        fq = fa_fastq(L, st, fa_eq16(c.raw, '@') & vm, fa_eq16(c.raw, '+') & vm);
+        fq = fa_fastq(L, st, fa_eq16(c.raw, '@') & vm, fa_eq16(c.raw, '+') & vm, c.gt);
     }
     if (__any_sync(0xFFFFFFFFu, fq) && lane == 0) atomicOr(&flags[s_file], 1u);
     // exclusive scan of the lanes' counts

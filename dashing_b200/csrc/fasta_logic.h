@@ -125,10 +125,19 @@ FA_HD uint32_t fa_starts(const FaLane &L, uint32_t s, uint32_t K) {
     return st;
 }
 
-// FASTQ record syntax seen by a lane entered in state s: '@' at a line start, or '+' at a line start inside a record
-// (kseq.h:183, :196).  at / pl: byte-class masks of '@' and '+'.
-FA_HD bool fa_fastq(const FaLane &L, uint32_t s, uint32_t at, uint32_t pl) {
-    return (L.ls & at) != 0 || (L.ls & pl & ((s != FS_SKIP ? L.mid : 0u) | L.tail)) != 0;
+// What this parser does not cover, seen by a lane entered in state s (the file is flagged and the host sketches it through the
+// record interface):
+//   * FASTQ record syntax: '@' at a line start, or '+' at a line start inside a record (kseq.h:183, :196);
+//   * a '>' in mid-line, or an '@' anywhere, BEFORE the file's first header line: without a pending header kseq scans
+//     characters, not lines, for the next '>' / '@' (kseq.h:183), so such a byte would open a record there.
+// at / pl / gt: byte-class masks of '@', '+' and '>'.
+FA_HD bool fa_fastq(const FaLane &L, uint32_t s, uint32_t at, uint32_t pl, uint32_t gt) {
+    if ((L.ls & at) != 0 || (L.ls & pl & ((s != FS_SKIP ? L.mid : 0u) | L.tail)) != 0) return true;
+    if (s == FS_SKIP) {
+        const uint32_t skipped = L.hs ? fa_below(FA_FFS(L.hs) - 1u) : 0xFFFFu;     // bytes before the lane's first header line
+        return (((gt & ~L.ls) | at) & skipped) != 0;
+    }
+    return false;
 }
 
 // Removes the bits of v at the positions NOT in keep (16-bit), closing the gaps: a software pext, one step per run of

@@ -34,7 +34,7 @@ int main(int argc, char **argv) {
         const uint8_t *w = t.data() + 1;
         // lane infos and ballots
         FaLane L[32];
-        uint32_t at[32], pl[32], b_hs = 0, b_ls = 0, b_kab = 0, b_kb = 0;
+        uint32_t at[32], pl[32], gtm[32], b_hs = 0, b_ls = 0, b_kab = 0, b_kb = 0;
         for (int l = 0; l < 32; ++l) {
             uint32_t nl = 0, cr = 0, gt = 0; at[l] = pl[l] = 0;
             for (int i = 0; i < 16; ++i) {
@@ -42,6 +42,7 @@ int main(int argc, char **argv) {
                 nl |= (uint32_t)(c == '\n') << i; cr |= (uint32_t)(c == '\r') << i; gt |= (uint32_t)(c == '>') << i;
                 at[l] |= (uint32_t)(c == '@') << i; pl[l] |= (uint32_t)(c == '+') << i;
             }
+            gtm[l] = gt;
             L[l] = fa_lane(nl, cr, gt, w[l * 16 - 1] == '\n', w[l * 16 + 16] == '\n');
             b_hs |= (uint32_t)(L[l].hs != 0) << l; b_ls |= (uint32_t)(L[l].ls != 0) << l;
             b_kab |= (uint32_t)(L[l].kA || L[l].kB) << l; b_kb |= (uint32_t)(L[l].kB != 0) << l;
@@ -62,12 +63,13 @@ int main(int argc, char **argv) {
                     const uint32_t c = w[p];
                     const bool ls = w[p - 1] == '\n', drop = c == '\n' || (c == '\r' && w[p + 1] == '\n');
                     fq |= ls && (c == '@' || (c == '+' && state != FS_SKIP));
+                    fq |= state == FS_SKIP && ((c == '>' && !ls) || c == '@');      // kseq's character scan for the first header
                     bool first;
                     if (step(state, c, ls, drop, first)) { K |= 1u << i; ST |= (uint32_t)first << i; }
                 }
                 const uint32_t gk = fa_keep(L[l], got), gs = fa_starts(L[l], got, gk);
                 if (gk != K || gs != ST) { std::printf("round %d S=%u lane %d: keep %04x/%04x starts %04x/%04x\n", r, S, l, gk, K, gs, ST); return 1; }
-                fq_fast |= fa_fastq(L[l], got, at[l], pl[l]);
+                fq_fast |= fa_fastq(L[l], got, at[l], pl[l], gtm[l]);
                 // compress: flags and 2-bit codes
                 const uint32_t v = (uint32_t)rng() & 0xFFFFu, c2 = (uint32_t)rng();
                 uint32_t wv = 0, wc = 0; int n = 0;

@@ -109,8 +109,13 @@ def test_fastq_syntax_is_flagged(gpu):
     at_inside = b">x\n" + g[1][:1000].tobytes() + b"\n@y\n" + g[1][1000:2000].tobytes() + b"\n"
     ok = fasta([g[1].tobytes()])
     plus_in_header_or_midline = b">x + @\n" + g[1][:1000].tobytes() + b"+@\n"
-    _, status = gpu.sketch_fasta([[fq], [plus_inside], [ok], [at_inside], [plus_in_header_or_midline]], 21, 10, True)
-    assert list(status) == [1, 1, 0, 1, 0]
+    # before a file's first header kseq scans CHARACTERS for '>' / '@' (kseq.h:183): junk holding either would open a record
+    gt_in_junk = b"some junk > here\n" + ok
+    at_in_junk = b"mail me: a@b.c\n\n" + ok
+    plain_junk = b"no special bytes in this junk + nor here\n+ or here\n" + ok
+    _, status = gpu.sketch_fasta([[fq], [plus_inside], [ok], [at_inside], [plus_in_header_or_midline], [gt_in_junk], [at_in_junk], [plain_junk]],
+                                 21, 10, True)
+    assert list(status) == [1, 1, 0, 1, 0, 1, 1, 0]
 
 
 def test_large_batch_default_chunks(gpu, checker, host, tmp_path):
