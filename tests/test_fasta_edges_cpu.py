@@ -37,3 +37,50 @@ def test_reference_kseq_on_the_edge_case_files(ref, port, tmp_path):
             assert np.array_equal(port.sketch(recs, k, p, True), want), name
     finally:
         os.chdir(cwd)
+
+
+def _random_text(rng, fastq_ok):
+    """Adversarial line soup: headers, '@' / '+' lines, blank lines, CRLF, CR and '>' / '@' / '+' inside lines, no final newline."""
+    parts = []
+    for _ in range(int(rng.integers(0, 25))):
+        kind, L = rng.random(), int(rng.integers(0, 40))
+        body = bytes(rng.choice(list(b"ACGTACGTACGTacgtNn >@+-\r\t"), L).tolist()) if L else b""
+        if kind < 0.25:
+            line = b">" + body
+        elif kind < 0.30 and fastq_ok:
+            line = b"@" + body
+        elif kind < 0.33 and fastq_ok:
+            line = b"+" + body
+        elif kind < 0.40:
+            line = b""
+        else:
+            line = bytes(rng.choice(list(b"ACGT"), L).tolist()) if rng.random() < 0.7 else body
+            if not fastq_ok and line[:1] in (b"@", b"+"):
+                line = b"A" + line
+        parts.append(line + (b"\r\n" if rng.random() < 0.2 else b"\n"))
+    s = b"".join(parts)
+    return s[:-1] if (rng.random() < 0.3 and s.endswith(b"\n")) else s
+
+
+def test_host_reader_fuzz_against_reference_kseq(ref, port, tmp_path):
+    """The kseq-compatible host reader on 400 random files against the reference's own kseq_read + sketch (k = 5 so that every
+    misplaced record boundary or stray byte changes the registers).  This fuzz is what found the three rules a line-based
+    reader gets wrong: the character scan for the next header when none is pending (kseq.h:183), truncated-quality records
+    ending the file (:214), and empty lines stripping no CR (:195)."""
+    host = hostlib.load()
+    rng = np.random.default_rng(20261017)
+    k, p = 5, 8
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        for it in range(400):
+            raw = _random_text(rng, fastq_ok=(it % 3 == 0))
+            fn = f"f{it}.fa"
+            with open(fn, "wb") as f:
+                f.write(raw)
+            ref.cli_sketch([fn], k=k, p=p, nthreads=1)
+            want = np.frombuffer(gzip.open(ref.make_fname(fn, p, k, k, k)).read()[28:], dtype=np.uint8)
+            recs = hostlib.read_records(host, fn, cap=1 << 16)
+            assert np.array_equal(port.sketch(recs, k, p, True), want), (it, raw)
+    finally:
+        os.chdir(cwd)
