@@ -84,3 +84,49 @@ def test_host_reader_fuzz_against_reference_kseq(ref, port, tmp_path):
             assert np.array_equal(port.sketch(recs, k, p, True), want), (it, raw)
     finally:
         os.chdir(cwd)
+
+
+def _emulated_records(exe, path, tmp):
+    import subprocess
+    out = os.path.join(tmp, "emul.out")
+    subprocess.check_call([exe, path, out])
+    data = open(out, "rb").read()
+    nl = data.index(b"\n")
+    flag, recs, at = int(data[:nl]), [], nl + 1
+    while at < len(data):
+        n = int.from_bytes(data[at:at + 8], "little")
+        recs.append(data[at + 8:at + 8 + n])
+        at += 8 + n
+    return flag, recs
+
+
+def test_device_parser_rules_against_reference_kseq(ref, port, tmp_path):
+    """The per-warp logic the FASTA kernels run (fasta_logic.h), emulated lane by lane over whole files on the CPU
+    (tests/fasta_device_emul.cpp), against the reference's kseq on the edge-case files and on random line soup: every file the
+    parser does NOT flag must sketch to the reference's registers; files it flags go to the host reader (checked above)."""
+    import subprocess
+    exe = str(tmp_path / "fasta_device_emul")
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O2", "-Wall", "-o", exe, os.path.join(ROOT, "tests", "fasta_device_emul.cpp")])
+    rng = np.random.default_rng(77)
+    k, p = 5, 8
+    cases = list(_edge_files().items()) + [(f"r{it}", _random_text(rng, fastq_ok=(it % 4 == 0))) for it in range(500)]
+    # longer random files, so that lines, headers and CRs straddle the 16-byte lanes and 512-byte warps in every phase
+    cases += [(f"long{it}", b"".join(_random_text(rng, fastq_ok=False) for _ in range(12))) for it in range(60)]
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    unflagged = 0
+    try:
+        for name, raw in cases:
+            fn = name + ".fa"
+            with open(fn, "wb") as f:
+                f.write(raw)
+            flag, recs = _emulated_records(exe, fn, str(tmp_path))
+            if flag:
+                continue
+            unflagged += 1
+            ref.cli_sketch([fn], k=k, p=p, nthreads=1)
+            want = np.frombuffer(gzip.open(ref.make_fname(fn, p, k, k, k)).read()[28:], dtype=np.uint8)
+            assert np.array_equal(port.sketch(recs, k, p, True), want), (name, raw)
+    finally:
+        os.chdir(cwd)
+    assert unflagged > 300          # the comparison must not be vacuous
