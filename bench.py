@@ -8,11 +8,19 @@ on one B200).  A "step" is one pass of the hot path over one batch: (N>1: NCCL a
 shards) -> threshold-plane build + per-sketch cardinalities -> tiled all-pairs kernel.  `value` times it with
 the register matrix resident in HBM; `e2e` times the reference-facing C-ABI call with HOST buffers (H2D of
 the registers and D2H of the float matrix inside the timed region).
-The same JSON line carries a `sketch` object with the second half of the metric (k-mers hashed/s,
-configs[1]: 1,000 x 5 Mbp genomes, k=31, p=14), measured the same way; `--workload sketch` makes it primary.
+The same JSON line carries
+  * `parity`  — the GPU values of THIS run against the reference's values for the rows its `cpu_baseline` leg
+                computes (N=1) / a reference sample of rank 0's rows (N>1), true relative error (tests/parity.py policy);
+  * `sketch`  — the second half of the metric (k-mers hashed/s, configs[1]: 1,000 x 5 Mbp genomes, k=31, p=14);
+  * `jmle`    — (N=1) Ertl joint MLE all-pairs at p=16, k=21 (the estimator of configs[4]) with its own parity object;
+  * `c4`,`c5` — (N=8, or one emulated rank with --emulate-world 8) BASELINE configs[3] (100,000 p=14 sketches over
+                8 ranks) and configs[4] (50,000 x 5 Mbp genomes, k=21, p=16, joint MLE, sketch + all-gather + all pairs).
 
 Multi-GPU (torchrun, one rank per GPU): weak scaling.  dist: n(N) = round(10000*sqrt(N)) sketches, each rank
 holds n/N of them, one all-gather, block-rows balanced by pair count; sketch: 1,000 genomes per rank.
+
+Both arms draw the register matrix from dashing_b200.synth.registers_block (row i depends on (seed, i // 16) only),
+so the GPU ranks and the reference arm consume identical bytes and print identical `config` objects.
 
 `--impl reference` times the reference's own CPU implementation (oracle/_ref: the unmodified dashing headers
 compiled with g++; falls back to the pinned C port if that library did not travel) on all host threads.
@@ -37,6 +45,10 @@ sys.path.insert(0, ROOT)
 P_DIST, K_MER, P_SKETCH = 14, 31, 14
 N_DIST_1GPU = 10_000
 N_GENOMES, GENOME_LEN = 1000, 5_000_000
+SEED_DIST, SEED_JMLE, SEED_C4, SEED_C5 = 2026, 2027, 2028, 2029
+N_JMLE, P_JMLE, K_JMLE = 4000, 16, 21
+C4_N, C5_GENOMES, C5_P, C5_K, C45_WORLD = 100_000, 50_000, 16, 21, 8
+RTOL, RESIDUE = 1e-6, 1e-9          # parity policy of tests/parity.py
 
 
 def log(*a):
@@ -88,9 +100,15 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # synthetic inputs
 # ------------------------------------------------------------------------------------------------
+def host_registers(seed, start, count, p, out=None):
+    """Rows [start, start+count) of the seeded register matrix both arms use (host numpy, all usable cores)."""
+    from dashing_b200 import synth
+    return synth.registers_block_mt(seed, start, count, p, threads=usable_cores(), out=out)
+
+
 def synth_registers_torch(torch, n, p, seed, device, card=5e6, group=16):
-    """Device-side version of dashing_b200.synth.registers (same construction, torch RNG): correlated groups of
-    HLL register arrays drawn from the exact register distribution of an HLL holding `card` items."""
+    """Device-side register synthesis (same construction as dashing_b200.synth.registers, torch RNG).  Only used to stand in
+    for the OTHER ranks' sketches when one rank of an 8-GPU configuration is emulated on a single GPU."""
     from dashing_b200.synth import RATE_LADDER
     g = torch.Generator(device=device); g.manual_seed(seed)
     m, q = 1 << p, 64 - p
@@ -114,21 +132,27 @@ def synth_registers_torch(torch, n, p, seed, device, card=5e6, group=16):
     return out
 
 
-def synth_genomes_torch(torch, n, length, seed, device, group=50):
+def synth_genomes_torch(torch, n, length, seed, device, group=50, first=0, out=None):
     """n single-record genomes of `length` ASCII bases on the device: groups share an ancestor, members are
-    mutated copies (substitution-rate ladder of SURVEY.md §8(d)).  Returns a uint8 [n*length] tensor."""
+    mutated copies (substitution-rate ladder of SURVEY.md §8(d)).  Returns a uint8 [n*length] tensor.
+    Genome `first + i` belongs to ancestor group (first + i) // group, seeded by (seed, group index)."""
     from dashing_b200.synth import RATE_LADDER
-    g = torch.Generator(device=device); g.manual_seed(seed)
     lut = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=device)
-    out = torch.empty(n * length, dtype=torch.uint8, device=device)
-    anc = None
+    if out is None:
+        out = torch.empty(n * length, dtype=torch.uint8, device=device)
+    g = torch.Generator(device=device)
+    anc, anc_group = None, -1
     for i in range(n):
-        if i % group == 0:
-            anc = torch.randint(0, 4, (length,), generator=g, device=device, dtype=torch.uint8)
-        rate = RATE_LADDER[i % len(RATE_LADDER)]
+        gi = first + i
+        if gi // group != anc_group:
+            anc_group = gi // group
+            ga = torch.Generator(device=device); ga.manual_seed(seed * 1_000_003 + anc_group)
+            anc = torch.randint(0, 4, (length,), generator=ga, device=device, dtype=torch.uint8)
+        rate = RATE_LADDER[gi % len(RATE_LADDER)]
         if rate <= 0:
             code = anc
         else:
+            g.manual_seed(seed * 7_000_003 + gi)
             hit = torch.rand(length, generator=g, device=device) < rate
             shift = torch.randint(1, 4, (length,), generator=g, device=device, dtype=torch.uint8)
             code = torch.where(hit, (anc + shift) & 3, anc)
@@ -147,13 +171,17 @@ def load_peaks():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def load_traffic(kind):
-    """ncu dram bytes per launch of the dominant kernel, if a capture has been summarised under profiles/."""
+def load_traffic(kind, n, world):
+    """ncu dram bytes per launch of the dominant kernel — only when the capture summarised under profiles/traffic.json was
+    taken on THIS problem (same sketch / genome count, one GPU); otherwise null (a constant from another size is not a
+    measurement of this run)."""
     try:
-        d = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        return d.get(kind)
+        d = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(kind)
+        if isinstance(d, dict) and world == 1 and int(d.get("n", -1)) == int(n):
+            return d.get("bytes")
     except Exception:
-        return None
+        pass
+    return None
 
 
 def usable_cores():
@@ -163,6 +191,60 @@ def usable_cores():
 
 def dist_n_for(world):
     return int(round(N_DIST_1GPU * math.sqrt(world)))
+
+
+def tri(n, r):
+    return r * (2 * n - r - 1) // 2
+
+
+def rows_for_pairs(n, row0, target_pairs):
+    """Smallest R such that rows [row0, row0+R) hold at least target_pairs pairs (or all remaining rows)."""
+    r = row0
+    while r < n - 1 and tri(n, r) - tri(n, row0) < target_pairs:
+        r += 1
+    return max(r - row0, 1)
+
+
+def dist_config(n, world, p=P_DIST, k=K_MER, seed=SEED_DIST, what="ERTL_MLE union JI"):
+    """The `config` object of the dist workload — printed verbatim by BOTH arms."""
+    m = 1 << p
+    return {"workload": f"dist all-pairs {n} p={p} sketches ({n * (n - 1) // 2} pairs), {what}", "n_sketches": n, "p": p, "k": k,
+            "estimator": "ERTL_MLE", "result": "JI",
+            "generator": f"dashing_b200.synth.registers_block(seed={seed}, card=5e6, group=16), rows [0,{n}) — identical bytes in both arms",
+            "parallelism": f"block-row x{world}" + (" + 1 NCCL all-gather" if world > 1 else ""),
+            "l2": "inputs (register matrix %d MB + threshold planes) larger than the 126 MB L2" % (n * m >> 20)}
+
+
+def sketch_config(world):
+    return {"workload": f"sketch {N_GENOMES * world} x {GENOME_LEN} bp synthetic genomes, k={K_MER}, p={P_SKETCH}, canonical",
+            "genomes_per_gpu": N_GENOMES, "k": K_MER, "p": P_SKETCH, "parallelism": f"genomes x{world} (no collective)",
+            "l2": "packed input 1788 MB per GPU, larger than the 126 MB L2"}
+
+
+def parity_stats(got, want, scale=1.0, ignore=None, what=""):
+    """tests/parity.py policy: true relative error |got-want|/|want|; only where |want| < 1e-9*scale (a cancellation residue
+    in the reference itself) is the error measured against `scale`."""
+    got = np.asarray(got, dtype=np.float64).ravel()
+    want = np.asarray(want, dtype=np.float64).ravel()
+    same = (got == want) | (np.isnan(got) & np.isnan(want))
+    with np.errstate(invalid="ignore", divide="ignore"):
+        den = np.where(np.abs(want) >= RESIDUE * scale, np.abs(want), scale)
+        err = np.abs(got - want) / den
+    err = np.where(same, 0.0, err)
+    err = np.where(np.isnan(err), np.inf, err)
+    n_ign = 0
+    if ignore is not None:
+        ignore = np.asarray(ignore).ravel()
+        n_ign = int(ignore.sum())
+        err = np.where(ignore, 0.0, err)
+    bad = np.nonzero(err > RTOL)[0]
+    out = {"pairs_compared": int(got.size - n_ign), "max_rel_err": float(err.max()) if err.size else 0.0, "n_over_1e-6": int(bad.size),
+           "n_ignored": n_ign, "n_bit_identical": int(same.sum()), "policy": "true relative; floor only where |want| < 1e-9 (tests/parity.py)"}
+    if what:
+        out["against"] = what
+    if bad.size:
+        out["first_bad"] = [{"idx": int(i), "got": float(got[i]), "want": float(want[i])} for i in bad[:5]]
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -176,31 +258,35 @@ def reference_checker():
     return O.port(), "port", "oracle/oracle_port.c (scalar C restatement; oracle/_ref did not travel)"
 
 
-def cpu_dist_sample(chk, kind, regs_np, n, target_s, threads):
-    """Time rows [0, R) of the SAME all-pairs workload on the host cores (the perform_core_op loop: OpenMP dynamic
+def ref_threads(kind):
+    # torchrun exports OMP_NUM_THREADS=1: the thread count is passed to the reference's loops explicitly (num_threads clause)
+    return usable_cores() if kind == "reference" else 1
+
+
+def cpu_dist_sample(chk, kind, regs_np, n, target_s, threads, p=P_DIST, k=K_MER, jestim=2, rtype=1, row0=0, min_pairs=0):
+    """Time rows [row0, row0+R) of the SAME all-pairs workload on the host cores (the perform_core_op loop: OpenMP dynamic
     over one matrix row at a time).  The n sketches are constructed and report()ed once, outside the timed region,
-    as the reference does before its pair loop."""
-    p = P_DIST
+    as the reference does before its pair loop.  Returns (pairs/s, pairs, rows, seconds, values of the last pass)."""
     if kind == "reference":
-        hs = chk.set_create(regs_np, p, 2, 2)
-        run = lambda r: chk.set_dist_rows(hs, K_MER, 1, 0, 0, r, threads)
+        hs = chk.set_create(regs_np, p, 2, jestim)
+        run = lambda r: chk.set_dist_rows(hs, k, rtype, 0, row0, row0 + r, threads)
     else:
         hs = None
-        run = lambda r: chk.dist_rows(regs_np, p, k=K_MER, rtype=1, row_begin=0, row_end=r)
+        run = lambda r: chk.dist_rows(regs_np, p, k=k, jestim=jestim, rtype=rtype, row_begin=row0, row_end=row0 + r)[tri(n, row0):tri(n, row0 + r)]
     run(2)  # warm caches / thread pool
-    rows = 8
+    rows = max(8, rows_for_pairs(n, row0, min_pairs) if min_pairs else 8)
     while True:
-        t0 = time.perf_counter(); run(rows); dt = time.perf_counter() - t0
-        if dt >= 0.5 * target_s or rows >= n - 1:
+        t0 = time.perf_counter(); vals = run(rows); dt = time.perf_counter() - t0
+        if dt >= 0.5 * target_s or row0 + rows >= n - 1:
             break
-        rows = min(n - 1, int(rows * min(8.0, max(2.0, target_s / max(dt, 1e-3)))))
+        rows = min(n - 1 - row0, int(rows * min(8.0, max(2.0, target_s / max(dt, 1e-3)))))
     if hs is not None:
         chk.set_free(hs)
-    pairs = rows * (2 * n - rows - 1) // 2
-    return pairs / dt, pairs, rows, dt
+    pairs = tri(n, row0 + rows) - tri(n, row0)
+    return pairs / dt, pairs, rows, dt, np.asarray(vals)[:pairs]
 
 
-def cpu_sketch_sample(chk, kind, genomes_np, length, threads, target_s=6.0):
+def cpu_sketch_sample(chk, kind, genomes_np, length, threads, target_s=6.0, k=K_MER, p=P_SKETCH):
     """Repeated passes over a block of in-memory genomes (Encoder::for_each + hll_t::addh, one genome per OpenMP task)
     until ~target_s of CPU work has been timed."""
     ng = genomes_np.size // length
@@ -209,10 +295,10 @@ def cpu_sketch_sample(chk, kind, genomes_np, length, threads, target_s=6.0):
 
     def one_pass():
         if kind == "reference":
-            chk.sketch_many(genomes_np, offs, grb, K_MER, P_SKETCH, True, threads)
+            chk.sketch_many(genomes_np, offs, grb, k, p, True, threads)
         else:
             for gi in range(ng):
-                chk.sketch([genomes_np[gi * length:(gi + 1) * length].tobytes()], K_MER, P_SKETCH, True)
+                chk.sketch([genomes_np[gi * length:(gi + 1) * length].tobytes()], k, p, True)
     one_pass()
     passes, t0 = 0, time.perf_counter()
     while True:
@@ -220,7 +306,7 @@ def cpu_sketch_sample(chk, kind, genomes_np, length, threads, target_s=6.0):
         dt = time.perf_counter() - t0
         if dt >= target_s or passes >= 200:
             break
-    kmers = passes * ng * (length - K_MER + 1)
+    kmers = passes * ng * (length - k + 1)
     return kmers / dt, kmers, dt
 
 
@@ -229,7 +315,7 @@ def run_reference(args):
     if rank != 0:
         return 0
     chk, kind, desc = reference_checker()
-    threads = (min(chk.max_threads(), usable_cores()) if kind == "reference" else 1)
+    threads = ref_threads(kind)
     from dashing_b200 import synth
     n = dist_n_for(args.gpus)
     if args.workload == "sketch":
@@ -242,21 +328,22 @@ def run_reference(args):
                 vals.append((v, dt))
         value = float(np.mean([v for v, _ in vals])); ms = float(np.mean([d for _, d in vals])) * 1e3
         sample = f"{kmers} k-mers: repeated passes over {ng} of the {N_GENOMES * args.gpus} genomes ({GENOME_LEN} bp each), in-memory Encoder::for_each + hll_t::addh, {threads} threads"
-        metric, unit, workload = "k-mers hashed/s (sketch k=31 p=14)", "kmers/s", f"sketch {N_GENOMES * args.gpus} x {GENOME_LEN} bp, k=31, p=14"
+        metric, unit, config = "k-mers hashed/s (sketch k=31 p=14)", "kmers/s", sketch_config(args.gpus)
     else:
-        regs = synth.registers(2026, n if n <= 12000 else 12000, P_DIST)  # matrix rows only matter through the sampled rows
-        nn = regs.shape[0]
+        t0 = time.perf_counter()
+        regs = host_registers(SEED_DIST, 0, n, P_DIST)
+        log(f"[bench/reference] {n} x 2^{P_DIST} registers generated in {time.perf_counter() - t0:.1f}s; {threads} threads")
         vals = []
         for it in range(args.warmup + args.steps):
-            v, pairs, rows, dt = cpu_dist_sample(chk, kind, regs, nn, 6.0, threads)
+            v, pairs, rows, dt, _ = cpu_dist_sample(chk, kind, regs, n, 6.0, threads)
             if it >= args.warmup:
                 vals.append((v, dt, rows, pairs))
         value = float(np.mean([v[0] for v in vals])); ms = float(np.mean([v[1] for v in vals])) * 1e3
-        sample = f"rows [0,{vals[-1][2]}) = {vals[-1][3]} of the {n * (n - 1) // 2} pairs, perform_core_op loop (OpenMP dynamic), {threads} threads"
-        metric, unit, workload = "pairwise HLL cmp/s (dist p=14)", "pairs/s", f"dist all-pairs {n} p=14 sketches"
+        sample = f"rows [0,{vals[-1][2]}) = {vals[-1][3]} of the {n * (n - 1) // 2} pairs of the same matrix, perform_core_op loop (OpenMP dynamic), {threads} threads"
+        metric, unit, config = "pairwise HLL cmp/s (dist p=14)", "pairs/s", dist_config(n, args.gpus)
     line = {"impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8+f64", "data": "synthetic",
-            "config": {"workload": workload, "estimator": "ERTL_MLE", "result": "JI", "reference": desc},
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8 registers / u32 counts / f64 estimator -> f32 out",
+            "data": "synthetic", "config": config, "reference": desc,
             "cpu_baseline": {"value": value, "unit": unit, "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit_result(line)
@@ -266,24 +353,30 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+class Ctx:
+    pass
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
     from dashing_b200 import capi, multigpu
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cx = Ctx()
+    cx.torch, cx.dist, cx.capi, cx.multigpu, cx.args = torch, dist, capi, multigpu, args
+    cx.world = world = int(os.environ.get("WORLD_SIZE", "1"))
+    cx.rank = rank = int(os.environ.get("RANK", "0"))
+    cx.local_rank = local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world != args.gpus:
         log(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE")
     if capi.device_count() < 1:
         raise RuntimeError("bench.py: libdashing_b200 sees no CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
+    cx.dev = dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    stream = torch.cuda.current_stream().cuda_stream
-    peak, peak_src = load_peaks()
+    cx.stream = torch.cuda.current_stream().cuda_stream
+    cx.peak, cx.peak_src = load_peaks()
 
     def barrier():
         if world > 1:
@@ -297,311 +390,722 @@ def run_gpu(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    results = {}
+    def all_ok(ok):
+        """True only if every rank says so — the gate in front of every collective of the optional legs, so that a rank
+        that failed (caught exception) takes the others out of the leg with it instead of leaving them in a collective."""
+        if world == 1:
+            return bool(ok)
+        t = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t.item())
 
-    # ---------------------------------------------------------------- dist
-    def bench_dist():
-        p, n = P_DIST, dist_n_for(world)
-        m = 1 << p
-        counts = multigpu.shard_counts(n, world)
-        start = sum(counts[:rank])
-        # every rank generates the same matrix (seeded) and keeps its shard: stands in for "rank r sketched these genomes"
-        full_src = synth_registers_torch(torch, n, p, 2026, dev)
-        local = full_src[start:start + counts[rank]].contiguous()
-        del full_src
-        torch.cuda.empty_cache()
-        rb, re_ = multigpu.row_partition(n, world)[rank]
-        my_pairs = multigpu.tri_offset(n, re_) - multigpu.tri_offset(n, rb)
-        total_pairs = n * (n - 1) // 2
-        d_out = torch.empty(max(my_pairs, 1), dtype=torch.float32, device=dev)
-        plan = capi.DistPlan(local_rank)
-        prm = capi.dist_params(p, K_MER, capi.ERTL_MLE, capi.ERTL_MLE, capi.JI, capi.ORDER_ROW_FIRST)
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-
-        def step(timed):
-            ev[0].record()
-            full = multigpu.allgather_registers(local, counts, dist) if world > 1 else local
-            ev[1].record()
-            plan.prepare_dev(full.data_ptr(), n, p, capi.ERTL_MLE, stream)
-            ev[2].record()
-            plan.run_symmetric_dev(prm, rb, re_, d_out.data_ptr(), stream)
-            ev[3].record()
-            return full
-
-        for _ in range(args.warmup):
-            step(False)
-        barrier()
-        l0 = capi.kernel_launches()
-        t_wall0 = time.perf_counter()
-        ker_ms, prep_ms, ag_ms = [], [], []
-        e_start, e_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e_start.record()
-        for _ in range(args.steps):
-            step(True)
-            ev[3].synchronize()
-            ag_ms.append(ev[0].elapsed_time(ev[1])); prep_ms.append(ev[1].elapsed_time(ev[2])); ker_ms.append(ev[2].elapsed_time(ev[3]))
-        e_stop.record()
-        barrier()
-        t_wall1 = time.perf_counter()
-        total_ms = max_over_ranks(e_start.elapsed_time(e_stop))
-        launches = capi.kernel_launches() - l0
-        ms_per_step = total_ms / args.steps
-        value = total_pairs / (ms_per_step * 1e-3)
-        _, tiles, K = plan.last_run_info()
-        ker = float(np.mean(ker_ms))
-        alg_bytes = my_pairs * (2 * m + 4)
-        achieved = alg_bytes / (ker * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": "dist_kernel (TMA-tiled OR+POPC + fused Ertl MLE)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "peak_source": peak_src, "traffic": load_traffic("dist_kernel"),
-                "algorithmic_bytes_per_launch": alg_bytes, "bytes_per_pair": 2 * m + 4, "kernel_ms": ker,
-                "note": "algorithmic bytes = what the reference streams per pair (SURVEY.md §8(d)); the tiled kernel re-uses planes from SMEM/L2 so "
-                        "frac may exceed 1 — the binding unit is the integer POPC pipe",
-                "int_bound": {"word_ops_per_pair": K * (m // 32), "thresholds": K,
-                              "word_ops_per_s": my_pairs * K * (m // 32) / (ker * 1e-3)}}
-        clocks = sampler.window(t_wall0, t_wall1) if sampler else None
-
-        # ---- e2e: host buffers through the reference-facing C ABI (N=1) / the multi-GPU driver (N>1)
-        host_regs = capi.pinned_empty(counts[rank] * m)
-        host_regs[:] = local.cpu().numpy().reshape(-1)
-        host_out = capi.pinned_empty(max(my_pairs, 1) * 4).view(np.float32)
-        pin_t = torch.from_numpy(host_regs).view(counts[rank], m)
-        out_t = torch.from_numpy(host_out)
-
-        # N>1: the rank's rows in four blocks of equal pair counts; the device->host copy of block b runs on a second stream
-        # while block b+1 computes (what db200_dist_symmetric_rows does inside the library at N=1)
-        tri = lambda r: multigpu.tri_offset(n, r)
-        cuts = [rb]
-        for b in range(1, 4):
-            target = tri(rb) + my_pairs * b // 4
-            r = cuts[-1]
-            while r < re_ and tri(r) < target:
-                r += 1
-            cuts.append(r)
-        cuts.append(re_)
-        blocks = [(cuts[i], cuts[i + 1], tri(cuts[i]) - tri(rb), tri(cuts[i + 1]) - tri(cuts[i])) for i in range(4) if cuts[i + 1] > cuts[i]]
-        copy_stream = torch.cuda.Stream(device=dev)
-        blk_ev = [torch.cuda.Event() for _ in blocks]
-
-        def e2e_step():
-            if world == 1:
-                capi.dist_symmetric(host_regs, p, k=K_MER, result_type=capi.JI, device=local_rank, out=host_out)
-            else:
-                loc = pin_t.to(dev, non_blocking=True)
-                full = multigpu.allgather_registers(loc, counts, dist)
-                plan.prepare_dev(full.data_ptr(), n, p, capi.ERTL_MLE, stream)
-                for (b0, b1, off, cnt), e in zip(blocks, blk_ev):
-                    plan.run_symmetric_dev(prm, b0, b1, d_out.data_ptr() + off * 4, stream)
-                    e.record()
-                    if cnt:
-                        with torch.cuda.stream(copy_stream):
-                            copy_stream.wait_event(e)
-                            out_t[off:off + cnt].copy_(d_out[off:off + cnt], non_blocking=True)
-                torch.cuda.synchronize()
-        e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            e2e_step()
-        barrier()
-        e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps
-        # sanity: device-resident and host paths agree
-        if world == 1 and not np.array_equal(d_out.cpu().numpy()[:1000], host_out[:1000]):
-            raise RuntimeError("bench: device-resident and host-buffer results differ")
-        if world > 1:    # the blocked e2e path leaves the same rows in d_out / host_out as the one-launch step
-            plan.run_symmetric_dev(prm, rb, re_, d_out.data_ptr(), stream)
-            torch.cuda.synchronize()
-            if not np.array_equal(d_out[:my_pairs].cpu().numpy(), host_out[:my_pairs]):
-                raise RuntimeError("bench: blocked multi-GPU e2e rows differ from the one-launch rows")
-        e2e = {"value": total_pairs / (e2e_ms * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": int(counts[rank] * m),
-               "d2h_bytes_per_step": int(my_pairs * 4), "ms_per_step": e2e_ms,
-               "api": "db200_dist_symmetric(host regs -> host packed float matrix)" if world == 1 else "multigpu driver: pinned shard -> all-gather -> rows in 4 blocks (device->host copy of block b under the kernel of block b+1) -> pinned out"}
-        res = {"metric": "pairwise HLL cmp/s (dist p=14)", "value": value, "unit": "pairs/s", "ms_per_step": ms_per_step,
-               "config": {"workload": f"dist all-pairs {n} p=14 sketches ({total_pairs} pairs), ERTL_MLE union JI", "n_sketches": n, "p": p, "k": K_MER,
-                          "estimator": "ERTL_MLE", "result": "JI", "parallelism": f"block-row x{world}" + (" + 1 NCCL all-gather" if world > 1 else ""),
-                          "l2": "inputs (register matrix %d MB + threshold planes) larger than the 126 MB L2" % (n * m >> 20),
-                          "step_breakdown_ms": {"allgather": float(np.mean(ag_ms)), "planes+cardinalities": float(np.mean(prep_ms)), "all_pairs_kernel": ker},
-                          "tiles": tiles, "live_thresholds": K},
-               "roofline": roof, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "dtype": "u8 registers / u32 popcounts / f64 estimator -> f32 out"}
-        host_regs_np = local.cpu().numpy() if (rank == 0 and world == 1) else None
-        plan.close()
-        return res, host_regs_np
-
-    # ---------------------------------------------------------------- sketch
-    def bench_sketch():
-        k, p, ng, L = K_MER, P_SKETCH, N_GENOMES, GENOME_LEN
-        ascii_dev = synth_genomes_torch(torch, ng, L, 4242 + rank, dev)
-        offs = (np.arange(ng + 1, dtype=np.uint64) * np.uint64(L))
-        grb = np.arange(ng + 1, dtype=np.uint64)
-        pg = capi.PackedGenomes(int(ascii_dev.data_ptr()), offs, grb, k, device=local_rank)
-        d_regs = torch.empty((ng, 1 << p), dtype=torch.uint8, device=dev)
-        kmers_rank, total_kmers = pg.kmers, pg.kmers * world
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        for _ in range(args.warmup):
-            pg.sketch_dev(p, True, d_regs.data_ptr(), stream)
-        barrier()
-        l0 = capi.kernel_launches()
-        t_wall0 = time.perf_counter()
-        e0.record()
-        for _ in range(args.steps):
-            pg.sketch_dev(p, True, d_regs.data_ptr(), stream)
-        e1.record()
-        barrier()
-        t_wall1 = time.perf_counter()
-        launches = capi.kernel_launches() - l0
-        ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
-        value = total_kmers / (ms * 1e-3)
-        alg_bytes = pg.packed_bytes + ng * (1 << p)
-        achieved = alg_bytes / (ms * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": "sketch_kernel<smem registers>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "peak_source": peak_src, "traffic": load_traffic("sketch_kernel"), "algorithmic_bytes_per_launch": alg_bytes,
-                "bytes_per_kmer": alg_bytes / max(kmers_rank, 1), "kernel_ms": ms,
-                "note": "2-bit bases + validity + record-start planes + register write-back (SURVEY.md §8(d) + the start plane); "
-                        "0.5 B per k-mer cannot be HBM bound: the binding unit is the ALU pipe",
-                "int_bound": {"sass_instr_per_kmer": 48, "alu_pipe_instr_per_kmer": 25, "fma_pipe_instr_per_kmer": 18,
-                              "alu_ceiling_kmers_per_s": 148 * 64 / 25 * 1.965e9 * 1.0,
-                              "frac_of_alu_ceiling": value / world / (148 * 64 / 25 * 1.965e9),
-                              "source": "cuobjdump -sass of sketch_kernel<0,1,true>, one unrolled base step (DESIGN.md §3)"}}
-        clocks = sampler.window(t_wall0, t_wall1) if sampler else None
-        # e2e: host ASCII (pinned) -> db200_sketch_batch -> host registers
-        try:
-            host_ascii = capi.pinned_empty(ng * L)
-        except capi.Db200Error as e:   # a box that cannot pin 5 GB per rank still gets its device-resident numbers
-            log(f"[bench] pinned host allocation failed ({e}); using pageable memory for the sketch e2e leg")
-            host_ascii = np.empty(ng * L, dtype=np.uint8)
-        torch.from_numpy(host_ascii).copy_(ascii_dev.cpu())
-        del ascii_dev
-        regs_ref = d_regs.cpu().numpy()
-        pg.close()
-        torch.cuda.empty_cache()
-        out = capi.sketch_batch(host_ascii, offs, grb, k, p, True, device=local_rank)
-        if not np.array_equal(out, regs_ref):
-            raise RuntimeError("bench: host-buffer sketch differs from the device-resident sketch")
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            capi.sketch_batch(host_ascii, offs, grb, k, p, True, device=local_rank)
-        barrier()
-        e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps
-        e2e = {"value": total_kmers / (e2e_ms * 1e-3), "unit": "kmers/s", "h2d_bytes_per_step": int(ng * L), "d2h_bytes_per_step": int(ng << p),
-               "ms_per_step": e2e_ms, "api": "db200_sketch_batch(host ASCII records -> host registers)"}
-        # what bounds it: the host->device link.  Probe: one 1 GiB copy from the same page-locked buffer, best of 3.
-        try:
-            probe_n = min(1 << 30, ng * L)
-            d_probe = torch.empty(probe_n, dtype=torch.uint8, device=dev)
-            h_probe = torch.from_numpy(host_ascii[:probe_n])
-            best = 0.0
-            for _ in range(3):
-                torch.cuda.synchronize()
-                tp = time.perf_counter()
-                d_probe.copy_(h_probe, non_blocking=True)
-                torch.cuda.synchronize()
-                best = max(best, probe_n / (time.perf_counter() - tp) / 1e9)
-            del d_probe
-            e2e["link"] = {"bound": "pcie h2d", "achieved": ng * L / (e2e_ms * 1e-3) / 1e9, "peak": best, "unit": "GB/s",
-                           "frac": ng * L / (e2e_ms * 1e-3) / 1e9 / best,
-                           "note": "ASCII bytes per second through db200_sketch_batch against a plain 1 GiB cudaMemcpy from the same page-locked buffer"}
-        except Exception as ex:
-            log(f"[bench] link probe skipped: {ex}")
-        # second end-to-end form: RAW FASTA text (headers + 80-column lines) parsed on the device (db200_sketch_fasta_batch) —
-        # what the CLI feeds the library with; informational, the e2e key above stays the record interface
-        try:
-            if world > 1:
-                raise RuntimeError("single-GPU runs only (a second 5 GB page-locked buffer per rank)")
-            W = 80
-            assert L % W == 0
-            hdr_len = 16
-            per = hdr_len + (L // W) * (W + 1)
-            stride = (per + capi.FASTA_ALIGN - 1) // capi.FASTA_ALIGN * capi.FASTA_ALIGN
-            try:
-                text = capi.pinned_empty(ng * stride + 64)
-            except capi.Db200Error:
-                text = np.empty(ng * stride + 64, dtype=np.uint8)
-            tv = text[: ng * stride].reshape(ng, stride)
-            tv[:, :hdr_len] = np.frombuffer(b">genome 0000000\n", dtype=np.uint8)
-            body = tv[:, hdr_len:per].reshape(ng, L // W, W + 1)
-            body[:, :, :W] = host_ascii.reshape(ng, L // W, W)
-            body[:, :, W] = 10
-            foff = (np.arange(ng, dtype=np.uint64) * np.uint64(stride))
-            flen = np.full(ng, per, dtype=np.uint64)
-            out2 = np.zeros((ng, 1 << p), dtype=np.uint8)
-            status = np.zeros(ng, dtype=np.uint8)
-            import ctypes as C
-
-            def fasta_step():
-                capi._check(capi.lib.db200_sketch_fasta_batch(local_rank, p, k, 1, text.ctypes.data_as(C.c_void_p), foff.ctypes.data_as(capi.u64p),
-                                                              flen.ctypes.data_as(capi.u64p), ng, grb.ctypes.data_as(capi.u64p), ng,
-                                                              out2.ctypes.data_as(capi.u8p), status.ctypes.data_as(capi.u8p)))
-            fasta_step()
-            if status.any() or not np.array_equal(out2, regs_ref):
-                raise RuntimeError("device-parsed FASTA sketch differs from the device-resident sketch")
-            barrier()
-            t0 = time.perf_counter()
-            for _ in range(args.steps):
-                fasta_step()
-            barrier()
-            f_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps
-            e2e["fasta_text"] = {"value": total_kmers / (f_ms * 1e-3), "unit": "kmers/s", "ms_per_step": f_ms, "h2d_bytes_per_step": int(ng * per),
-                                 "api": "db200_sketch_fasta_batch(host FASTA text, 80-column lines -> host registers; kseq rules on the device)"}
-            del text, tv, body
-        except Exception as ex:   # informational leg: never lose the bench line over it
-            log(f"[bench] FASTA-text e2e leg skipped: {ex}")
-        res = {"metric": "k-mers hashed/s (sketch k=31 p=14)", "value": value, "unit": "kmers/s", "ms_per_step": ms,
-               "config": {"workload": f"sketch {ng * world} x {L} bp synthetic genomes, k={k}, p={p}, canonical", "genomes_per_gpu": ng, "k": k, "p": p,
-                          "parallelism": f"genomes x{world} (no collective)", "l2": "packed input %d MB per GPU, larger than the 126 MB L2" % (pg.packed_bytes >> 20)},
-               "roofline": roof, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "dtype": "2-bit bases / u64 k-mers / u8 registers"}
-        sample_np = host_ascii[: min(ng, 128) * L] if (rank == 0 and world == 1) else None
-        return res, sample_np
+    cx.barrier, cx.max_over_ranks, cx.all_ok = barrier, max_over_ranks, all_ok
+    cx.sampler = ClockSampler(local_rank) if rank == 0 else None
+    results, extra = {}, {}
 
     want = ("dist", "sketch") if args.workload == "both" else (args.workload,)
-    extra = {}
-    for w in want:
-        t0 = time.perf_counter()
-        results[w], extra[w] = bench_dist() if w == "dist" else bench_sketch()
-        log(f"[bench] {w}: {results[w]['value']:.4g} {results[w]['unit']} ({time.perf_counter() - t0:.1f}s incl. setup)")
-        torch.cuda.empty_cache()
-    if sampler:
-        sampler.stop()
+    emu = args.emulate_world > 1
+    if not emu:
+        for w in want:
+            t0 = time.perf_counter()
+            results[w], extra[w] = bench_dist(cx) if w == "dist" else bench_sketch(cx)
+            log(f"[bench] {w}: {results[w]['value']:.4g} {results[w]['unit']} ({time.perf_counter() - t0:.1f}s incl. setup)")
+            torch.cuda.empty_cache()
 
-    # ---- CPU baseline (rank 0, N=1 only): the reference's own loop on the host cores, bounded sample
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    # ---- CPU baseline + parity (rank 0): the reference's own loop on the host cores, bounded sample, values kept for parity
+    if rank == 0 and not args.no_cpu_baseline and not emu:
         try:
             chk, kind, desc = reference_checker()
-            threads = min(chk.max_threads(), usable_cores()) if kind == "reference" else 1
+            threads = ref_threads(kind)
             if "dist" in results:
                 n = results["dist"]["config"]["n_sketches"]
-                v, pairs, rows, dt = cpu_dist_sample(chk, kind, extra["dist"], n, 12.0, threads)
-                results["dist"]["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": threads, "kind": kind,
-                                                   "sample": f"rows [0,{rows}) = {pairs} of the {n * (n - 1) // 2} pairs of the same matrix in {dt:.1f}s; {desc}"}
-            if "sketch" in results:
+                ex = extra["dist"]
+                # N=1: ~12 s of reference work = the cpu_baseline sample; N>1: a short sample of rank 0's first rows, parity only
+                target_s, min_pairs = (12.0, 0) if world == 1 else (2.0, 1_000_000)
+                v, pairs, rows, dt, vals = cpu_dist_sample(chk, kind, ex["regs_np"], n, target_s, threads, min_pairs=min_pairs)
+                if world == 1:
+                    results["dist"]["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": threads, "kind": kind,
+                                                       "sample": f"rows [0,{rows}) = {pairs} of the {n * (n - 1) // 2} pairs of the same matrix in {dt:.1f}s; {desc}"}
+                results["dist"]["parity"] = parity_stats(ex["gpu_rows_np"][:pairs], vals, what=f"{kind}: rows [0,{rows}) of the same matrix ({desc})")
+            if "sketch" in results and world == 1:
                 gen = extra["sketch"]
                 ngs = min(gen.size // GENOME_LEN, max(16, min(2 * threads, 128)))
                 v, kmers, dt = cpu_sketch_sample(chk, kind, np.ascontiguousarray(gen[: ngs * GENOME_LEN]), GENOME_LEN, threads)
                 results["sketch"]["cpu_baseline"] = {"value": v, "unit": "kmers/s", "cores": threads, "kind": kind,
                                                      "sample": f"{kmers} k-mers in {dt:.1f}s: repeated passes over {ngs} of the {N_GENOMES} genomes, in-memory Encoder::for_each + addh; {desc}"}
         except Exception as e:  # the baseline is a report, never a reason to lose the GPU numbers
-            log(f"[bench] cpu_baseline failed: {e!r}")
+            log(f"[bench] cpu_baseline / parity failed: {e!r}")
+    extra.clear()
+
+    # ---- optional legs: joint MLE at the C5 shape (N=1), BASELINE configs[3] and [4] (N=8 or one emulated rank)
+    legs = {}
+    if world == 1 and not emu and args.workload == "both" and not args.no_extra:
+        try:
+            legs["jmle"] = bench_jmle(cx)
+        except Exception as e:
+            log(f"[bench] jmle leg failed: {e!r}")
+    if (world == C45_WORLD or emu) and not args.no_extra:
+        for name, fn in (("c4", bench_c4), ("c5", bench_c5)):
+            if args.only and name not in args.only.split(","):
+                continue
+            t0 = time.perf_counter()
+            try:
+                legs[name] = fn(cx)
+            except Exception as e:
+                import traceback
+                log(f"[bench] rank {rank}: {name} leg failed: {e!r}\n{traceback.format_exc()}")
+                legs[name] = {"failed": repr(e)}
+            log(f"[bench] rank {rank}: {name} done in {time.perf_counter() - t0:.1f}s")
+            torch.cuda.empty_cache()
+    if cx.sampler:
+        cx.sampler.stop()
 
     if rank == 0:
-        primary = "dist" if "dist" in results else "sketch"
-        r = results[primary]
-        line = {"metric": r["metric"], "value": r["value"], "unit": r["unit"], "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": r["dtype"],
-                "data": "synthetic", "config": r["config"], "clocks": r["clocks"], "e2e": r["e2e"], "gpu_launches": r["gpu_launches"],
-                "roofline": r["roofline"]}
-        if "cpu_baseline" in r:
-            line["cpu_baseline"] = r["cpu_baseline"]
-        for other in results:
-            if other != primary:
-                o = results[other]
-                line[other] = {k: o[k] for k in ("metric", "value", "unit", "ms_per_step", "config", "roofline", "e2e", "gpu_launches", "clocks") if k in o}
-                if "cpu_baseline" in o:
-                    line[other]["cpu_baseline"] = o["cpu_baseline"]
+        if results:
+            primary = "dist" if "dist" in results else "sketch"
+            r = results[primary]
+            line = {"metric": r["metric"], "value": r["value"], "unit": r["unit"], "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                    "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": r["dtype"],
+                    "data": "synthetic", "config": r["config"], "details": r.get("details"), "clocks": r["clocks"], "e2e": r["e2e"],
+                    "gpu_launches": r["gpu_launches"], "roofline": r["roofline"]}
+            for key in ("cpu_baseline", "parity"):
+                if key in r:
+                    line[key] = r[key]
+            for other in results:
+                if other != primary:
+                    o = results[other]
+                    line[other] = {k: o[k] for k in ("metric", "value", "unit", "ms_per_step", "config", "details", "roofline", "e2e", "gpu_launches", "clocks",
+                                                     "cpu_baseline", "parity") if k in o}
+        else:
+            line = {"metric": "emulated rank of an 8-GPU configuration (see c4 / c5)", "value": None, "n_gpus": 1, "emulated": {"world": args.emulate_world, "rank": args.emulate_rank}}
+        line.update(legs)
         emit_result(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+# ---------------------------------------------------------------- dist (primary)
+def bench_dist(cx):
+    torch, dist, capi, multigpu, args = cx.torch, cx.dist, cx.capi, cx.multigpu, cx.args
+    world, rank, dev, stream = cx.world, cx.rank, cx.dev, cx.stream
+    p, n = P_DIST, dist_n_for(world)
+    m = 1 << p
+    counts = multigpu.shard_counts(n, world)
+    start = sum(counts[:rank])
+    # every rank draws ITS rows of the seeded matrix (stands in for "rank r sketched these genomes") into page-locked memory
+    host_regs = capi.pinned_empty(counts[rank] * m)
+    t0 = time.perf_counter()
+    host_registers(SEED_DIST, start, counts[rank], p, out=host_regs.reshape(counts[rank], m))
+    log(f"[bench] rank {rank}: rows [{start},{start + counts[rank]}) of the register matrix generated in {time.perf_counter() - t0:.1f}s")
+    pin_t = torch.from_numpy(host_regs).view(counts[rank], m)
+    local = pin_t.to(dev)
+    rb, re_ = multigpu.row_partition(n, world)[rank]
+    my_pairs = tri(n, re_) - tri(n, rb)
+    total_pairs = n * (n - 1) // 2
+    d_out = torch.empty(max(my_pairs, 1), dtype=torch.float32, device=dev)
+    plan = capi.DistPlan(cx.local_rank)
+    prm = capi.dist_params(p, K_MER, capi.ERTL_MLE, capi.ERTL_MLE, capi.JI, capi.ORDER_ROW_FIRST)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+
+    def step():
+        ev[0].record()
+        full = multigpu.allgather_registers(local, counts, dist) if world > 1 else local
+        ev[1].record()
+        plan.prepare_dev(full.data_ptr(), n, p, capi.ERTL_MLE, stream)
+        ev[2].record()
+        plan.run_symmetric_dev(prm, rb, re_, d_out.data_ptr(), stream)
+        ev[3].record()
+        return full
+
+    for _ in range(args.warmup):
+        step()
+    cx.barrier()
+    l0 = capi.kernel_launches()
+    t_wall0 = time.perf_counter()
+    ker_ms, prep_ms, ag_ms = [], [], []
+    e_start, e_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e_start.record()
+    for _ in range(args.steps):
+        full = step()
+        ev[3].synchronize()
+        ag_ms.append(ev[0].elapsed_time(ev[1])); prep_ms.append(ev[1].elapsed_time(ev[2])); ker_ms.append(ev[2].elapsed_time(ev[3]))
+    e_stop.record()
+    cx.barrier()
+    t_wall1 = time.perf_counter()
+    total_ms = cx.max_over_ranks(e_start.elapsed_time(e_stop))
+    launches = capi.kernel_launches() - l0
+    ms_per_step = total_ms / args.steps
+    value = total_pairs / (ms_per_step * 1e-3)
+    _, tiles, K = plan.last_run_info()
+    ker = float(np.mean(ker_ms))
+    alg_bytes = my_pairs * (2 * m + 4)
+    achieved = alg_bytes / (ker * 1e-3) / 1e9
+    roof = {"bound": "hbm", "kernel": "dist_kernel (TMA-tiled OR+POPC + fused Ertl MLE)", "achieved": achieved, "peak": cx.peak, "unit": "GB/s",
+            "frac": achieved / cx.peak, "peak_source": cx.peak_src, "traffic": load_traffic("dist_kernel", n, world),
+            "algorithmic_bytes_per_launch": alg_bytes, "bytes_per_pair": 2 * m + 4, "kernel_ms": ker,
+            "compulsory_bytes_per_launch": int(n * m + 4 * my_pairs),
+            "note": "algorithmic bytes = what the reference streams per pair (SURVEY.md §8(d)); the tiled kernel re-uses planes from SMEM/L2 so "
+                    "frac exceeds 1 and says nothing about kernel quality — the binding units are the integer pipes (int_bound)",
+            "int_bound": {"word_ops_per_pair": K * (m // 32), "thresholds": K,
+                          "word_ops_per_s": my_pairs * K * (m // 32) / (ker * 1e-3)}}
+    clocks = cx.sampler.window(t_wall0, t_wall1) if cx.sampler else None
+    gpu_rows_np = None
+    regs_np = None
+    if rank == 0:
+        # values of the device-resident path for the parity check (rank 0's first rows), and the matrix the reference needs
+        keep = min(my_pairs, 64_000_000)
+        gpu_rows_np = d_out[:keep].cpu().numpy()
+        regs_np = full.cpu().numpy() if world > 1 else host_regs.reshape(n, m)
+
+    # ---- e2e: host buffers through the reference-facing C ABI (N=1) / the multi-GPU driver (N>1)
+    host_out = capi.pinned_empty(max(my_pairs, 1) * 4).view(np.float32)
+    out_t = torch.from_numpy(host_out)
+    # N>1: the rank's rows in four blocks of equal pair counts; the device->host copy of block b runs on a second stream
+    # while block b+1 computes (what db200_dist_symmetric_rows does inside the library at N=1)
+    cuts = [rb]
+    for b in range(1, 4):
+        target = tri(n, rb) + my_pairs * b // 4
+        r = cuts[-1]
+        while r < re_ and tri(n, r) < target:
+            r += 1
+        cuts.append(r)
+    cuts.append(re_)
+    blocks = [(cuts[i], cuts[i + 1], tri(n, cuts[i]) - tri(n, rb), tri(n, cuts[i + 1]) - tri(n, cuts[i])) for i in range(4) if cuts[i + 1] > cuts[i]]
+    copy_stream = torch.cuda.Stream(device=dev)
+    blk_ev = [torch.cuda.Event() for _ in blocks]
+
+    def e2e_step():
+        if world == 1:
+            capi.dist_symmetric(host_regs, p, k=K_MER, result_type=capi.JI, device=cx.local_rank, out=host_out)
+        else:
+            loc = pin_t.to(dev, non_blocking=True)
+            full = multigpu.allgather_registers(loc, counts, dist)
+            plan.prepare_dev(full.data_ptr(), n, p, capi.ERTL_MLE, stream)
+            for (b0, b1, off, cnt), e in zip(blocks, blk_ev):
+                plan.run_symmetric_dev(prm, b0, b1, d_out.data_ptr() + off * 4, stream)
+                e.record()
+                if cnt:
+                    with torch.cuda.stream(copy_stream):
+                        copy_stream.wait_event(e)
+                        out_t[off:off + cnt].copy_(d_out[off:off + cnt], non_blocking=True)
+            torch.cuda.synchronize()
+    e2e_step()
+    cx.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    cx.barrier()
+    e2e_ms = cx.max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps
+    # the host-buffer path must deliver the very same floats as the device-resident step
+    if world > 1:
+        plan.run_symmetric_dev(prm, rb, re_, d_out.data_ptr(), stream)
+        torch.cuda.synchronize()
+    if not np.array_equal(d_out[:my_pairs].cpu().numpy(), host_out[:my_pairs]):
+        raise RuntimeError("bench: device-resident and host-buffer results differ")
+    e2e = {"value": total_pairs / (e2e_ms * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": int(counts[rank] * m),
+           "d2h_bytes_per_step": int(my_pairs * 4), "ms_per_step": e2e_ms,
+           "api": "db200_dist_symmetric(host regs -> host packed float matrix)" if world == 1 else "multigpu driver: pinned shard -> all-gather -> rows in 4 blocks (device->host copy of block b under the kernel of block b+1) -> pinned out"}
+    res = {"metric": "pairwise HLL cmp/s (dist p=14)", "value": value, "unit": "pairs/s", "ms_per_step": ms_per_step,
+           "config": dist_config(n, world),
+           "details": {"step_breakdown_ms": {"allgather": float(np.mean(ag_ms)), "planes+cardinalities": float(np.mean(prep_ms)), "all_pairs_kernel": ker},
+                       "tiles": tiles, "live_thresholds": K, "rows_of_rank0": [rb, re_]},
+           "roofline": roof, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "dtype": "u8 registers / u32 popcounts / f64 estimator -> f32 out"}
+    plan.close()
+    return res, {"regs_np": regs_np, "gpu_rows_np": gpu_rows_np}
+
+
+# ---------------------------------------------------------------- sketch (second half of the metric)
+def bench_sketch(cx):
+    torch, capi, args = cx.torch, cx.capi, cx.args
+    world, rank, dev, stream, local_rank = cx.world, cx.rank, cx.dev, cx.stream, cx.local_rank
+    k, p, ng, L = K_MER, P_SKETCH, N_GENOMES, GENOME_LEN
+    ascii_dev = synth_genomes_torch(torch, ng, L, 4242, dev, first=rank * ng)
+    offs = (np.arange(ng + 1, dtype=np.uint64) * np.uint64(L))
+    grb = np.arange(ng + 1, dtype=np.uint64)
+    pg = capi.PackedGenomes(int(ascii_dev.data_ptr()), offs, grb, k, device=local_rank)
+    d_regs = torch.empty((ng, 1 << p), dtype=torch.uint8, device=dev)
+    kmers_rank, total_kmers = pg.kmers, pg.kmers * world
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(args.warmup):
+        pg.sketch_dev(p, True, d_regs.data_ptr(), stream)
+    cx.barrier()
+    l0 = capi.kernel_launches()
+    t_wall0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        pg.sketch_dev(p, True, d_regs.data_ptr(), stream)
+    e1.record()
+    cx.barrier()
+    t_wall1 = time.perf_counter()
+    launches = capi.kernel_launches() - l0
+    ms = cx.max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    value = total_kmers / (ms * 1e-3)
+    alg_bytes = pg.packed_bytes + ng * (1 << p)
+    achieved = alg_bytes / (ms * 1e-3) / 1e9
+    roof = {"bound": "hbm", "kernel": "sketch_kernel<smem registers>", "achieved": achieved, "peak": cx.peak, "unit": "GB/s", "frac": achieved / cx.peak,
+            "peak_source": cx.peak_src, "traffic": load_traffic("sketch_kernel", ng, world), "algorithmic_bytes_per_launch": alg_bytes,
+            "bytes_per_kmer": alg_bytes / max(kmers_rank, 1), "kernel_ms": ms,
+            "note": "2-bit bases + validity + record-start planes + register write-back (SURVEY.md §8(d) + the start plane); "
+                    "0.5 B per k-mer cannot be HBM bound: the binding unit is the ALU pipe",
+            "int_bound": {"sass_instr_per_kmer": 48, "alu_pipe_instr_per_kmer": 25, "fma_pipe_instr_per_kmer": 18,
+                          "alu_ceiling_kmers_per_s": 148 * 64 / 25 * 1.965e9 * 1.0,
+                          "frac_of_alu_ceiling": value / world / (148 * 64 / 25 * 1.965e9),
+                          "source": "cuobjdump -sass of sketch_kernel<0,1,true>, one unrolled base step (DESIGN.md §3)"}}
+    clocks = cx.sampler.window(t_wall0, t_wall1) if cx.sampler else None
+    # e2e: host ASCII (pinned) -> db200_sketch_batch -> host registers
+    try:
+        host_ascii = capi.pinned_empty(ng * L)
+    except capi.Db200Error as e:   # a box that cannot pin 5 GB per rank still gets its device-resident numbers
+        log(f"[bench] pinned host allocation failed ({e}); using pageable memory for the sketch e2e leg")
+        host_ascii = np.empty(ng * L, dtype=np.uint8)
+    torch.from_numpy(host_ascii).copy_(ascii_dev.cpu())
+    del ascii_dev
+    regs_ref = d_regs.cpu().numpy()
+    pg.close()
+    torch.cuda.empty_cache()
+    e2e_variants = {}
+
+    def time_e2e(label, env):
+        old = {kk: os.environ.get(kk) for kk in env}
+        os.environ.update(env)
+        try:
+            out = capi.sketch_batch(host_ascii, offs, grb, k, p, True, device=local_rank)
+            if not np.array_equal(out, regs_ref):
+                raise RuntimeError(f"bench: host-buffer sketch ({label}) differs from the device-resident sketch")
+            cx.barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                capi.sketch_batch(host_ascii, offs, grb, k, p, True, device=local_rank)
+            cx.barrier()
+            return cx.max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps
+        finally:
+            for kk, vv in old.items():
+                if vv is None:
+                    os.environ.pop(kk, None)
+                else:
+                    os.environ[kk] = vv
+
+    for label, env in (("ascii_upload", {"DB200_HOST_PACK": "0"}), ("host_pack_hybrid", {"DB200_HOST_PACK": "1"})):
+        try:
+            e2e_variants[label] = time_e2e(label, env)
+        except capi.Db200Error as ex:
+            log(f"[bench] sketch e2e variant {label} skipped: {ex}")
+    best_label = min(e2e_variants, key=e2e_variants.get)
+    e2e_ms = e2e_variants[best_label]
+    e2e = {"value": total_kmers / (e2e_ms * 1e-3), "unit": "kmers/s", "h2d_bytes_per_step": int(ng * L), "d2h_bytes_per_step": int(ng << p),
+           "ms_per_step": e2e_ms, "api": "db200_sketch_batch(host ASCII records -> host registers)", "variant": best_label,
+           "variants_ms": e2e_variants,
+           "variants_note": "ascii_upload: 8 bits/base over PCIe, packed on the device; host_pack_hybrid: host threads pack to 2 bits + validity "
+                            "(0.375 B/base) from one end of the batch while ASCII chunks go up from the other end, so the link never idles"}
+    # what bounds it: the host->device link.  Probe: one 1 GiB copy from the same page-locked buffer, best of 3.
+    try:
+        probe_n = min(1 << 30, ng * L)
+        d_probe = torch.empty(probe_n, dtype=torch.uint8, device=dev)
+        h_probe = torch.from_numpy(host_ascii[:probe_n])
+        best = 0.0
+        for _ in range(3):
+            torch.cuda.synchronize()
+            tp = time.perf_counter()
+            d_probe.copy_(h_probe, non_blocking=True)
+            torch.cuda.synchronize()
+            best = max(best, probe_n / (time.perf_counter() - tp) / 1e9)
+        del d_probe
+        e2e["link"] = {"bound": "pcie h2d", "achieved_ascii_equivalent": ng * L / (e2e_ms * 1e-3) / 1e9, "peak": best, "unit": "GB/s",
+                       "frac_ascii_equivalent": ng * L / (e2e_ms * 1e-3) / 1e9 / best,
+                       "note": "ASCII bytes of input consumed per second through db200_sketch_batch against a plain 1 GiB cudaMemcpy from the same "
+                               "page-locked buffer; above 1 means the host-packed share of the batch crossed the link at 0.375 B/base"}
+    except Exception as ex:
+        log(f"[bench] link probe skipped: {ex}")
+    # second end-to-end form: RAW FASTA text (headers + 80-column lines) parsed on the device (db200_sketch_fasta_batch) —
+    # what the CLI feeds the library with; informational, the e2e key above stays the record interface
+    try:
+        if world > 1:
+            raise RuntimeError("single-GPU runs only (a second 5 GB page-locked buffer per rank)")
+        W = 80
+        assert L % W == 0
+        hdr_len = 16
+        per = hdr_len + (L // W) * (W + 1)
+        stride = (per + capi.FASTA_ALIGN - 1) // capi.FASTA_ALIGN * capi.FASTA_ALIGN
+        try:
+            text = capi.pinned_empty(ng * stride + 64)
+        except capi.Db200Error:
+            text = np.empty(ng * stride + 64, dtype=np.uint8)
+        tv = text[: ng * stride].reshape(ng, stride)
+        tv[:, :hdr_len] = np.frombuffer(b">genome 0000000\n", dtype=np.uint8)
+        body = tv[:, hdr_len:per].reshape(ng, L // W, W + 1)
+        body[:, :, :W] = host_ascii.reshape(ng, L // W, W)
+        body[:, :, W] = 10
+        foff = (np.arange(ng, dtype=np.uint64) * np.uint64(stride))
+        flen = np.full(ng, per, dtype=np.uint64)
+        out2 = np.zeros((ng, 1 << p), dtype=np.uint8)
+        status = np.zeros(ng, dtype=np.uint8)
+        import ctypes as C
+
+        def fasta_step():
+            capi._check(capi.lib.db200_sketch_fasta_batch(local_rank, p, k, 1, text.ctypes.data_as(C.c_void_p), foff.ctypes.data_as(capi.u64p),
+                                                          flen.ctypes.data_as(capi.u64p), ng, grb.ctypes.data_as(capi.u64p), ng,
+                                                          out2.ctypes.data_as(capi.u8p), status.ctypes.data_as(capi.u8p)))
+        fasta_step()
+        if status.any() or not np.array_equal(out2, regs_ref):
+            raise RuntimeError("device-parsed FASTA sketch differs from the device-resident sketch")
+        cx.barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            fasta_step()
+        cx.barrier()
+        f_ms = cx.max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps
+        e2e["fasta_text"] = {"value": total_kmers / (f_ms * 1e-3), "unit": "kmers/s", "ms_per_step": f_ms, "h2d_bytes_per_step": int(ng * per),
+                             "api": "db200_sketch_fasta_batch(host FASTA text, 80-column lines -> host registers; kseq rules on the device)"}
+        del text, tv, body
+    except Exception as ex:   # informational leg: never lose the bench line over it
+        log(f"[bench] FASTA-text e2e leg skipped: {ex}")
+    res = {"metric": "k-mers hashed/s (sketch k=31 p=14)", "value": value, "unit": "kmers/s", "ms_per_step": ms,
+           "config": sketch_config(world),
+           "roofline": roof, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "dtype": "2-bit bases / u64 k-mers / u8 registers"}
+    sample_np = host_ascii[: min(ng, 128) * L] if (rank == 0 and world == 1) else None
+    return res, sample_np
+
+
+# ---------------------------------------------------------------- joint MLE at the C5 shape (N=1)
+def bench_jmle(cx):
+    """Ertl joint MLE all pairs, p=16, k=21 (estimator and sketch shape of BASELINE configs[4]) on N_JMLE sketches: kernel rate and
+    parity of >= 1e6 pairs against the reference's ertl_joint path."""
+    torch, capi, args = cx.torch, cx.capi, cx.args
+    dev, stream = cx.dev, cx.stream
+    n, p, k = N_JMLE, P_JMLE, K_JMLE
+    m = 1 << p
+    regs_np = host_registers(SEED_JMLE, 0, n, p)
+    d_regs = torch.from_numpy(regs_np).to(dev)
+    pairs = n * (n - 1) // 2
+    d_out = torch.empty(pairs, dtype=torch.float32, device=dev)
+    plan = capi.DistPlan(cx.local_rank)
+    prm = capi.dist_params(p, k, capi.ERTL_MLE, capi.ERTL_JOINT_MLE, capi.JI, capi.ORDER_ROW_FIRST)
+    plan.prepare_dev(d_regs.data_ptr(), n, p, capi.ERTL_MLE, stream)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(2):
+        plan.run_symmetric_dev(prm, 0, n, d_out.data_ptr(), stream)
+    torch.cuda.synchronize()
+    steps = max(2, min(args.steps, 5))
+    e0.record()
+    for _ in range(steps):
+        plan.run_symmetric_dev(prm, 0, n, d_out.data_ptr(), stream)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    _, tiles, K = plan.last_run_info()
+    out = {"metric": "pairwise HLL cmp/s (dist p=16, Ertl joint MLE)", "value": pairs / (ms * 1e-3), "unit": "pairs/s", "ms_per_step": ms, "steps": steps,
+           "config": dist_config(n, 1, p=p, k=k, seed=SEED_JMLE, what="ERTL_JOINT_MLE JI"), "details": {"tiles": tiles, "live_thresholds": K},
+           "roofline": {"bound": "hbm", "kernel": "dist_jmle (three count families per threshold + three MLE solves per pair)",
+                        "achieved": pairs * (2 * m + 4) / (ms * 1e-3) / 1e9, "peak": cx.peak, "unit": "GB/s",
+                        "frac": pairs * (2 * m + 4) / (ms * 1e-3) / 1e9 / cx.peak, "traffic": None, "bytes_per_pair": 2 * m + 4}}
+    if not args.no_cpu_baseline:
+        chk, kind, desc = reference_checker()
+        threads = ref_threads(kind)
+        got = d_out.cpu().numpy()
+        v, npairs, rows, dt, vals = cpu_dist_sample(chk, kind, regs_np, n, 1.0, threads, p=p, k=k, jestim=3, rtype=1, min_pairs=1_000_000)
+        out["parity"] = parity_stats(got[:npairs], vals, what=f"{kind}: ertl_joint JI, rows [0,{rows}) of the same matrix")
+        out["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": threads, "kind": kind, "sample": f"rows [0,{rows}) = {npairs} pairs in {dt:.1f}s; {desc}"}
+    plan.close()
+    return out
+
+
+# ---------------------------------------------------------------- helpers for the 8-GPU configurations
+def emu_world(cx):
+    """(world, rank) the configuration is sized for: the real ones, or the emulated rank of --emulate-world."""
+    if cx.args.emulate_world > 1:
+        return cx.args.emulate_world, cx.args.emulate_rank
+    return cx.world, cx.rank
+
+
+def stream_rows(cx, plan, prm, n, rb, re_, block_pairs, ring, on_block=None):
+    """Rows [rb, re) of the symmetric matrix in blocks of whole rows (about block_pairs values): kernel -> device ring slot ->
+    page-locked ring slot, copy of block b under the kernel of block b+1; the host touches every delivered block.  The multi-process
+    counterpart of db200_dist_symmetric_stream (no buffer of the rank's 2.5 GB of floats exists on either side)."""
+    torch = cx.torch
+    d_ring, h_ring, copied, cstream = ring
+    ns = len(d_ring)
+    pending = []          # (slot, count, rb, re)
+    acc = 0.0
+
+    def deliver():
+        nonlocal acc
+        sl, cnt, b0, b1 = pending.pop(0)
+        copied[sl].synchronize()
+        if cnt:
+            blk = h_ring[sl][:cnt]
+            acc += float(blk[0]) + float(blk[cnt - 1])
+            if on_block is not None:
+                on_block(b0, b1, blk)
+    r = rb
+    issued = 0
+    while r < re_:
+        r1 = r + 1
+        while r1 < re_ and tri(n, r1) - tri(n, r) < block_pairs:
+            r1 += 1
+        cnt = tri(n, r1) - tri(n, r)
+        if len(pending) == ns:
+            deliver()
+        sl = issued % ns
+        plan.run_symmetric_dev(prm, r, r1, d_ring[sl].data_ptr(), cx.stream)
+        ev = torch.cuda.Event()
+        ev.record()
+        with torch.cuda.stream(cstream):
+            cstream.wait_event(ev)
+            if cnt:
+                h_ring[sl][:cnt].copy_(d_ring[sl][:cnt], non_blocking=True)
+            copied[sl].record()
+        pending.append((sl, cnt, r, r1))
+        issued += 1
+        r = r1
+    while pending:
+        deliver()
+    torch.cuda.synchronize()
+    return acc
+
+
+def make_ring(cx, slot_vals, ns=3):
+    torch = cx.torch
+    d_ring = [torch.empty(slot_vals, dtype=torch.float32, device=cx.dev) for _ in range(ns)]
+    h_ring = [torch.from_numpy(cx.capi.pinned_empty(slot_vals * 4).view(np.float32)) for _ in range(ns)]
+    copied = [torch.cuda.Event() for _ in range(ns)]
+    return d_ring, h_ring, copied, torch.cuda.Stream(device=cx.dev)
+
+
+# ---------------------------------------------------------------- C4: 100,000 p=14 sketches over 8 ranks
+def bench_c4(cx):
+    torch, dist, capi, multigpu, args = cx.torch, cx.dist, cx.capi, cx.multigpu, cx.args
+    dev, stream = cx.dev, cx.stream
+    W, R = emu_world(cx)
+    emulated = args.emulate_world > 1
+    n, p, k = C4_N, P_DIST, K_MER
+    m = 1 << p
+    counts = multigpu.shard_counts(n, W)
+    start = sum(counts[:R])
+    rb, re_ = multigpu.row_partition(n, W)[R]
+    my_pairs, total_pairs = tri(n, re_) - tri(n, rb), n * (n - 1) // 2
+    steps, warm = 2, 1
+    state = {}
+
+    # phase 1 (local): this rank's shard of the seeded matrix in page-locked memory
+    ok = True
+    try:
+        t0 = time.perf_counter()
+        host_regs = capi.pinned_empty(counts[R] * m)
+        host_registers(SEED_C4, start, counts[R], p, out=host_regs.reshape(counts[R], m))
+        pin_t = torch.from_numpy(host_regs).view(counts[R], m)
+        local = pin_t.to(dev)
+        others = None
+        if emulated:   # the other ranks' shards: device-side synthesis (any valid sketches do; only this rank's rows are checked bit for bit)
+            others = synth_registers_torch(torch, n - counts[R], p, SEED_C4 + 1, dev)
+        plan = capi.DistPlan(cx.local_rank)
+        prm = capi.dist_params(p, k, capi.ERTL_MLE, capi.ERTL_MLE, capi.JI, capi.ORDER_ROW_FIRST)
+        block_pairs = 32 << 20
+        ring = make_ring(cx, block_pairs + n)
+        d_out = torch.empty(my_pairs, dtype=torch.float32, device=dev)
+        log(f"[bench/c4] rank {R}: shard rows [{start},{start + counts[R]}) ready in {time.perf_counter() - t0:.1f}s; block rows [{rb},{re_}) = {my_pairs} pairs")
+    except Exception as e:
+        log(f"[bench/c4] rank {R}: setup failed: {e!r}")
+        ok = False
+    if not cx.all_ok(ok):
+        return {"failed": "setup failed on at least one rank"}
+
+    def gather(loc):
+        if emulated:
+            full = torch.empty((n, m), dtype=torch.uint8, device=dev)
+            full[:start] = others[:start]
+            full[start:start + counts[R]] = loc
+            full[start + counts[R]:] = others[start:]
+            return full
+        return multigpu.allgather_registers(loc, counts, dist)
+
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    ag, prep, ker, tot = [], [], [], []
+    for it in range(warm + steps):
+        cx.barrier()
+        ev[0].record()
+        full = gather(local)
+        ev[1].record()
+        plan.prepare_dev(full.data_ptr(), n, p, capi.ERTL_MLE, stream)
+        ev[2].record()
+        plan.run_symmetric_dev(prm, rb, re_, d_out.data_ptr(), stream)
+        ev[3].record()
+        torch.cuda.synchronize()
+        if it >= warm:
+            ag.append(ev[0].elapsed_time(ev[1])); prep.append(ev[1].elapsed_time(ev[2])); ker.append(ev[2].elapsed_time(ev[3]))
+            tot.append(cx.max_over_ranks(ev[0].elapsed_time(ev[3])))
+    _, tiles, K = plan.last_run_info()
+    ms = float(np.mean(tot))
+    # e2e: pinned shard -> H2D -> all-gather -> planes -> row blocks streamed to page-locked host buffers
+    e2e_ms = []
+    for it in range(1 + steps):
+        cx.barrier()
+        t0 = time.perf_counter()
+        loc = pin_t.to(dev, non_blocking=True)
+        full = gather(loc)
+        plan.prepare_dev(full.data_ptr(), n, p, capi.ERTL_MLE, stream)
+        stream_rows(cx, plan, prm, n, rb, re_, block_pairs, ring)
+        cx.barrier()
+        if it >= 1:
+            e2e_ms.append(cx.max_over_ranks((time.perf_counter() - t0) * 1e3))
+    e2e_t = float(np.mean(e2e_ms))
+    scale = (W if emulated else 1)     # an emulated rank reports the whole-job figure its time implies (every rank holds 1/W of the pairs)
+    out = {"metric": "pairwise HLL cmp/s (dist p=14)", "value": total_pairs / (ms * 1e-3), "unit": "pairs/s", "ms_per_step": ms, "steps": steps, "warmup": warm,
+           "n_gpus": W, "config": dist_config(n, W, seed=SEED_C4),
+           "details": {"step_breakdown_ms": {"allgather": float(np.mean(ag)), "planes+cardinalities": float(np.mean(prep)), "all_pairs_kernel": float(np.mean(ker))},
+                       "tiles": tiles, "live_thresholds": K, "rows_of_this_rank": [rb, re_], "pairs_of_this_rank": my_pairs,
+                       "hbm_bytes": {"registers": n * m, "planes": K * n * (m // 8), "out_per_rank": my_pairs * 4}},
+           "e2e": {"value": total_pairs / (e2e_t * 1e-3), "unit": "pairs/s", "ms_per_step": e2e_t, "h2d_bytes_per_step": int(counts[R] * m),
+                   "d2h_bytes_per_step": int(my_pairs * 4),
+                   "api": "multigpu driver: pinned shard -> all-gather -> planes -> row blocks of 32 Mi pairs through a 3-slot device/page-locked ring (the multi-process form of db200_dist_symmetric_stream)"},
+           "roofline": {"bound": "hbm", "kernel": "dist_kernel", "achieved": my_pairs * (2 * m + 4) / (float(np.mean(ker)) * 1e-3) / 1e9, "peak": cx.peak, "unit": "GB/s",
+                        "frac": my_pairs * (2 * m + 4) / (float(np.mean(ker)) * 1e-3) / 1e9 / cx.peak, "traffic": None}}
+    if emulated:
+        out["emulated"] = {"world": W, "rank": R, "note": "one rank's share on one GPU; the all-gather is replaced by a device copy, the other ranks' sketches are device-synthesised"}
+    # parity (rank 0 of the job / the emulated rank): the first rows of this rank's block against the reference on the same matrix
+    if cx.rank == 0 and not args.no_cpu_baseline:
+        try:
+            chk, kind, desc = reference_checker()
+            threads = ref_threads(kind)
+            regs_np = full.cpu().numpy()
+            v, npairs, rows, dt, vals = cpu_dist_sample(chk, kind, regs_np, n, 1.0, threads, row0=rb, min_pairs=2_000_000)
+            got = d_out[:npairs].cpu().numpy()
+            out["parity"] = parity_stats(got, vals, what=f"{kind}: rows [{rb},{rb + rows}) of the gathered matrix")
+            del regs_np
+        except Exception as e:
+            log(f"[bench/c4] parity failed: {e!r}")
+    plan.close()
+    return out
+
+
+# ---------------------------------------------------------------- C5: 50,000 x 5 Mbp, k=21, p=16, joint MLE, sketch + all pairs
+def bench_c5(cx):
+    torch, dist, capi, multigpu, args = cx.torch, cx.dist, cx.capi, cx.multigpu, cx.args
+    dev, stream = cx.dev, cx.stream
+    W, R = emu_world(cx)
+    emulated = args.emulate_world > 1
+    n, p, k, L = C5_GENOMES, C5_P, C5_K, GENOME_LEN
+    m = 1 << p
+    counts = multigpu.shard_counts(n, W)
+    start = sum(counts[:R])
+    ng = counts[R]
+    rb, re_ = multigpu.row_partition(n, W)[R]
+    my_pairs, total_pairs = tri(n, re_) - tri(n, rb), n * (n - 1) // 2
+    B = 625                                   # genomes per on-device batch (3.1 GB of ASCII)
+    steps, warm = 1, 1
+    ok = True
+    try:
+        local = torch.zeros((ng, m), dtype=torch.uint8, device=dev)
+        ascii_buf = torch.empty(B * L, dtype=torch.uint8, device=dev)
+        others = synth_registers_torch(torch, n - ng, p, SEED_C5 + 1, dev) if emulated else None
+        plan = capi.DistPlan(cx.local_rank)
+        prm = capi.dist_params(p, k, capi.ERTL_MLE, capi.ERTL_JOINT_MLE, capi.JI, capi.ORDER_ROW_FIRST)
+        block_pairs = 32 << 20
+        ring = make_ring(cx, block_pairs + n)
+        keep_rows = rows_for_pairs(n, rb, 300_000)
+        d_keep = torch.empty(tri(n, rb + keep_rows) - tri(n, rb), dtype=torch.float32, device=dev)
+    except Exception as e:
+        log(f"[bench/c5] rank {R}: setup failed: {e!r}")
+        ok = False
+    if not cx.all_ok(ok):
+        return {"failed": "setup failed on at least one rank"}
+
+    def gather(loc):
+        if emulated:
+            full = torch.empty((n, m), dtype=torch.uint8, device=dev)
+            full[:start] = others[:start]
+            full[start:start + ng] = loc
+            full[start + ng:] = others[start:]
+            return full
+        return multigpu.allgather_registers(loc, counts, dist)
+
+    sample_genomes = {}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    res = []
+    for it in range(warm + steps):
+        # ---- sketch: genomes are generated on the device batch by batch (untimed), packed and sketched (timed)
+        t_pack = t_sk = 0.0
+        kmers = 0
+        for b0 in range(0, ng, B):
+            nb = min(B, ng - b0)
+            synth_genomes_torch(torch, nb, L, SEED_C5, dev, first=start + b0, out=ascii_buf)
+            if it == 0 and b0 == 0 and cx.rank == 0:
+                for gi in (0, 1):
+                    sample_genomes[start + gi] = ascii_buf[gi * L:(gi + 1) * L].cpu().numpy()
+            offs = (np.arange(nb + 1, dtype=np.uint64) * np.uint64(L))
+            grb = np.arange(nb + 1, dtype=np.uint64)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            pg = capi.PackedGenomes(int(ascii_buf.data_ptr()), offs, grb, k, device=cx.local_rank)   # ASCII in HBM -> 2-bit store (synchronous)
+            t_pack += (time.perf_counter() - t0) * 1e3
+            e0.record()
+            pg.sketch_dev(p, True, local[b0:b0 + nb].data_ptr(), stream)
+            e1.record()
+            torch.cuda.synchronize()
+            t_sk += e0.elapsed_time(e1)
+            kmers += pg.kmers
+            pg.close()
+        # ---- all-gather + planes + joint-MLE all pairs, row blocks streamed to the host
+        cx.barrier()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        t0 = time.perf_counter()
+        ev[0].record()
+        full = gather(local)
+        ev[1].record()
+        plan.prepare_dev(full.data_ptr(), n, p, capi.ERTL_MLE, stream)
+        ev[2].record()
+        stream_rows(cx, plan, prm, n, rb, re_, block_pairs, ring)
+        t_pairs_wall = (time.perf_counter() - t0) * 1e3
+        cx.barrier()
+        if it >= warm:
+            res.append({"pack": t_pack, "sketch": t_sk, "allgather": ev[0].elapsed_time(ev[1]), "planes": ev[1].elapsed_time(ev[2]),
+                        "gather+planes+pairs+d2h_wall": t_pairs_wall, "kmers": kmers})
+    r0 = res[-1]
+    _, tiles, K = plan.last_run_info()
+    sketch_ms = cx.max_over_ranks(r0["pack"] + r0["sketch"])
+    pairs_ms = cx.max_over_ranks(r0["gather+planes+pairs+d2h_wall"])
+    total_ms = sketch_ms + pairs_ms
+    out = {"metric": "end-to-end sketch + all-pairs time, 50,000 genomes (genomes/s)", "value": n / (total_ms * 1e-3), "unit": "genomes/s", "ms_per_step": total_ms,
+           "steps": steps, "warmup": warm, "n_gpus": W,
+           "config": {"workload": f"e2e sketch+dist: {n} x {L} bp synthetic genomes, k={k}, p={p}, Ertl joint MLE JI ({total_pairs} pairs)", "genomes_per_gpu": ng,
+                      "data": "genomes generated on the device batch by batch (SURVEY.md §8(d): C5 is never written to disk); sketch time = ASCII in HBM -> 2-bit store -> registers",
+                      "parallelism": f"genomes x{W}, 1 NCCL all-gather of {n * m >> 20} MB of registers, block-row x{W}"},
+           "details": {"step_breakdown_ms": {"pack_ascii_to_2bit": r0["pack"], "sketch_kernel": r0["sketch"], "allgather": r0["allgather"], "planes+cardinalities": r0["planes"],
+                                             "allgather+planes+all_pairs+d2h (wall)": r0["gather+planes+pairs+d2h_wall"]},
+                       "sketch_kmers_per_s_whole_job": r0["kmers"] * W / (sketch_ms * 1e-3), "dist_pairs_per_s_whole_job": total_pairs / (pairs_ms * 1e-3),
+                       "tiles": tiles, "live_thresholds": K, "rows_of_this_rank": [rb, re_], "pairs_of_this_rank": my_pairs,
+                       "hbm_bytes": {"registers": n * m, "planes": K * n * (m // 8)}},
+           "e2e": {"value": n / (total_ms * 1e-3), "unit": "genomes/s", "ms_per_step": total_ms, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": int(my_pairs * 4),
+                   "note": "inputs are device-generated (31 GB of ASCII per rank has no host copy); the float matrix is streamed to page-locked host buffers inside the timed region"}}
+    if emulated:
+        out["emulated"] = {"world": W, "rank": R, "note": "one rank's share on one GPU; the other ranks' sketches are device-synthesised register arrays"}
+    if cx.rank == 0 and not args.no_cpu_baseline:
+        try:
+            chk, kind, desc = reference_checker()
+            # (a) registers of two device-generated genomes against the reference's Encoder + addh, bit for bit
+            reg_ok = True
+            for gidx, seq in sample_genomes.items():
+                wantr = chk.sketch([seq.tobytes()], k, p, True)
+                reg_ok = reg_ok and bool(np.array_equal(local[gidx - start].cpu().numpy(), wantr))
+            # (b) a sample of this rank's first rows against the reference's joint MLE
+            plan.run_symmetric_dev(prm, rb, rb + keep_rows, d_keep.data_ptr(), stream)
+            torch.cuda.synchronize()
+            got_rows = d_keep.cpu().numpy()
+            rng = np.random.default_rng(5)
+            ns = 2000
+            ii = rb + rng.integers(0, keep_rows, size=ns)
+            jj = np.array([rng.integers(i + 1, n) for i in ii])
+            rows_needed = np.unique(np.concatenate([ii, jj]))
+            host_rows = {int(r): full[int(r)].cpu().numpy() for r in rows_needed}
+            got = np.array([got_rows[tri(n, int(i)) - tri(n, rb) + int(j) - int(i) - 1] for i, j in zip(ii, jj)])
+            wantv = np.array([chk.pair(host_rows[int(i)], host_rows[int(j)], p, estim=2, jestim=3, rtype=1, k=k) for i, j in zip(ii, jj)])
+            out["parity"] = parity_stats(got, wantv, what=f"{kind}: {ns} sampled pairs of rows [{rb},{rb + keep_rows}) through ertl_joint; registers of 2 device-generated genomes bit-identical: {reg_ok}")
+            out["parity"]["registers_bit_identical"] = reg_ok
+        except Exception as e:
+            log(f"[bench/c5] parity failed: {e!r}")
+    plan.close()
+    return out
 
 
 _RESULT_OUT = None
@@ -628,6 +1132,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="both", choices=["dist", "sketch", "both"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the jmle / c4 / c5 legs")
+    ap.add_argument("--only", default="", help="comma list of extra legs to run (c4,c5)")
+    ap.add_argument("--emulate-world", type=int, default=0, help="single GPU: run ONE rank's share of the 8-GPU configurations c4 / c5")
+    ap.add_argument("--emulate-rank", type=int, default=0)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         log("note: fewer than 3 warm-up steps; timing rules ask for W >= 3")

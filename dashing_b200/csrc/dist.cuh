@@ -54,8 +54,14 @@ __global__ void __launch_bounds__(256) range_kernel(const uint4 *__restrict__ re
 
 // ---------------------------------------------------------------------------------------------
 // threshold bit-planes + per-sketch threshold counts.  One CTA (4 warps) per sketch; a warp turns
-// 1024 registers (8 coalesced 128-byte loads) into 32 plane words per threshold with ballots.
-// Register r = g*1024 + gg*128 + lane*4 + j lands in word g*32 + gg*4 + j, bit `lane`.
+// 1024 registers (8 coalesced 128-byte loads, 32 registers per lane) into one plane word per lane and
+// threshold WITHOUT leaving the lane: registers are < 64, so byte-wise x + (0x80 - k) sets bit 7 of a
+// byte exactly when the register is >= k and never carries into the next byte; shifting word gg's
+// four flag bits right by 7 - gg interleaves the 8 words into 32 distinct bit positions.
+// Register r = g*1024 + gg*128 + lane*4 + j lands in word g*32 + lane, bit 8*j + gg (any fixed
+// permutation of register positions serves: the pair histogram does not depend on it).
+// (Round 1 built the words with 32 ballots per threshold: 4x the instructions, 2.8 ms for 28,284
+// sketches; profiles/r02_planes_kernel_ncu.txt.)
 // counts[s][t] = #{ registers of sketch s >= gmin + 1 + t }.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) planes_kernel(const uint32_t *__restrict__ regs32, uint64_t n, uint64_t row0, int p, int gmin, int K,
@@ -74,33 +80,38 @@ __global__ void __launch_bounds__(128) planes_kernel(const uint32_t *__restrict_
     const uint32_t *src = regs32 + s * (m >> 2);
     for (uint32_t g = warp; g < ngroups; g += 4) {
         uint32_t x[8];
+        uint32_t valid = 0;                      // bit 8*j + gg set: that register exists (p < 10 only has holes)
 #pragma unroll
         for (int gg = 0; gg < 8; ++gg) {
             const uint32_t wi = g * 256 + gg * 32 + lane;
             x[gg] = wi < nwords ? __ldg(src + wi) : 0u;
+            if (wi < nwords) valid |= 0x01010101u << gg;
         }
-        // thresholds above the largest register of this group of 1024 have empty planes: no ballots for them
-        uint32_t mx4 = x[0];
+        // thresholds above the largest register of this group of 1024 have empty planes, thresholds up to the smallest
+        // one full planes: neither needs the compare sweep
+        uint32_t mx4 = x[0], mn4 = valid == 0xFFFFFFFFu ? x[0] : 0u;
 #pragma unroll
-        for (int gg = 1; gg < 8; ++gg) mx4 = __vmaxu4(mx4, x[gg]);
+        for (int gg = 1; gg < 8; ++gg) { mx4 = __vmaxu4(mx4, x[gg]); mn4 = __vminu4(mn4, valid == 0xFFFFFFFFu ? x[gg] : 0u); }
         mx4 = max(max(mx4 & 0xFFu, (mx4 >> 8) & 0xFFu), max((mx4 >> 16) & 0xFFu, mx4 >> 24));
-        const int tl = min(K, max(0, (int)__reduce_max_sync(0xFFFFFFFFu, mx4) - gmin));
-        for (int t = tl; t < K; ++t) planes[((uint64_t)t * n + s) * W + g * 32 + lane] = 0u;
-        for (int t = 0; t < tl; ++t) {
-            const uint32_t k4 = (uint32_t)(gmin + 1 + t) * 0x01010101u;
-            uint32_t kept = 0;
+        mn4 = min(min(mn4 & 0xFFu, (mn4 >> 8) & 0xFFu), min((mn4 >> 16) & 0xFFu, mn4 >> 24));
+        const int th = min(K, max(0, (int)__reduce_max_sync(0xFFFFFFFFu, mx4) - gmin));    // thresholds [th, K) are empty
+        const int tf = min(th, max(0, (int)__reduce_min_sync(0xFFFFFFFFu, mn4) - gmin));   // thresholds [0, tf) are full
+        uint32_t *dst = planes + s * W + g * 32 + lane;
+        const uint64_t tstride = n * W;
+        for (int t = th; t < K; ++t) dst[(uint64_t)t * tstride] = 0u;
+        for (int t = 0; t < tf; ++t) dst[(uint64_t)t * tstride] = 0xFFFFFFFFu;
+        if (lane == 0)
+            for (int t = 0; t < tf; ++t) atomicAdd(&cnt[t], 1024u);
+        // byte-wise bias: bit 7 of a byte of x + c is set iff that register >= k = gmin + 1 + t
+        uint32_t c4 = (uint32_t)(0x80 - (gmin + 1 + tf)) * 0x01010101u;
+        for (int t = tf; t < th; ++t) {
+            uint32_t word = 0;
 #pragma unroll
-            for (int gg = 0; gg < 8; ++gg) {
-                const uint32_t ge = __vcmpgeu4(x[gg], k4);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const uint32_t word = __ballot_sync(0xFFFFFFFFu, (ge >> (8 * j)) & 1u);
-                    if (lane == (uint32_t)(gg * 4 + j)) kept = word;
-                }
-            }
-            planes[((uint64_t)t * n + s) * W + g * 32 + lane] = kept;
-            const uint32_t tot = __reduce_add_sync(0xFFFFFFFFu, (uint32_t)__popc(kept));
+            for (int gg = 0; gg < 8; ++gg) word |= ((x[gg] + c4) >> (7 - gg)) & (0x01010101u << gg);
+            dst[(uint64_t)t * tstride] = word;
+            const uint32_t tot = __reduce_add_sync(0xFFFFFFFFu, (uint32_t)__popc(word));
             if (lane == 0) atomicAdd(&cnt[t], tot);
+            c4 -= 0x01010101u;
         }
     }
     __syncthreads();

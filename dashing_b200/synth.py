@@ -92,6 +92,65 @@ def registers(seed: int, n: int, p: int, card: float = 5e6, group: int = 16) -> 
     return out
 
 
+def _rho_table(lam: float, q: int) -> np.ndarray:
+    """cdf[r] = P(reg <= r) of `_rho_sample`'s distribution, r = 0..q+1 (the last entry is 1)."""
+    cdf = np.exp(-lam * np.exp2(-np.arange(q + 2, dtype=np.float64)))
+    cdf[q + 1] = 1.0
+    return cdf
+
+
+def registers_block_mt(seed: int, start: int, count: int, p: int, card: float = 5e6, group: int = 16, threads: int = 1, out=None) -> np.ndarray:
+    """`registers_block` over several host threads (numpy's generators and searchsorted release the GIL); `out`, if given,
+    is a uint8 [count, 2^p] array (e.g. a view of page-locked memory) that receives the rows."""
+    from concurrent.futures import ThreadPoolExecutor
+    m = 1 << p
+    if out is None:
+        out = np.empty((count, m), dtype=np.uint8)
+    step = max(group, (count + max(threads, 1) * 4 - 1) // (max(threads, 1) * 4) // group * group)
+    cuts = list(range(start - start % group, start + count, step))
+    def work(a):
+        lo, hi = max(a, start), min(a + step, start + count)
+        if hi > lo:
+            out[lo - start:hi - start] = registers_block(seed, lo, hi - lo, p, card, group)
+    if threads <= 1 or len(cuts) <= 1:
+        for a in cuts:
+            work(a)
+    else:
+        with ThreadPoolExecutor(max_workers=threads) as ex:
+            list(ex.map(work, cuts))
+    return out
+
+
+def registers_block(seed: int, start: int, count: int, p: int, card: float = 5e6, group: int = 16) -> np.ndarray:
+    """Rows [start, start + count) of an endless seeded register matrix with the construction of `registers`
+    (correlated groups of `group` sketches sharing an ancestor component).  Row i depends on (seed, i // group) only, so
+    any shard can be produced on its own — every rank of the multi-process bench, and the reference arm, draw the very
+    same bytes for the rows they need.  Inverse-CDF sampling from the register distribution's table (3 uniforms per
+    register, no transcendental per element)."""
+    m, q = 1 << p, 64 - p
+    out = np.empty((count, m), dtype=np.uint8)
+    lam = card / m
+    full = _rho_table(lam, q)
+    g0, g1 = start // group, (start + count + group - 1) // group
+    for g in range(g0, g1):
+        rng = np.random.default_rng([seed, g])
+        shared = np.searchsorted(full, rng.random(m)).astype(np.uint8)
+        for j in range(group):
+            i = g * group + j
+            frac = 1.0 - RATE_LADDER[i % len(RATE_LADDER)]
+            # every member consumes the same number of uniforms whatever its rate: rows stay independent of the shard cut
+            u1, u2 = rng.random(m), rng.random(m)
+            if not (start <= i < start + count):
+                continue
+            if frac >= 1.0:
+                row = shared
+            else:
+                sh = np.minimum(shared, np.searchsorted(_rho_table(frac * lam, q), u1).astype(np.uint8)) if frac > 0.0 else np.zeros(m, np.uint8)
+                row = np.maximum(sh, np.searchsorted(_rho_table((1.0 - frac) * lam, q), u2).astype(np.uint8))
+            out[i - start] = row
+    return out
+
+
 def adversarial_registers(seed: int, p: int) -> np.ndarray:
     """Edge-case sketches: empty, saturated, constant, full value range, single hot register."""
     rng = np.random.default_rng(seed)

@@ -7,8 +7,10 @@ Floating point (estimator values, Jaccard / Mash / containment floats): BASELINE
 
 * Cancellation residues.  Quantities such as |A \\ B| = cA - I are differences of ~1e5-sized doubles;
   when the true value is 0 the reference returns whatever its compiler's FMA contraction leaves
-  (0, 1.4e-11, 2.9e-11 ...).  The error is therefore measured relative to max(|got|, |want|, scale),
-  scale = 1 for index/distance outputs and the largest finite cardinality for SIZES.
+  (0, 1.4e-11, 2.9e-11 ...).  The error is TRUE relative error, |got - want| / |want|, wherever the
+  checker's value is not such a residue; only where |want| < 1e-9 * scale (scale = 1 for index / distance
+  outputs, the largest finite cardinality for SIZES) is it measured against `scale` instead, because
+  a value that small is decided by the last bits of ~scale-sized operands in the reference itself.
 * Discontinuity at 0.  dist_index / containment_dist map ji == 0 to exactly 1 and ji = 1e-17 to ~1.17
   (src/dashing.h:154-165), and 0/0 vs 1e-11/1e-11 decides between NaN and 1.  Where the checker's own
   intersection size for a pair is such a residue (< 1e-9 of the largest cardinality), infinite or
@@ -17,6 +19,7 @@ Floating point (estimator values, Jaccard / Mash / containment floats): BASELINE
 import numpy as np
 
 RTOL = 1e-6
+RESIDUE = 1e-9      # |want| below RESIDUE * scale: a cancellation residue, compared on the absolute scale
 
 
 def rel_err(got, want, scale=1.0):
@@ -24,7 +27,8 @@ def rel_err(got, want, scale=1.0):
     want = np.asarray(want, dtype=np.float64)
     same = (got == want) | (np.isnan(got) & np.isnan(want))
     with np.errstate(invalid="ignore", divide="ignore"):
-        err = np.abs(got - want) / np.maximum(np.maximum(np.abs(got), np.abs(want)), scale)
+        den = np.where(np.abs(want) >= RESIDUE * scale, np.abs(want), scale)
+        err = np.abs(got - want) / den
     err = np.where(same, 0.0, err)
     return np.where(np.isnan(err), np.inf, err)
 
@@ -65,7 +69,7 @@ def assert_knn_close(got, want, rtol=RTOL, what=""):
     for r, j in zip(bad_rows, bad_cols):
         v = gv[r, j]
         pos = np.nonzero(wi[r] == gi[r, j])[0]
-        near = lambda x: abs(x - v) <= rtol * max(abs(x), abs(v), 1.0)
+        near = lambda x: abs(x - v) <= rtol * max(min(abs(x), abs(v)), RESIDUE)
         if pos.size:
             ok = near(wv[r, pos[0]])
         else:
