@@ -1003,7 +1003,7 @@ int dist_main(int argc, char **argv) {
             case L_DEFER_HLL: o.defer_hll = true; break;
             case L_DEVICE: o.device = parse_device(optarg); break;
             case 's': if (*optarg) unsupported("-s/--spacing"); break;
-            case 'w': if (std::atoi(optarg) > o.k) unsupported("-w/--window-size"); break;   // wsz <= k is "unwindowed" (src/distmain.cpp:168)
+            case 'w': o.wsz = std::atoi(optarg); break;   // judged once k is final: wsz <= k is "unwindowed" (src/distmain.cpp:168)
             case L_COUNTMIN: unsupported("--countmin");
             case L_BY_FNAME: unsupported("--sketch-by-fname");
             case L_ENTROPY: case 'g': unsupported("-g/--by-entropy");
@@ -1018,7 +1018,8 @@ int dist_main(int argc, char **argv) {
             default: break;   // -n X, -c X, -q X, -t X, -R X, -D X, -B X, -e, -H, -Z, -N, -y, -a, -z, --nperbatch: accepted, no effect on the HLL path
         }
     }
-    if (o.k > 32) throw Error("k must be <= 32 for non-rolling hashes.");     // src/distmain.cpp:101-102
+    if (o.k > 32) throw Error("k must be <= 32 for non-rolling hashes.");
+    if (o.wsz > o.k) unsupported("-w/--window-size (windowed minimizers: w > k)");   // option order must not matter: `-w 30 -k 21` is windowed     // src/distmain.cpp:101-102
     if (o.nthreads < 1) o.nthreads = 1;
     std::vector<std::string> inpaths = paths_file.empty() ? std::vector<std::string>(argv + optind, argv + argc) : get_paths(paths_file);
     if (inpaths.empty()) throw Error("No paths. See usage.");
@@ -1067,7 +1068,7 @@ static bool sketch_option(int co, SketchOptions &o, bool &defer_hll) {
         case L_DEVICE: o.device = parse_device(optarg); return true;
         case L_DEFER_HLL: defer_hll = true; return true;
         case 's': if (*optarg) unsupported("-s/--spacing"); return true;
-        case 'w': if (std::atoi(optarg) > o.k) unsupported("-w/--window-size"); return true;
+        case 'w': o.wsz = std::atoi(optarg); return true;   // judged by the caller once k is final
         case 'b': case L_COUNTMIN: unsupported("-b/--countmin");
         case L_BY_FNAME: unsupported("--sketch-by-fname");
         case L_ENTROPY: unsupported("--by-entropy");
@@ -1094,6 +1095,7 @@ int sketch_main(int argc, char **argv) {
     // sketch_core<HyperLogLogHasher<>>::write is BBitMinHasher's: it emits a b-bit minhash under the .hll name (bbmh.h:962-969)
     if (defer_hll) unsupported("--defer-hll (`sketch` then writes b-bit minhash files, not HLLs)");
     if (o.k > 32) throw Error("k must be <= 32 for non-rolling hashes.");
+    if (o.wsz > o.k) unsupported("-w/--window-size (windowed minimizers: w > k)");   // option order must not matter: `-w 30 -k 21` is windowed
     o.nthreads = std::max(o.nthreads, 1);
     std::vector<std::string> inpaths = (!paths_file.empty() && isfile(paths_file)) ? get_paths(paths_file) : std::vector<std::string>(argv + optind, argv + argc);
     if (inpaths.empty()) throw Error("No paths. See usage.");
@@ -1190,6 +1192,7 @@ int hll_main(int argc, char **argv) {
     if (!spacing.empty()) unsupported("-s (spacing)");
     if (wsz > o.k) unsupported("-w (window size)");
     if (o.k > 32) throw Error("k must be <= 32 for non-rolling hashes.");
+    if (o.wsz > o.k) unsupported("-w/--window-size (windowed minimizers: w > k)");   // option order must not matter: `-w 30 -k 21` is windowed
     if (o.nthreads < 1) o.nthreads = 16;                               // negative -> hardware_concurrency (src/dashing.h:622-625)
     std::vector<std::string> inpaths(argv + optind, argv + argc);      // (-F is parsed nowhere in the reference's getopt string)
     // one "genome" whose files are all the inputs: FNAME_SEP-joined paths are exactly that (src/substrs.h:7-26)
@@ -1297,7 +1300,7 @@ int card_main(int argc, char **argv) {
             case L_DEVICE: o.device = parse_device(optarg); break;
             case L_DEFER_HLL: o.defer_hll = true; break;
             case 's': if (*optarg) unsupported("-s/--spacing"); break;
-            case 'w': if (std::atoi(optarg) > o.k) unsupported("-w/--window-size"); break;
+            case 'w': o.wsz = std::atoi(optarg); break;
             case L_COUNTMIN: unsupported("--countmin");
             case L_BY_FNAME: unsupported("--sketch-by-fname");
             case L_OTHER_SKETCH: case '8': unsupported("a non-HLL sketch type");
@@ -1307,6 +1310,7 @@ int card_main(int argc, char **argv) {
         }
     }
     if (o.k > 32) throw Error("k must be <= 32 for non-rolling hashes.");
+    if (o.wsz > o.k) unsupported("-w/--window-size (windowed minimizers: w > k)");   // option order must not matter: `-w 30 -k 21` is windowed
     if (o.nthreads < 1) o.nthreads = 1;
     if (o.defer_hll) o.estim = o.jestim = DB200_ERTL_MLE;
     std::vector<std::string> inpaths = paths_file.empty() ? std::vector<std::string>(argv + optind, argv + argc) : get_paths(paths_file);
@@ -1361,6 +1365,7 @@ int sketch_by_seq_main(int argc, char **argv) {
         if (co == 'o') outpath = optarg;
     }
     if (o.k > 32) throw Error("k must be <= 32 for non-rolling hashes.");
+    if (o.wsz > o.k) unsupported("-w/--window-size (windowed minimizers: w > k)");   // option order must not matter: `-w 30 -k 21` is windowed
     if (argc != optind + 1) throw Error("Usage: sketch_by_seq <opts> [same as sketch] -o out_path sequence_file");
     // src/dashing.cpp:541-544 tests the flag the wrong way round: WITHOUT --defer-hll it instantiates HyperLogLogHasher, whose
     // inherited write(gzFile) emits b-bit minhash records (bbmh.h:962-969); only --defer-hll yields hll_t records

@@ -59,6 +59,7 @@ void write_binary_matrix(std::FILE *fp, const float *packed, uint64_t n);   // '
 // ---- drivers ----------------------------------------------------------------------------------------------------
 struct SketchOptions {
     int k = 31, p = 10, nthreads = 1, device = 0;
+    int wsz = 0;                            // -w: checked against k AFTER all options are parsed (the reference builds Spacer(k, wsz) then)
     int estim = 2, jestim = 2;              // -E/-I/-J: stored in the header of every .hll written (set_estim_and_jestim)
     bool canon = true, skip_cached = false, avoid_sorting = false;
     std::string prefix, suffix;

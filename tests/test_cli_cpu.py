@@ -29,6 +29,10 @@ def test_option_rules_and_declined_paths(tmp_path):
     for flags in (["-s", "1,1,1"], ["-w", "50"], ["--countmin"], ["-8"], ["--use-nthash"], ["--wj"], ["--use-bloom-filter"]):
         r = cli(tmp_path, "dist", "-k31", *flags, "x.fa")
         assert r.returncode == 1 and b"outside the B200 engine" in r.stderr, flags
+    # option order must not matter: `-w 30 -k 21` is windowed (30 > 21) although 30 <= the default k = 31
+    for sub_cmd in ("dist", "sketch", "card"):
+        r = cli(tmp_path, sub_cmd, "-w", "30", "-k", "21", "x.fa")
+        assert r.returncode == 1 and b"outside the B200 engine" in r.stderr, sub_cmd
     r = cli(tmp_path, "dist", "-w", "20", "-k31", "--containment-index")                       # no paths at all
     assert r.returncode == 1 and b"No paths" in r.stderr
     r = cli(tmp_path, "sketch", "-k31", "--defer-hll", "x.fa")
