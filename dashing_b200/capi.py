@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(_HERE, "libdashing_b200.so")
 OK, EINVAL, EUNSUPPORTED, ENODEV, ECUDA, ENOMEM = range(6)
 ORIGINAL, ERTL_IMPROVED, ERTL_MLE, ERTL_JOINT_MLE = 0, 1, 2, 3
 MASH_DIST, JI, SIZES, FULL_MASH_DIST, FULL_CONTAINMENT_DIST, CONTAINMENT_INDEX, CONTAINMENT_DIST, \
-    SYMMETRIC_CONTAINMENT_INDEX, SYMMETRIC_CONTAINMENT_DIST = range(9)
+    SYMMETRIC_CONTAINMENT_INDEX, SYMMETRIC_CONTAINMENT_DIST, UNION_SIZE = range(10)
 ORDER_ROW_FIRST, ORDER_COL_FIRST = 0, 1
 ALL_DEVICES = -1   # DB200_ALL_DEVICES: host-pointer entry points shard over every visible GPU
 
@@ -31,7 +31,8 @@ class Db200Error(RuntimeError):
 
 class DistParams(C.Structure):
     _fields_ = [("p", C.c_int32), ("k", C.c_int32), ("estim", C.c_int32), ("jestim", C.c_int32),
-                ("result_type", C.c_int32), ("order", C.c_int32)]
+                ("result_type", C.c_int32), ("order", C.c_int32),
+                ("card", C.POINTER(C.c_double)), ("card_queries", C.POINTER(C.c_double))]
 
 
 u8p, u64p, f32p, f64p, vp = C.POINTER(C.c_uint8), C.POINTER(C.c_uint64), C.POINTER(C.c_float), C.POINTER(C.c_double), C.c_void_p
@@ -56,6 +57,7 @@ _SIGS = {
     "db200_sketch_batch": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, vp, u64p, C.c_uint64, u64p, C.c_uint64, u8p]),
     "db200_sketch_fasta_batch": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, vp, u64p, u64p, C.c_uint64, u64p, C.c_uint64, u8p, u8p]),
     "db200_pack_genomes": (C.c_int, [C.c_int, vp, u64p, C.c_uint64, u64p, C.c_uint64, C.c_int, C.POINTER(vp)]),
+    "db200_repack_genomes": (C.c_int, [vp, vp, u64p, C.c_uint64, u64p, C.c_uint64, C.c_int]),
     "db200_packed_genomes_free": (C.c_int, [vp]),
     "db200_packed_genomes_stats": (C.c_int, [vp, u64p, u64p, u64p]),
     "db200_sketch_packed_dev": (C.c_int, [vp, C.c_int, C.c_int, vp, vp]),
@@ -66,7 +68,6 @@ _SIGS = {
     "db200_dist_symmetric_rows": (C.c_int, [C.c_int, u8p, C.c_uint64, C.POINTER(DistParams), C.c_uint64, C.c_uint64, f32p]),
     "db200_dist_symmetric_stream": (C.c_int, [C.c_int, u8p, C.c_uint64, C.POINTER(DistParams), C.c_uint64, C.c_uint64, C.c_uint64, ROWS_CB, vp]),
     "db200_dist_rect": (C.c_int, [C.c_int, u8p, C.c_uint64, u8p, C.c_uint64, C.POINTER(DistParams), f32p]),
-    "db200_dist_use_cardinalities": (C.c_int, [f64p, C.c_uint64]),
     "db200_dist_plan_create": (C.c_int, [C.c_int, C.POINTER(vp)]),
     "db200_dist_plan_destroy": (C.c_int, [vp]),
     "db200_dist_plan_prepare_dev": (C.c_int, [vp, vp, C.c_uint64, C.c_int, C.c_int, vp]),
@@ -105,8 +106,18 @@ def kernel_launches() -> int:
     return int(lib.db200_kernel_launches())
 
 
-def dist_params(p, k=31, estim=ERTL_MLE, jestim=ERTL_MLE, result_type=JI, order=ORDER_ROW_FIRST) -> DistParams:
-    return DistParams(p, k, estim, jestim, result_type, order)
+def dist_params(p, k=31, estim=ERTL_MLE, jestim=ERTL_MLE, result_type=JI, order=ORDER_ROW_FIRST, card=None, card_queries=None) -> DistParams:
+    """card / card_queries: cached per-sketch cardinalities (db200_dist_params.card; float64 arrays, kept alive on the returned
+    object), None = the library evaluates them from the registers."""
+    prm = DistParams(p, k, estim, jestim, result_type, order, None, None)
+    keep = []
+    for name, arr in (("card", card), ("card_queries", card_queries)):
+        if arr is not None:
+            arr = np.ascontiguousarray(arr, dtype=np.float64)
+            keep.append(arr)
+            setattr(prm, name, arr.ctypes.data_as(f64p))
+    prm._keep = keep
+    return prm
 
 
 def pinned_empty(nbytes: int) -> np.ndarray:
@@ -221,6 +232,22 @@ class PackedGenomes:
         self.ngenomes = grb.size - 1
         _check(lib.db200_pack_genomes(device, bases_ptr, offs.ctypes.data_as(u64p), offs.size - 1,
                                       grb.ctypes.data_as(u64p), self.ngenomes, k, C.byref(self.h)))
+        self._stats()
+
+    def repack(self, bases, rec_offsets, genome_rec_begin, k):
+        """Another batch into the same store (db200_repack_genomes): device buffers are reused."""
+        if isinstance(bases, int):
+            bases_ptr = vp(bases)
+        else:
+            bases = _np(bases, np.uint8)
+            bases_ptr = bases.ctypes.data_as(vp)
+        offs = _np(rec_offsets, np.uint64)
+        grb = _np(genome_rec_begin, np.uint64)
+        self.ngenomes = grb.size - 1
+        _check(lib.db200_repack_genomes(self.h, bases_ptr, offs.ctypes.data_as(u64p), offs.size - 1, grb.ctypes.data_as(u64p), self.ngenomes, k))
+        self._stats()
+
+    def _stats(self):
         pb, km, nb = C.c_uint64(), C.c_uint64(), C.c_uint64()
         _check(lib.db200_packed_genomes_stats(self.h, C.byref(pb), C.byref(km), C.byref(nb)))
         self.packed_bytes, self.kmers, self.nbases = pb.value, km.value, nb.value
@@ -260,18 +287,8 @@ def compress(regs, p, new_p, device=0) -> np.ndarray:
     return out
 
 
-def use_cardinalities(card):
-    """Cached per-sketch cardinalities for this thread's next dist_* / knn_* call (db200_dist_use_cardinalities)."""
-    if card is None:
-        _check(lib.db200_dist_use_cardinalities(None, 0))
-        return None
-    card = _np(card, np.float64)
-    _check(lib.db200_dist_use_cardinalities(card.ctypes.data_as(f64p), card.size))
-    return card      # keep alive until the call
-
-
 def dist_symmetric(regs, p, k=31, estim=ERTL_MLE, jestim=ERTL_MLE, result_type=JI, order=ORDER_ROW_FIRST, device=0,
-                   row_begin=0, row_end=None, out=None) -> np.ndarray:
+                   row_begin=0, row_end=None, out=None, card=None) -> np.ndarray:
     regs = _np(regs, np.uint8).reshape(-1, 1 << p)
     n = regs.shape[0]
     re_ = n if row_end is None else min(row_end, n)
@@ -279,13 +296,15 @@ def dist_symmetric(regs, p, k=31, estim=ERTL_MLE, jestim=ERTL_MLE, result_type=J
     npairs = tri(re_) - tri(row_begin)
     if out is None:
         out = np.zeros(npairs, dtype=np.float32)
-    prm = dist_params(p, k, estim, jestim, result_type, order)
+    if card is not None and np.size(card) != n:
+        raise ValueError(f"card holds {np.size(card)} values for {n} sketches")
+    prm = dist_params(p, k, estim, jestim, result_type, order, card=card)
     _check(lib.db200_dist_symmetric_rows(device, regs.ctypes.data_as(u8p), n, C.byref(prm), row_begin, re_, out.ctypes.data_as(f32p)))
     return out
 
 
 def dist_symmetric_stream(regs, p, on_rows, k=31, estim=ERTL_MLE, jestim=ERTL_MLE, result_type=JI, order=ORDER_ROW_FIRST, device=0,
-                          row_begin=0, row_end=None, block_pairs=0):
+                          row_begin=0, row_end=None, block_pairs=0, card=None):
     """Row-block streaming: on_rows(row_begin, row_end, values float32[]) per block (values are copied for the caller);
     a non-zero / raising callback aborts the call."""
     regs = _np(regs, np.uint8).reshape(-1, 1 << p)
@@ -300,7 +319,7 @@ def dist_symmetric_stream(regs, p, on_rows, k=31, estim=ERTL_MLE, jestim=ERTL_ML
             err.append(e)
             return 1
     cb = ROWS_CB(tramp)
-    prm = dist_params(p, k, estim, jestim, result_type, order)
+    prm = dist_params(p, k, estim, jestim, result_type, order, card=card)
     rc = lib.db200_dist_symmetric_stream(device, regs.ctypes.data_as(u8p), n, C.byref(prm), row_begin, n if row_end is None else row_end,
                                          block_pairs, cb, None)
     if err:
@@ -308,11 +327,11 @@ def dist_symmetric_stream(regs, p, on_rows, k=31, estim=ERTL_MLE, jestim=ERTL_ML
     _check(rc)
 
 
-def dist_rect(refs, qrys, p, k=31, estim=ERTL_MLE, jestim=ERTL_MLE, result_type=JI, device=0) -> np.ndarray:
+def dist_rect(refs, qrys, p, k=31, estim=ERTL_MLE, jestim=ERTL_MLE, result_type=JI, device=0, card=None, card_queries=None) -> np.ndarray:
     refs = _np(refs, np.uint8).reshape(-1, 1 << p)
     qrys = _np(qrys, np.uint8).reshape(-1, 1 << p)
     out = np.zeros((qrys.shape[0], refs.shape[0]), dtype=np.float32)
-    prm = dist_params(p, k, estim, jestim, result_type, ORDER_COL_FIRST)
+    prm = dist_params(p, k, estim, jestim, result_type, ORDER_COL_FIRST, card=card, card_queries=card_queries)
     _check(lib.db200_dist_rect(device, refs.ctypes.data_as(u8p), refs.shape[0], qrys.ctypes.data_as(u8p), qrys.shape[0],
                                C.byref(prm), out.ctypes.data_as(f32p)))
     return out
@@ -324,20 +343,20 @@ DIST_MEASURES = (MASH_DIST, FULL_MASH_DIST, CONTAINMENT_DIST, FULL_CONTAINMENT_D
 
 
 def knn_symmetric(regs, p, nneighbors, k=31, estim=ERTL_MLE, jestim=ERTL_MLE, result_type=JI, order=ORDER_COL_FIRST,
-                  device=0) -> np.ndarray:
+                  device=0, card=None) -> np.ndarray:
     """-> structured array [n][nneighbors] of (value, index), best first (nndist_loop, src/sketch_and_cmp.h:712-783)."""
     regs = _np(regs, np.uint8).reshape(-1, 1 << p)
     out = np.zeros((regs.shape[0], nneighbors), dtype=NEIGHBOR_DTYPE)
-    prm = dist_params(p, k, estim, jestim, result_type, order)
+    prm = dist_params(p, k, estim, jestim, result_type, order, card=card)
     _check(lib.db200_dist_knn_symmetric(device, regs.ctypes.data_as(u8p), regs.shape[0], C.byref(prm), nneighbors, vp(out.ctypes.data)))
     return out
 
 
-def knn_rect(refs, qrys, p, nneighbors, k=31, estim=ERTL_MLE, jestim=ERTL_MLE, result_type=JI, device=0) -> np.ndarray:
+def knn_rect(refs, qrys, p, nneighbors, k=31, estim=ERTL_MLE, jestim=ERTL_MLE, result_type=JI, device=0, card=None, card_queries=None) -> np.ndarray:
     refs = _np(refs, np.uint8).reshape(-1, 1 << p)
     qrys = _np(qrys, np.uint8).reshape(-1, 1 << p)
     out = np.zeros((qrys.shape[0], nneighbors), dtype=NEIGHBOR_DTYPE)
-    prm = dist_params(p, k, estim, jestim, result_type, ORDER_COL_FIRST)
+    prm = dist_params(p, k, estim, jestim, result_type, ORDER_COL_FIRST, card=card, card_queries=card_queries)
     _check(lib.db200_dist_knn_rect(device, refs.ctypes.data_as(u8p), refs.shape[0], qrys.ctypes.data_as(u8p), qrys.shape[0],
                                    C.byref(prm), nneighbors, vp(out.ctypes.data)))
     return out

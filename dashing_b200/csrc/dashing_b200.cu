@@ -53,6 +53,9 @@ struct db200_packed_genomes {
     std::vector<uint32_t> group_item_begin;   // items of genome group g: [group_item_begin[g], group_item_begin[g+1])
     std::vector<uint64_t> group_end;          // one past the last base of group g
     db200::DevBuf bases2, nb, st, items, counter, starts;
+    // work counters: [0, 8) belong to the pipelined genome groups of one pack call, [8, 16) rotate over the launches of
+    // db200_sketch_packed_dev so that sketches of the same store on different streams never share (or reset) a counter
+    mutable std::atomic<uint32_t> launch_seq{0};
 };
 
 namespace db200 {
@@ -402,8 +405,9 @@ static int sketch_packed_impl(const db200_packed_genomes *pg, int p, int canon, 
     if (pg->k < 1 || pg->k > 32) { set_error("sketch: k=%d outside [1,32]", pg->k); return DB200_EUNSUPPORTED; }
     DB200_CUDA(cudaMemsetAsync(d_regs, 0, pg->ngenomes << p, stream));
     if (pg->nitems == 0) return DB200_OK;
-    DB200_CUDA(cudaMemsetAsync(pg->counter.ptr, 0, 64, stream));
-    return sketch_launch(pg, p, canon, d_regs, stream, 0, pg->nitems, 0);
+    const int ci = 8 + (int)(pg->launch_seq.fetch_add(1) % 8u);
+    DB200_CUDA(cudaMemsetAsync(pg->counter.as<uint32_t>() + ci, 0, 4, stream));
+    return sketch_launch(pg, p, canon, d_regs, stream, 0, pg->nitems, ci);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -572,7 +576,7 @@ static int plan_run(db200_dist_plan *pl, const db200_dist_params *prm, int rect,
                     float *d_out, cudaStream_t stream, int slot = 0, bool ksinv_double = false) {
     if (!pl->ready) { set_error("dist plan not prepared"); return DB200_EINVAL; }
     if (prm->p != pl->p || prm->estim != pl->estim) { set_error("dist params (p=%d, estim=%d) differ from the prepared plan (p=%d, estim=%d)", prm->p, prm->estim, pl->p, pl->estim); return DB200_EINVAL; }
-    if (prm->result_type < 0 || prm->result_type > 8) { set_error("dist: unknown result type %d", prm->result_type); return DB200_EINVAL; }
+    if (prm->result_type < 0 || prm->result_type > DB200_UNION_SIZE) { set_error("dist: unknown result type %d", prm->result_type); return DB200_EINVAL; }
     if (prm->k < 1) { set_error("dist: k must be positive"); return DB200_EINVAL; }
     const bool joint = prm->jestim == DB200_ERTL_JOINT_MLE;
     DB200_TRY(plan_tiles(pl, slot, rect, joint ? JT : DT, rb, re, nr, nq, stream));
@@ -659,7 +663,7 @@ static int plan_knn(db200_dist_plan *pl, const db200_dist_params *prm, uint64_t 
                     cudaStream_t stream, uint64_t sym_row_begin = 0, uint64_t sym_row_end = ~0ull) {
     if (!pl->ready) { set_error("dist plan not prepared"); return DB200_EINVAL; }
     if (nn < 1 || nn > 1024) { set_error("nearest neighbours: nneighbors=%u outside the GPU path's range [1,1024]", nn); return DB200_EUNSUPPORTED; }
-    if (prm->result_type < 0 || prm->result_type > 8) { set_error("dist: unknown result type %d", prm->result_type); return DB200_EINVAL; }
+    if (prm->result_type < 0 || prm->result_type > DB200_UNION_SIZE) { set_error("dist: unknown result type %d", prm->result_type); return DB200_EINVAL; }
     const int rect = nq != 0, sim = is_similarity(prm->result_type);
     const uint64_t n = pl->nrows, rows = rect ? nq : n;
     // all-pairs values held in HBM at a time (1 GiB of floats unless DB200_KNN_BLOCK_PAIRS says otherwise)
@@ -755,7 +759,9 @@ struct HostCtx {
     }
 };
 static HostCtx &host_ctx(int device) {
-    static HostCtx ctx[64];
+    // leaked on purpose: static destructors would call cudaFree / cudaStreamDestroy after the CUDA runtime may already have
+    // been torn down at process exit (undefined behaviour).  check_device() has bounded `device` by logical_device_count() <= 64.
+    static HostCtx *ctx = new HostCtx[64];
     return ctx[device & 63];
 }
 
@@ -843,6 +849,19 @@ int db200_pack_genomes(int device, const char *bases, const uint64_t *rec_offset
     DB200_TRY(pack_genomes_impl(device, bases, rec_offsets, nrecords, genome_rec_begin, ngenomes, k, pg.get(), hc.up, hc.stream));
     *out = pg.release();
     return DB200_OK;
+}
+
+int db200_repack_genomes(db200_packed_genomes *g, const char *bases, const uint64_t *rec_offsets, uint64_t nrecords,
+                         const uint64_t *genome_rec_begin, uint64_t ngenomes, int k) {
+    if (!g || !rec_offsets || !genome_rec_begin || (!bases && nrecords)) { set_error("db200_repack_genomes: null argument"); return DB200_EINVAL; }
+    if (k < 1 || k > 32) { set_error("sketch: k=%d outside [1,32]", k); return DB200_EUNSUPPORTED; }
+    if (ngenomes >= (1ull << 32)) { set_error("too many genomes"); return DB200_EINVAL; }
+    const int device = g->device;
+    DB200_TRY(check_device(device));
+    HostCtx &hc = host_ctx(device);
+    std::lock_guard<std::mutex> lk(hc.mu);
+    DB200_TRY(hc.init(device));
+    return pack_genomes_impl(device, bases, rec_offsets, nrecords, genome_rec_begin, ngenomes, k, g, hc.up, hc.stream);
 }
 
 int db200_packed_genomes_free(db200_packed_genomes *g) {
@@ -1334,40 +1353,23 @@ static int symmetric_stream_impl(int device, const uint8_t *regs, uint64_t n, co
     return DB200_OK;
 }
 
-// ---- public all-pairs entry points: they consume the calling thread's pending cardinality override ----------------------
-namespace db200 {
-struct CardOverride { const double *ptr = nullptr; uint64_t n = 0; };
-static thread_local CardOverride t_cards;
-static CardOverride take_cards() { const CardOverride c = t_cards; t_cards = CardOverride{}; return c; }
-} // namespace db200
-
+// ---- public all-pairs entry points (cached cardinalities travel in the params: prm->card / prm->card_queries) ----------
 extern "C" {
-
-int db200_dist_use_cardinalities(const double *card, uint64_t n) {
-    t_cards.ptr = card; t_cards.n = card ? n : 0;
-    return DB200_OK;
-}
 
 int db200_dist_symmetric_rows(int device, const uint8_t *regs, uint64_t n, const db200_dist_params *prm, uint64_t row_begin, uint64_t row_end,
                               float *out) {
-    const CardOverride c = take_cards();
-    if (c.ptr && c.n != n) { set_error("cardinality override holds %llu values for %llu sketches", (unsigned long long)c.n, (unsigned long long)n); return DB200_EINVAL; }
-    return symmetric_rows_impl(device, regs, n, prm, row_begin, row_end, out, c.ptr);
+    return symmetric_rows_impl(device, regs, n, prm, row_begin, row_end, out, prm ? prm->card : nullptr);
 }
 int db200_dist_symmetric(int device, const uint8_t *regs, uint64_t n, const db200_dist_params *prm, float *out) {
     return db200_dist_symmetric_rows(device, regs, n, prm, 0, n, out);
 }
 int db200_dist_symmetric_stream(int device, const uint8_t *regs, uint64_t n, const db200_dist_params *prm, uint64_t row_begin, uint64_t row_end,
                                 uint64_t block_pairs, db200_rows_cb cb, void *user) {
-    const CardOverride c = take_cards();
-    if (c.ptr && c.n != n) { set_error("cardinality override holds %llu values for %llu sketches", (unsigned long long)c.n, (unsigned long long)n); return DB200_EINVAL; }
-    return symmetric_stream_impl(device, regs, n, prm, row_begin, row_end, block_pairs, cb, user, c.ptr);
+    return symmetric_stream_impl(device, regs, n, prm, row_begin, row_end, block_pairs, cb, user, prm ? prm->card : nullptr);
 }
 int db200_dist_rect(int device, const uint8_t *ref_regs, uint64_t nr, const uint8_t *qry_regs, uint64_t nq, const db200_dist_params *prm,
                     float *out) {
-    const CardOverride c = take_cards();
-    if (c.ptr && c.n != nr + nq) { set_error("cardinality override holds %llu values for %llu + %llu sketches", (unsigned long long)c.n, (unsigned long long)nr, (unsigned long long)nq); return DB200_EINVAL; }
-    return rect_impl(device, ref_regs, nr, qry_regs, nq, prm, out, c.ptr, c.ptr ? c.ptr + nr : nullptr);
+    return rect_impl(device, ref_regs, nr, qry_regs, nq, prm, out, prm ? prm->card : nullptr, prm ? prm->card_queries : nullptr);
 }
 int db200_dist_plan_run_knn_rows_dev(db200_dist_plan *pl, const db200_dist_params *prm, uint64_t row_begin, uint64_t row_end, uint32_t nneighbors,
                                      db200_neighbor *d_out, void *stream) {
@@ -1379,15 +1381,11 @@ int db200_dist_plan_run_knn_rows_dev(db200_dist_plan *pl, const db200_dist_param
 }
 int db200_dist_knn_symmetric(int device, const uint8_t *regs, uint64_t n, const db200_dist_params *prm, uint32_t nneighbors,
                              db200_neighbor *out) {
-    const CardOverride c = take_cards();
-    if (c.ptr && c.n != n) { set_error("cardinality override holds %llu values for %llu sketches", (unsigned long long)c.n, (unsigned long long)n); return DB200_EINVAL; }
-    return knn_symmetric_impl(device, regs, n, prm, nneighbors, out, c.ptr);
+    return knn_symmetric_impl(device, regs, n, prm, nneighbors, out, prm ? prm->card : nullptr);
 }
 int db200_dist_knn_rect(int device, const uint8_t *ref_regs, uint64_t nr, const uint8_t *qry_regs, uint64_t nq, const db200_dist_params *prm,
                         uint32_t nneighbors, db200_neighbor *out) {
-    const CardOverride c = take_cards();
-    if (c.ptr && c.n != nr + nq) { set_error("cardinality override holds %llu values for %llu + %llu sketches", (unsigned long long)c.n, (unsigned long long)nr, (unsigned long long)nq); return DB200_EINVAL; }
-    return knn_rect_impl(device, ref_regs, nr, qry_regs, nq, prm, nneighbors, out, c.ptr, c.ptr ? c.ptr + nr : nullptr);
+    return knn_rect_impl(device, ref_regs, nr, qry_regs, nq, prm, nneighbors, out, prm ? prm->card : nullptr, prm ? prm->card_queries : nullptr);
 }
 
 } // extern "C"

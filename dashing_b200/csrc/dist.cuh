@@ -627,7 +627,8 @@ __global__ void __launch_bounds__(DIST_THREADS, 2) dist_kernel(const __grid_cons
         double t0 = cl - is, t1 = cr - is;
         t0 = t0 < 0. ? 0. : t0;
         t1 = t1 < 0. ? 0. : t1;
-        a.out[oidx] = emit_value(a.rtype, ji, t0, t1, is, a.ksinv);
+        // DB200_UNION_SIZE (extension): hll_t::union_size itself, hll.h:1125-1138
+        a.out[oidx] = a.rtype == DB200_UNION_SIZE ? (float)us : emit_value(a.rtype, ji, t0, t1, is, a.ksinv);
     }
 }
 
@@ -841,7 +842,8 @@ __global__ void __launch_bounds__(JTHREADS, 1) dist_jmle_kernel(const __grid_con
         const double h = 0.5 * (cX1 + cX2);
         const double t2 = 0. < h ? h : 0.;
         const double ji = t2 / (t0 + t1 + t2);   // hll.h:1175-1178
-        a.out[oidx] = emit_value(a.rtype, ji, t0, t1, t2, a.ksinv);
+        // DB200_UNION_SIZE (extension): union_size under the joint MLE is the sum of the triple, hll.h:1139-1140
+        a.out[oidx] = a.rtype == DB200_UNION_SIZE ? (float)(t0 + t1 + t2) : emit_value(a.rtype, ji, t0, t1, t2, a.ksinv);
     }
 }
 

@@ -700,11 +700,11 @@ void write_binary_neighbors(std::FILE *fp, uint32_t npaths, const Neighbor *nb, 
 void compare_and_emit(const DistOptions &o, const std::vector<std::string> &inpaths, const std::vector<uint8_t> &regs, size_t nq,
                       const double *cached_card) {
     const size_t n = inpaths.size(), m = size_t(1) << o.p;
-    // cached value_ of loaded sketches: handed to the library before every all-pairs call (each call consumes it)
-    auto use_cards = [&] { if (cached_card) check(db200_dist_use_cardinalities(cached_card, n)); };
     std::FILE *pfp = o.dist_path.empty() ? stdout : std::fopen(o.dist_path.c_str(), "wb");
     if (!pfp) throw Error("Could not open file at " + o.dist_path + " for writing.");
-    db200_dist_params prm{o.p, o.k, o.estim, o.jestim, o.result_type, DB200_ORDER_ROW_FIRST};
+    // cached value_ of loaded sketches travel in the params (db200_dist_params.card); in the -Q/-F forms the references are the
+    // first n - nq sketches and the queries the last nq
+    db200_dist_params prm{o.p, o.k, o.estim, o.jestim, o.result_type, DB200_ORDER_ROW_FIRST, cached_card, (cached_card && nq) ? cached_card + (n - nq) : nullptr};
     const bool joint = o.jestim == DB200_ERTL_JOINT_MLE;
     if (o.nneighbors) {
         // nndist_loop (src/sketch_and_cmp.h:712-783): the all-pairs values never leave the GPU, only rows x nn pairs do
@@ -718,7 +718,6 @@ void compare_and_emit(const DistOptions &o, const std::vector<std::string> &inpa
         std::vector<Neighbor> nb(rows * nn);
         static_assert(sizeof(Neighbor) == sizeof(db200_neighbor), "neighbour layout");
         prm.order = DB200_ORDER_COL_FIRST;                                     // func(sketches[j], h1), :670
-        use_cards();
         if (nq) check(db200_dist_knn_rect(o.device, regs.data(), n - nq, regs.data() + (n - nq) * m, nq, &prm, nn, reinterpret_cast<db200_neighbor *>(nb.data())));
         else check(db200_dist_knn_symmetric(o.device, regs.data(), n, &prm, nn, reinterpret_cast<db200_neighbor *>(nb.data())));
         // The reference's emitters loop over ALL paths even in the -Q/-F mode, where only nq rows exist (an out-of-bounds
@@ -729,7 +728,6 @@ void compare_and_emit(const DistOptions &o, const std::vector<std::string> &inpa
         if (nq >= n) throw Error("Wrong number of query/references.");
         const size_t nr = n - nq;
         std::vector<float> out(nr * nq);
-        use_cards();
         check(db200_dist_rect(o.device, regs.data(), nr, regs.data() + nr * m, nq, &prm, out.data()));
         if (o.emit_fmt == UPPER_TRIANGULAR) std::fprintf(pfp, "%zu\n", n);     // :394-397 runs before dist_loop even in this mode
         for (size_t q = 0; q < nq; ++q) {
@@ -765,7 +763,6 @@ void compare_and_emit(const DistOptions &o, const std::vector<std::string> &inpa
             std::fflush(pfp);
             sc.fd = fileno(pfp);
             if (::ftruncate(sc.fd, (off_t)(9 + np * sizeof(float))) != 0) throw Error("Error writing to binary file");
-            use_cards();
             const int rc = db200_dist_symmetric_stream(o.device, regs.data(), n, &prm, 0, n, 0,
                 [](void *ud, uint64_t rb, uint64_t, const float *vals, uint64_t nv) -> int {
                     StreamCtx *c = static_cast<StreamCtx *>(ud);
@@ -785,7 +782,6 @@ void compare_and_emit(const DistOptions &o, const std::vector<std::string> &inpa
                 const std::string h = o.emit_fmt == UT_TSV ? format_ut_tsv_header(inpaths) : std::to_string(n) + "\n";   // :388-397
                 std::fwrite(h.data(), 1, h.size(), pfp);
             }
-            use_cards();
             const int rc = db200_dist_symmetric_stream(o.device, regs.data(), n, &prm, 0, n, 0,
                 [](void *ud, uint64_t rb, uint64_t re, const float *vals, uint64_t) -> int {
                     StreamCtx *c = static_cast<StreamCtx *>(ud);
@@ -800,7 +796,7 @@ void compare_and_emit(const DistOptions &o, const std::vector<std::string> &inpa
             if (rc != DB200_OK) throw Error(std::string("Error writing distances: ") + db200_last_error());
         } else {
             std::vector<float> out(std::max<size_t>(np, 1)), lower;
-            if (n >= 2) { use_cards(); check(db200_dist_symmetric(o.device, regs.data(), n, &prm, out.data())); }
+            if (n >= 2) { check(db200_dist_symmetric(o.device, regs.data(), n, &prm, out.data())); }
             if (o.emit_fmt == BINARY) {
                 write_binary_matrix(pfp, out.data(), n);
                 write_labels();
@@ -808,7 +804,6 @@ void compare_and_emit(const DistOptions &o, const std::vector<std::string> &inpa
                 if (o.emit_fmt == FULL_TSV && joint && n >= 2) {
                     lower.resize(np);
                     prm.order = DB200_ORDER_COL_FIRST;
-                    use_cards();
                     check(db200_dist_symmetric(o.device, regs.data(), n, &prm, lower.data()));
                 }
                 const std::string s = format_symmetric(inpaths, out.data(), o.emit_fmt, lower.empty() ? nullptr : lower.data());

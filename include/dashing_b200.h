@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define DB200_VERSION 100
+#define DB200_VERSION 101
 #if defined(__GNUC__)
 #define DB200_API __attribute__((visibility("default")))
 #else
@@ -63,7 +63,10 @@ enum db200_jestim { DB200_ERTL_JOINT_MLE = 3 };
 enum db200_emission {
     DB200_MASH_DIST = 0, DB200_JI = 1, DB200_SIZES = 2, DB200_FULL_MASH_DIST = 3,
     DB200_FULL_CONTAINMENT_DIST = 4, DB200_CONTAINMENT_INDEX = 5, DB200_CONTAINMENT_DIST = 6,
-    DB200_SYMMETRIC_CONTAINMENT_INDEX = 7, DB200_SYMMETRIC_CONTAINMENT_DIST = 8
+    DB200_SYMMETRIC_CONTAINMENT_INDEX = 7, DB200_SYMMETRIC_CONTAINMENT_DIST = 8,
+    /* extension (not an EmissionType): the union cardinality itself — hll_t::union_size (hll.h:1125-1141), what the
+     * reference's Python helper union_size_matrix returns (bonsai/hll/python/util.cpp:164) */
+    DB200_UNION_SIZE = 9
 };
 /* Operand order of result_cmp in the symmetric loop: the reference's TSV/PHYLIP path evaluates
  * cmp(sketches[j], sketches[i]) for j > i (perform_core_op, src/sketch_and_cmp.h:702) while its
@@ -78,6 +81,15 @@ typedef struct db200_dist_params {
     int32_t jestim;      /* DB200_ERTL_JOINT_MLE or anything else for the union path */
     int32_t result_type; /* enum db200_emission */
     int32_t order;       /* enum db200_order (symmetric mode only) */
+    /* Cached cardinalities (optional, NULL = evaluate them from the registers under `estim`).  The reference's hll_t carries a
+     * cached estimate (value_): a sketch loaded from a file keeps what hll_t::read() computed under the FILE's estimation
+     * method (csum(), hll.h:1078) — or the value stored in the file — and the pair loop uses that for the per-sketch terms
+     * (creport(), hll.h:780-783) even when the command line names another estimator.  A host that loaded such sketches
+     * passes their cached values here (host pointers, read during the call): `card` holds one double per sketch of the
+     * symmetric / knn_symmetric matrix, or per REFERENCE of the rectangular forms; `card_queries` one per query.
+     * Ignored by the `_dev` plan entry points (a plan's cardinalities are its own). */
+    const double *card;
+    const double *card_queries;
 } db200_dist_params;
 
 /* S4 multi-GPU: every HOST-pointer compute entry point accepts device = DB200_ALL_DEVICES and then
@@ -148,6 +160,11 @@ typedef struct db200_packed_genomes db200_packed_genomes;
  * pointer (pinned memory is DMA'd directly) or, under unified addressing, a device pointer. */
 DB200_API int db200_pack_genomes(int device, const char *bases, const uint64_t *rec_offsets, uint64_t nrecords,
                        const uint64_t *genome_rec_begin, uint64_t ngenomes, int k, db200_packed_genomes **out);
+/* Packs another batch into an EXISTING store (its device buffers are reused and only grow): what a host that streams batch
+ * after batch through one GPU calls instead of free + pack (cudaMalloc / cudaFree of GB-sized buffers cost tens of ms).
+ * Any sketch of the store's previous content must have completed. */
+DB200_API int db200_repack_genomes(db200_packed_genomes *g, const char *bases, const uint64_t *rec_offsets, uint64_t nrecords,
+                         const uint64_t *genome_rec_begin, uint64_t ngenomes, int k);
 DB200_API int db200_packed_genomes_free(db200_packed_genomes *g);
 /* Bytes the sketch kernel streams for this store (2-bit + validity + start planes) and its k-mer count. */
 DB200_API int db200_packed_genomes_stats(const db200_packed_genomes *g, uint64_t *packed_bytes, uint64_t *kmers, uint64_t *bases);
@@ -189,15 +206,6 @@ DB200_API int db200_dist_rect(int device, const uint8_t *ref_regs, uint64_t nr, 
 typedef int (*db200_rows_cb)(void *user, uint64_t row_begin, uint64_t row_end, const float *values, uint64_t nvalues);
 DB200_API int db200_dist_symmetric_stream(int device, const uint8_t *regs, uint64_t n, const db200_dist_params *prm,
                                           uint64_t row_begin, uint64_t row_end, uint64_t block_pairs, db200_rows_cb cb, void *user);
-
-/* Cached cardinalities.  The reference's hll_t carries a cached estimate (value_): a sketch loaded from a file keeps what
- * hll_t::read() computed under the FILE's estimation method (csum(), hll.h:1078) — or the value stored in the file — and the
- * pair loop uses that for the per-sketch terms (creport(), hll.h:780-783) even when the command line names another estimator.
- * A host that loaded such sketches passes their cached values here; they then replace the per-sketch cardinalities the
- * library would evaluate from the registers, for the calling thread's NEXT db200_dist_symmetric[_rows] / db200_dist_rect /
- * db200_dist_knn_* call only (n values in sketch order; rect / knn_rect: the nr references, then the nq queries).
- * NULL clears a pending override. */
-DB200_API int db200_dist_use_cardinalities(const double *card, uint64_t n);
 
 /* Device-resident form.  A plan owns the derived HBM structures (threshold bit-planes,
  * per-sketch cardinalities and value ranges); prepare() builds them from a device register

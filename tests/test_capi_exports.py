@@ -22,7 +22,7 @@ def test_header_symbols_exported(capi):
     missing = [s for s in syms if not hasattr(lib, s)]
     assert not missing, f"declared in include/dashing_b200.h but not exported: {missing}"
     assert set(syms) == set(capi.EXPORTS), "capi.py binds a different symbol set than the header declares"
-    assert capi.lib.db200_version() == 100
+    assert capi.lib.db200_version() == 101
 
 
 def test_product_does_not_touch_oracle():

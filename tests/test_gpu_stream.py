@@ -54,12 +54,9 @@ def test_stream_callback_failure_and_cached_cards(gpu):
         gpu.dist_symmetric_stream(regs, p, lambda rb, re_, v: 7, block_pairs=3000)
     # the library is usable afterwards, and the cached-cardinality override reaches the streaming form too
     card = gpu.cardinalities(regs, p) * 1.05
-    keep = gpu.use_cardinalities(card)
-    want = gpu.dist_symmetric(regs, p)
-    keep = gpu.use_cardinalities(card)
-    got, _ = collect(gpu, regs, p, block_pairs=3000)
+    want = gpu.dist_symmetric(regs, p, card=card)
+    got, _ = collect(gpu, regs, p, block_pairs=3000, card=card)
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
-    del keep
 
 
 def test_stream_all_devices(gpu, monkeypatch):

@@ -100,35 +100,43 @@ def test_compress_golden_and_errors(gpu, sub):
 
 
 def test_cached_cardinality_override(gpu):
-    """db200_dist_use_cardinalities: the per-sketch terms of the next all-pairs call come from the caller (the reference's
-    cached hll_t::value_), the union term still from the registers; consumed by exactly one call."""
+    """db200_dist_params.card / card_queries: the per-sketch terms of an all-pairs call come from the caller (the reference's
+    cached hll_t::value_), the union term still from the registers; nothing lingers between calls."""
     p = 12
     regs = synth.registers(77, 40, p, card=1e5, group=8)
     card = gpu.cardinalities(regs, p)
     base = gpu.dist_symmetric(regs, p, result_type=gpu.JI)
-    keep = gpu.use_cardinalities(card)
-    same = gpu.dist_symmetric(regs, p, result_type=gpu.JI)
+    same = gpu.dist_symmetric(regs, p, result_type=gpu.JI, card=card)
     assert np.array_equal(same.view(np.uint32), base.view(np.uint32))
     scaled = card * np.linspace(0.9, 1.1, card.size)
-    keep = gpu.use_cardinalities(scaled)
-    got = gpu.dist_symmetric(regs, p, result_type=gpu.JI).astype(np.float64)
-    again = gpu.dist_symmetric(regs, p, result_type=gpu.JI)               # the override is gone
+    got = gpu.dist_symmetric(regs, p, result_type=gpu.JI, card=scaled).astype(np.float64)
+    again = gpu.dist_symmetric(regs, p, result_type=gpu.JI)               # no override without the pointer
     assert np.array_equal(again.view(np.uint32), base.view(np.uint32))
     iu = np.triu_indices(card.size, 1)
-    union = gpu.dist_symmetric(regs, p, result_type=gpu.SIZES).astype(np.float64)   # I = cA + cB - U  ->  U
-    U = card[iu[0]] + card[iu[1]] - union
-    pos = union > 1e-3 * card.max()
+    U = gpu.dist_symmetric(regs, p, result_type=gpu.UNION_SIZE).astype(np.float64)   # the union term itself (extension type)
     want = np.maximum(0.0, (scaled[iu[0]] + scaled[iu[1]] - U) / U)
+    pos = want > 1e-3
     assert_close(got[pos], want[pos], rtol=2e-5, what="JI under overridden cardinalities")
-    # rect: references then queries; wrong length is an error
-    keep = gpu.use_cardinalities(scaled)
-    r = gpu.dist_rect(regs[:25], regs[25:], p, result_type=gpu.JI).astype(np.float64)
+    # rect: references and queries have their own pointers
+    r = gpu.dist_rect(regs[:25], regs[25:], p, result_type=gpu.JI, card=scaled[:25], card_queries=scaled[25:]).astype(np.float64)
     full = np.zeros((card.size, card.size)); full[iu] = got; full = full + full.T
     assert_close(r, full[25:, :25], rtol=1e-6, what="rect under overridden cardinalities")
-    keep = gpu.use_cardinalities(scaled[:-1])
-    with pytest.raises(gpu.Db200Error):
-        gpu.dist_symmetric(regs, p)
-    del keep
+    with pytest.raises(ValueError):
+        gpu.dist_symmetric(regs, p, card=scaled[:-1])
+
+
+def test_union_size_extension(gpu, checker):
+    """DB200_UNION_SIZE: hll_t::union_size (hll.h:1125-1141) for every pair — MLE of the register-wise maximum on the union
+    path, the sum of the ertl_joint triple under the joint MLE."""
+    p = 12
+    regs = synth.registers(78, 30, p, card=2e5, group=6)
+    got = gpu.dist_symmetric(regs, p, result_type=gpu.UNION_SIZE).astype(np.float64)
+    iu = np.triu_indices(regs.shape[0], 1)
+    want = checker.cardinalities(np.maximum(regs[iu[0]], regs[iu[1]]), p, 2)
+    assert_close(got, want.astype(np.float32), what="union_size, union path")
+    gotj = gpu.dist_symmetric(regs, p, jestim=3, result_type=gpu.UNION_SIZE)
+    wantj = np.array([checker.triple(regs[i], regs[j], p, jestim=3).sum() for i, j in zip(*iu)])
+    assert_close(gotj, wantj.astype(np.float32), what="union_size, joint MLE")
 
 
 # ---- multi-device form of the host-pointer entry points ---------------------------------------------------------------
