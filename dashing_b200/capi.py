@@ -56,6 +56,8 @@ _SIGS = {
     "db200_sketcher_destroy": (C.c_int, [vp]),
     "db200_sketch_batch": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, vp, u64p, C.c_uint64, u64p, C.c_uint64, u8p]),
     "db200_sketch_fasta_batch": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, vp, u64p, u64p, C.c_uint64, u64p, C.c_uint64, u8p, u8p]),
+    "db200_hostpack": (None, [vp, C.c_size_t, C.POINTER(C.c_uint32), C.POINTER(C.c_uint16)]),
+    "db200_hostpack_isa": (C.c_char_p, []),
     "db200_pack_genomes": (C.c_int, [C.c_int, vp, u64p, C.c_uint64, u64p, C.c_uint64, C.c_int, C.POINTER(vp)]),
     "db200_repack_genomes": (C.c_int, [vp, vp, u64p, C.c_uint64, u64p, C.c_uint64, C.c_int]),
     "db200_packed_genomes_free": (C.c_int, [vp]),
@@ -191,6 +193,15 @@ def sketch_fasta(genome_files, k, p, canon=True, device=0):
 
 def sketch_genomes(genomes, k, p, canon=True, device=0) -> np.ndarray:
     return sketch_batch(*records_layout(genomes), k, p, canon, device)
+
+
+def hostpack(ascii_bases) -> tuple:
+    """ASCII bases -> (codes uint32[ceil(n/16)], valid uint16[ceil(n/16)]) with the library's host-side packer (no device needed)."""
+    a = _np(ascii_bases, np.uint8)
+    ng = (a.size + 15) // 16
+    codes, valid = np.zeros(ng, np.uint32), np.zeros(ng, np.uint16)
+    lib.db200_hostpack(a.ctypes.data_as(vp), a.size, codes.ctypes.data_as(C.POINTER(C.c_uint32)), valid.ctypes.data_as(C.POINTER(C.c_uint16)))
+    return codes, valid
 
 
 class Sketcher:

@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <cstring>
+#include <sched.h>
 #include <mutex>
 #include <thread>
 #include <condition_variable>
@@ -56,9 +57,30 @@ struct db200_packed_genomes {
     // work counters: [0, 8) belong to the pipelined genome groups of one pack call, [8, 16) rotate over the launches of
     // db200_sketch_packed_dev so that sketches of the same store on different streams never share (or reset) a counter
     mutable std::atomic<uint32_t> launch_seq{0};
+    uint64_t host_packed_chunks = 0, ascii_chunks = 0;   // how the last pack call split its chunks between the two upload routes
 };
 
+extern "C" void db200_hostpack(const uint8_t *ascii, size_t nbases, uint32_t *codes, uint16_t *valid);   // hostpack.cpp
+
 namespace db200 {
+// CPUs this process may really use: the affinity mask capped by the cgroup CPU quota (the GPU boxes expose 128 logical CPUs
+// but grant 16 CPUs of time; oversubscribing a quota is far slower than matching it).
+static unsigned usable_cpus() {
+    unsigned n = std::max(1u, std::thread::hardware_concurrency());
+    cpu_set_t set;
+    if (sched_getaffinity(0, sizeof set, &set) == 0) n = std::max(1, CPU_COUNT(&set));
+    if (std::FILE *f = std::fopen("/sys/fs/cgroup/cpu.max", "r")) {
+        char q[64] = {0};
+        unsigned long long per = 0;
+        if (std::fscanf(f, "%63s %llu", q, &per) == 2 && std::strcmp(q, "max") != 0 && per > 0) {
+            const unsigned long long quota = std::strtoull(q, nullptr, 10);
+            if (quota > 0) n = std::min<unsigned>(n, (unsigned)std::max<unsigned long long>(1, (quota + per - 1) / per));
+        }
+        std::fclose(f);
+    }
+    return n;
+}
+
 // Host -> device copies from PAGEABLE memory.  cudaMemcpyAsync would stage them through the driver's own bounce buffer with one
 // thread (~10 GB/s measured on the B200 boxes, against ~55 GB/s for page-locked sources); page-locking the caller's buffer
 // costs ~0.5 s per GB.  Instead the library keeps a small ring of page-locked buffers per device and fills it with several
@@ -76,17 +98,23 @@ public:
     // dst[0, n) = src[0, n), split over the workers and the calling thread
     void copy(char *dst, const char *src, size_t n) {
         if (n < (size_t(1) << 20) || nworkers_ == 0) { std::memcpy(dst, src, n); return; }
-        const size_t parts = nworkers_ + 1, each = ((n + parts - 1) / parts + 4095) & ~size_t(4095);
+        parallel(n, 4096, [dst, src](size_t b, size_t e) { std::memcpy(dst + b, src + b, e - b); });
+    }
+    // fn(begin, end) over [0, n) in nworkers + 1 contiguous parts whose boundaries are multiples of `align`
+    void parallel(size_t n, size_t align, const std::function<void(size_t, size_t)> &fn) {
+        if (nworkers_ == 0 || n <= align) { fn(0, n); return; }
+        const size_t parts = nworkers_ + 1, each = ((n + parts - 1) / parts + align - 1) / align * align;
         {
             std::lock_guard<std::mutex> lk(mu_);
-            dst_ = dst; src_ = src; n_ = n; each_ = each; pending_ = nworkers_; ++gen_;
+            fn_ = &fn; n_ = n; each_ = each; pending_ = nworkers_; ++gen_;
         }
         cv_.notify_all();
         const size_t off = each * nworkers_;
-        if (off < n) std::memcpy(dst + off, src + off, n - off);
+        if (off < n) fn(off, n);
         std::unique_lock<std::mutex> lk(mu_);
         done_.wait(lk, [this] { return pending_ == 0; });
     }
+    unsigned workers() const { return nworkers_; }
 private:
     void run(unsigned i) {
         uint64_t seen = 0;
@@ -95,10 +123,10 @@ private:
             cv_.wait(lk, [&] { return gen_ != seen; });
             seen = gen_;
             if (stop_) return;
-            char *d = dst_; const char *s = src_; const size_t n = n_, each = each_;
+            const std::function<void(size_t, size_t)> *fn = fn_; const size_t n = n_, each = each_;
             lk.unlock();
             const size_t off = each * i;
-            if (off < n) std::memcpy(d + off, s + off, std::min(each, n - off));
+            if (off < n) (*fn)(off, off + std::min(each, n - off));
             lk.lock();
             if (--pending_ == 0) done_.notify_one();
         }
@@ -107,7 +135,7 @@ private:
     std::vector<std::thread> th_;
     std::mutex mu_;
     std::condition_variable cv_, done_;
-    char *dst_ = nullptr; const char *src_ = nullptr;
+    const std::function<void(size_t, size_t)> *fn_ = nullptr;
     size_t n_ = 0, each_ = 0;
     unsigned pending_ = 0;
     uint64_t gen_ = 0;
@@ -185,18 +213,41 @@ struct HostStager {
 // ASCII upload pipeline state (two device staging buffers, a copy stream and events), kept across calls:
 // cudaMalloc/cudaFree of multi-GB buffers costs more than the transfers they serve.
 struct Uploader {
-    DevBuf stage[2];
+    static constexpr int NSTAGE = 4;           // device staging buffers for ASCII chunks = ASCII copies that may be queued at once
+    DevBuf stage[NSTAGE];
     cudaStream_t cs = nullptr;
-    cudaEvent_t copied[2] = {nullptr, nullptr}, packed[2] = {nullptr, nullptr};
+    cudaEvent_t copied[NSTAGE] = {}, packed[NSTAGE] = {};
     static constexpr int NGROUP = 8;           // only the LAST group's sketch is exposed after the upload: keep it short
     HostStager stager;                         // pageable sources go through page-locked bounce buffers filled by several threads
     cudaStream_t ss = nullptr;                 // sketch stream: group g is sketched while later groups are still uploading
     cudaEvent_t group_packed[NGROUP] = {};
+    // host-packed share of a batch (hostpack.cpp): page-locked slots of 2-bit codes + validity for one 64 Mbase chunk each,
+    // filled by the pack threads and copied straight into the store on a second copy stream
+    static constexpr int NPSLOT = 3;
+    static constexpr uint64_t CHUNK = 64ull << 20;     // bases per chunk (a multiple of 64)
+    char *pslot[NPSLOT] = {nullptr, nullptr, nullptr};
+    cudaEvent_t pslot_done[NPSLOT] = {nullptr, nullptr, nullptr};
+    bool pslot_used[NPSLOT] = {false, false, false};
+    cudaStream_t cs2 = nullptr;
+    std::unique_ptr<CopyPool> packers;
+    int init_hostpack() {
+        if (pslot[0]) return DB200_OK;
+        DB200_CUDA(cudaStreamCreateWithFlags(&cs2, cudaStreamNonBlocking));
+        for (int i = 0; i < NPSLOT; ++i) {
+            DB200_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&pslot[i]), CHUNK / 16 * 6, cudaHostAllocDefault));
+            DB200_CUDA(cudaEventCreateWithFlags(&pslot_done[i], cudaEventDisableTiming));
+        }
+        const char *e = std::getenv("DB200_PACK_THREADS");
+        int n = e ? std::atoi(e) : (int)usable_cpus();
+        n = std::max(1, std::min(n, 64));
+        packers.reset(new CopyPool((unsigned)n - 1));
+        return DB200_OK;
+    }
     int init() {
         if (cs) return DB200_OK;
         DB200_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
         DB200_CUDA(cudaStreamCreateWithFlags(&ss, cudaStreamNonBlocking));
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < NSTAGE; ++i) {
             DB200_CUDA(cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming));
             DB200_CUDA(cudaEventCreateWithFlags(&packed[i], cudaEventDisableTiming));
         }
@@ -296,32 +347,75 @@ static int pack_genomes_impl(int device, const char *bases, const uint64_t *rec_
     }
     DB200_CUDA(cudaMemsetAsync(pg->counter.ptr, 0, 64, stream));
     if (ps) DB200_CUDA(cudaMemsetAsync(ps->d_regs, 0, ngenomes << ps->p, stream));
-    size_t next_group = 0;
-    // ASCII upload in 64-base-aligned chunks through two device staging buffers; the pack kernel of
-    // chunk c overlaps the H2D copy of chunk c+1.
-    const uint64_t CH = 64ull << 20;
+    // ASCII -> packed store in 64-base-aligned chunks, by two routes that share the host->device link:
+    //  (A) the ASCII bytes go up through two device staging buffers and pack_kernel packs them (1 byte per base on the link;
+    //      the pack kernel of chunk c overlaps the copy of the next chunk);
+    //  (B) host threads pack the chunk to 2-bit codes + validity (hostpack.cpp) into a page-locked slot that is copied
+    //      straight into the store (0.375 bytes per base on the link).
+    // With a page-locked source the chunks are consumed from BOTH ends — (B) from the front as fast as the host cores pack,
+    // (A) from the back whenever fewer than two ASCII copies are queued — so the link never idles and the split follows
+    // the measured speeds.  A pageable source would have to be copied by host threads anyway (HostStager): it is packed
+    // instead, all of it.  DB200_HOST_PACK=0 keeps everything on route (A).
+    uint64_t CH = Uploader::CHUNK;
+    if (const char *cenv = std::getenv("DB200_UPLOAD_CHUNK")) {     // testing knob: many small chunks exercise the two-ended schedule
+        const uint64_t v = std::strtoull(cenv, nullptr, 10) / 4096 * 4096;
+        if (v) CH = std::min(v, CH);
+    }
     const uint64_t nchunks = (T + CH - 1) / CH;
     // `bases` may already live in device memory (unified addressing): pack straight from it when aligned
     cudaPointerAttributes pat;
     const bool on_dev = T && cudaPointerGetAttributes(&pat, bases) == cudaSuccess && pat.type == cudaMemoryTypeDevice &&
                         ((reinterpret_cast<uintptr_t>(bases) + base0) & 15) == 0;
     cudaGetLastError();
+    const char *hpenv = std::getenv("DB200_HOST_PACK");
+    const bool host_pack = !on_dev && T && !(hpenv && hpenv[0] == '0');
+    const bool src_locked = !on_dev && T && HostStager::page_locked(bases);
     if (!on_dev && T) {
         DB200_TRY(up.init());
-        for (int i = 0; i < 2; ++i) DB200_TRY(up.stage[i].reserve(std::min<uint64_t>(CH, T)));
-        // the copy stream must not run ahead of work already queued on `stream` that still reads the staging buffers
+        if (!host_pack || src_locked)
+            for (int i = 0; i < (host_pack ? Uploader::NSTAGE : 2); ++i) DB200_TRY(up.stage[i].reserve(std::min<uint64_t>(CH, T)));
+        if (host_pack) DB200_TRY(up.init_hostpack());
+        // the copy streams must not run ahead of work already queued on `stream` (memsets above, kernels still reading the staging buffers)
         DB200_CUDA(cudaEventRecord(up.packed[0], stream));
         DB200_CUDA(cudaStreamWaitEvent(up.cs, up.packed[0], 0));
+        if (host_pack) DB200_CUDA(cudaStreamWaitEvent(up.cs2, up.packed[0], 0));
     }
-    for (uint64_t c = 0; c < nchunks; ++c) {
-        const int b = (int)(c & 1);
+    std::vector<char> chunk_done(nchunks, 0), group_launched(pg->group_end.size(), 0);
+    // genome groups all of whose chunks have been enqueued start sketching on their own stream
+    auto launch_ready_groups = [&]() -> int {
+        if (!ps) return DB200_OK;
+        uint64_t gb = 0;
+        for (size_t g = 0; g < pg->group_end.size(); ++g) {
+            const uint64_t ge = pg->group_end[g];
+            if (!group_launched[g]) {
+                bool ready = true;
+                for (uint64_t c = gb / CH; ready && c < nchunks && c * CH < std::max(ge, gb + 1); ++c) ready = chunk_done[c] != 0;
+                if (ready) {
+                    group_launched[g] = 1;
+                    const uint32_t ib = pg->group_item_begin[g], ie = pg->group_item_begin[g + 1];
+                    if (ie > ib) {
+                        DB200_TRY(up.init());
+                        DB200_CUDA(cudaEventRecord(up.group_packed[g], stream));
+                        DB200_CUDA(cudaStreamWaitEvent(up.ss, up.group_packed[g], 0));
+                        DB200_TRY(sketch_launch(pg, ps->p, ps->canon, ps->d_regs, up.ss, ib, ie - ib, (int)g));
+                    }
+                }
+            }
+            gb = ge;
+        }
+        return DB200_OK;
+    };
+    bool stage_used[Uploader::NSTAGE] = {};
+    uint64_t ascii_seq = 0;
+    // route (A): chunk c through staging buffer b
+    auto enqueue_ascii = [&](uint64_t c, int b) -> int {
         const uint64_t off = c * CH, len = std::min<uint64_t>(CH, T - off);
         const uint64_t ngroups = (len + 15) / 16;
         const uint8_t *src;
         if (on_dev) {
             src = reinterpret_cast<const uint8_t *>(bases) + base0 + off;
         } else {
-            if (c >= 2) DB200_CUDA(cudaStreamWaitEvent(up.cs, up.packed[b], 0));  // staging buffer free again
+            if (stage_used[b]) DB200_CUDA(cudaStreamWaitEvent(up.cs, up.packed[b], 0));  // staging buffer free again
             DB200_TRY(up.stager.upload(up.stage[b].ptr, bases + base0 + off, len, up.cs));
             DB200_CUDA(cudaEventRecord(up.copied[b], up.cs));
             DB200_CUDA(cudaStreamWaitEvent(stream, up.copied[b], 0));
@@ -330,19 +424,55 @@ static int pack_genomes_impl(int device, const char *bases, const uint64_t *rec_
         pack_kernel<<<(unsigned)((ngroups + 255) / 256), 256, 0, stream>>>(src, len, pg->bases2.as<uint32_t>() + off / 16,
                                                                           pg->nb.as<uint16_t>() + off / 16, ngroups);
         DB200_LAUNCHED();
-        if (!on_dev) DB200_CUDA(cudaEventRecord(up.packed[b], stream));
-        // genome groups whose last base is now packed start sketching on their own stream
-        while (ps && next_group < pg->group_end.size() && pg->group_end[next_group] <= off + len) {
-            const uint32_t ib = pg->group_item_begin[next_group], ie = pg->group_item_begin[next_group + 1];
-            if (ie > ib) {
-                DB200_TRY(up.init());
-                DB200_CUDA(cudaEventRecord(up.group_packed[next_group], stream));
-                DB200_CUDA(cudaStreamWaitEvent(up.ss, up.group_packed[next_group], 0));
-                DB200_TRY(sketch_launch(pg, ps->p, ps->canon, ps->d_regs, up.ss, ib, ie - ib, (int)next_group));
-            }
-            ++next_group;
+        if (!on_dev) { DB200_CUDA(cudaEventRecord(up.packed[b], stream)); stage_used[b] = true; }
+        chunk_done[c] = 1;
+        return DB200_OK;
+    };
+    // route (B): chunk c packed on the host into page-locked slot `sl`
+    uint64_t pack_seq = 0;
+    auto enqueue_packed = [&](uint64_t c) -> int {
+        const uint64_t off = c * CH, len = std::min<uint64_t>(CH, T - off);
+        const uint64_t ngroups = (len + 15) / 16;
+        const int sl = (int)(pack_seq++ % Uploader::NPSLOT);
+        if (up.pslot_used[sl]) DB200_CUDA(cudaEventSynchronize(up.pslot_done[sl]));
+        uint32_t *hc = reinterpret_cast<uint32_t *>(up.pslot[sl]);
+        uint16_t *hv = reinterpret_cast<uint16_t *>(up.pslot[sl] + Uploader::CHUNK / 16 * 4);
+        const uint8_t *srcb = reinterpret_cast<const uint8_t *>(bases) + base0 + off;
+        up.packers->parallel(len, 4096, [=](size_t b0, size_t b1) { db200_hostpack(srcb + b0, b1 - b0, hc + b0 / 16, hv + b0 / 16); });
+        DB200_CUDA(cudaMemcpyAsync(pg->bases2.as<uint32_t>() + off / 16, hc, ngroups * 4, cudaMemcpyHostToDevice, up.cs2));
+        DB200_CUDA(cudaMemcpyAsync(pg->nb.as<uint16_t>() + off / 16, hv, ngroups * 2, cudaMemcpyHostToDevice, up.cs2));
+        DB200_CUDA(cudaEventRecord(up.pslot_done[sl], up.cs2));
+        up.pslot_used[sl] = true;
+        DB200_CUDA(cudaStreamWaitEvent(stream, up.pslot_done[sl], 0));
+        chunk_done[c] = 1;
+        return DB200_OK;
+    };
+    if (!host_pack) {
+        for (uint64_t c = 0; c < nchunks; ++c) {
+            DB200_TRY(enqueue_ascii(c, (int)(c & 1)));
+            DB200_TRY(launch_ready_groups());
         }
+    } else {
+        uint64_t front = 0, back = nchunks;
+        while (front < back) {
+            if (src_locked) {
+                // keep up to NSTAGE ASCII copies queued; a buffer is reused only once its previous copy has left the queue
+                while (front < back) {
+                    const int b = (int)(ascii_seq % Uploader::NSTAGE);
+                    bool busy = false;
+                    if (stage_used[b]) { busy = cudaEventQuery(up.copied[b]) == cudaErrorNotReady; cudaGetLastError(); }
+                    if (busy) break;
+                    --back;
+                    DB200_TRY(enqueue_ascii(back, b));
+                    ++ascii_seq;
+                }
+            }
+            if (front < back) { DB200_TRY(enqueue_packed(front)); ++front; }
+            DB200_TRY(launch_ready_groups());
+        }
+        pg->host_packed_chunks = front; pg->ascii_chunks = nchunks - front;
     }
+    DB200_TRY(launch_ready_groups());
     DB200_CUDA(cudaGetLastError());
     if (ps && up.ss) {
         const cudaError_t es = cudaStreamSynchronize(up.ss);

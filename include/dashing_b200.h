@@ -152,6 +152,15 @@ DB200_API int db200_sketch_fasta_batch(int device, int p, int k, int canon, cons
                                        const uint64_t *file_len, uint64_t nfiles, const uint64_t *genome_file_begin, uint64_t ngenomes,
                                        uint8_t *registers_out, uint8_t *file_status_out);
 
+/* The host-side half of the batch upload (dashing_b200/csrc/hostpack.cpp): ASCII bases -> the packed store's 2-bit code words
+ * (16 bases per uint32, base j at bits [2j, 2j+1], A0 C1 G2 T3) and validity bits (16 bases per uint16; ACGTacgt valid —
+ * alph::DNA4, bonsai/include/bonsai/alphabet.h:128).  db200_sketch_batch runs it on a pool of host threads for a share of
+ * every batch so that the link carries 0.375 bytes per base for that share (DB200_HOST_PACK=0 disables it; pure CPU code,
+ * usable and testable without a device).  codes / valid hold ceil(nbases / 16) entries; a partial last group is zero padded.
+ * db200_hostpack_isa(): "avx512bw" | "avx2" | "scalar" — the variant picked at run time. */
+DB200_API void db200_hostpack(const uint8_t *ascii, size_t nbases, uint32_t *codes, uint16_t *valid);
+DB200_API const char *db200_hostpack_isa(void);
+
 /* Device-resident form used by bench.py (`value`) and the multi-GPU driver.  The packed genome
  * store is the HBM-resident input format of the sketch kernel: 2-bit bases (64 per 16-byte word),
  * a validity bit-plane and a record-start bit-plane (DESIGN.md "Data layout"). */

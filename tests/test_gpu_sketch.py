@@ -92,3 +92,30 @@ def test_properties_at_bench_scale(gpu, checker):
     # (e) cardinality of a 5 Mbp random genome is within HLL error (1.04/sqrt(m)) x 3 of its distinct k-mer count
     card = gpu.cardinalities(regs, p)
     assert abs(card[0] - (5_000_000 - k + 1)) < 3 * 1.04 / np.sqrt(1 << p) * 5_000_000
+
+
+@pytest.mark.parametrize("pinned", [False, True])
+def test_host_packed_upload_matches_ascii_upload(gpu, checker, monkeypatch, pinned):
+    """db200_sketch_batch uploads a batch by two routes at once (host-packed 2-bit chunks from the front, ASCII chunks from
+    the back when the source is page-locked): registers must not depend on the route or on where the chunk cuts fall."""
+    k, p = 21, 12
+    rng = np.random.default_rng(11)
+    genomes = synth.genomes(5, 9, 150_001, group=3)
+    genomes[2] = synth.sprinkle(rng, genomes[2])
+    genomes[7] = [genomes[7][:70_000], genomes[7][70_000:70_013], genomes[7][70_013:]]     # multi-record, one record shorter than k
+    bases, offs, grb = gpu.records_layout(genomes)
+    if pinned:
+        buf = gpu.pinned_empty(bases.size)
+        buf[:] = bases
+        bases = buf
+    monkeypatch.setenv("DB200_HOST_PACK", "0")
+    want = gpu.sketch_batch(bases, offs, grb, k, p, True)
+    for i in (0, 2, 7):
+        g = genomes[i] if isinstance(genomes[i], list) else [genomes[i]]
+        assert np.array_equal(want[i], checker.sketch([np.asarray(r).tobytes() for r in g], k, p, True))
+    for chunk in ("4096", "65536", "1000000"):
+        monkeypatch.setenv("DB200_UPLOAD_CHUNK", chunk)
+        monkeypatch.setenv("DB200_HOST_PACK", "1")
+        assert np.array_equal(gpu.sketch_batch(bases, offs, grb, k, p, True), want), (chunk, "hybrid")
+        monkeypatch.setenv("DB200_HOST_PACK", "0")
+        assert np.array_equal(gpu.sketch_batch(bases, offs, grb, k, p, True), want), (chunk, "ascii")
