@@ -246,8 +246,8 @@ class Port(_Common):
 class Ref(_Common):
     kind = "reference"
 
-    def __init__(self):
-        l, self.libname = _load_ref()
+    def __init__(self, lib=None, libname=None):
+        l, self.libname = (lib, libname) if lib is not None else _load_ref()
         self.l = l
         l.dref_simd_tier.restype = C.c_int
         l.dref_max_threads.restype = C.c_int
@@ -528,6 +528,24 @@ def port() -> Port:
 @lru_cache(maxsize=None)
 def ref() -> Ref:
     return Ref()
+
+
+PATCHED_SO = os.path.join(REF_DIR, "libdashing_ref_patched.so")
+
+
+def patched_available() -> bool:
+    return os.path.exists(PATCHED_SO)
+
+
+@lru_cache(maxsize=None)
+def ref_patched() -> Ref:
+    """The SAME driver built against the reference headers with oracle/integration.patch applied (-DDASHING_B200): its
+    sketch_core / dist_sketch_and_cmp / dist_loop / partdist_loop run their hot paths through libdashing_b200's C ABI.
+    Needs a CUDA device for anything that sketches or compares (DASHING_GPU=0 in the environment switches it back to the
+    reference's own code paths).  Test infrastructure for INTEGRATION.md, like everything else under oracle/."""
+    if not patched_available():
+        raise FileNotFoundError("oracle/_ref/libdashing_ref_patched.so is not built (run `make -C oracle patched` where /root/reference exists)")
+    return Ref(C.CDLL(PATCHED_SO), "libdashing_ref_patched.so")
 
 
 def best():
