@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <cstring>
 #include <sched.h>
+#include <chrono>
 #include <mutex>
 #include <thread>
 #include <condition_variable>
@@ -22,6 +23,7 @@
 namespace db200 {
 
 static thread_local std::string t_err;
+static thread_local double g_dbg_pack_ms = 0, g_dbg_wait_ms = 0;   // DB200_DEBUG_UPLOAD accounting
 std::atomic<uint64_t> g_kernel_launches{0};
 
 void set_error(const char *fmt, ...) {
@@ -228,10 +230,12 @@ struct Uploader {
     char *pslot[NPSLOT] = {nullptr, nullptr, nullptr};
     cudaEvent_t pslot_done[NPSLOT] = {nullptr, nullptr, nullptr};
     bool pslot_used[NPSLOT] = {false, false, false};
+    std::atomic<bool> pslot_inflight[NPSLOT];   // a packed copy has been enqueued from this slot (read by the feeder thread)
     cudaStream_t cs2 = nullptr;
     std::unique_ptr<CopyPool> packers;
     int init_hostpack() {
         if (pslot[0]) return DB200_OK;
+        for (auto &f : pslot_inflight) f.store(false);
         DB200_CUDA(cudaStreamCreateWithFlags(&cs2, cudaStreamNonBlocking));
         for (int i = 0; i < NPSLOT; ++i) {
             DB200_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&pslot[i]), CHUNK / 16 * 6, cudaHostAllocDefault));
@@ -356,12 +360,6 @@ static int pack_genomes_impl(int device, const char *bases, const uint64_t *rec_
     // (A) from the back whenever fewer than two ASCII copies are queued — so the link never idles and the split follows
     // the measured speeds.  A pageable source would have to be copied by host threads anyway (HostStager): it is packed
     // instead, all of it.  DB200_HOST_PACK=0 keeps everything on route (A).
-    uint64_t CH = Uploader::CHUNK;
-    if (const char *cenv = std::getenv("DB200_UPLOAD_CHUNK")) {     // testing knob: many small chunks exercise the two-ended schedule
-        const uint64_t v = std::strtoull(cenv, nullptr, 10) / 4096 * 4096;
-        if (v) CH = std::min(v, CH);
-    }
-    const uint64_t nchunks = (T + CH - 1) / CH;
     // `bases` may already live in device memory (unified addressing): pack straight from it when aligned
     cudaPointerAttributes pat;
     const bool on_dev = T && cudaPointerGetAttributes(&pat, bases) == cudaSuccess && pat.type == cudaMemoryTypeDevice &&
@@ -370,6 +368,15 @@ static int pack_genomes_impl(int device, const char *bases, const uint64_t *rec_
     const char *hpenv = std::getenv("DB200_HOST_PACK");
     const bool host_pack = !on_dev && T && !(hpenv && hpenv[0] == '0');
     const bool src_locked = !on_dev && T && HostStager::page_locked(bases);
+    // unit of the schedule: 64 Mbases on the ASCII-only route; 16 Mbases when both routes share the link, so that a host-packed
+    // copy never queues behind more than two short ASCII copies (the first version used 64 MB units and four queued ASCII
+    // copies: the packed copies waited 35 ms of a 66 ms batch behind them and only 28 of 75 chunks got packed)
+    uint64_t CH = host_pack ? Uploader::CHUNK / 4 : Uploader::CHUNK;
+    if (const char *cenv = std::getenv("DB200_UPLOAD_CHUNK")) {     // testing knob: many small chunks exercise the two-ended schedule
+        const uint64_t v = std::strtoull(cenv, nullptr, 10) / 4096 * 4096;
+        if (v) CH = std::min(v, CH);
+    }
+    const uint64_t nchunks = (T + CH - 1) / CH;
     if (!on_dev && T) {
         DB200_TRY(up.init());
         if (!host_pack || src_locked)
@@ -405,7 +412,8 @@ static int pack_genomes_impl(int device, const char *bases, const uint64_t *rec_
         }
         return DB200_OK;
     };
-    bool stage_used[Uploader::NSTAGE] = {};
+    std::atomic<bool> stage_used[Uploader::NSTAGE];
+    for (auto &f : stage_used) f.store(false);
     uint64_t ascii_seq = 0;
     // route (A): chunk c through staging buffer b
     auto enqueue_ascii = [&](uint64_t c, int b) -> int {
@@ -425,52 +433,88 @@ static int pack_genomes_impl(int device, const char *bases, const uint64_t *rec_
                                                                           pg->nb.as<uint16_t>() + off / 16, ngroups);
         DB200_LAUNCHED();
         if (!on_dev) { DB200_CUDA(cudaEventRecord(up.packed[b], stream)); stage_used[b] = true; }
-        chunk_done[c] = 1;
         return DB200_OK;
     };
     // route (B): chunk c packed on the host into page-locked slot `sl`
     uint64_t pack_seq = 0;
-    auto enqueue_packed = [&](uint64_t c) -> int {
-        const uint64_t off = c * CH, len = std::min<uint64_t>(CH, T - off);
+    auto enqueue_packed = [&](uint64_t c, uint64_t nunits) -> int {
+        const uint64_t off = c * CH, len = std::min<uint64_t>(nunits * CH, T - off);
         const uint64_t ngroups = (len + 15) / 16;
         const int sl = (int)(pack_seq++ % Uploader::NPSLOT);
+        const auto tw0 = std::chrono::steady_clock::now();
         if (up.pslot_used[sl]) DB200_CUDA(cudaEventSynchronize(up.pslot_done[sl]));
+        const auto tw1 = std::chrono::steady_clock::now();
         uint32_t *hc = reinterpret_cast<uint32_t *>(up.pslot[sl]);
         uint16_t *hv = reinterpret_cast<uint16_t *>(up.pslot[sl] + Uploader::CHUNK / 16 * 4);
         const uint8_t *srcb = reinterpret_cast<const uint8_t *>(bases) + base0 + off;
         up.packers->parallel(len, 4096, [=](size_t b0, size_t b1) { db200_hostpack(srcb + b0, b1 - b0, hc + b0 / 16, hv + b0 / 16); });
+        g_dbg_wait_ms += std::chrono::duration<double, std::milli>(tw1 - tw0).count();
+        g_dbg_pack_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tw1).count();
         DB200_CUDA(cudaMemcpyAsync(pg->bases2.as<uint32_t>() + off / 16, hc, ngroups * 4, cudaMemcpyHostToDevice, up.cs2));
         DB200_CUDA(cudaMemcpyAsync(pg->nb.as<uint16_t>() + off / 16, hv, ngroups * 2, cudaMemcpyHostToDevice, up.cs2));
         DB200_CUDA(cudaEventRecord(up.pslot_done[sl], up.cs2));
         up.pslot_used[sl] = true;
+        up.pslot_inflight[sl].store(true, std::memory_order_release);
         DB200_CUDA(cudaStreamWaitEvent(stream, up.pslot_done[sl], 0));
-        chunk_done[c] = 1;
         return DB200_OK;
     };
     if (!host_pack) {
         for (uint64_t c = 0; c < nchunks; ++c) {
             DB200_TRY(enqueue_ascii(c, (int)(c & 1)));
+            chunk_done[c] = 1;
             DB200_TRY(launch_ready_groups());
         }
     } else {
+        // Two-ended schedule.  This thread packs from the front (32 Mbases per parallel pack) and enqueues the packed copies; a
+        // FEEDER thread (page-locked sources only) watches the link and, whenever neither an ASCII copy nor a packed copy is in
+        // flight, sends one 16 MB ASCII unit from the back — ASCII only fills the link time the packed copies leave idle, so the
+        // split follows the measured host-pack and link speeds.  (Topping the ASCII queue up from this thread once per pack,
+        // the previous version, kept the packed copies queued behind ASCII: 58 ms instead of 47 for 5 GB.)
         uint64_t front = 0, back = nchunks;
-        while (front < back) {
-            if (src_locked) {
-                // keep up to NSTAGE ASCII copies queued; a buffer is reused only once its previous copy has left the queue
-                while (front < back) {
-                    const int b = (int)(ascii_seq % Uploader::NSTAGE);
-                    bool busy = false;
-                    if (stage_used[b]) { busy = cudaEventQuery(up.copied[b]) == cudaErrorNotReady; cudaGetLastError(); }
-                    if (busy) break;
-                    --back;
-                    DB200_TRY(enqueue_ascii(back, b));
-                    ++ascii_seq;
-                }
+        std::mutex mu;                       // cursors, chunk_done / group_launched, launches of ready groups
+        const bool dbg = std::getenv("DB200_DEBUG_UPLOAD") != nullptr;
+        const auto t_begin = std::chrono::steady_clock::now();
+        int feeder_rc = DB200_OK;
+        std::string feeder_err;
+        std::thread feeder;
+        if (src_locked) feeder = std::thread([&] {
+            cudaSetDevice(phys_of(device));
+            for (;;) {
+                { std::lock_guard<std::mutex> lk(mu); if (front >= back) return; }
+                bool busy = false;
+                for (int b2 = 0; b2 < Uploader::NSTAGE && !busy; ++b2)
+                    if (stage_used[b2]) busy = cudaEventQuery(up.copied[b2]) == cudaErrorNotReady;
+                for (int sl = 0; sl < Uploader::NPSLOT && !busy; ++sl)
+                    if (up.pslot_inflight[sl].load(std::memory_order_acquire)) busy = cudaEventQuery(up.pslot_done[sl]) == cudaErrorNotReady;
+                cudaGetLastError();
+                // (sleeping, not spinning: every host CPU is packing; a spinning feeder slowed the pack threads by a third)
+                if (busy) { std::this_thread::sleep_for(std::chrono::microseconds(30)); continue; }
+                uint64_t c;
+                { std::lock_guard<std::mutex> lk(mu); if (front >= back) return; c = --back; }
+                int rc = enqueue_ascii(c, (int)(ascii_seq++ % Uploader::NSTAGE));
+                if (rc == DB200_OK) { std::lock_guard<std::mutex> lk(mu); chunk_done[c] = 1; rc = launch_ready_groups(); }
+                if (rc != DB200_OK) { feeder_rc = rc; feeder_err = t_err; std::lock_guard<std::mutex> lk(mu); back = front; return; }
             }
-            if (front < back) { DB200_TRY(enqueue_packed(front)); ++front; }
-            DB200_TRY(launch_ready_groups());
+        });
+        int rc_main = DB200_OK;
+        for (;;) {
+            uint64_t c, npk;
+            { std::lock_guard<std::mutex> lk(mu); if (front >= back) break; npk = std::min<uint64_t>(2, back - front); c = front; front += npk; }
+            rc_main = enqueue_packed(c, npk);
+            if (rc_main == DB200_OK) { std::lock_guard<std::mutex> lk(mu); for (uint64_t u = c; u < c + npk; ++u) chunk_done[u] = 1; rc_main = launch_ready_groups(); }
+            if (rc_main != DB200_OK) { std::lock_guard<std::mutex> lk(mu); back = front; break; }
         }
-        pg->host_packed_chunks = front; pg->ascii_chunks = nchunks - front;
+        if (feeder.joinable()) feeder.join();
+        if (rc_main != DB200_OK) return rc_main;
+        if (feeder_rc != DB200_OK) { set_error("%s", feeder_err.c_str()); return feeder_rc; }
+        pg->ascii_chunks = ascii_seq; pg->host_packed_chunks = nchunks - ascii_seq;
+        if (dbg) {
+            const double t_all = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+            std::fprintf(stderr, "[db200 upload] %llu units of %llu bases: %llu host-packed, %llu ascii; enqueue loop %.2f ms (pack %.2f ms, slot waits %.2f ms), %u pack threads\n",
+                         (unsigned long long)nchunks, (unsigned long long)CH, (unsigned long long)(nchunks - ascii_seq), (unsigned long long)ascii_seq, t_all, g_dbg_pack_ms, g_dbg_wait_ms,
+                         up.packers ? up.packers->workers() + 1 : 0u);
+            g_dbg_pack_ms = g_dbg_wait_ms = 0;
+        }
     }
     DB200_TRY(launch_ready_groups());
     DB200_CUDA(cudaGetLastError());
