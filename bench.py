@@ -511,9 +511,15 @@ def bench_dist(cx):
 
     def step():
         ev[0].record()
-        full = multigpu.allgather_registers(local, counts, dist) if world > 1 else local
-        ev[1].record()
-        plan.prepare_dev(full.data_ptr(), n, p, capi.ERTL_MLE, stream)
+        if world > 1:
+            # exchange and plane build overlapped: global register range (all-reduce of two scalars), one broadcast per shard,
+            # planes / counts / cardinalities of each shard built as it lands (multigpu.allgather_prepare_overlapped)
+            full = multigpu.allgather_prepare_overlapped(plan, local, counts, dist, p, capi.ERTL_MLE, stream)
+            ev[1].record()
+        else:
+            full = local
+            ev[1].record()
+            plan.prepare_dev(full.data_ptr(), n, p, capi.ERTL_MLE, stream)
         ev[2].record()
         plan.run_symmetric_dev(prm, rb, re_, d_out.data_ptr(), stream)
         ev[3].record()
@@ -581,8 +587,7 @@ def bench_dist(cx):
             capi.dist_symmetric(host_regs, p, k=K_MER, result_type=capi.JI, device=cx.local_rank, out=host_out)
         else:
             loc = pin_t.to(dev, non_blocking=True)
-            full = multigpu.allgather_registers(loc, counts, dist)
-            plan.prepare_dev(full.data_ptr(), n, p, capi.ERTL_MLE, stream)
+            full = multigpu.allgather_prepare_overlapped(plan, loc, counts, dist, p, capi.ERTL_MLE, stream)
             for (b0, b1, off, cnt), e in zip(blocks, blk_ev):
                 plan.run_symmetric_dev(prm, b0, b1, d_out.data_ptr() + off * 4, stream)
                 e.record()
@@ -609,7 +614,9 @@ def bench_dist(cx):
            "api": "db200_dist_symmetric(host regs -> host packed float matrix)" if world == 1 else "multigpu driver: pinned shard -> all-gather -> rows in 4 blocks (device->host copy of block b under the kernel of block b+1) -> pinned out"}
     res = {"metric": "pairwise HLL cmp/s (dist p=14)", "value": value, "unit": "pairs/s", "ms_per_step": ms_per_step,
            "config": dist_config(n, world),
-           "details": {"step_breakdown_ms": {"allgather": float(np.mean(ag_ms)), "planes+cardinalities": float(np.mean(prep_ms)), "all_pairs_kernel": ker},
+           "details": {"step_breakdown_ms": ({"allgather": float(np.mean(ag_ms)), "planes+cardinalities": float(np.mean(prep_ms)), "all_pairs_kernel": ker} if world == 1 else
+                                             {"exchange+planes+cardinalities (overlapped: range all-reduce, per-shard broadcast, planes per shard as it lands)": float(np.mean(ag_ms)) + float(np.mean(prep_ms)),
+                                              "all_pairs_kernel": ker}),
                        "tiles": tiles, "live_thresholds": K, "rows_of_rank0": [rb, re_]},
            "roofline": roof, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "dtype": "u8 registers / u32 popcounts / f64 estimator -> f32 out"}
     plan.close()
@@ -920,14 +927,20 @@ def bench_c4(cx):
             return full
         return multigpu.allgather_registers(loc, counts, dist)
 
+    def gather_prepare(loc):
+        if emulated:
+            full_ = gather(loc)
+            plan.prepare_dev(full_.data_ptr(), n, p, capi.ERTL_MLE, stream)
+            return full_
+        return multigpu.allgather_prepare_overlapped(plan, loc, counts, dist, p, capi.ERTL_MLE, stream)
+
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     ag, prep, ker, tot = [], [], [], []
     for it in range(warm + steps):
         cx.barrier()
         ev[0].record()
-        full = gather(local)
+        full = gather_prepare(local)
         ev[1].record()
-        plan.prepare_dev(full.data_ptr(), n, p, capi.ERTL_MLE, stream)
         ev[2].record()
         plan.run_symmetric_dev(prm, rb, re_, d_out.data_ptr(), stream)
         ev[3].record()
@@ -943,8 +956,7 @@ def bench_c4(cx):
         cx.barrier()
         t0 = time.perf_counter()
         loc = pin_t.to(dev, non_blocking=True)
-        full = gather(loc)
-        plan.prepare_dev(full.data_ptr(), n, p, capi.ERTL_MLE, stream)
+        full = gather_prepare(loc)
         stream_rows(cx, plan, prm, n, rb, re_, block_pairs, ring)
         cx.barrier()
         if it >= 1:
@@ -953,7 +965,7 @@ def bench_c4(cx):
     scale = (W if emulated else 1)     # an emulated rank reports the whole-job figure its time implies (every rank holds 1/W of the pairs)
     out = {"metric": "pairwise HLL cmp/s (dist p=14)", "value": total_pairs / (ms * 1e-3), "unit": "pairs/s", "ms_per_step": ms, "steps": steps, "warmup": warm,
            "n_gpus": W, "config": dist_config(n, W, seed=SEED_C4),
-           "details": {"step_breakdown_ms": {"allgather": float(np.mean(ag)), "planes+cardinalities": float(np.mean(prep)), "all_pairs_kernel": float(np.mean(ker))},
+           "details": {"step_breakdown_ms": {"exchange+planes+cardinalities" + ("" if emulated else " (overlapped)"): float(np.mean(ag)) + float(np.mean(prep)), "all_pairs_kernel": float(np.mean(ker))},
                        "tiles": tiles, "live_thresholds": K, "rows_of_this_rank": [rb, re_], "pairs_of_this_rank": my_pairs,
                        "hbm_bytes": {"registers": n * m, "planes": K * n * (m // 8), "out_per_rank": my_pairs * 4}},
            "e2e": {"value": total_pairs / (e2e_t * 1e-3), "unit": "pairs/s", "ms_per_step": e2e_t, "h2d_bytes_per_step": int(counts[R] * m),
@@ -1054,15 +1066,19 @@ def bench_c5(cx):
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         t0 = time.perf_counter()
         ev[0].record()
-        full = gather(local)
-        ev[1].record()
-        plan.prepare_dev(full.data_ptr(), n, p, capi.ERTL_MLE, stream)
+        if emulated:
+            full = gather(local)
+            ev[1].record()
+            plan.prepare_dev(full.data_ptr(), n, p, capi.ERTL_MLE, stream)
+        else:
+            full = multigpu.allgather_prepare_overlapped(plan, local, counts, dist, p, capi.ERTL_MLE, stream)
+            ev[1].record()
         ev[2].record()
         stream_rows(cx, plan, prm, n, rb, re_, block_pairs, ring)
         t_pairs_wall = (time.perf_counter() - t0) * 1e3
         cx.barrier()
         if it >= warm:
-            res.append({"pack": t_pack, "sketch": t_sk, "allgather": ev[0].elapsed_time(ev[1]), "planes": ev[1].elapsed_time(ev[2]),
+            res.append({"pack": t_pack, "sketch": t_sk, "exchange+planes": ev[0].elapsed_time(ev[2]),
                         "gather+planes+pairs+d2h_wall": t_pairs_wall, "kmers": kmers})
     if pg is not None:
         pg.close()
@@ -1076,8 +1092,8 @@ def bench_c5(cx):
            "config": {"workload": f"e2e sketch+dist: {n} x {L} bp synthetic genomes, k={k}, p={p}, Ertl joint MLE JI ({total_pairs} pairs)", "genomes_per_gpu": ng,
                       "data": "genomes generated on the device batch by batch (SURVEY.md §8(d): C5 is never written to disk); sketch time = ASCII in HBM -> 2-bit store -> registers",
                       "parallelism": f"genomes x{W}, 1 NCCL all-gather of {n * m >> 20} MB of registers, block-row x{W}"},
-           "details": {"step_breakdown_ms": {"pack_ascii_to_2bit": r0["pack"], "sketch_kernel": r0["sketch"], "allgather": r0["allgather"], "planes+cardinalities": r0["planes"],
-                                             "allgather+planes+all_pairs+d2h (wall)": r0["gather+planes+pairs+d2h_wall"]},
+           "details": {"step_breakdown_ms": {"pack_ascii_to_2bit": r0["pack"], "sketch_kernel": r0["sketch"], "exchange+planes+cardinalities": r0["exchange+planes"],
+                                             "exchange+planes+all_pairs+d2h (wall)": r0["gather+planes+pairs+d2h_wall"]},
                        "sketch_kmers_per_s_whole_job": r0["kmers"] * W / (sketch_ms * 1e-3), "dist_pairs_per_s_whole_job": total_pairs / (pairs_ms * 1e-3),
                        "tiles": tiles, "live_thresholds": K, "rows_of_this_rank": [rb, re_], "pairs_of_this_rank": my_pairs,
                        "hbm_bytes": {"registers": n * m, "planes": K * n * (m // 8)}},

@@ -73,6 +73,9 @@ _SIGS = {
     "db200_dist_plan_create": (C.c_int, [C.c_int, C.POINTER(vp)]),
     "db200_dist_plan_destroy": (C.c_int, [vp]),
     "db200_dist_plan_prepare_dev": (C.c_int, [vp, vp, C.c_uint64, C.c_int, C.c_int, vp]),
+    "db200_dist_plan_begin_dev": (C.c_int, [vp, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
+    "db200_dist_plan_add_rows_dev": (C.c_int, [vp, vp, C.c_uint64, C.c_uint64, vp]),
+    "db200_dist_plan_finish_dev": (C.c_int, [vp]),
     "db200_dist_plan_run_symmetric_dev": (C.c_int, [vp, C.POINTER(DistParams), C.c_uint64, C.c_uint64, vp, vp]),
     "db200_dist_plan_run_rect_dev": (C.c_int, [vp, C.POINTER(DistParams), C.c_uint64, C.c_uint64, vp, vp]),
     "db200_dist_knn_symmetric": (C.c_int, [C.c_int, u8p, C.c_uint64, C.POINTER(DistParams), C.c_uint32, vp]),
@@ -382,6 +385,15 @@ class DistPlan:
 
     def prepare_dev(self, d_regs: int, n: int, p: int, estim=ERTL_MLE, stream: int = 0):
         _check(lib.db200_dist_plan_prepare_dev(self.h, vp(d_regs), n, p, estim, vp(stream)))
+
+    def begin_dev(self, n: int, p: int, estim, reg_min: int, reg_max: int, stream: int = 0):
+        _check(lib.db200_dist_plan_begin_dev(self.h, n, p, estim, reg_min, reg_max, vp(stream)))
+
+    def add_rows_dev(self, d_regs: int, row_begin: int, nrows: int, stream: int = 0):
+        _check(lib.db200_dist_plan_add_rows_dev(self.h, vp(d_regs), row_begin, nrows, vp(stream)))
+
+    def finish_dev(self):
+        _check(lib.db200_dist_plan_finish_dev(self.h))
 
     def run_symmetric_dev(self, prm: DistParams, row_begin: int, row_end: int, d_out: int, stream: int = 0):
         _check(lib.db200_dist_plan_run_symmetric_dev(self.h, C.byref(prm), row_begin, row_end, vp(d_out), vp(stream)))

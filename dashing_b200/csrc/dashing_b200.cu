@@ -628,34 +628,22 @@ struct db200_dist_plan {
 
 namespace db200 {
 
-static int plan_prepare(db200_dist_plan *pl, const uint8_t *d_regs, uint64_t nrows, uint64_t n1, uint64_t qbase, uint64_t n2, int p,
-                        int estim, cudaStream_t stream) {
+// A plan is built in three steps so that the multi-process driver can overlap the plane build with the exchange of the register
+// shards: begin (allocations for a KNOWN global register range), add_rows (planes + counts + tails + cardinalities of a row
+// range, as soon as those rows are on the device), finish (tensor maps).  plan_prepare is the one-shot form.
+static int plan_begin(db200_dist_plan *pl, uint64_t nrows, uint64_t n1, uint64_t qbase, uint64_t n2, int p, int estim, int gmin, int gmax,
+                      cudaStream_t stream) {
     if (p < 7 || p > 20) { set_error("dist: p=%d outside the GPU path's range [7,20]", p); return DB200_EUNSUPPORTED; }
     if (estim < 0 || estim > 2) { set_error("dist: unknown estimation method %d", estim); return DB200_EINVAL; }
     if (nrows == 0 || nrows > (1ull << 31) - 64) { set_error("dist: %llu sketches unsupported", (unsigned long long)nrows); return DB200_EINVAL; }
-    PFN_encodeTiled enc = get_encode();
-    if (!enc) { set_error("cuTensorMapEncodeTiled not available from the driver"); return DB200_ECUDA; }
+    if (gmin < 0 || gmax < gmin) { set_error("dist: bad register range [%d,%d]", gmin, gmax); return DB200_EINVAL; }
+    if (gmax > 64 - p + 1) { set_error("dist: register value %d exceeds 64-p+1=%d (corrupt sketch?)", gmax, 64 - p + 1); return DB200_EINVAL; }
+    if (!get_encode()) { set_error("cuTensorMapEncodeTiled not available from the driver"); return DB200_ECUDA; }
     pl->ready = false;
     pl->nrows = nrows; pl->n1 = n1; pl->qbase = qbase; pl->n2 = n2; pl->p = p; pl->estim = estim;
     // tile lists depend only on (n, row range, mode), not on the register data: they stay cached across prepares
     const uint64_t m = 1ull << p, W = std::max<uint64_t>(m >> 5, 32), npan = (nrows + DT - 1) / DT;
-    DB200_TRY(pl->minmax.reserve(8));
-    DB200_CUDA(cudaMemsetAsync(pl->minmax.ptr, 0xFF, 4, stream));
-    DB200_CUDA(cudaMemsetAsync(pl->minmax.as<uint8_t>() + 4, 0, 4, stream));
-    const int sms = g_num_sms(pl->device);
-    for (int seg = 0; seg < 2; ++seg) {
-        const uint64_t r0 = seg ? qbase : 0, cnt = seg ? n2 : n1;
-        if (!cnt) continue;
-        const uint64_t n16 = cnt * m / 16;
-        const unsigned grid = (unsigned)std::min<uint64_t>((n16 + 255) / 256, (uint64_t)sms * 8);
-        range_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const uint4 *>(d_regs + r0 * m), n16, pl->minmax.as<uint32_t>());
-        DB200_LAUNCHED();
-    }
-    uint32_t mm[2];
-    DB200_CUDA(cudaMemcpyAsync(mm, pl->minmax.ptr, 8, cudaMemcpyDeviceToHost, stream));
-    DB200_CUDA(cudaStreamSynchronize(stream));
-    if (mm[1] > (uint32_t)(64 - p + 1)) { set_error("dist: register value %u exceeds 64-p+1=%d (corrupt sketch?)", mm[1], 64 - p + 1); return DB200_EINVAL; }
-    pl->gmin = (int)mm[0]; pl->gmax = (int)mm[1]; pl->K = pl->gmax - pl->gmin;
+    pl->gmin = gmin; pl->gmax = gmax; pl->K = gmax - gmin;
     const uint64_t Kalloc = std::max(pl->K, 1);
     DB200_TRY(pl->planes.reserve(Kalloc * nrows * W * 4));
     DB200_TRY(pl->counts.reserve(nrows * 64 * 4));
@@ -682,25 +670,34 @@ static int plan_prepare(db200_dist_plan *pl, const uint8_t *d_regs, uint64_t nro
         DB200_CUDA(cudaMemsetAsync(pl->llists.ptr, 0, nrows * SPARSE_C * 4, stream));
     }
     DB200_CUDA(cudaMemsetAsync(pl->counts.ptr, 0, nrows * 64 * 4, stream));
-    for (int seg = 0; seg < 2; ++seg) {
-        const uint64_t r0 = seg ? qbase : 0, cnt = seg ? n2 : n1;
-        if (!cnt) continue;
-        if (pl->K > 0) {
-            planes_kernel<<<(unsigned)cnt, 128, 0, stream>>>(reinterpret_cast<const uint32_t *>(d_regs), nrows, r0, p, pl->gmin, pl->K,
-                                                            pl->planes.as<uint32_t>(), pl->counts.as<uint32_t>(), pl->lists.as<uint32_t>(),
-                                                            pl->sthr.as<uint8_t>(), pl->pthr.as<uint32_t>(), pl->llists.as<uint32_t>(),
-                                                            pl->ptl.as<uint32_t>());
-            DB200_LAUNCHED();
-        }
-        card_kernel<<<(unsigned)((cnt + 127) / 128), 128, 0, stream>>>(pl->counts.as<uint32_t>(), r0, cnt, p, pl->gmin, pl->gmax, estim,
-                                                                      pl->card.as<double>(), pl->smin.as<uint8_t>(), pl->smax.as<uint8_t>(),
-                                                                      pl->pmin.as<uint32_t>(), pl->pmax.as<uint32_t>());
+    return DB200_OK;
+}
+
+// rows [r0, r0 + cnt) of the register matrix at d_regs (row-major base of ALL nrows rows): planes, counts, tails, cardinalities
+static int plan_add_rows(db200_dist_plan *pl, const uint8_t *d_regs, uint64_t r0, uint64_t cnt, cudaStream_t stream) {
+    if (!cnt) return DB200_OK;
+    if (r0 + cnt > pl->nrows) { set_error("dist plan: rows [%llu,%llu) outside the plan's %llu", (unsigned long long)r0, (unsigned long long)(r0 + cnt), (unsigned long long)pl->nrows); return DB200_EINVAL; }
+    if (pl->K > 0) {
+        planes_kernel<<<(unsigned)cnt, 128, 0, stream>>>(reinterpret_cast<const uint32_t *>(d_regs), pl->nrows, r0, pl->p, pl->gmin, pl->K,
+                                                        pl->planes.as<uint32_t>(), pl->counts.as<uint32_t>(), pl->lists.as<uint32_t>(),
+                                                        pl->sthr.as<uint8_t>(), pl->pthr.as<uint32_t>(), pl->llists.as<uint32_t>(),
+                                                        pl->ptl.as<uint32_t>());
         DB200_LAUNCHED();
     }
+    card_kernel<<<(unsigned)((cnt + 127) / 128), 128, 0, stream>>>(pl->counts.as<uint32_t>(), r0, cnt, pl->p, pl->gmin, pl->gmax, pl->estim,
+                                                                  pl->card.as<double>(), pl->smin.as<uint8_t>(), pl->smax.as<uint8_t>(),
+                                                                  pl->pmin.as<uint32_t>(), pl->pmax.as<uint32_t>());
+    DB200_LAUNCHED();
     DB200_CUDA(cudaGetLastError());
+    return DB200_OK;
+}
+
+static int plan_finish(db200_dist_plan *pl) {
+    PFN_encodeTiled enc = get_encode();
+    const uint64_t m = 1ull << pl->p, W = std::max<uint64_t>(m >> 5, 32), Kalloc = std::max(pl->K, 1);
     // 3-D tensor {W words, nrows sketches, K thresholds}, box {32, 32, 1}, 128-byte swizzle
-    cuuint64_t dims[3] = {W, nrows, Kalloc};
-    cuuint64_t strides[2] = {W * 4, nrows * W * 4};
+    cuuint64_t dims[3] = {W, pl->nrows, Kalloc};
+    cuuint64_t strides[2] = {W * 4, pl->nrows * W * 4};
     cuuint32_t box[3] = {32, (cuuint32_t)DT, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(&pl->tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, pl->planes.ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -712,6 +709,34 @@ static int plan_prepare(db200_dist_plan *pl, const uint8_t *d_regs, uint64_t nro
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (16-row box) failed with CUresult %d", (int)r); return DB200_ECUDA; }
     pl->ready = true;
     return DB200_OK;
+}
+
+static int plan_prepare(db200_dist_plan *pl, const uint8_t *d_regs, uint64_t nrows, uint64_t n1, uint64_t qbase, uint64_t n2, int p,
+                        int estim, cudaStream_t stream) {
+    if (p < 7 || p > 20) { set_error("dist: p=%d outside the GPU path's range [7,20]", p); return DB200_EUNSUPPORTED; }
+    pl->ready = false;
+    const uint64_t m = 1ull << p;
+    DB200_TRY(pl->minmax.reserve(8));
+    DB200_CUDA(cudaMemsetAsync(pl->minmax.ptr, 0xFF, 4, stream));
+    DB200_CUDA(cudaMemsetAsync(pl->minmax.as<uint8_t>() + 4, 0, 4, stream));
+    const int sms = g_num_sms(pl->device);
+    for (int seg = 0; seg < 2; ++seg) {
+        const uint64_t r0 = seg ? qbase : 0, cnt = seg ? n2 : n1;
+        if (!cnt) continue;
+        const uint64_t n16 = cnt * m / 16;
+        const unsigned grid = (unsigned)std::min<uint64_t>((n16 + 255) / 256, (uint64_t)sms * 8);
+        range_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const uint4 *>(d_regs + r0 * m), n16, pl->minmax.as<uint32_t>());
+        DB200_LAUNCHED();
+    }
+    uint32_t mm[2];
+    DB200_CUDA(cudaMemcpyAsync(mm, pl->minmax.ptr, 8, cudaMemcpyDeviceToHost, stream));
+    DB200_CUDA(cudaStreamSynchronize(stream));
+    if (mm[1] > (uint32_t)(64 - p + 1)) { set_error("dist: register value %u exceeds 64-p+1=%d (corrupt sketch?)", mm[1], 64 - p + 1); return DB200_EINVAL; }
+    if (mm[0] > mm[1]) mm[0] = mm[1] = 0;      // (no rows at all)
+    DB200_TRY(plan_begin(pl, nrows, n1, qbase, n2, p, estim, (int)mm[0], (int)mm[1], stream));
+    DB200_TRY(plan_add_rows(pl, d_regs, 0, n1, stream));
+    DB200_TRY(plan_add_rows(pl, d_regs, qbase, n2, stream));
+    return plan_finish(pl);
 }
 
 static int plan_tiles(db200_dist_plan *pl, int slot, int rect, int ta, uint64_t rb, uint64_t re, uint64_t nr, uint64_t nq, cudaStream_t stream) {
@@ -1237,6 +1262,24 @@ int db200_dist_plan_prepare_dev(db200_dist_plan *pl, const uint8_t *d_regs, uint
     DB200_TRY(check_device(pl->device));
     std::lock_guard<std::mutex> lk(pl->mu);
     return plan_prepare(pl, d_regs, n, n, 0, 0, p, estim, (cudaStream_t)stream);
+}
+int db200_dist_plan_begin_dev(db200_dist_plan *pl, uint64_t n, int p, int estim, int reg_min, int reg_max, void *stream) {
+    if (!pl) { set_error("db200_dist_plan_begin_dev: null plan"); return DB200_EINVAL; }
+    DB200_TRY(check_device(pl->device));
+    std::lock_guard<std::mutex> lk(pl->mu);
+    return plan_begin(pl, n, n, 0, 0, p, estim, reg_min, reg_max, (cudaStream_t)stream);
+}
+int db200_dist_plan_add_rows_dev(db200_dist_plan *pl, const uint8_t *d_regs, uint64_t row_begin, uint64_t nrows, void *stream) {
+    if (!pl || !d_regs) { set_error("db200_dist_plan_add_rows_dev: null argument"); return DB200_EINVAL; }
+    DB200_TRY(check_device(pl->device));
+    std::lock_guard<std::mutex> lk(pl->mu);
+    return plan_add_rows(pl, d_regs, row_begin, nrows, (cudaStream_t)stream);
+}
+int db200_dist_plan_finish_dev(db200_dist_plan *pl) {
+    if (!pl) { set_error("db200_dist_plan_finish_dev: null plan"); return DB200_EINVAL; }
+    DB200_TRY(check_device(pl->device));
+    std::lock_guard<std::mutex> lk(pl->mu);
+    return plan_finish(pl);
 }
 int db200_dist_plan_run_symmetric_dev(db200_dist_plan *pl, const db200_dist_params *prm, uint64_t row_begin, uint64_t row_end, float *d_out,
                                       void *stream) {

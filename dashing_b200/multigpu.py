@@ -87,6 +87,37 @@ def allgather_registers(local, counts: Sequence[int], dist, out=None):
     return out
 
 
+def allgather_prepare_overlapped(plan, local, counts: Sequence[int], dist, p: int, estim: int, stream: int = 0):
+    """The exchange step and the plane build, overlapped: the global register range first (two scalars, one all-reduce), then
+    one broadcast per shard; every shard's threshold planes / counts / cardinalities are built (plan.add_rows_dev) as soon as that
+    shard has landed, while the later shards are still in flight on NCCL's stream.  Returns the full [n, 2^p] matrix.
+    `plan` needs begin_dev / add_rows_dev / finish_dev (capi.DistPlan; the gloo test passes a recorder)."""
+    import torch
+
+    rank, world = dist.get_rank(), dist.get_world_size()
+    m = local.shape[1]
+    n = int(sum(counts))
+    offs = [0]
+    for c in counts:
+        offs.append(offs[-1] + int(c))
+    if local.shape[0]:
+        mm = torch.stack([local.amin().to(torch.int32), -(local.amax().to(torch.int32))])
+    else:
+        mm = torch.tensor([255, 0], dtype=torch.int32, device=local.device)
+    dist.all_reduce(mm, op=dist.ReduceOp.MIN)
+    gmin, gmax = int(mm[0].item()), -int(mm[1].item())          # (synchronises: the plan's shapes depend on the range)
+    full = torch.empty((n, m), dtype=local.dtype, device=local.device)
+    full[offs[rank]:offs[rank + 1]] = local
+    plan.begin_dev(n, p, estim, gmin, gmax, stream)
+    works = [dist.broadcast(full[offs[r]:offs[r + 1]], src=r, async_op=True) if counts[r] else None for r in range(world)]
+    for r in range(world):
+        if works[r] is not None:
+            works[r].wait()           # NCCL: the current stream waits for that broadcast; the host does not block
+            plan.add_rows_dev(full.data_ptr(), offs[r], int(counts[r]), stream)
+    plan.finish_dev()
+    return full
+
+
 def dist_symmetric_sharded(local_regs, counts: Sequence[int], dist, compute_rows: Callable, gather_out: bool = False):
     """All-gather + block-row computation.
     compute_rows(full_regs, n, row_begin, row_end) -> 1-D float32 tensor/array with that row range.

@@ -224,6 +224,15 @@ DB200_API int db200_dist_plan_create(int device, db200_dist_plan **out);
 DB200_API int db200_dist_plan_destroy(db200_dist_plan *pl);
 /* d_regs: device uint8_t[n][2^p].  Synchronises once (reads back the global register range). */
 DB200_API int db200_dist_plan_prepare_dev(db200_dist_plan *pl, const uint8_t *d_regs, uint64_t n, int p, int estim, void *stream);
+/* The same in three steps, for a driver that overlaps the plane build with the exchange of the register shards (one rank per
+ * GPU: dashing_b200/multigpu.py::allgather_prepare_overlapped).  begin: allocations for n sketches whose registers all lie in
+ * [reg_min, reg_max] (the exact global range, e.g. an all-reduce of the ranks' local minima / maxima — a looser range only
+ * costs thresholds).  add_rows: threshold planes, counts, tails and cardinalities of rows [row_begin, row_begin + nrows) of the
+ * matrix at d_regs (the base of all n rows), enqueued on `stream` — call it for each shard as soon as it has landed.
+ * finish: after every row has been added (no synchronisation). */
+DB200_API int db200_dist_plan_begin_dev(db200_dist_plan *pl, uint64_t n, int p, int estim, int reg_min, int reg_max, void *stream);
+DB200_API int db200_dist_plan_add_rows_dev(db200_dist_plan *pl, const uint8_t *d_regs, uint64_t row_begin, uint64_t nrows, void *stream);
+DB200_API int db200_dist_plan_finish_dev(db200_dist_plan *pl);
 /* Rows [row_begin,row_end) of the symmetric matrix into d_out (device floats, rows contiguous from d_out[0]). */
 DB200_API int db200_dist_plan_run_symmetric_dev(db200_dist_plan *pl, const db200_dist_params *prm,
                                       uint64_t row_begin, uint64_t row_end, float *d_out, void *stream);

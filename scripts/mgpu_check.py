@@ -29,7 +29,9 @@ def main():
 
     def compute_rows(full, n, rb, re_):
         out = torch.empty(max(multigpu.tri_offset(n, re_) - multigpu.tri_offset(n, rb), 1), dtype=torch.float32, device=dev)
-        plan.prepare_dev(full.data_ptr(), n, p, capi.ERTL_MLE, stream)
+        # (the plan is rebuilt here through the overlapped exchange: it must hold exactly what prepare_dev builds)
+        full2 = multigpu.allgather_prepare_overlapped(plan, local, counts, dist, p, capi.ERTL_MLE, stream)
+        assert torch.equal(full2, full)
         plan.run_symmetric_dev(prm, rb, re_, out.data_ptr(), stream)
         torch.cuda.synchronize()
         return out[: multigpu.tri_offset(n, re_) - multigpu.tri_offset(n, rb)].cpu()

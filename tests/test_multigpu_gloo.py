@@ -158,3 +158,57 @@ def test_sharded_knn_gloo_world2():
         pr.join(timeout=60)
         assert pr.exitcode == 0
     assert all(res), "merged per-rank neighbour tables differ from the single-process table"
+
+
+class _PlanRecorder:
+    """Stands in for capi.DistPlan in allgather_prepare_overlapped: records what the driver hands to the C ABI."""
+
+    def __init__(self):
+        self.calls = []
+
+    def begin_dev(self, n, p, estim, reg_min, reg_max, stream=0):
+        self.calls.append(("begin", n, p, estim, reg_min, reg_max))
+
+    def add_rows_dev(self, d_regs, row_begin, nrows, stream=0):
+        self.calls.append(("add", row_begin, nrows))
+
+    def finish_dev(self):
+        self.calls.append(("finish",))
+
+
+def _overlap_worker(rank, world, port, n, p, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        regs = synth.registers(9, n, p, card=1e5)
+        regs[n - 1, 5] = 0                      # the global minimum lives on the last rank, the maximum on the first
+        regs[0, 7] = 40
+        counts = multigpu.shard_counts(n, world)
+        start = sum(counts[:rank])
+        local = torch.from_numpy(regs[start:start + counts[rank]].copy())
+        plan = _PlanRecorder()
+        full = multigpu.allgather_prepare_overlapped(plan, local, counts, dist, p, 2)
+        q.put((rank, bool((full.numpy() == regs).all()), plan.calls, int(regs.min()), int(regs.max())))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_overlapped_exchange_and_plane_build_gloo_world2():
+    """The chunked exchange (global register range by all-reduce, one broadcast per shard, planes built per shard as it lands):
+    every rank ends with the full matrix, begins the plan with the GLOBAL range and adds every row exactly once."""
+    world, n, p = 2, 37, 10
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_overlap_worker, args=(r, world, port, n, p, q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for pr in procs:
+        pr.join(timeout=60)
+    counts = multigpu.shard_counts(n, world)
+    for rank, ok, calls, gmin, gmax in res:
+        assert ok
+        assert calls[0] == ("begin", n, p, 2, gmin, gmax) and calls[-1] == ("finish",)
+        adds = [c for c in calls if c[0] == "add"]
+        assert adds == [("add", sum(counts[:r]), counts[r]) for r in range(world)]
