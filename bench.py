@@ -371,6 +371,9 @@ def run_gpu(args):
         log(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE")
     if capi.device_count() < 1:
         raise RuntimeError("bench.py: libdashing_b200 sees no CUDA device (there is no CPU fallback)")
+    if world > 1:
+        # the ranks of one node share its host cores: each rank's library gets its share for the host-side packer
+        os.environ.setdefault("DB200_PACK_THREADS", str(max(2, usable_cores() // world)))
     torch.cuda.set_device(local_rank)
     cx.dev = dev = torch.device("cuda", local_rank)
     if world > 1:
