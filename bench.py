@@ -442,28 +442,8 @@ def run_gpu(args):
 
     # ---- optional legs: joint MLE at the C5 shape (N=1), BASELINE configs[3] and [4] (N=8 or one emulated rank)
     legs = {}
-    if world == 1 and not emu and args.workload == "both" and not args.no_extra:
-        try:
-            legs["jmle"] = bench_jmle(cx)
-        except Exception as e:
-            log(f"[bench] jmle leg failed: {e!r}")
-    if (world == C45_WORLD or emu) and not args.no_extra:
-        for name, fn in (("c4", bench_c4), ("c5", bench_c5)):
-            if args.only and name not in args.only.split(","):
-                continue
-            t0 = time.perf_counter()
-            try:
-                legs[name] = fn(cx)
-            except Exception as e:
-                import traceback
-                log(f"[bench] rank {rank}: {name} leg failed: {e!r}\n{traceback.format_exc()}")
-                legs[name] = {"failed": repr(e)}
-            log(f"[bench] rank {rank}: {name} done in {time.perf_counter() - t0:.1f}s")
-            torch.cuda.empty_cache()
-    if cx.sampler:
-        cx.sampler.stop()
 
-    if rank == 0:
+    def build_line():
         if results:
             primary = "dist" if "dist" in results else "sketch"
             r = results[primary]
@@ -482,7 +462,71 @@ def run_gpu(args):
         else:
             line = {"metric": "emulated rank of an 8-GPU configuration (see c4 / c5)", "value": None, "n_gpus": 1, "emulated": {"world": args.emulate_world, "rank": args.emulate_rank}}
         line.update(legs)
-        emit_result(line)
+        return line
+
+    # The optional legs run collectives of their own.  If a rank fails inside one of them the others would sit in a collective until
+    # NCCL's watchdog (10 minutes) kills the job and the primary result with it — what happened to the first 8-GPU run of round 2.
+    # A timer thread therefore bounds the legs: when it fires, rank 0 prints the line with what it has and every rank leaves.
+    emitted = threading.Event()
+
+    def bail_out():
+        if emitted.is_set():
+            return
+        emitted.set()
+        if rank == 0:
+            for name in ("c4", "c5"):
+                if (world == C45_WORLD or emu) and name not in legs and not (args.only and name not in args.only.split(",")):
+                    legs[name] = {"failed": f"leg did not finish within {args.legs_timeout:.0f} s (timer); see stderr"}
+            try:
+                emit_result(build_line())
+            finally:
+                os._exit(0)
+        time.sleep(2.0)
+        os._exit(0)
+
+    timer = None
+    if world > 1 and not args.no_extra and world == C45_WORLD:
+        timer = threading.Timer(args.legs_timeout, bail_out)
+        timer.daemon = True
+        timer.start()
+    if world == 1 and not emu and args.workload == "both" and not args.no_extra:
+        try:
+            legs["jmle"] = bench_jmle(cx)
+        except Exception as e:
+            log(f"[bench] jmle leg failed: {e!r}")
+    if (world == C45_WORLD or emu) and not args.no_extra:
+        for name, fn in (("c4", bench_c4), ("c5", bench_c5)):
+            if args.only and name not in args.only.split(","):
+                continue
+            t0 = time.perf_counter()
+            torch.cuda.set_device(local_rank)        # (library calls take a device index and leave that device current)
+            try:
+                res_leg = fn(cx)
+            except Exception as e:
+                import traceback
+                log(f"[bench] rank {rank}: {name} leg failed: {e!r}\n{traceback.format_exc()}")
+                res_leg = {"failed": repr(e)}
+            # a leg counts only if it went through on EVERY rank (a rank that dropped out leaves the others' numbers meaningless)
+            ok_all = True
+            try:
+                ok_all = all_ok("failed" not in res_leg)
+            except Exception as e:
+                log(f"[bench] rank {rank}: status exchange after {name} failed: {e!r}")
+            if not ok_all and "failed" not in res_leg:
+                res_leg = {"failed": "another rank failed in this leg; see stderr"}
+            legs[name] = res_leg
+            log(f"[bench] rank {rank}: {name} done in {time.perf_counter() - t0:.1f}s")
+            torch.cuda.empty_cache()
+    if timer is not None:
+        timer.cancel()
+    if cx.sampler:
+        cx.sampler.stop()
+    if emitted.is_set():          # the timer got there first and is printing / leaving
+        time.sleep(10.0)
+        return 0
+    emitted.set()
+    if rank == 0:
+        emit_result(build_line())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -514,15 +558,12 @@ def bench_dist(cx):
 
     def step():
         ev[0].record()
-        if world > 1:
-            # exchange and plane build overlapped: global register range (all-reduce of two scalars), one broadcast per shard,
-            # planes / counts / cardinalities of each shard built as it lands (multigpu.allgather_prepare_overlapped)
-            full = multigpu.allgather_prepare_overlapped(plan, local, counts, dist, p, capi.ERTL_MLE, stream)
-            ev[1].record()
-        else:
-            full = local
-            ev[1].record()
-            plan.prepare_dev(full.data_ptr(), n, p, capi.ERTL_MLE, stream)
+        # ONE collective.  (multigpu.allgather_prepare_overlapped — global range by all-reduce, one broadcast per shard, planes built per
+        # shard as it lands — was measured instead: 1.47 ms at N=2 against 0.46 + 0.7 ms here, and 8 ms at N=8: once the plane build
+        # takes 0.35 ms per 10,000 sketches there is nothing left to hide behind eight broadcasts.)
+        full = multigpu.allgather_registers(local, counts, dist) if world > 1 else local
+        ev[1].record()
+        plan.prepare_dev(full.data_ptr(), n, p, capi.ERTL_MLE, stream)
         ev[2].record()
         plan.run_symmetric_dev(prm, rb, re_, d_out.data_ptr(), stream)
         ev[3].record()
@@ -590,7 +631,8 @@ def bench_dist(cx):
             capi.dist_symmetric(host_regs, p, k=K_MER, result_type=capi.JI, device=cx.local_rank, out=host_out)
         else:
             loc = pin_t.to(dev, non_blocking=True)
-            full = multigpu.allgather_prepare_overlapped(plan, loc, counts, dist, p, capi.ERTL_MLE, stream)
+            full = multigpu.allgather_registers(loc, counts, dist)
+            plan.prepare_dev(full.data_ptr(), n, p, capi.ERTL_MLE, stream)
             for (b0, b1, off, cnt), e in zip(blocks, blk_ev):
                 plan.run_symmetric_dev(prm, b0, b1, d_out.data_ptr() + off * 4, stream)
                 e.record()
@@ -617,9 +659,7 @@ def bench_dist(cx):
            "api": "db200_dist_symmetric(host regs -> host packed float matrix)" if world == 1 else "multigpu driver: pinned shard -> all-gather -> rows in 4 blocks (device->host copy of block b under the kernel of block b+1) -> pinned out"}
     res = {"metric": "pairwise HLL cmp/s (dist p=14)", "value": value, "unit": "pairs/s", "ms_per_step": ms_per_step,
            "config": dist_config(n, world),
-           "details": {"step_breakdown_ms": ({"allgather": float(np.mean(ag_ms)), "planes+cardinalities": float(np.mean(prep_ms)), "all_pairs_kernel": ker} if world == 1 else
-                                             {"exchange+planes+cardinalities (overlapped: range all-reduce, per-shard broadcast, planes per shard as it lands)": float(np.mean(ag_ms)) + float(np.mean(prep_ms)),
-                                              "all_pairs_kernel": ker}),
+           "details": {"step_breakdown_ms": {"allgather": float(np.mean(ag_ms)), "planes+cardinalities": float(np.mean(prep_ms)), "all_pairs_kernel": ker},
                        "tiles": tiles, "live_thresholds": K, "rows_of_rank0": [rb, re_]},
            "roofline": roof, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "dtype": "u8 registers / u32 popcounts / f64 estimator -> f32 out"}
     plan.close()
@@ -931,19 +971,18 @@ def bench_c4(cx):
         return multigpu.allgather_registers(loc, counts, dist)
 
     def gather_prepare(loc):
-        if emulated:
-            full_ = gather(loc)
-            plan.prepare_dev(full_.data_ptr(), n, p, capi.ERTL_MLE, stream)
-            return full_
-        return multigpu.allgather_prepare_overlapped(plan, loc, counts, dist, p, capi.ERTL_MLE, stream)
+        full_ = gather(loc)
+        ev[1].record()
+        plan.prepare_dev(full_.data_ptr(), n, p, capi.ERTL_MLE, stream)
+        return full_
 
+    torch.cuda.set_device(cx.local_rank)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     ag, prep, ker, tot = [], [], [], []
     for it in range(warm + steps):
         cx.barrier()
         ev[0].record()
         full = gather_prepare(local)
-        ev[1].record()
         ev[2].record()
         plan.run_symmetric_dev(prm, rb, re_, d_out.data_ptr(), stream)
         ev[3].record()
@@ -968,7 +1007,7 @@ def bench_c4(cx):
     scale = (W if emulated else 1)     # an emulated rank reports the whole-job figure its time implies (every rank holds 1/W of the pairs)
     out = {"metric": "pairwise HLL cmp/s (dist p=14)", "value": total_pairs / (ms * 1e-3), "unit": "pairs/s", "ms_per_step": ms, "steps": steps, "warmup": warm,
            "n_gpus": W, "config": dist_config(n, W, seed=SEED_C4),
-           "details": {"step_breakdown_ms": {"exchange+planes+cardinalities" + ("" if emulated else " (overlapped)"): float(np.mean(ag)) + float(np.mean(prep)), "all_pairs_kernel": float(np.mean(ker))},
+           "details": {"step_breakdown_ms": {"allgather": float(np.mean(ag)), "planes+cardinalities": float(np.mean(prep)), "all_pairs_kernel": float(np.mean(ker))},
                        "tiles": tiles, "live_thresholds": K, "rows_of_this_rank": [rb, re_], "pairs_of_this_rank": my_pairs,
                        "hbm_bytes": {"registers": n * m, "planes": K * n * (m // 8), "out_per_rank": my_pairs * 4}},
            "e2e": {"value": total_pairs / (e2e_t * 1e-3), "unit": "pairs/s", "ms_per_step": e2e_t, "h2d_bytes_per_step": int(counts[R] * m),
@@ -1035,6 +1074,7 @@ def bench_c5(cx):
             return full
         return multigpu.allgather_registers(loc, counts, dist)
 
+    torch.cuda.set_device(cx.local_rank)
     sample_genomes = {}
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     res = []
@@ -1069,19 +1109,15 @@ def bench_c5(cx):
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         t0 = time.perf_counter()
         ev[0].record()
-        if emulated:
-            full = gather(local)
-            ev[1].record()
-            plan.prepare_dev(full.data_ptr(), n, p, capi.ERTL_MLE, stream)
-        else:
-            full = multigpu.allgather_prepare_overlapped(plan, local, counts, dist, p, capi.ERTL_MLE, stream)
-            ev[1].record()
+        full = gather(local)
+        ev[1].record()
+        plan.prepare_dev(full.data_ptr(), n, p, capi.ERTL_MLE, stream)
         ev[2].record()
         stream_rows(cx, plan, prm, n, rb, re_, block_pairs, ring)
         t_pairs_wall = (time.perf_counter() - t0) * 1e3
         cx.barrier()
         if it >= warm:
-            res.append({"pack": t_pack, "sketch": t_sk, "exchange+planes": ev[0].elapsed_time(ev[2]),
+            res.append({"pack": t_pack, "sketch": t_sk, "allgather": ev[0].elapsed_time(ev[1]), "planes": ev[1].elapsed_time(ev[2]),
                         "gather+planes+pairs+d2h_wall": t_pairs_wall, "kmers": kmers})
     if pg is not None:
         pg.close()
@@ -1095,8 +1131,8 @@ def bench_c5(cx):
            "config": {"workload": f"e2e sketch+dist: {n} x {L} bp synthetic genomes, k={k}, p={p}, Ertl joint MLE JI ({total_pairs} pairs)", "genomes_per_gpu": ng,
                       "data": "genomes generated on the device batch by batch (SURVEY.md §8(d): C5 is never written to disk); sketch time = ASCII in HBM -> 2-bit store -> registers",
                       "parallelism": f"genomes x{W}, 1 NCCL all-gather of {n * m >> 20} MB of registers, block-row x{W}"},
-           "details": {"step_breakdown_ms": {"pack_ascii_to_2bit": r0["pack"], "sketch_kernel": r0["sketch"], "exchange+planes+cardinalities": r0["exchange+planes"],
-                                             "exchange+planes+all_pairs+d2h (wall)": r0["gather+planes+pairs+d2h_wall"]},
+           "details": {"step_breakdown_ms": {"pack_ascii_to_2bit": r0["pack"], "sketch_kernel": r0["sketch"], "allgather": r0["allgather"], "planes+cardinalities": r0["planes"],
+                                             "allgather+planes+all_pairs+d2h (wall)": r0["gather+planes+pairs+d2h_wall"]},
                        "sketch_kmers_per_s_whole_job": r0["kmers"] * W / (sketch_ms * 1e-3), "dist_pairs_per_s_whole_job": total_pairs / (pairs_ms * 1e-3),
                        "tiles": tiles, "live_thresholds": K, "rows_of_this_rank": [rb, re_], "pairs_of_this_rank": my_pairs,
                        "hbm_bytes": {"registers": n * m, "planes": K * n * (m // 8)}},
@@ -1160,6 +1196,7 @@ def main():
     ap.add_argument("--only", default="", help="comma list of extra legs to run (c4,c5)")
     ap.add_argument("--emulate-world", type=int, default=0, help="single GPU: run ONE rank's share of the 8-GPU configurations c4 / c5")
     ap.add_argument("--emulate-rank", type=int, default=0)
+    ap.add_argument("--legs-timeout", type=float, default=300.0, help="N=8: seconds the c4 + c5 legs may take before rank 0 prints the line without them")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         log("note: fewer than 3 warm-up steps; timing rules ask for W >= 3")

@@ -1025,7 +1025,10 @@ int db200_warmup(int device) {
 
 int db200_host_alloc(void **out, size_t bytes) {
     if (!out) { set_error("db200_host_alloc: null out"); return DB200_EINVAL; }
-    DB200_TRY(check_device(0));
+    // On the calling thread's CURRENT device, which is left alone: a rank of a multi-process job that had selected GPU r found
+    // device 0 current after this call (round 2, 8-GPU run: the host's next CUDA event then belonged to the wrong device).
+    // Page-locked memory is usable from every device under unified addressing.
+    if (phys_device_count() == 0) { set_error("no usable CUDA device; libdashing_b200 has no CPU fallback"); return DB200_ENODEV; }
     DB200_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
     return DB200_OK;
 }
