@@ -204,3 +204,17 @@ def test_jmle_parity_at_c5_shape(gpu, checker):
         got = gpu.dist_symmetric(regs, p, k=k, jestim=3, result_type=1, order=order)
         want = checker.dist_rows(regs, p, k=k, jestim=3, rtype=1, order=order)
         assert_close(got, want, what=f"JMLE n={n} p={p} k={k} order={order}")
+
+
+def test_joint_mle_threshold_limit_is_an_explicit_error(gpu):
+    """the joint-MLE kernel keeps three count families of every live threshold in shared memory; with 32-bit counts
+    (p > 16) that fits about 32 thresholds.  A matrix whose registers span the whole range at p=17 (48 live thresholds) must be
+    declined loudly (DB200_EUNSUPPORTED, so that a host keeps the reference's code for it) — never answered wrongly.  The union
+    path takes the same matrix (test_wide_counts_full_value_range)."""
+    p = 17
+    regs = synth.adversarial_registers(4, p)[[0, 3, 4]]          # empty sketch + two sketches uniform over 0..q+1
+    assert int(regs.max()) - int(regs.min()) == 64 - p + 1
+    with pytest.raises(gpu.Db200Error) as ei:
+        gpu.dist_symmetric(regs, p, k=21, jestim=3, result_type=1)
+    assert ei.value.code == gpu.EUNSUPPORTED and "live thresholds" in str(ei.value)
+    assert np.isfinite(gpu.dist_symmetric(regs[1:], p, k=21, result_type=1)).all()
