@@ -140,3 +140,27 @@ def test_argument_checks(gpu):
     rc = gpu.lib.db200_sketch_fasta_batch(0, 10, 33, 1, text.ctypes.data_as(C.c_void_p), offs.ctypes.data_as(gpu.u64p), lens.ctypes.data_as(gpu.u64p),
                                           2, gfb.ctypes.data_as(gpu.u64p), 2, out.ctypes.data_as(gpu.u8p), None)
     assert rc == gpu.EUNSUPPORTED
+
+
+def test_device_parser_against_the_reference_drivers_directly(gpu, ref, tmp_path):
+    """no link through this repo's host reader — the reference's own sketch_core<hll_t> (kseq_read +
+    Encoder::for_each + hll_t::addh + hll_t::write, run from oracle/_ref) writes the .hll file of every edge-case input, and the
+    device parser's registers for the same raw bytes must be that file's payload."""
+    import gzip
+    k, p = 21, 10
+    files = edge_files()
+    names = list(files)
+    got, status = gpu.sketch_fasta([[files[n]] for n in names], k, p, True)
+    assert not status.any()
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        for i, n in enumerate(names):
+            fn = n + ".fa"
+            with open(fn, "wb") as f:
+                f.write(files[n])
+            ref.cli_sketch([fn], k=k, p=p, nthreads=1)
+            want = np.frombuffer(gzip.open(ref.make_fname(fn, p, k, k, k)).read()[28:], dtype=np.uint8)
+            assert np.array_equal(got[i], want), n
+    finally:
+        os.chdir(cwd)
