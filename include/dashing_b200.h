@@ -28,6 +28,9 @@
  *     `_dev` entry points take DEVICE pointers plus a cudaStream_t (passed as void*), enqueue
  *     work on that stream and return without synchronising, so callers can bracket them with
  *     CUDA events (bench.py) or chain them after a collective (multi-GPU driver).
+ *   - CUDA device: an entry point that takes a `device` (or an object bound to one) makes that device current on the calling
+ *     thread and leaves it current, as CUDA libraries do; db200_host_alloc / db200_host_free / db200_hostpack / db200_last_error /
+ *     db200_kernel_launches never change it.  A host that drives several GPUs from one thread re-selects its device after a call.
  */
 #ifndef DASHING_B200_H
 #define DASHING_B200_H
