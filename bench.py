@@ -357,6 +357,62 @@ class Ctx:
     pass
 
 
+def attach_collectives(cx):
+    """barrier / max_over_ranks / all_ok on cx, over cx.torch, cx.dist, cx.dev (NCCL on the GPU box; the CPU tier drives the same
+    functions over gloo with a stubbed torch.cuda, tests/test_bench_legs_gloo.py)."""
+    torch, dist, world, dev = cx.torch, cx.dist, cx.world, cx.dev
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def all_ok(ok):
+        """True only if every rank says so — the gate in front of every collective of the optional legs, so that a rank
+        that failed (caught exception) takes the others out of the leg with it instead of leaving them in a collective."""
+        if world == 1:
+            return bool(ok)
+        t = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t.item())
+
+    cx.barrier, cx.max_over_ranks, cx.all_ok = barrier, max_over_ranks, all_ok
+
+
+def run_legs(cx, legs):
+    """BASELINE configs[3] and [4] (world == C45_WORLD, or one emulated rank): every rank calls this; a leg counts only if it went
+    through on EVERY rank (a rank that dropped out leaves the others' numbers meaningless)."""
+    args, rank = cx.args, cx.rank
+    for name, fn in (("c4", bench_c4), ("c5", bench_c5)):
+        if args.only and name not in args.only.split(","):
+            continue
+        t0 = time.perf_counter()
+        cx.torch.cuda.set_device(cx.local_rank)        # (library calls take a device index and leave that device current)
+        try:
+            res_leg = fn(cx)
+        except Exception as e:
+            import traceback
+            log(f"[bench] rank {rank}: {name} leg failed: {e!r}\n{traceback.format_exc()}")
+            res_leg = {"failed": repr(e)}
+        ok_all = True
+        try:
+            ok_all = cx.all_ok("failed" not in res_leg)
+        except Exception as e:
+            log(f"[bench] rank {rank}: status exchange after {name} failed: {e!r}")
+        if not ok_all and "failed" not in res_leg:
+            res_leg = {"failed": "another rank failed in this leg; see stderr"}
+        legs[name] = res_leg
+        log(f"[bench] rank {rank}: {name} done in {time.perf_counter() - t0:.1f}s")
+        cx.torch.cuda.empty_cache()
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -381,28 +437,7 @@ def run_gpu(args):
     cx.stream = torch.cuda.current_stream().cuda_stream
     cx.peak, cx.peak_src = load_peaks()
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def all_ok(ok):
-        """True only if every rank says so — the gate in front of every collective of the optional legs, so that a rank
-        that failed (caught exception) takes the others out of the leg with it instead of leaving them in a collective."""
-        if world == 1:
-            return bool(ok)
-        t = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MIN)
-        return bool(t.item())
-
-    cx.barrier, cx.max_over_ranks, cx.all_ok = barrier, max_over_ranks, all_ok
+    attach_collectives(cx)
     cx.sampler = ClockSampler(local_rank) if rank == 0 else None
     results, extra = {}, {}
 
@@ -495,28 +530,7 @@ def run_gpu(args):
         except Exception as e:
             log(f"[bench] jmle leg failed: {e!r}")
     if (world == C45_WORLD or emu) and not args.no_extra:
-        for name, fn in (("c4", bench_c4), ("c5", bench_c5)):
-            if args.only and name not in args.only.split(","):
-                continue
-            t0 = time.perf_counter()
-            torch.cuda.set_device(local_rank)        # (library calls take a device index and leave that device current)
-            try:
-                res_leg = fn(cx)
-            except Exception as e:
-                import traceback
-                log(f"[bench] rank {rank}: {name} leg failed: {e!r}\n{traceback.format_exc()}")
-                res_leg = {"failed": repr(e)}
-            # a leg counts only if it went through on EVERY rank (a rank that dropped out leaves the others' numbers meaningless)
-            ok_all = True
-            try:
-                ok_all = all_ok("failed" not in res_leg)
-            except Exception as e:
-                log(f"[bench] rank {rank}: status exchange after {name} failed: {e!r}")
-            if not ok_all and "failed" not in res_leg:
-                res_leg = {"failed": "another rank failed in this leg; see stderr"}
-            legs[name] = res_leg
-            log(f"[bench] rank {rank}: {name} done in {time.perf_counter() - t0:.1f}s")
-            torch.cuda.empty_cache()
+        run_legs(cx, legs)
     if timer is not None:
         timer.cancel()
     if cx.sampler:
@@ -1154,7 +1168,7 @@ def bench_c5(cx):
             got_rows = d_keep.cpu().numpy()
             rng = np.random.default_rng(5)
             ns = 2000
-            ii = rb + rng.integers(0, keep_rows, size=ns)
+            ii = rb + rng.integers(0, max(1, min(keep_rows, n - 1 - rb)), size=ns)
             jj = np.array([rng.integers(i + 1, n) for i in ii])
             rows_needed = np.unique(np.concatenate([ii, jj]))
             host_rows = {int(r): full[int(r)].cpu().numpy() for r in rows_needed}
