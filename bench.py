@@ -613,7 +613,14 @@ def bench_dist(cx):
             "note": "algorithmic bytes = what the reference streams per pair (SURVEY.md §8(d)); the tiled kernel re-uses planes from SMEM/L2 so "
                     "frac exceeds 1 and says nothing about kernel quality — the binding units are the integer pipes (int_bound)",
             "int_bound": {"word_ops_per_pair": K * (m // 32), "thresholds": K,
-                          "word_ops_per_s": my_pairs * K * (m // 32) / (ker * 1e-3)}}
+                          "word_ops_per_s": my_pairs * K * (m // 32) / (ker * 1e-3),
+                          # static pipe model of the sweep (DESIGN.md §4 "Round 2"): on this data 11 of the K thresholds are swept densely
+                          # (the others come from the merged sparse / low tails), 512 plane words each; at the optimum POPC : carry-save
+                          # mix a word costs 2.0 cycles of the 64-lane ALU pipe (and as much of the 16-lane XU pipe), 148 SMs, 1.965 GHz
+                          "pipe_model": {"dense_thresholds_assumed": 11, "alu_cycles_per_word_at_optimum": 2.0,
+                                         "ceiling_pairs_per_s_per_gpu": 148 * 64 * 1.965e9 / (11 * (m // 32) * 2.0),
+                                         "frac_of_ceiling": (my_pairs / (ker * 1e-3)) / (148 * 64 * 1.965e9 / (11 * (m // 32) * 2.0)),
+                                         "measured_pipe_utilisation": "ALU 66 %, XU 63 %, issue 60 % (profiles/r01n_dist_kernel_ncu.txt; same with 24 resident warps: profiles/r02b)"}}}
     clocks = cx.sampler.window(t_wall0, t_wall1) if cx.sampler else None
     gpu_rows_np = None
     regs_np = None
