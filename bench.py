@@ -413,6 +413,101 @@ def run_legs(cx, legs):
         cx.torch.cuda.empty_cache()
 
 
+def legs_child_port():
+    """Rendezvous port of the children's process group: away from the parent's."""
+    p = int(os.environ.get("MASTER_PORT", "29500"))
+    return p + 101 if p + 101 < 65536 else p - 101
+
+
+def run_legs_isolated(cx, timeout, cmd=None):
+    """Every rank starts `bench.py --legs-child` (same RANK / WORLD_SIZE / LOCAL_RANK, own rendezvous port), waits for it at most
+    `timeout` seconds and kills it otherwise; rank 0's child leaves the legs' results in a file.  -> {"c4": ..., "c5": ...} on rank 0
+    (failure notes when the file is missing), {} elsewhere.  `cmd` replaces the child command in the CPU-tier test."""
+    import subprocess
+    import tempfile
+    args, rank = cx.args, cx.rank
+    names = [n for n in ("c4", "c5") if not (args.only and n not in args.only.split(","))]
+    out_path = os.path.join(tempfile.gettempdir(), f"db200_legs_{os.getpid()}_{rank}.json")
+    if os.path.exists(out_path):
+        os.remove(out_path)
+    env = dict(os.environ)
+    env["DB200_LEGS_OUT"] = out_path
+    env["DB200_LEGS_PORT"] = str(legs_child_port())
+    if cmd is None:
+        cmd = [sys.executable, os.path.abspath(__file__), "--gpus", str(cx.world), "--legs-child"]
+        if args.only:
+            cmd += ["--only", args.only]
+        if args.no_cpu_baseline:
+            cmd += ["--no-cpu-baseline"]
+    t0 = time.perf_counter()
+    why = None
+    try:
+        # the child's stdout must never reach this process's stdout (the ONE line of the contract): send it to stderr
+        r = subprocess.run(cmd, env=env, timeout=timeout, stdout=sys.stderr, stderr=sys.stderr)
+        if r.returncode != 0:
+            why = f"child exited with status {r.returncode}"
+    except subprocess.TimeoutExpired:
+        why = f"child did not finish within {timeout:.0f} s and was killed"
+    except Exception as e:        # noqa: BLE001 - the legs are optional, the primary line is not
+        why = f"could not run the child: {e!r}"
+    log(f"[bench] rank {rank}: legs child finished in {time.perf_counter() - t0:.1f}s" + (f" ({why})" if why else ""))
+    if rank != 0:
+        return {}
+    legs = {}
+    try:
+        if os.path.exists(out_path):
+            legs = json.load(open(out_path))
+            os.remove(out_path)
+    except Exception as e:        # noqa: BLE001
+        why = why or f"unreadable result file: {e!r}"
+    for n in names:
+        if n not in legs:
+            legs[n] = {"failed": (why or "the child left no result for this leg") + "; see stderr"}
+    return legs
+
+
+def run_legs_child(args, backend="nccl", stubs=None):
+    """`bench.py --legs-child` (started by run_legs_isolated, one per rank): its own process group, the two legs, rank 0 writes the
+    results to $DB200_LEGS_OUT.  `backend` / `stubs` = (torch-like, capi-like, device) let the CPU tier run the very same function
+    over gloo with the device stubbed (tests/test_bench_legs_gloo.py)."""
+    import datetime
+    import torch
+    import torch.distributed as dist
+    from dashing_b200 import multigpu
+    cx = Ctx()
+    cx.world = int(os.environ["WORLD_SIZE"]); cx.rank = int(os.environ["RANK"]); cx.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if stubs is None:
+        from dashing_b200 import capi
+        torch.cuda.set_device(cx.local_rank)
+        cx.torch, cx.capi, cx.dev = torch, capi, torch.device("cuda", cx.local_rank)
+        pg_kw = {"device_id": cx.dev}
+        cx.stream = torch.cuda.current_stream().cuda_stream
+    else:
+        cx.torch, cx.capi, cx.dev = stubs
+        pg_kw = {}
+        cx.stream = 0
+    cx.dist, cx.multigpu, cx.args = dist, multigpu, args
+    os.environ.setdefault("DB200_PACK_THREADS", str(max(2, usable_cores() // cx.world)))
+    dist.init_process_group(backend, init_method=f"tcp://127.0.0.1:{os.environ['DB200_LEGS_PORT']}", rank=cx.rank, world_size=cx.world,
+                            timeout=datetime.timedelta(seconds=240), **pg_kw)
+    cx.peak, cx.peak_src = load_peaks()
+    cx.sampler = None
+    attach_collectives(cx)
+    legs = {}
+    run_legs(cx, legs)
+    if cx.rank == 0:
+        tmp = os.environ["DB200_LEGS_OUT"] + ".tmp"
+        with open(tmp, "w") as f:
+            json.dump(legs, f)
+        os.replace(tmp, os.environ["DB200_LEGS_OUT"])
+    try:
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception as e:        # noqa: BLE001
+        log(f"[bench/legs-child] rank {cx.rank}: shutdown: {e!r}")
+    return 0
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -499,46 +594,22 @@ def run_gpu(args):
         line.update(legs)
         return line
 
-    # The optional legs run collectives of their own.  If a rank fails inside one of them the others would sit in a collective until
-    # NCCL's watchdog (10 minutes) kills the job and the primary result with it — what happened to the first 8-GPU run of round 2.
-    # A timer thread therefore bounds the legs: when it fires, rank 0 prints the line with what it has and every rank leaves.
-    emitted = threading.Event()
-
-    def bail_out():
-        if emitted.is_set():
-            return
-        emitted.set()
-        if rank == 0:
-            for name in ("c4", "c5"):
-                if (world == C45_WORLD or emu) and name not in legs and not (args.only and name not in args.only.split(",")):
-                    legs[name] = {"failed": f"leg did not finish within {args.legs_timeout:.0f} s (timer); see stderr"}
-            try:
-                emit_result(build_line())
-            finally:
-                os._exit(0)
-        time.sleep(2.0)
-        os._exit(0)
-
-    timer = None
-    if world > 1 and not args.no_extra and world == C45_WORLD:
-        timer = threading.Timer(args.legs_timeout, bail_out)
-        timer.daemon = True
-        timer.start()
     if world == 1 and not emu and args.workload == "both" and not args.no_extra:
         try:
             legs["jmle"] = bench_jmle(cx)
         except Exception as e:
             log(f"[bench] jmle leg failed: {e!r}")
-    if (world == C45_WORLD or emu) and not args.no_extra:
-        run_legs(cx, legs)
-    if timer is not None:
-        timer.cancel()
+    if emu and not args.no_extra:
+        run_legs(cx, legs)                       # one emulated rank, in this process
+    elif world == C45_WORLD and not args.no_extra:
+        # The c4 / c5 legs run collectives of their own.  In the first 8-GPU run of round 2 a rank failed inside one of them, the
+        # others sat in a collective until NCCL's watchdog killed the job 10 minutes later, and the primary result died with it.
+        # They therefore run in CHILD processes (one per rank, their own process group on another port): whatever happens in
+        # there — exception, hang, NCCL abort, crash — this process survives, waits at most --legs-timeout and prints its line.
+        torch.cuda.empty_cache()
+        legs.update(run_legs_isolated(cx, args.legs_timeout))
     if cx.sampler:
         cx.sampler.stop()
-    if emitted.is_set():          # the timer got there first and is printing / leaving
-        time.sleep(10.0)
-        return 0
-    emitted.set()
     if rank == 0:
         emit_result(build_line())
     if world > 1:
@@ -1217,7 +1288,8 @@ def main():
     ap.add_argument("--only", default="", help="comma list of extra legs to run (c4,c5)")
     ap.add_argument("--emulate-world", type=int, default=0, help="single GPU: run ONE rank's share of the 8-GPU configurations c4 / c5")
     ap.add_argument("--emulate-rank", type=int, default=0)
-    ap.add_argument("--legs-timeout", type=float, default=300.0, help="N=8: seconds the c4 + c5 legs may take before rank 0 prints the line without them")
+    ap.add_argument("--legs-timeout", type=float, default=300.0, help="N=8: seconds the c4 + c5 legs (child processes) may take before the line is printed without them")
+    ap.add_argument("--legs-child", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         log("note: fewer than 3 warm-up steps; timing rules ask for W >= 3")
@@ -1225,6 +1297,8 @@ def main():
         if args.workload == "both":
             args.workload = "dist"
         return run_reference(args)
+    if args.legs_child:
+        return run_legs_child(args)
     return run_gpu(args)
 
 

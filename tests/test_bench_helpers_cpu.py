@@ -61,3 +61,44 @@ def test_register_generator_is_shard_invariant():
     same = (full[1] == full[2]).mean()
     diff = (full[1] == full[17]).mean()
     assert same > diff + 0.1
+
+
+def _cx(rank=0, only=""):
+    class Args:
+        no_cpu_baseline = True
+    Args.only = only
+    cx = bench.Ctx()
+    cx.args, cx.rank, cx.world = Args, rank, 8
+    return cx
+
+
+def test_isolated_legs_survive_whatever_the_child_does(tmp_path, capfd):
+    """run_legs_isolated (bench.py at N=8): the c4 / c5 legs run in a child process per rank; the parent — which owns the primary
+    result — must come back with results or failure notes whether the child succeeds, crashes, hangs or cannot be started."""
+    import sys
+    import time
+    py = sys.executable
+    ok = [py, "-c", "import json, os; json.dump({'c4': {'value': 1.0}, 'c5': {'value': 2.0}}, open(os.environ['DB200_LEGS_OUT'], 'w')); print('child chatter on stdout')"]
+    legs = bench.run_legs_isolated(_cx(), 30, cmd=ok)
+    assert legs == {"c4": {"value": 1.0}, "c5": {"value": 2.0}}
+    out, err = capfd.readouterr()
+    assert "child chatter" not in out, "the child's stdout leaked into the result stream"
+    assert bench.run_legs_isolated(_cx(rank=3), 30, cmd=ok) == {}                      # only rank 0 reports
+    crash = [py, "-c", "import os, signal; os.kill(os.getpid(), signal.SIGSEGV)"]
+    legs = bench.run_legs_isolated(_cx(), 30, cmd=crash)
+    assert set(legs) == {"c4", "c5"} and all("failed" in v and "status" in v["failed"] for v in legs.values())
+    t0 = time.perf_counter()
+    legs = bench.run_legs_isolated(_cx(), 2, cmd=[py, "-c", "import time; time.sleep(60)"])
+    assert time.perf_counter() - t0 < 20 and all("killed" in v["failed"] for v in legs.values())
+    half = [py, "-c", "import json, os; json.dump({'c4': {'value': 1.0}}, open(os.environ['DB200_LEGS_OUT'], 'w')); raise SystemExit(3)"]
+    legs = bench.run_legs_isolated(_cx(), 30, cmd=half)
+    assert legs["c4"] == {"value": 1.0} and "failed" in legs["c5"]                     # what finished is kept
+    legs = bench.run_legs_isolated(_cx(only="c4"), 30, cmd=["/nonexistent/interpreter"])
+    assert set(legs) == {"c4"} and "could not run" in legs["c4"]["failed"]
+
+
+def test_legs_child_port_is_off_the_parents(monkeypatch):
+    monkeypatch.setenv("MASTER_PORT", "29500")
+    assert bench.legs_child_port() == 29601
+    monkeypatch.setenv("MASTER_PORT", "65500")
+    assert bench.legs_child_port() == 65399

@@ -229,3 +229,77 @@ def test_a_rank_failing_inside_a_leg_is_reported_not_silently_mixed():
     legs0, _ = res[0]
     if legs0.get("_finished"):
         assert "failed" in legs0["c4"]
+
+
+# ---- the same legs through bench.py's process isolation: parent ranks (gloo) -> run_legs_isolated -> child ranks -> run_legs_child
+def _stub_capi():
+    from dashing_b200 import capi as real_capi
+
+    class FakeCapi:
+        ERTL_MLE, ERTL_JOINT_MLE, JI, ORDER_ROW_FIRST = real_capi.ERTL_MLE, real_capi.ERTL_JOINT_MLE, real_capi.JI, real_capi.ORDER_ROW_FIRST
+        dist_params = staticmethod(real_capi.dist_params)
+        DistPlan, PackedGenomes = _Plan, _Packed
+        kernel_launches = staticmethod(lambda: 0)
+        pinned_empty = staticmethod(lambda nbytes: np.zeros(nbytes, dtype=np.uint8))
+    return FakeCapi
+
+
+def child_main():
+    """What `bench.py --legs-child` does, with the device stubbed and gloo instead of NCCL (run as a script by the test below)."""
+    sys.path.insert(0, ROOT)
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    bench.C45_WORLD, bench.C4_N, bench.C5_GENOMES, bench.GENOME_LEN = int(os.environ["WORLD_SIZE"]), 96, 12, 3000
+    bench.usable_cores = lambda: 2
+    if os.environ.get("LEGS_TEST_MODE") == "hang" and os.environ["RANK"] == "1":
+        time.sleep(120)                        # a rank that never shows up: the others wait in the rendezvous
+
+    class Args:
+        emulate_world, emulate_rank, no_cpu_baseline, only, steps, warmup = 0, 0, True, "", 2, 1
+    return bench.run_legs_child(Args, backend="gloo", stubs=(_FakeTorch(), _stub_capi(), torch.device("cpu")))
+
+
+def _parent(rank, world, port, mode, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank),
+                      LEGS_TEST_MODE=mode)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+
+    class Args:
+        no_cpu_baseline, only = True, ""
+    cx = bench.Ctx()
+    cx.args, cx.rank, cx.world = Args, rank, world
+    cmd = [sys.executable, "-c", "import sys; sys.path.insert(0, %r); import test_bench_legs_gloo as t; sys.exit(t.child_main())" % os.path.join(ROOT, "tests")]
+    t0 = time.perf_counter()
+    legs = bench.run_legs_isolated(cx, 15 if mode == "hang" else 150, cmd=cmd)
+    dist.barrier()                              # the parents' own process group is alive and well afterwards
+    q.put((rank, legs, time.perf_counter() - t0))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("mode", ["ok", "hang"])
+def test_legs_in_child_processes_world2(mode):
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_parent, args=(r, world, port, mode, q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    res = {}
+    for _ in range(world):
+        rank, legs, dt = q.get(timeout=240)
+        res[rank] = (legs, dt)
+    for pr in procs:
+        pr.join(timeout=30)
+    assert res[1][0] == {}
+    legs = res[0][0]
+    assert set(legs) == {"c4", "c5"}
+    if mode == "ok":
+        assert all("failed" not in v and v["value"] > 0 and v["n_gpus"] == world for v in legs.values()), legs
+    else:
+        assert all("failed" in v for v in legs.values()) and res[0][1] < 60      # bounded, and the parents went on
