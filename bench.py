@@ -15,6 +15,8 @@ The same JSON line carries
   * `jmle`    — (N=1) Ertl joint MLE all-pairs at p=16, k=21 (the estimator of configs[4]) with its own parity object;
   * `c4`,`c5` — (N=8, or one emulated rank with --emulate-world 8) BASELINE configs[3] (100,000 p=14 sketches over
                 8 ranks) and configs[4] (50,000 x 5 Mbp genomes, k=21, p=16, joint MLE, sketch + all-gather + all pairs).
+                At N=8 these two legs run in child processes (`--legs-child`, own NCCL group, at most --legs-timeout seconds)
+                so that nothing they do can cost the primary line.
 
 Multi-GPU (torchrun, one rank per GPU): weak scaling.  dist: n(N) = round(10000*sqrt(N)) sketches, each rank
 holds n/N of them, one all-gather, block-rows balanced by pair count; sketch: 1,000 genomes per rank.
