@@ -303,3 +303,40 @@ def test_legs_in_child_processes_world2(mode):
         assert all("failed" not in v and v["value"] > 0 and v["n_gpus"] == world for v in legs.values()), legs
     else:
         assert all("failed" in v for v in legs.values()) and res[0][1] < 60      # bounded, and the parents went on
+
+
+def test_primary_and_jmle_legs_world1_stubbed():
+    """The N=1 branches of bench_dist / bench_jmle (host-pointer e2e call, roofline object, traffic lookup) with the device stubbed."""
+    sys.path.insert(0, ROOT)
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    from dashing_b200 import multigpu
+    bench.N_DIST_1GPU, bench.N_JMLE = 80, 40
+    bench.usable_cores = lambda: 2
+    FakeCapi = _stub_capi()
+
+    def dist_symmetric(regs, p, k=31, result_type=1, device=0, out=None, **kw):
+        n = regs.size >> p
+        out[: n * (n - 1) // 2] = np.arange(n * (n - 1) // 2, dtype=np.float32)
+        return out
+    FakeCapi.dist_symmetric = staticmethod(dist_symmetric)
+
+    class Args:
+        emulate_world, emulate_rank, no_cpu_baseline, only, steps, warmup = 0, 0, True, "", 2, 1
+    cx = bench.Ctx()
+    cx.torch, cx.dist, cx.capi, cx.multigpu, cx.args = _FakeTorch(), dist, FakeCapi, multigpu, Args
+    cx.world, cx.rank, cx.local_rank, cx.dev, cx.stream = 1, 0, 0, torch.device("cpu"), 0
+    cx.peak, cx.peak_src, cx.sampler = 6467.7, "test", None
+    bench.attach_collectives(cx)
+    res, extra = bench.bench_dist(cx)
+    assert res["config"] == bench.dist_config(80, 1) and res["value"] > 0 and res["e2e"]["value"] > 0
+    assert res["roofline"]["traffic"] is None                                      # the ncu capture is for n = 10,000 only
+    pm = res["roofline"]["int_bound"]["pipe_model"]
+    assert 1.6e9 < pm["ceiling_pairs_per_s_per_gpu"] < 1.7e9 and pm["frac_of_ceiling"] > 0
+    assert extra["regs_np"].shape == (80, 1 << 14) and extra["gpu_rows_np"].size == 80 * 79 // 2
+    assert np.array_equal(extra["regs_np"], bench.host_registers(bench.SEED_DIST, 0, 80, 14))     # the bytes the reference arm draws
+    j = bench.bench_jmle(cx)
+    assert j["config"]["n_sketches"] == 40 and j["config"]["p"] == 16 and j["value"] > 0
+    import json
+    json.dumps(res); json.dumps(j)                                                  # everything in the line must serialise
